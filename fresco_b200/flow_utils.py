@@ -1,0 +1,121 @@
+"""Drop-in for the reference's ``src/flow_utils.py`` + the geometry helpers it
+uses, backed by the sm_100a kernels (no PyTorch fallback for the hot ops).
+
+Public names and argument meaning follow the reference:
+``warp_tensor`` (src/flow_utils.py:18-53), ``get_single_mapping_ind`` (:56-102),
+``get_mapping_ind`` (:105-138), ``flow_warp`` / ``forward_backward_consistency_check``
+(gmflow/geometry.py:65-96).  Small per-batch preparation (resizing flows, pooling
+occlusion masks) stays in torch; the per-step work runs in libfresco_b200.so.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence
+
+import torch
+import torch.nn.functional as F
+
+from . import ops
+
+
+# --------------------------------------------------------------------------- geometry
+def flow_warp(feature: torch.Tensor, flow: torch.Tensor) -> torch.Tensor:
+    """Bilinear warp at pixel coordinates (x+flow_x, y+flow_y), zeros outside.
+    gmflow/geometry.py:65-72.  fp32 kernel; other dtypes are converted."""
+    out = ops.flow_warp(feature.float().contiguous(), flow.float().contiguous())
+    return out.to(feature.dtype)
+
+
+def forward_backward_consistency_check(fwd_flow, bwd_flow, alpha=0.01, beta=0.5):
+    """gmflow/geometry.py:75-96."""
+    mag = torch.norm(fwd_flow, dim=1) + torch.norm(bwd_flow, dim=1)
+    warped_bwd = flow_warp(bwd_flow, fwd_flow)
+    warped_fwd = flow_warp(fwd_flow, bwd_flow)
+    thr = alpha * mag + beta
+    fwd_occ = (torch.norm(fwd_flow + warped_bwd, dim=1) > thr).float()
+    bwd_occ = (torch.norm(bwd_flow + warped_fwd, dim=1) > thr).float()
+    return fwd_occ, bwd_occ
+
+
+def _dilate(x: torch.Tensor, k: int) -> torch.Tensor:
+    """k x k binary dilation with replicate padding (src/utils.py:81-93)."""
+    p = (k - 1) // 2
+    x = F.pad(x, (p, p, p, p), mode="replicate")
+    return torch.clamp(F.conv2d(x, torch.ones(1, 1, k, k, dtype=x.dtype, device=x.device)), 0, 1)
+
+
+def resize_flows_occs(flows: Sequence[torch.Tensor], occs: Sequence[torch.Tensor], size_h: int):
+    """Flows / occlusions at the resolution of a feature map.
+    src/flow_utils.py:24-33 == src/diffusion_hacked.py:437-442."""
+    scale = size_h * 1.0 / flows[0].shape[2]
+    kernel = int(1 / scale)
+    bwd_flow = F.interpolate(flows[1] * scale, scale_factor=scale, mode="bilinear")
+    fwd_flow = F.interpolate(flows[0] * scale, scale_factor=scale, mode="bilinear")
+    bwd_occ = F.max_pool2d(occs[1].unsqueeze(1), kernel_size=kernel)
+    fwd_occ = F.max_pool2d(occs[0].unsqueeze(1), kernel_size=kernel)
+    return scale, fwd_flow.float().contiguous(), bwd_flow.float().contiguous(), fwd_occ.float(), bwd_occ.float()
+
+
+# --------------------------------------------------------------------------- warp_tensor
+@torch.no_grad()
+def warp_tensor(sample, flows, occs, saliency, unet_chunk_size):
+    """Warp + fuse along the frame chain (src/flow_utils.py:18-53).
+
+    Unlike the reference (which aliases and mutates fp32 inputs, :36) this never
+    modifies ``sample``; the result has the dtype of ``sample``."""
+    n = sample.shape[0] // unet_chunk_size
+    h = sample.shape[2]
+    scale, fwd_flow, bwd_flow, fwd_occ, bwd_occ = resize_flows_occs(flows, occs, h)
+    if scale == 1:
+        bwd_occ = _dilate(bwd_occ, 13)
+        fwd_occ = _dilate(fwd_occ, 13)
+    scale2 = h * 1.0 / saliency.shape[2]
+    sal = F.interpolate(saliency.float(), scale_factor=scale2, mode="bilinear").contiguous()
+    warp_sal = ops.flow_warp(sal, bwd_flow)                                    # :38
+    warp_sal_last = ops.flow_warp(sal[0:1].contiguous(), fwd_flow[n - 1:n].contiguous())   # :39
+    blend = torch.empty(n, 1, sample.shape[2], sample.shape[3], dtype=torch.float32, device=sample.device)
+    blend[:n - 1] = (1 - bwd_occ[:n - 1]) * sal[1:n] * warp_sal[:n - 1]       # :45
+    blend[n - 1:] = (1 - fwd_occ[n - 1:n]) * sal[n - 1:n] * warp_sal_last      # :50
+    x = sample.contiguous()
+    if x.dtype not in (torch.float16, torch.float32):
+        x = x.float()
+    out = ops.warp_fuse_chain(x, bwd_flow, fwd_flow[n - 1].contiguous(), blend.contiguous(), unet_chunk_size)
+    return out.to(sample.dtype)
+
+
+# --------------------------------------------------------------------------- pixel mapping
+@torch.no_grad()
+def get_single_mapping_ind(bwd_flow, bwd_occ, imgs, scale=1.0):
+    """Pixel correspondence between two frames (src/flow_utils.py:56-102).
+    The sequential conflict loop (:84-97) is replaced by a parallel lexicographic
+    arg-min kernel; results are bit-identical to the reference's CPU output."""
+    mapping, unlinked = ops.mapping_single(bwd_flow.float().contiguous(), bwd_occ.float().contiguous(),
+                                           imgs.float().contiguous(), int(scale))
+    return mapping, unlinked
+
+
+@torch.no_grad()
+def get_mapping_ind(bwd_flows, bwd_occs, imgs, scale=1.0):
+    """Chain pairwise correspondences over the N frames of a batch
+    (src/flow_utils.py:105-138): returns fwd_mappings [N,1,L], bwd_mappings
+    [N,1,L] (int64) and the trajectory mask [L,1,N,N] (bool)."""
+    n = imgs.shape[0]
+    H, W = int(imgs.shape[2] // scale), int(imgs.shape[3] // scale)
+    L = H * W
+    dev = imgs.device
+    mask = torch.ones(L, n, n, dtype=torch.bool, device=dev)
+    ar = torch.arange(L, device=dev)
+    fwd: List[torch.Tensor] = [ar]
+    bwd: List[torch.Tensor] = [ar]
+    for i in range(n - 1):
+        cut = torch.ones(n, n, dtype=torch.bool, device=dev)
+        cut[:i + 1, i + 1:] = False
+        cut[i + 1:, :i + 1] = False
+        mp, unl = get_single_mapping_ind(bwd_flows[i:i + 1], bwd_occs[i:i + 1], imgs[i:i + 2], scale)
+        sel = unl[fwd[-1]]
+        mask[sel] = mask[sel] & cut
+        nxt = mp[fwd[-1]]
+        fwd.append(nxt)
+        inv = torch.empty_like(nxt)
+        inv[nxt] = ar                       # argsort of a permutation == its inverse
+        bwd.append(inv)
+    return torch.stack(fwd, 0).unsqueeze(1), torch.stack(bwd, 0).unsqueeze(1), mask.unsqueeze(1)

@@ -1,0 +1,149 @@
+"""Tensor-level wrappers over the C ABI: allocate outputs with torch, pass raw
+device pointers + the current CUDA stream.  No arithmetic happens here."""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+
+
+def kv_compact(k: torch.Tensor, v: torch.Tensor, idx: torch.Tensor, chunks: int):
+    """k, v [chunks*frames, tokens, C] fp16; idx int32 [n_sel] over (frame, token) -> [chunks, n_sel, C]."""
+    B, tokens, C = k.shape
+    rows = (B // chunks) * tokens
+    n_sel = idx.numel()
+    k_out = torch.empty(chunks, n_sel, C, dtype=k.dtype, device=k.device)
+    v_out = torch.empty_like(k_out)
+    L.check(L.lib().fresco_kv_compact(L.ptr(k), L.ptr(v), L.ptr(idx), L.ptr(k_out), L.ptr(v_out), chunks, rows,
+                                      n_sel, C, L.stream()), "fresco_kv_compact")
+    return k_out, v_out
+
+
+def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, q_per_kv: int = 1,
+             softmax_scale: Optional[float] = None, diag_bias: float = 0.0, out: Optional[torch.Tensor] = None):
+    """q [Bq, Lq, C], k/v [Bq/q_per_kv, Lk, C] fp16 token-major -> [Bq, Lq, C]."""
+    Bq, Lq, C = q.shape
+    d = C // heads
+    if q.dtype != torch.float16 or k.dtype != torch.float16 or v.dtype != torch.float16:
+        raise L.FrescoError("fresco attention kernels are fp16 (the reference's GPU dtype)")
+    if softmax_scale is None:
+        softmax_scale = 1.0 / math.sqrt(d)
+    if out is None:
+        out = torch.empty_like(q)
+    L.check(L.lib().fresco_attn_fwd(L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(out), Bq, Lq, k.shape[1], heads, d,
+                                    q_per_kv, float(softmax_scale), float(diag_bias), L.stream()),
+            "fresco_attn_fwd")
+    return out
+
+
+def temporal_attn_fwd(q_raw, k_raw, v_src, fwd_map, traj_mask, chunks: int, heads: int, scale: float):
+    B, tokens, C = q_raw.shape
+    frames = B // chunks
+    out = torch.empty_like(v_src)
+    L.check(L.lib().fresco_temporal_attn_fwd(L.ptr(q_raw), L.ptr(k_raw), L.ptr(v_src), L.ptr(out), L.ptr(fwd_map),
+                                             L.ptr(traj_mask), chunks, frames, tokens, heads, C // heads,
+                                             float(scale), L.stream()), "fresco_temporal_attn_fwd")
+    return out
+
+
+def flow_warp(src: torch.Tensor, flow: torch.Tensor) -> torch.Tensor:
+    """fp32 [B,C,h,w] warped by flow [Bf,2,h,w] (sample b uses flow b % Bf)."""
+    B, C, h, w = src.shape
+    dst = torch.empty_like(src)
+    L.check(L.lib().fresco_flow_warp(L.ptr(src), L.ptr(flow), L.ptr(dst), B, C, h, w, flow.shape[0], L.stream()),
+            "fresco_flow_warp")
+    return dst
+
+
+def warp_fuse_chain(sample, bwd_flow, fwd_flow_last, blend, chunks: int, out=None):
+    B, C, h, w = sample.shape
+    if out is None:
+        out = torch.empty_like(sample)
+    is_half = 1 if sample.dtype == torch.float16 else 0
+    if not is_half and sample.dtype != torch.float32:
+        raise L.FrescoError("warp_fuse_chain: fp16 or fp32 only")
+    L.check(L.lib().fresco_warp_fuse_chain(L.ptr(sample), L.ptr(out), is_half, L.ptr(bwd_flow), L.ptr(fwd_flow_last),
+                                           L.ptr(blend), chunks, B // chunks, C, h, w, L.stream()),
+            "fresco_warp_fuse_chain")
+    return out
+
+
+def warp_loss_fwd_bwd(cs, fwd_flow, bwd_flow, fwd_keep, bwd_keep, grad, loss_acc=None, accumulate=False):
+    chunks, frames, C, h, w = cs.shape
+    L.check(L.lib().fresco_warp_loss_fwd_bwd(L.ptr(cs), L.ptr(fwd_flow), L.ptr(bwd_flow), L.ptr(fwd_keep),
+                                             L.ptr(bwd_keep), L.ptr(grad),
+                                             L.ptr(loss_acc) if loss_acc is not None else None,
+                                             1 if accumulate else 0, chunks, frames, C, h, w, L.stream()),
+            "fresco_warp_loss_fwd_bwd")
+    return grad
+
+
+def gram_normalize(cs_bcl: torch.Tensor):
+    """cs [B, C, L] fp32 -> xhat [B, L, C] fp16, norms [B, L] fp32."""
+    B, C, Lt = cs_bcl.shape
+    xhat = torch.empty(B, Lt, C, dtype=torch.float16, device=cs_bcl.device)
+    norms = torch.empty(B, Lt, dtype=torch.float32, device=cs_bcl.device)
+    L.check(L.lib().fresco_gram_normalize(L.ptr(cs_bcl), L.ptr(xhat), L.ptr(norms), B, C, Lt, L.stream()),
+            "fresco_gram_normalize")
+    return xhat, norms
+
+
+def gram_sign(xhat, target, weight: float, loss_acc=None):
+    B, Lt, C = xhat.shape
+    tsign = torch.empty(B, Lt, Lt, dtype=torch.float16, device=xhat.device)
+    L.check(L.lib().fresco_gram_sign(L.ptr(xhat), L.ptr(target), L.ptr(tsign),
+                                     L.ptr(loss_acc) if loss_acc is not None else None, B, Lt, C, float(weight),
+                                     L.stream()), "fresco_gram_sign")
+    return tsign
+
+
+def gram_grad(tsign, xhat, norms, grad_bcl, weight: float):
+    B, Lt, C = xhat.shape
+    nbytes = int(L.lib().fresco_gram_grad_workspace_bytes(B, Lt, C))
+    ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=xhat.device)
+    L.check(L.lib().fresco_gram_grad(L.ptr(tsign), L.ptr(xhat), L.ptr(norms), L.ptr(grad_bcl), B, Lt, C,
+                                     float(weight), L.ptr(ws), nbytes, L.stream()), "fresco_gram_grad")
+    return grad_bcl
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, step: int, lr=0.2, beta1=0.9, beta2=0.999, eps=1e-8):
+    L.check(L.lib().fresco_adam_step(L.ptr(param), L.ptr(grad), L.ptr(exp_avg), L.ptr(exp_avg_sq), param.numel(),
+                                     int(step), lr, beta1, beta2, eps, L.stream()), "fresco_adam_step")
+
+
+def adain(content_f32: torch.Tensor, style: torch.Tensor) -> torch.Tensor:
+    n, c, h, w = style.shape
+    out = torch.empty_like(style)
+    is_half = 1 if style.dtype == torch.float16 else 0
+    if not is_half and style.dtype != torch.float32:
+        raise L.FrescoError("adain: fp16 or fp32 style only")
+    L.check(L.lib().fresco_adain(L.ptr(content_f32), L.ptr(style), L.ptr(out), is_half, n * c, h * w, L.stream()),
+            "fresco_adain")
+    return out
+
+
+def gmflow_global_corr_softmax(f0: torch.Tensor, f1: torch.Tensor, bidir: bool):
+    b, c, h, w = f0.shape
+    flow = torch.empty(b * (2 if bidir else 1), 2, h, w, dtype=torch.float32, device=f0.device)
+    nbytes = int(L.lib().fresco_gmflow_corr_workspace_bytes(b, c, h, w))
+    ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=f0.device)
+    L.check(L.lib().gmflow_global_corr_softmax(L.ptr(f0), L.ptr(f1), L.ptr(flow), b, c, h, w, 1 if bidir else 0,
+                                               L.ptr(ws), nbytes, L.stream()), "gmflow_global_corr_softmax")
+    return flow
+
+
+def mapping_single(bwd_flow: torch.Tensor, bwd_occ: torch.Tensor, imgs: torch.Tensor, scale: int):
+    """bwd_flow [1,2,H,W], bwd_occ [1,H,W], imgs [2,3,H,W] fp32 -> mapping int64 [L], unlinked bool [L]."""
+    H, W = imgs.shape[2], imgs.shape[3]
+    Lt = (H // scale) * (W // scale)
+    mapping = torch.empty(Lt, dtype=torch.int64, device=imgs.device)
+    unlinked = torch.empty(Lt, dtype=torch.uint8, device=imgs.device)
+    nbytes = int(L.lib().fresco_mapping_workspace_bytes(Lt))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=imgs.device)
+    L.check(L.lib().fresco_mapping_single(L.ptr(bwd_flow), L.ptr(bwd_occ), L.ptr(imgs), H, W, int(scale),
+                                          L.ptr(mapping), L.ptr(unlinked), L.ptr(ws), nbytes, L.stream()),
+            "fresco_mapping_single")
+    return mapping, unlinked.bool()

@@ -1,0 +1,140 @@
+/* fresco_b200 -- C ABI of the B200-native FRESCO hot path (libfresco_b200.so).
+ *
+ * The reference (williamyang1991/FRESCO) has no FFI on this path: its boundary is a Python
+ * monkey-patch surface over diffusers.  The host side of this repo
+ * (fresco_b200/*.py) mirrors that surface and binds these entry points with ctypes; each
+ * entry point cites the reference lines whose work it replaces (paths relative to the
+ * reference root).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller (torch allocator); nothing is
+ *    allocated, freed or synchronised inside; `stream` is a cudaStream_t.
+ *  - return value: 0 = ok, negative = FRESCO_ERR_*; fresco_last_error() gives the text
+ *    (thread-local).  Functions never throw and never touch the host-side oracle.
+ *  - "half" tensors are IEEE fp16; layouts are stated per function, innermost dimension last.
+ */
+#ifndef FRESCO_B200_H_
+#define FRESCO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FRESCO_ABI_VERSION 1
+
+#define FRESCO_OK 0
+#define FRESCO_ERR_ARG (-1)          /* null pointer / inconsistent shape            */
+#define FRESCO_ERR_UNSUPPORTED (-2)  /* shape outside what the kernels are built for */
+#define FRESCO_ERR_CUDA (-3)         /* CUDA runtime / launch error                  */
+#define FRESCO_ERR_TENSORMAP (-4)    /* cuTensorMapEncodeTiled failed                */
+
+int fresco_abi_version(void);
+const char* fresco_last_error(void);
+/* number of kernels launched by this library in this process (for bench.py's gpu_launches) */
+long long fresco_launch_count(void);
+
+/* ---- A2: cross-frame K/V selection --------------------------------------------------------
+ * replaces src/diffusion_hacked.py:234-247 (`key[:, attn_mask]` + `repeat(...)`).
+ * k, v      half [chunks, rows_per_chunk, channels]   (rows_per_chunk = frames * tokens)
+ * idx       int32 [n_sel] row indices into one chunk (row-major over (frame, token))
+ * k_out/v_out half [chunks, n_sel, channels]; shared by every query frame (no N x broadcast) */
+int fresco_kv_compact(const void* k, const void* v, const int32_t* idx, void* k_out, void* v_out, int chunks,
+                      int rows_per_chunk, int n_sel, int channels, void* stream);
+
+/* ---- A3 / A4: dense attention forward (tcgen05 + TMEM + TMA) -------------------------------
+ * replaces F.scaled_dot_product_attention at src/diffusion_hacked.py:281-285 (spatial-guided:
+ * q = to_q(ref), k = to_k(ref), v = current query, softmax_scale = 0.2/sqrt(d), diag_bias =
+ * intraattn_bias) and :303-305 (cross-frame: shared compacted K/V, q_per_kv = frames).
+ * q, out  half [batch_q, q_len, heads*head_dim];  k, v half [batch_q/q_per_kv, kv_len, heads*head_dim]
+ * out = softmax(q k^T * softmax_scale + diag_bias * I) v, per head. head_dim in {40,64,80,128}. */
+int fresco_attn_fwd(const void* q, const void* k, const void* v, void* out, int batch_q, int q_len, int kv_len,
+                    int heads, int head_dim, int q_per_kv, float softmax_scale, float diag_bias, void* stream);
+
+/* ---- A5: temporal-guided (FLATTEN) attention, fused gather -> N x N softmax -> scatter -----
+ * replaces src/diffusion_hacked.py:320-367.
+ * q_raw, k_raw, v_src, out  half [chunks*frames, tokens, heads*head_dim]  (v_src = output of A4)
+ * fwd_map int64 [frames, tokens] (trajectory p sits at token fwd_map[f][p] of frame f; a permutation)
+ * traj_mask uint8 [tokens, frames, frames] (1 = attend)
+ * out[b,f,fwd_map[f][p]] = sum_g softmax_g(q[f,pos]·k[g,pos] * scale, masked) v[g,pos]          */
+int fresco_temporal_attn_fwd(const void* q_raw, const void* k_raw, const void* v_src, void* out,
+                             const int64_t* fwd_map, const uint8_t* traj_mask, int chunks, int frames, int tokens,
+                             int heads, int head_dim, float scale, void* stream);
+
+/* ---- W3: bilinear flow warp (zero padding per tap, pixel coordinates) ----------------------
+ * replaces gmflow/geometry.py:65-72 (flow_warp) + :41-62 (grid_sample, align_corners=True).
+ * src, dst float [batch, channels, h, w]; flow float [flow_batch, 2, h, w] (x, y); sample b uses
+ * flow (b % flow_batch).                                                                        */
+int fresco_flow_warp(const float* src, const float* flow, float* dst, int batch, int channels, int h, int w,
+                     int flow_batch, void* stream);
+
+/* ---- W1: warp_tensor frame chain ----------------------------------------------------------
+ * replaces the loop at src/flow_utils.py:41-51.  One CTA per (chunk, channel) keeps the running
+ * frame plane in shared memory; the N-1 sequential blends need no grid-wide sync.
+ * sample/out  [chunks*frames, channels, h, w], half (is_half=1) or float; may alias.
+ * bwd_flow    float [frames, 2, h, w] (resized);  fwd_flow_last float [2, h, w] (frame N-1)
+ * blend       float [frames, h, w]: entries 0..N-2 = (1-bwd_occ[i])*sal[i+1]*warp_sal[i];
+ *             entry N-1 = closing mask (1-fwd_occ[N-1])*sal[N-1]*warp_sal_last                   */
+int fresco_warp_fuse_chain(const void* sample, void* out, int is_half, const float* bwd_flow,
+                           const float* fwd_flow_last, const float* blend, int chunks, int frames, int channels,
+                           int h, int w, void* stream);
+
+/* ---- O2: temporal-consistency loss, forward + backward -------------------------------------
+ * replaces src/diffusion_hacked.py:461-466 and its autograd backward.
+ * cs, grad float [chunks, frames, channels, h, w]; fwd_flow/bwd_flow float [frames,2,h,w];
+ * fwd_keep/bwd_keep float [frames,h,w] (= 1 - occlusion).  grad is overwritten (accumulate=0)
+ * or added to; *loss_acc (device float, may be null) gets the loss value added.                  */
+int fresco_warp_loss_fwd_bwd(const float* cs, const float* fwd_flow, const float* bwd_flow, const float* fwd_keep,
+                             const float* bwd_keep, float* grad, float* loss_acc, int accumulate, int chunks,
+                             int frames, int channels, int h, int w, void* stream);
+
+/* ---- O3: spatial-consistency (normalised Gram, L1) loss, forward + backward -----------------
+ * replaces src/diffusion_hacked.py:469-476 and its backward.
+ * step 1  fresco_gram_normalize: cs float [batch, channels, tokens] -> xhat half [batch, tokens, channels]
+ *         (row-normalised, token-major) and norms float [batch, tokens].
+ * step 2  fresco_gram_sign (tcgen05): G = xhat xhat^T per batch; T = sign(G - A) + sign(G - A^T)
+ *         written as half [batch, tokens, tokens]; loss += weight/(batch*tokens^2) * sum|G - A|.
+ *         target float [batch, tokens, tokens] is the reference's correlation_matrix entry.
+ * step 3  fresco_gram_grad (tcgen05): ghat = T xhat * weight/(batch*tokens^2), projected through the
+ *         normalisation Jacobian and added to grad float [batch, channels, tokens].             */
+int fresco_gram_normalize(const float* cs, void* xhat, float* norms, int batch, int channels, int tokens,
+                          void* stream);
+int fresco_gram_sign(const void* xhat, const float* target, void* tsign, float* loss_acc, int batch, int tokens,
+                     int channels, float weight, void* stream);
+int fresco_gram_grad(const void* tsign, const void* xhat, const float* norms, float* grad, int batch, int tokens,
+                     int channels, float weight, void* workspace, size_t workspace_bytes, void* stream);
+size_t fresco_gram_grad_workspace_bytes(int batch, int tokens, int channels);
+
+/* ---- O4 / O5: Adam update and AdaIN ---------------------------------------------------------
+ * fresco_adam_step replaces torch.optim.Adam.step at src/diffusion_hacked.py:433,485
+ * (betas 0.9/0.999, eps 1e-8, bias correction; `step` is 1-based).
+ * fresco_adain replaces src/utils.py:70-78 incl. the eps quirk (style eps = 1, content eps = 1e-5,
+ * unbiased variance).  content float [planes, hw]; style/out half or float [planes, hw].          */
+int fresco_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, int step,
+                     float lr, float beta1, float beta2, float eps, void* stream);
+int fresco_adain(const float* content, const void* style, void* out, int is_half, int planes, int hw, void* stream);
+
+/* ---- G1: GMFlow global correlation + softmax + expected coordinates -------------------------
+ * replaces gmflow/matching.py:7-36.  feature0/1 float [batch, channels, h, w];
+ * flow float [batch*(bidir?2:1), 2, h, w], order [fwd(batch), bwd(batch)].  The L x L volume is
+ * never materialised.  workspace: fresco_gmflow_corr_workspace_bytes().                           */
+int gmflow_global_corr_softmax(const float* feature0, const float* feature1, float* flow, int batch, int channels,
+                               int h, int w, int bidir, void* workspace, size_t workspace_bytes, void* stream);
+size_t fresco_gmflow_corr_workspace_bytes(int batch, int channels, int h, int w);
+
+/* ---- M1: pixel correspondence between two frames (integer, bit-exact) -----------------------
+ * replaces get_single_mapping_ind, src/flow_utils.py:57-102 (incl. the sequential loop :84-101).
+ * bwd_flow float [2,H,W] (x,y), bwd_occ float [H,W], imgs float [2,3,H,W] = [frame1, frame2];
+ * scale = integer downsample factor (1 or even).  Outputs over L = (H/scale)*(W/scale) pixels:
+ * mapping int64 [L], unlinked uint8 [L].  workspace: fresco_mapping_workspace_bytes(L).          */
+int fresco_mapping_single(const float* bwd_flow, const float* bwd_occ, const float* imgs, int height, int width,
+                          int scale, int64_t* mapping, uint8_t* unlinked, void* workspace, size_t workspace_bytes,
+                          void* stream);
+size_t fresco_mapping_workspace_bytes(int tokens);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FRESCO_B200_H_ */

@@ -1,0 +1,341 @@
+"""GPU parity tests: every kernel is called through the C ABI (ctypes) and compared
+with the CPU oracle / the golden vectors generated from the reference.
+
+Tolerances (stated per test): integer / index / mask outputs are bit-exact; fp16
+attention is compared with the fp32 oracle at 2e-3 * max|y| absolute (SURVEY 9:
+the reference's own fp16-vs-fp32 gap is ~3e-4 relative); fp32 warp / loss /
+Adam kernels at 1e-5 .. 1e-4.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import fresco_oracle as O  # noqa: E402  (checker only)
+
+
+def T(a, device="cuda"):
+    return torch.from_numpy(np.asarray(a)).to(device)
+
+
+@pytest.fixture(scope="module")
+def fb():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import fresco_b200
+    from fresco_b200 import _lib, diffusion_hacked, flow_utils, ops
+    _lib.lib()      # fails loudly if the extension is missing
+
+    class NS:
+        pass
+    ns = NS()
+    ns.ops, ns.dh, ns.fu, ns.lib = ops, diffusion_hacked, flow_utils, _lib
+    return ns
+
+
+def sdpa_ref(q, k, v, heads, q_per_kv=1, scale=None, diag_bias=0.0):
+    """fp32 reference of fresco_attn_fwd on token-major tensors."""
+    q, k, v = q.float(), k.float(), v.float()
+    B, Lq, C = q.shape
+    d = C // heads
+    scale = scale if scale is not None else 1 / math.sqrt(d)
+    k = k.repeat_interleave(q_per_kv, 0)
+    v = v.repeat_interleave(q_per_kv, 0)
+    qh = q.view(B, Lq, heads, d).transpose(1, 2)
+    kh = k.view(B, -1, heads, d).transpose(1, 2)
+    vh = v.view(B, -1, heads, d).transpose(1, 2)
+    s = qh @ kh.transpose(-1, -2) * scale
+    if diag_bias != 0.0:
+        s = s + torch.eye(Lq, kh.shape[2], device=q.device) * diag_bias
+    return (torch.softmax(s, -1) @ vh).transpose(1, 2).reshape(B, Lq, C)
+
+
+@pytest.mark.parametrize("d,heads,B,Lq,Lk,qpk,gain", [
+    (40, 2, 4, 128, 128, 1, 1.0),
+    (40, 8, 4, 256, 300, 2, 1.0),       # ragged kv tail, shared K/V
+    (40, 2, 2, 200, 77, 1, 8.0),        # ragged q tail, single partial kv tile, peaky softmax
+    (80, 2, 4, 256, 419, 2, 1.0),
+    (80, 8, 2, 128, 1024, 1, 8.0),
+    (64, 4, 2, 256, 256, 1, 1.0),
+    (128, 2, 2, 128, 384, 1, 1.0),
+])
+def test_attn_fwd_vs_fp32(fb, d, heads, B, Lq, Lk, qpk, gain):
+    g = torch.Generator(device="cuda").manual_seed(d * 1000 + Lk)
+    C = heads * d
+    q = (torch.randn(B, Lq, C, device="cuda", generator=g) * gain).half()
+    k = torch.randn(B // qpk, Lk, C, device="cuda", generator=g).half()
+    v = torch.randn(B // qpk, Lk, C, device="cuda", generator=g).half()
+    out = fb.ops.attn_fwd(q, k, v, heads, qpk)
+    torch.cuda.synchronize()
+    ref = sdpa_ref(q, k, v, heads, qpk)
+    err = (out.float() - ref).abs().max().item()
+    assert err < 2e-3 * max(1.0, ref.abs().max().item()), err
+
+
+def test_attn_fwd_scale_and_diag_bias(fb):
+    g = torch.Generator(device="cuda").manual_seed(5)
+    B, L, heads, d = 2, 256, 2, 40
+    q = torch.randn(B, L, heads * d, device="cuda", generator=g).half()
+    k = torch.randn(B, L, heads * d, device="cuda", generator=g).half()
+    v = torch.randn(B, L, heads * d, device="cuda", generator=g).half()
+    out = fb.ops.attn_fwd(q, k, v, heads, 1, softmax_scale=0.2 / math.sqrt(d), diag_bias=1.5)
+    ref = sdpa_ref(q, k, v, heads, 1, 0.2 / math.sqrt(d), 1.5)
+    assert (out.float() - ref).abs().max().item() < 2e-3 * ref.abs().max().item()
+
+
+def test_attn_fwd_full_size_rows_and_properties(fb):
+    """BASELINE size (level B: B=16, L=4096, d=40, Lk=11874): spot rows against the fp32
+    oracle + two size-independent properties (constant V, linearity in V)."""
+    g = torch.Generator(device="cuda").manual_seed(11)
+    N, chunks, L, heads, d, Lk = 8, 2, 4096, 8, 40, 11874
+    C = heads * d
+    q = torch.randn(chunks * N, L, C, device="cuda", generator=g).half()
+    k = torch.randn(chunks, Lk, C, device="cuda", generator=g).half()
+    v1 = torch.randn(chunks, Lk, C, device="cuda", generator=g).half()
+    v2 = torch.randn(chunks, Lk, C, device="cuda", generator=g).half()
+    o1 = fb.ops.attn_fwd(q, k, v1, heads, N).float()
+    o2 = fb.ops.attn_fwd(q, k, v2, heads, N).float()
+    o12 = fb.ops.attn_fwd(q, k, (v1.float() + v2.float()).half(), heads, N).float()
+    assert (o12 - (o1 + o2)).abs().max().item() < 6e-3            # linearity in V (fp16 rounding of v1+v2)
+    const = torch.full_like(v1, 0.75)
+    oc = fb.ops.attn_fwd(q, k, const, heads, N).float()
+    assert (oc - 0.75).abs().max().item() < 1e-3                   # rows of softmax sum to one
+    rows = torch.randint(0, L, (24,), generator=torch.Generator().manual_seed(1)).tolist()
+    for b in (0, 7, 15):
+        qs = q[b:b + 1, rows]
+        ref = sdpa_ref(qs, k[b // N:b // N + 1], v1[b // N:b // N + 1], heads)
+        assert (o1[b, rows] - ref[0]).abs().max().item() < 2e-3 * ref.abs().max().item()
+
+
+def test_kv_compact_bit_exact(fb):
+    g = torch.Generator(device="cuda").manual_seed(3)
+    chunks, N, L, C = 2, 4, 256, 320
+    k = torch.randn(chunks * N, L, C, device="cuda", generator=g).half()
+    v = torch.randn(chunks * N, L, C, device="cuda", generator=g).half()
+    mask = torch.rand(N, L, device="cuda", generator=g) > 0.6
+    mask[0] = True
+    idx = O.kv_select_indices(mask.cpu()).to(torch.int32).cuda()
+    ks, vs = fb.ops.kv_compact(k, v, idx, chunks)
+    ref_k = k.view(chunks, N * L, C)[:, idx.long()]
+    ref_v = v.view(chunks, N * L, C)[:, idx.long()]
+    assert torch.equal(ks, ref_k) and torch.equal(vs, ref_v)
+
+
+class FakeAttn(torch.nn.Module):
+    def __init__(self, g):
+        super().__init__()
+        c = g["wq"].shape[0]
+        self.heads = int(g["heads"])
+        self.spatial_norm = None
+        self.group_norm = None
+        self.norm_cross = False
+        self.residual_connection = False
+        self.rescale_output_factor = 1.0
+        self.to_q = torch.nn.Linear(c, c, bias=False)
+        self.to_k = torch.nn.Linear(c, c, bias=False)
+        self.to_v = torch.nn.Linear(c, c, bias=False)
+        self.to_out = torch.nn.ModuleList([torch.nn.Linear(c, c), torch.nn.Dropout(0.0)])
+        with torch.no_grad():
+            self.to_q.weight.copy_(T(g["wq"], "cpu"))
+            self.to_k.weight.copy_(T(g["wk"], "cpu"))
+            self.to_v.weight.copy_(T(g["wv"], "cpu"))
+            self.to_out[0].weight.copy_(T(g["wo"], "cpu"))
+            self.to_out[0].bias.copy_(T(g["bo"], "cpu"))
+
+
+def test_processor_golden_all_flag_combinations(fb, golden):
+    """The reference's own outputs (fp32 CPU) for all 8 on/off combinations of cross-frame /
+    spatial-guided / temporal-guided attention, N=4, L=64, d=40, vs our fp16 processor."""
+    g = golden("attention")
+    attn = FakeAttn(g).cuda().half()
+    x = T(g["x"]).half()
+    ref_hidden = T(g["ref_hidden"]).half()
+    masks = [T(g[f"attn_mask{i}"]) for i in range(3)]
+    paras = {"fwd_mappings": [T(g["fwd_map"])], "bwd_mappings": [T(g["bwd_map"])],
+             "interattn_masks": [T(g["inter_mask"])]}
+    for flags in range(8):
+        ctrl = fb.dh.AttentionControl()
+        proc = fb.dh.FRESCOAttnProcessor2_0(2, ctrl)
+        if flags & 2:
+            ctrl.stored_attn["decoder_attn"] = [ref_hidden.clone()]
+            ctrl.enable_intraattn()
+        if flags & 4:
+            ctrl.enable_interattn(paras)
+        if flags & 1:
+            ctrl.enable_cfattn(masks)
+        with torch.no_grad():
+            out = proc(attn, x.clone()).float().cpu()
+        ref = T(g[f"out_{flags}"], "cpu")
+        err = (out - ref).abs().max().item()
+        # fp16 weights/activations through 4 Linear layers + attention vs the fp32 reference
+        assert err < 1e-2 * ref.abs().max().item(), (flags, err, ref.abs().max().item())
+    ctrl = fb.dh.AttentionControl()
+    proc = fb.dh.FRESCOAttnProcessor2_0(2, ctrl)
+    ctrl.enable_cfattn([masks[1]])
+    with torch.no_grad():
+        out = proc(attn, x.clone()).float().cpu()
+    ref = T(g["out_cf_nomask"], "cpu")
+    assert (out - ref).abs().max().item() < 1e-2 * ref.abs().max().item()
+
+
+def test_temporal_attention_vs_oracle(fb, golden):
+    g = golden("attention")
+    N, L, heads = 4, 64, 2
+    gen = torch.Generator().manual_seed(2)
+    C = 80
+    q = torch.randn(2 * N, L, C, generator=gen).half()
+    k = torch.randn(2 * N, L, C, generator=gen).half()
+    a = torch.randn(2 * N, L, C, generator=gen).half()
+    fm, bm, im = T(g["fwd_map"], "cpu"), T(g["bwd_map"], "cpu"), T(g["inter_mask"], "cpu")
+    d = C // heads
+    # oracle: the temporal block of fresco_attention, isolated
+    pos = fm[:, 0]
+    gi = pos[None, :, :, None, None].expand(2, N, L, heads, d)
+    qt = torch.gather(q.float().view(2, N, L, heads, d), 2, gi)
+    kt = torch.gather(k.float().view(2, N, L, heads, d) * 0.2, 2, gi)
+    vt = torch.gather(a.float().view(2, N, L, heads, d), 2, gi)
+    s = torch.einsum("bfphd,bgphd->bphfg", qt, kt) / math.sqrt(d)
+    s = s.masked_fill(~im[:, 0][None, :, None], float("-inf"))
+    o = torch.einsum("bphfg,bgphd->bfphd", torch.softmax(s, -1), vt)
+    bi = bm[:, 0][None, :, :, None, None].expand(2, N, L, heads, d)
+    ref = torch.gather(o, 2, bi).reshape(2 * N, L, C)
+    out = fb.ops.temporal_attn_fwd(q.cuda(), k.cuda(), a.cuda(), fm[:, 0].contiguous().cuda(),
+                                   im[:, 0].to(torch.uint8).contiguous().cuda(), 2, heads, 0.2 / math.sqrt(d))
+    assert (out.float().cpu() - ref).abs().max().item() < 2e-3 * ref.abs().max().item()
+
+
+def test_flow_warp_and_consistency(fb, golden):
+    g = golden("geometry")
+    feat, bwd, fwd = T(g["feat"]), T(g["bwd"]), T(g["fwd"])
+    w = fb.fu.flow_warp(feat, bwd)
+    assert (w.cpu() - T(g["warped"], "cpu")).abs().max().item() < 2e-5
+    fo, bo = fb.fu.forward_backward_consistency_check(fwd, bwd)
+    # thresholded output: allow a handful of pixels sitting exactly on the threshold
+    assert (fo.cpu() != T(g["fwd_occ"], "cpu")).float().mean().item() < 1e-3
+    assert (bo.cpu() != T(g["bwd_occ"], "cpu")).float().mean().item() < 1e-3
+
+
+def test_warp_tensor_golden(fb, golden):
+    g = golden("warp_tensor")
+    flows = [T(g["fwd"]), T(g["bwd"])]
+    occs = [T(g["fwd_occ"]), T(g["bwd_occ"])]
+    sal = T(g["saliency"])
+    o = fb.fu.warp_tensor(T(g["sample_feat"]), flows, occs, sal, 2)
+    assert (o.cpu() - T(g["out_feat"], "cpu")).abs().max().item() < 2e-5
+    o = fb.fu.warp_tensor(T(g["sample_img"]), flows, occs, sal, 1)          # scale 1: dilation path
+    assert (o.cpu() - T(g["out_img"], "cpu")).abs().max().item() < 2e-5
+    # fp16 activations, as on the reference's GPU path
+    o16 = fb.fu.warp_tensor(T(g["sample_feat"]).half(), flows, occs, sal, 2)
+    assert o16.dtype == torch.float16
+    assert (o16.float().cpu() - T(g["out_feat"], "cpu")).abs().max().item() < 1e-2
+
+
+def test_warp_tensor_large_plane_path(fb):
+    """planes that do not fit shared memory (image resolution) use the per-step kernels"""
+    N, H, W = 3, 256, 256
+    flows, occs = O.synth_flows(N, H, W, seed=4, mag=6.0)
+    sal = torch.rand(N, 1, 128, 128, generator=torch.Generator().manual_seed(0))
+    img = torch.randn(N, 3, H, W, generator=torch.Generator().manual_seed(1))
+    ref = O.warp_tensor(img, flows, occs, sal, 1)
+    out = fb.fu.warp_tensor(img.cuda(), [f.cuda() for f in flows], [o.cuda() for o in occs], sal.cuda(), 1)
+    assert (out.cpu() - ref).abs().max().item() < 5e-5
+
+
+def test_warp_loss_forward_backward(fb, golden):
+    g = golden("optimize")
+    N = 4
+    sample = T(g["sample"], "cpu")
+    _, C, h, w = sample.shape
+    cs = sample.reshape(2, N, C, h, w).clone()
+    flows = [T(g["fwd"], "cpu"), T(g["bwd"], "cpu")]
+    occs = [T(g["fwd_occ"], "cpu"), T(g["bwd_occ"], "cpu")]
+    ff, bf, fo, bo = O._resize_flow_occ(flows, occs, h / flows[0].shape[2])
+    loss_ref, grad_ref = O.temporal_loss_and_grad(cs, ff.repeat(2, 1, 1, 1), bf.repeat(2, 1, 1, 1),
+                                                  1 - fo.repeat(2, 1, 1, 1), 1 - bo.repeat(2, 1, 1, 1))
+    grad = torch.full_like(cs, 7.0).cuda()
+    loss = torch.zeros(1, device="cuda")
+    fb.ops.warp_loss_fwd_bwd(cs.cuda(), ff.cuda().contiguous(), bf.cuda().contiguous(),
+                             (1 - fo).reshape(N, h, w).cuda().contiguous(), (1 - bo).reshape(N, h, w).cuda().contiguous(),
+                             grad, loss, accumulate=False)
+    assert abs(loss.item() - float(loss_ref)) < 1e-5 * max(1.0, abs(float(loss_ref)))
+    assert (grad.cpu() - grad_ref).abs().max().item() < 1e-6 + 1e-4 * grad_ref.abs().max().item()
+    grad2 = torch.ones_like(grad)
+    fb.ops.warp_loss_fwd_bwd(cs.cuda(), ff.cuda().contiguous(), bf.cuda().contiguous(),
+                             (1 - fo).reshape(N, h, w).cuda().contiguous(), (1 - bo).reshape(N, h, w).cuda().contiguous(),
+                             grad2, None, accumulate=True)
+    assert (grad2.cpu() - 1 - grad_ref).abs().max().item() < 1e-5
+
+
+def test_adam_matches_torch(fb):
+    g = torch.Generator().manual_seed(0)
+    p0 = torch.randn(5000, generator=g)
+    p_ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([p_ref], lr=0.2)
+    p = p0.clone().cuda()
+    m = torch.zeros_like(p)
+    v = torch.zeros_like(p)
+    for step in range(1, 6):
+        grad = torch.randn(5000, generator=g)
+        p_ref.grad = grad.clone()
+        opt.step()
+        fb.ops.adam_step(p, grad.cuda(), m, v, step, lr=0.2)
+        assert (p.cpu() - p_ref.data).abs().max().item() < 2e-6
+
+
+def test_adain_eps_quirk(fb, golden):
+    g = golden("optimize")
+    out = fb.ops.adain(T(g["adain_content"]).contiguous(), T(g["sample"]).contiguous())
+    assert (out.cpu() - T(g["adain_out"], "cpu")).abs().max().item() < 2e-5
+    out16 = fb.ops.adain(T(g["adain_content"]).contiguous(), T(g["sample"]).half().contiguous())
+    assert (out16.float().cpu() - T(g["adain_out"], "cpu")).abs().max().item() < 2e-2
+
+
+def test_mapping_bit_exact_golden(fb, golden):
+    g = golden("mapping")
+    for tag in "abc":
+        bf, bo, im = T(g[f"{tag}_bwd_flows"]), T(g[f"{tag}_bwd_occs"]), T(g[f"{tag}_imgs"])
+        sc = float(g[f"{tag}_scale"])
+        mp, unl = fb.fu.get_single_mapping_ind(bf[0:1], bo[0:1], im[0:2], sc)
+        assert torch.equal(mp.cpu(), T(g[f"{tag}_single_map"], "cpu")), tag
+        assert torch.equal(unl.cpu(), T(g[f"{tag}_single_unl"], "cpu")), tag
+        fm, bm, mask = fb.fu.get_mapping_ind(bf, bo, im, sc)
+        assert torch.equal(fm.cpu(), T(g[f"{tag}_fwd_map"], "cpu"))
+        assert torch.equal(bm.cpu(), T(g[f"{tag}_bwd_map"], "cpu"))
+        assert torch.equal(mask.cpu(), T(g[f"{tag}_mask"], "cpu"))
+
+
+def test_mapping_bit_exact_full_size(fb):
+    """512x512 frames, scale 8 (L = 4096), smooth flows with conflicts: GPU kernel == CPU oracle."""
+    N, H, W = 3, 512, 512
+    flows, occs = O.synth_flows(N, H, W, seed=9, mag=12.0)
+    imgs = torch.rand(N, 3, H, W, generator=torch.Generator().manual_seed(3)) * 2 - 1
+    fm_ref, bm_ref, mk_ref = O.mapping_ind(flows[1], occs[1], imgs, 8.0)
+    fm, bm, mk = fb.fu.get_mapping_ind(flows[1].cuda(), occs[1].cuda(), imgs.cuda(), 8.0)
+    assert torch.equal(fm.cpu(), fm_ref) and torch.equal(bm.cpu(), bm_ref) and torch.equal(mk.cpu(), mk_ref)
+
+
+def test_gram_normalize(fb):
+    g = torch.Generator().manual_seed(1)
+    B, C, L = 3, 320, 200
+    cs = torch.randn(B, C, L, generator=g)
+    xhat, norms = fb.ops.gram_normalize(cs.cuda())
+    X = cs.transpose(1, 2)
+    n = (X ** 2).sum(2) ** 0.5
+    assert (norms.cpu() - n).abs().max().item() < 1e-4
+    assert (xhat.float().cpu() - X / n[..., None]).abs().max().item() < 1e-3
+
+
+def test_optimize_feature_temporal_only_golden(fb, golden):
+    g = golden("optimize")
+    flows = [T(g["fwd"]), T(g["bwd"])]
+    occs = [T(g["fwd_occ"]), T(g["bwd_occ"])]
+    tr = fb.dh.OptimizeTrace()
+    out = fb.dh.optimize_feature(T(g["sample"]), flows, occs, correlation_matrix=[], iters=3, trace=tr)
+    ref_losses = g["temporal3_losses"]
+    assert np.allclose(np.array(tr.losses), ref_losses, rtol=1e-3), (tr.losses, ref_losses)
+    ref = T(g["temporal3_out"], "cpu")
+    rel = (out.cpu() - ref).abs().mean() / ref.abs().mean()
+    assert rel < 5e-2
