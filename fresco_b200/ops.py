@@ -9,6 +9,25 @@ import torch
 
 from . import _lib as L
 
+# Optional device-side timing of individual launches (bench.py sets this to a list; each entry is
+# (tag, work, start_event, end_event) recorded on the launching stream).
+PROFILE = None
+
+
+def _prof_begin():
+    if PROFILE is None:
+        return None
+    ev = torch.cuda.Event(enable_timing=True)
+    ev.record(torch.cuda.current_stream())
+    return ev
+
+
+def _prof_end(ev, tag, work):
+    if ev is not None:
+        end = torch.cuda.Event(enable_timing=True)
+        end.record(torch.cuda.current_stream())
+        PROFILE.append((tag, work, ev, end))
+
 
 def kv_compact(k: torch.Tensor, v: torch.Tensor, idx: torch.Tensor, chunks: int):
     """k, v [chunks*frames, tokens, C] fp16; idx int32 [n_sel] over (frame, token) -> [chunks, n_sel, C]."""
@@ -33,9 +52,11 @@ def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, q_pe
         softmax_scale = 1.0 / math.sqrt(d)
     if out is None:
         out = torch.empty_like(q)
+    ev = _prof_begin()
     L.check(L.lib().fresco_attn_fwd(L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(out), Bq, Lq, k.shape[1], heads, d,
                                     q_per_kv, float(softmax_scale), float(diag_bias), L.stream()),
             "fresco_attn_fwd")
+    _prof_end(ev, "attn_d%d_L%d_Lk%d" % (d, Lq, k.shape[1]), 4.0 * Bq * Lq * k.shape[1] * C)
     return out
 
 

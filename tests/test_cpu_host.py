@@ -1,0 +1,142 @@
+"""CPU-only tests: the C-ABI library loads and exports every symbol the header declares,
+the host-side mirror of the reference's hook surface behaves like the reference, and the
+product path refuses to run without CUDA (no silent fallback)."""
+import ctypes
+import os
+import re
+import sys
+import types
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as g
+    g.build()
+    from fresco_b200 import _lib
+    return _lib
+
+
+def test_library_exports_every_header_symbol(built_lib):
+    hdr = open(os.path.join(ROOT, "include", "fresco_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b((?:fresco|gmflow)_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 18
+    l = ctypes.CDLL(built_lib.LIB_PATH)
+    for n in sorted(names):
+        assert hasattr(l, n), f"libfresco_b200.so does not export {n}"
+    assert names == set(built_lib.EXPORTED_SYMBOLS), names ^ set(built_lib.EXPORTED_SYMBOLS)
+    assert l.fresco_abi_version() == 1
+
+
+def test_argument_errors_do_not_touch_the_gpu(built_lib):
+    l = built_lib.lib()
+    rc = l.fresco_attn_fwd(None, None, None, None, 1, 1, 1, 1, 40, 1, 1.0, 0.0, None)
+    assert rc == -1 and b"null pointer" in l.fresco_last_error()
+    rc = l.fresco_kv_compact(None, None, None, None, None, 2, 8, 4, 320, None)
+    assert rc == -1
+
+
+def test_no_cpu_fallback(built_lib):
+    from fresco_b200 import ops
+    from fresco_b200._lib import FrescoError
+    q = torch.zeros(2, 128, 80, dtype=torch.float16)
+    with pytest.raises(FrescoError):
+        ops.attn_fwd(q, q, q, 2)
+    from fresco_b200 import flow_utils
+    with pytest.raises(FrescoError):
+        flow_utils.flow_warp(torch.zeros(1, 1, 4, 4), torch.zeros(1, 2, 4, 4))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "fresco_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, os.path.join(dp, f)
+
+
+def _import_reference():
+    for name, attrs in (("diffusers", {}), ("diffusers.models", {}),
+                        ("diffusers.models.unet_2d_condition", {"UNet2DConditionOutput": object}),
+                        ("diffusers.models.attention_processor", {"AttnProcessor2_0": object}),
+                        ("matplotlib", {}), ("matplotlib.pyplot", {})):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            for k, v in attrs.items():
+                setattr(m, k, v)
+            sys.modules[name] = m
+    cwd = os.getcwd()
+    os.chdir(REF)
+    sys.path.insert(0, REF)
+    try:
+        import src.diffusion_hacked as dh
+    finally:
+        os.chdir(cwd)
+    return dh
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present")
+def test_attention_control_state_machine_matches_reference():
+    """drive the reference's AttentionControl and ours through the same call sequence"""
+    ref_dh = _import_reference()
+    from fresco_b200 import diffusion_hacked as my_dh
+    a, b = ref_dh.AttentionControl(), my_dh.AttentionControl()
+
+    def snap(c):
+        return (c.store, c.index, c.use_intraattn, c.use_interattn, c.use_cfattn, len(c.stored_attn["decoder_attn"]))
+
+    t = [torch.full((1,), float(i)) for i in range(6)]
+    seq = [("enable_controller", ()), ("enable_store", ()), ("call", (t[0],)), ("call", (t[1],)), ("call", (t[2],)),
+           ("disable_store", ()), ("enable_intraattn", ()), ("call", (None,)), ("call", (None,)), ("call", (None,)),
+           ("call", (None,)), ("enable_cfattn", ([torch.ones(2, 4, dtype=torch.bool)],)),
+           ("enable_interattn", ({"fwd_mappings": [1]},)), ("disable_interattn", ()), ("enable_interattn", ()),
+           ("disable_controller", ()), ("enable_controller", ()), ("clear_store", ()), ("enable_intraattn", ()),
+           ("call", (t[3],))]
+    for name, args in seq:
+        if name == "call":
+            ra, rb = a(*args), b(*args)
+            assert (ra is None and rb is None) or torch.equal(ra, rb)
+        else:
+            getattr(a, name)(*args)
+            getattr(b, name)(*args)
+        assert snap(a) == snap(b), (name, snap(a), snap(b))
+    for attr in ("intraattn_bias", "intraattn_scale_factor", "interattn_scale_factor"):
+        assert getattr(a, attr) == getattr(b, attr)
+
+
+def test_hook_surface_on_harness_unet():
+    """apply_FRESCO_attn installs the shared processor on the 12 up_blocks.2/3 attentions;
+    apply_FRESCO_opt's forward returns (sample, *4 decoder features) with return_dict=False."""
+    from fresco_b200 import diffusion_hacked as dh
+    from fresco_b200.harness.sd15_unet import FakePipe, SD15UNet
+    torch.manual_seed(0)
+    unet = SD15UNet(block_out=(32, 64, 128, 128), heads=8, cross_dim=24)
+    pipe = FakePipe(unet)
+    keys = list(unet.attn_processors.keys())
+    assert len(keys) == 32 and "up_blocks.3.attentions.2.transformer_blocks.0.attn1.processor" in keys
+    x, e = torch.randn(2, 4, 16, 16), torch.randn(2, 7, 24)
+    with torch.no_grad():
+        plain = unet(x, 500, e).sample
+    dh.apply_FRESCO_opt(pipe)            # == disable_FRESCO_opt: hooks record only
+    with torch.no_grad():
+        out = unet(x, torch.tensor(500), e, return_dict=False)
+    assert len(out) == 5 and torch.equal(out[0], plain)
+    assert [tuple(o.shape) for o in out[1:]] == [(2, 128, 2, 2), (2, 128, 4, 4), (2, 128, 8, 8), (2, 64, 16, 16)]
+    proc = dh.apply_FRESCO_attn(pipe)
+    table = unet.attn_processors
+    assert sum(1 for v in table.values() if v is proc) == 12
+    assert all(k.startswith(("up_blocks.2", "up_blocks.3")) for k, v in table.items() if v is proc)
+    # cross-attention (encoder_hidden_states given) must behave as plain SDPA even with the FRESCO processor
+    attn2 = unet.up_blocks[3].attentions[0].transformer_blocks[0].attn2
+    h = torch.randn(2, 256, 32)
+    from fresco_b200.harness.sd15_unet import PlainProcessor
+    with torch.no_grad():
+        assert torch.allclose(proc(attn2, h, encoder_hidden_states=e), PlainProcessor()(attn2, h, e), atol=1e-6)
