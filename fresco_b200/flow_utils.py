@@ -43,9 +43,35 @@ def _dilate(x: torch.Tensor, k: int) -> torch.Tensor:
     return torch.clamp(F.conv2d(x, torch.ones(1, 1, k, k, dtype=x.dtype, device=x.device)), 0, 1)
 
 
+_PREP_CACHE: dict = {}
+_PREP_CACHE_MAX = 32
+
+
+def _tensor_key(t: torch.Tensor):
+    return (t.data_ptr(), t._version, tuple(t.shape), t.dtype)
+
+
+def _cache_get(key, make):
+    """Per-batch preparation (resized flows, pooled masks, blend weights) depends only on the flow /
+    occlusion / saliency tensors, which are constant over the denoise steps of a batch: the reference
+    recomputes it at every call (flow_utils.py:24-39); we key it on tensor identity + version."""
+    hit = _PREP_CACHE.get(key)
+    if hit is None:
+        if len(_PREP_CACHE) >= _PREP_CACHE_MAX:
+            _PREP_CACHE.clear()
+        hit = make()
+        _PREP_CACHE[key] = hit
+    return hit
+
+
 def resize_flows_occs(flows: Sequence[torch.Tensor], occs: Sequence[torch.Tensor], size_h: int):
     """Flows / occlusions at the resolution of a feature map.
     src/flow_utils.py:24-33 == src/diffusion_hacked.py:437-442."""
+    key = ("resize", size_h) + tuple(_tensor_key(t) for t in (flows[0], flows[1], occs[0], occs[1]))
+    return _cache_get(key, lambda: _resize_flows_occs(flows, occs, size_h))
+
+
+def _resize_flows_occs(flows, occs, size_h):
     scale = size_h * 1.0 / flows[0].shape[2]
     kernel = int(1 / scale)
     bwd_flow = F.interpolate(flows[1] * scale, scale_factor=scale, mode="bilinear")
@@ -63,22 +89,28 @@ def warp_tensor(sample, flows, occs, saliency, unet_chunk_size):
     Unlike the reference (which aliases and mutates fp32 inputs, :36) this never
     modifies ``sample``; the result has the dtype of ``sample``."""
     n = sample.shape[0] // unet_chunk_size
-    h = sample.shape[2]
-    scale, fwd_flow, bwd_flow, fwd_occ, bwd_occ = resize_flows_occs(flows, occs, h)
-    if scale == 1:
-        bwd_occ = _dilate(bwd_occ, 13)
-        fwd_occ = _dilate(fwd_occ, 13)
-    scale2 = h * 1.0 / saliency.shape[2]
-    sal = F.interpolate(saliency.float(), scale_factor=scale2, mode="bilinear").contiguous()
-    warp_sal = ops.flow_warp(sal, bwd_flow)                                    # :38
-    warp_sal_last = ops.flow_warp(sal[0:1].contiguous(), fwd_flow[n - 1:n].contiguous())   # :39
-    blend = torch.empty(n, 1, sample.shape[2], sample.shape[3], dtype=torch.float32, device=sample.device)
-    blend[:n - 1] = (1 - bwd_occ[:n - 1]) * sal[1:n] * warp_sal[:n - 1]       # :45
-    blend[n - 1:] = (1 - fwd_occ[n - 1:n]) * sal[n - 1:n] * warp_sal_last      # :50
+    h, w = sample.shape[2], sample.shape[3]
+
+    def prepare():
+        scale, fwd_flow, bwd_flow, fwd_occ, bwd_occ = resize_flows_occs(flows, occs, h)
+        if scale == 1:
+            bwd_occ = _dilate(bwd_occ, 13)
+            fwd_occ = _dilate(fwd_occ, 13)
+        scale2 = h * 1.0 / saliency.shape[2]
+        sal = F.interpolate(saliency.float(), scale_factor=scale2, mode="bilinear").contiguous()
+        warp_sal = ops.flow_warp(sal, bwd_flow)                                    # :38
+        warp_sal_last = ops.flow_warp(sal[0:1].contiguous(), fwd_flow[n - 1:n].contiguous())   # :39
+        blend = torch.empty(n, 1, h, w, dtype=torch.float32, device=sample.device)
+        blend[:n - 1] = (1 - bwd_occ[:n - 1]) * sal[1:n] * warp_sal[:n - 1]       # :45
+        blend[n - 1:] = (1 - fwd_occ[n - 1:n]) * sal[n - 1:n] * warp_sal_last      # :50
+        return bwd_flow, fwd_flow[n - 1].contiguous(), blend.contiguous()
+
+    key = ("warp_tensor", n, h, w) + tuple(_tensor_key(t) for t in (flows[0], flows[1], occs[0], occs[1], saliency))
+    bwd_flow, fwd_flow_last, blend = _cache_get(key, prepare)
     x = sample.contiguous()
     if x.dtype not in (torch.float16, torch.float32):
         x = x.float()
-    out = ops.warp_fuse_chain(x, bwd_flow, fwd_flow[n - 1].contiguous(), blend.contiguous(), unet_chunk_size)
+    out = ops.warp_fuse_chain(x, bwd_flow, fwd_flow_last, blend, unet_chunk_size)
     return out.to(sample.dtype)
 
 

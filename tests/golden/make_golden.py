@@ -151,7 +151,7 @@ def main():
         out_img=fu.warp_tensor(s_img.clone(), [fwd, bwd], [fo, bocc], sal, 1).numpy())
 
     # ---------------- optimize_feature (losses captured through Adam.step's return value) ----------------
-    Cc, h, w = 12, 8, 8
+    Cc, h, w = 16, 8, 8
     sample = torch.randn(2 * N, Cc, h, w)
     other = sample + 0.5 * torch.randn(2 * N, Cc, h, w)
     lv = other.reshape(2 * N, Cc, h * w).transpose(1, 2)
