@@ -13,9 +13,12 @@
 //   warp 8   TMA producer   Q once, K/V tiles through a kStages-deep mbarrier ring
 //   warp 9   MMA issuer     S_s = Q K_t^T  (tcgen05.mma SS, M128 N64, fp32 in TMEM)
 //                           O_s = P_s V_t  (tcgen05.mma TS, P read from TMEM, V MN-major)
-//   warps 0-7 softmax       one query row per thread (= one TMEM lane): row max over the tile,
-//                           p = exp2(s*scale*log2e - m) with packed fp32x2 math, P written to
-//                           TMEM as fp16 over the first half of S, O folded into registers.
+//   warps 0-7 softmax       one query row per thread (= one TMEM lane): the 64 scores of the tile are
+//                           read from TMEM once into registers; row max, p = exp2(s*scale*log2e - m)
+//                           with packed fp32x2 math, P written back to TMEM as fp16 over the first
+//                           half of S.  O accumulates in TMEM across tiles; the running max is only
+//                           raised (and O rescaled in TMEM) when it grows by more than 2^8, so the
+//                           common tile costs no O traffic at all.
 //
 // Token-major [batch, tokens, heads*head_dim] fp16 tensors are consumed in place: the TMA tensor
 // map views them as {head_dim, heads, tokens, batch}; a {64,1,rows,1} box lands one head's tile
@@ -44,7 +47,9 @@ struct AttnCfg {
   static constexpr int TMEM_COLS = SMALL ? 256 : 512;
   static constexpr int STREAM_STRIDE = SMALL ? 128 : 256;   // TMEM columns between the two streams
   static constexpr int O_OFF = 64;                          // O region inside a stream (after S/P)
-  static constexpr int STAGES = SMALL ? 4 : 3;
+  // even, so that stream s only ever touches ring stages of parity s: the two streams then never wait on each
+  // other's tiles (an odd depth can deadlock the single MMA thread)
+  static constexpr int STAGES = 4;
   static constexpr int Q_BYTES = NATOM * kQAtomBytes;
   static constexpr int STAGE_BYTES = 2 * NATOM * kKVAtomBytes;
   static constexpr int SMEM_BYTES = 1024 + Q_BYTES + STAGES * STAGE_BYTES + 256;
@@ -104,6 +109,20 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
                ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
+}
+
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&r)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+               "r"(r[3])
+               : "memory");
+}
+// wait for the outstanding tcgen05.ld's; the registers are listed as in/out operands so that no use of
+// them can be scheduled above the wait
+__device__ __forceinline__ void tmem_ld_wait_dep64(uint32_t (&r)[64]) {
+#define FR8(b) "+r"(r[b]), "+r"(r[b + 1]), "+r"(r[b + 2]), "+r"(r[b + 3]), "+r"(r[b + 4]), "+r"(r[b + 5]), "+r"(r[b + 6]), "+r"(r[b + 7])
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : FR8(0), FR8(8), FR8(16), FR8(24) : : "memory");
+  asm volatile("" : FR8(32), FR8(40), FR8(48), FR8(56) : : "memory");
+#undef FR8
 }
 
 template <int D>
@@ -187,9 +206,12 @@ fresco_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       constexpr uint32_t idesc_pv0 = make_idesc_f16(kTileM, Cfg::N0, 1);
       constexpr uint32_t idesc_pv1 = make_idesc_f16(kTileM, Cfg::N1 > 0 ? Cfg::N1 : 16, 1);
       const uint32_t q_addr = smem_u32(s_q);
+      // Non-blocking state machine over the two streams: the single MMA thread never parks on one stream's
+      // barrier while the other stream has work (and the K/V ring can therefore never deadlock).
+      //   state 0: next tile's K/V not yet confirmed in smem -> poll kv_full, then issue S = Q K^T
+      //   state 1: S issued, waiting for the stream's P          -> poll bar_p,  then issue O = P V
       auto issue_qk = [&](int s, int t) {
         const int st = t % ST;
-        mbar_wait(bar_kv_full + st, (t / ST) & 1);
         tc_fence_after();
         const uint32_t k_addr = smem_u32(s_kv + st * Cfg::STAGE_BYTES);
         const uint32_t d_tmem = tmem + s * Cfg::STREAM_STRIDE;
@@ -202,38 +224,56 @@ fresco_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         }
         umma_commit(bar_s + s);
       };
-      auto issue_pv = [&](int s, int t) {
+      auto issue_pv = [&](int s, int t, bool first, bool last) {
         const int st = t % ST;
+        tc_fence_after();
         const uint32_t v_addr = smem_u32(s_kv + st * Cfg::STAGE_BYTES + Cfg::NATOM * kKVAtomBytes);
         const uint32_t p_tmem = tmem + s * Cfg::STREAM_STRIDE;
         const uint32_t o_tmem = p_tmem + Cfg::O_OFF;
 #pragma unroll
         for (int k2 = 0; k2 < kTileN / 16; ++k2) {
+          const uint32_t acc = (k2 > 0 || !first) ? 1u : 0u;      // O accumulates in TMEM across the stream's tiles
           umma_ts(o_tmem, p_tmem + k2 * 8, make_smem_desc_sw128(v_addr + k2 * 2048, kKVAtomBytes, 1024), idesc_pv0,
-                  k2 > 0);
+                  acc);
           if (Cfg::N1 > 0)
             umma_ts(o_tmem + 64, p_tmem + k2 * 8,
-                    make_smem_desc_sw128(v_addr + kKVAtomBytes + k2 * 2048, kKVAtomBytes, 1024), idesc_pv1, k2 > 0);
+                    make_smem_desc_sw128(v_addr + kKVAtomBytes + k2 * 2048, kKVAtomBytes, 1024), idesc_pv1, acc);
         }
         umma_commit(bar_kv_empty + st);
-        umma_commit(bar_o + s);
+        if (last) umma_commit(bar_o + s);                         // single-phase "stream finished" signal
       };
-      mbar_wait(bar_q, 0);
+      mbar_wait(bar_q, 0, 1);
       int it[2] = {0, 0};                     // per-stream step counter; stream s handles tiles s, s+2, ...
-      int cnt[2] = {(n_tiles + 1) / 2, n_tiles / 2};
-      if (cnt[0] > 0) issue_qk(0, 0);
-      if (cnt[1] > 0) issue_qk(1, 1);
+      int state[2] = {0, 0};
+      const int cnt[2] = {(n_tiles + 1) / 2, n_tiles / 2};
       int remaining = cnt[0] + cnt[1];
+      uint32_t idle = 0;
       while (remaining > 0) {
+        bool progressed = false;
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
-          if (it[s] < cnt[s] && mbar_try_wait(bar_p + s, it[s] & 1)) {
-            tc_fence_after();
-            issue_pv(s, s + 2 * it[s]);
+          if (it[s] >= cnt[s]) continue;
+          const int t = s + 2 * it[s];
+          if (state[s] == 0) {
+            if (mbar_try_wait(bar_kv_full + (t % ST), (t / ST) & 1)) {
+              issue_qk(s, t);
+              state[s] = 1;
+              progressed = true;
+            }
+          } else if (mbar_try_wait(bar_p + s, it[s] & 1)) {
+            issue_pv(s, t, it[s] == 0, it[s] + 1 == cnt[s]);
             ++it[s];
             --remaining;
-            if (it[s] < cnt[s]) issue_qk(s, s + 2 * it[s]);
+            state[s] = 0;
+            progressed = true;
           }
+        }
+        if (progressed) {
+          idle = 0;
+        } else if (++idle > FRESCO_WATCHDOG_POLLS) {
+          printf("fresco_b200 watchdog: attention MMA issuer stalled, block (%d,%d,%d) it=(%d,%d)/(%d,%d) state=(%d,%d)\n",
+                 blockIdx.x, blockIdx.y, blockIdx.z, it[0], it[1], cnt[0], cnt[1], state[0], state[1]);
+          __trap();
         }
       }
     }
@@ -244,90 +284,109 @@ fresco_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     const uint32_t t_lane = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16) + s * Cfg::STREAM_STRIDE;
     const int q_row = q0 + row;
     const int my_tiles = s == 0 ? (n_tiles + 1) / 2 : n_tiles / 2;
+    const int kv_len = p.kv_len;
+    const float scale_log2 = p.scale_log2, bias_log2 = p.diag_bias_log2;
+    const bool use_bias = bias_log2 != 0.f;
+    const unsigned long long scale2 = pack_f2(scale_log2, scale_log2);
     float m_run = -INFINITY, l_run = 0.f;
-    float o_acc[D];
-#pragma unroll
-    for (int i = 0; i < D; ++i) o_acc[i] = 0.f;
-    const bool use_bias = p.diag_bias_log2 != 0.f;
-    const unsigned long long scale2 = pack_f2(p.scale_log2, p.scale_log2);
 
     for (int i = 0; i < my_tiles; ++i) {
       const int col0 = (s + 2 * i) * kTileN;
       // warp-uniform: does this tile need masking (ragged tail) or the diagonal bias?
-      const bool special = (col0 + kTileN > p.kv_len) ||
+      const bool special = (col0 + kTileN > kv_len) ||
                            (use_bias && (q0 + (warp & 3) * 32) < col0 + kTileN && (q0 + (warp & 3) * 32 + 32) > col0);
-      mbar_wait(bar_s + s, i & 1);
+      mbar_wait(bar_s + s, i & 1, 2);          // S_i ready; this also implies the stream's previous P V has retired
       tc_fence_after();
-      // ---- pass 1: row maximum of the raw scores
-      float mx0 = -INFINITY, mx1 = -INFINITY;
+      // ---- the whole 64-column row of scores, once, into registers
+      uint32_t r[64];
+      tmem_ld16(t_lane + 0, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+      tmem_ld16(t_lane + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+      tmem_ld16(t_lane + 32, *reinterpret_cast<uint32_t(*)[16]>(&r[32]));
+      tmem_ld16(t_lane + 48, *reinterpret_cast<uint32_t(*)[16]>(&r[48]));
+      tmem_ld_wait_dep64(r);
+      if (special) {                            // rare path: fold mask / bias into the raw scores
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[16];
-        tmem_ld16_sync(t_lane + c * 16, r);
-        if (!special) {
+        for (int j = 0; j < 64; ++j) {
+          const int col = col0 + j;
+          float v = __uint_as_float(r[j]);
+          if (use_bias && col == q_row) v += bias_log2 / scale_log2;
+          if (col >= kv_len) v = -INFINITY;
+          r[j] = __float_as_uint(v);
+        }
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            mx0 = max3(mx0, __uint_as_float(r[j]), __uint_as_float(r[j + 1]));
-            mx1 = max3(mx1, __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+      for (int j = 0; j < 64; j += 8) {
+        mx0 = max3(mx0, __uint_as_float(r[j]), __uint_as_float(r[j + 1]));
+        mx1 = max3(mx1, __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+        mx2 = max3(mx2, __uint_as_float(r[j + 4]), __uint_as_float(r[j + 5]));
+        mx3 = max3(mx3, __uint_as_float(r[j + 6]), __uint_as_float(r[j + 7]));
+      }
+      const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
+      // ---- lazy running max: raise it (and rescale O in TMEM) only when it grows by more than 2^8
+      if (i == 0) {
+        m_run = m_tile;
+      } else {
+        const bool need = m_tile > m_run + 8.0f;
+        if (__any_sync(0xffffffffu, need)) {
+          const float alpha = need ? fast_exp2(m_run - m_tile) : 1.0f;
+          if (need) {
+            l_run *= alpha;
+            m_run = m_tile;
           }
-        } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int col = col0 + c * 16 + j;
-            float v = __uint_as_float(r[j]);
-            if (use_bias && col == q_row) v += p.diag_bias_log2 / p.scale_log2;
-            if (col >= p.kv_len) v = -INFINITY;
-            mx0 = fmaxf(mx0, v);
+          for (int c = 0; c < D / 8; ++c) {
+            uint32_t o[8];
+            const int col = c * 8;
+            const uint32_t addr = t_lane + Cfg::O_OFF + (col < Cfg::N0 ? col : 64 + (col - Cfg::N0));
+            tmem_ld8_sync(addr, o);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
+            tmem_st8(addr, o);
           }
         }
       }
-      const float m_new = fmaxf(m_run, fmaxf(mx0, mx1) * p.scale_log2);
-      const float alpha = fast_exp2(m_run - m_new);
-      const unsigned long long negm2 = pack_f2(-m_new, -m_new);
-      unsigned long long sum2 = pack_f2(0.f, 0.f);
-      // ---- pass 2: p = exp2(s*scale - m), packed to fp16 over the first 32 columns of S
+      // ---- p = exp2(s*scale - m), packed to fp16 over the first 32 columns of S
+      const unsigned long long negm2 = pack_f2(-m_run, -m_run);
+      unsigned long long sum2a = pack_f2(0.f, 0.f), sum2b = pack_f2(0.f, 0.f);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[16];
-        tmem_ld16_sync(t_lane + c * 16, r);
-        uint32_t pk[8];
+      for (int c = 0; c < 8; ++c) {
+        uint32_t pk[4];
 #pragma unroll
-        for (int j = 0; j < 16; j += 2) {
+        for (int j = 0; j < 8; j += 2) {
           float t0, t1;
-          unpack_f2(fma2(pack_f2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), scale2, negm2), t0, t1);
-          if (special) {
-            const int col = col0 + c * 16 + j;
-            if (use_bias && col == q_row) t0 += p.diag_bias_log2;
-            if (use_bias && col + 1 == q_row) t1 += p.diag_bias_log2;
-            if (col >= p.kv_len) t0 = -INFINITY;
-            if (col + 1 >= p.kv_len) t1 = -INFINITY;
-          }
+          unpack_f2(fma2(pack_f2(__uint_as_float(r[c * 8 + j]), __uint_as_float(r[c * 8 + j + 1])), scale2, negm2), t0, t1);
           const float p0 = fast_exp2(t0);
           const float p1 = fast_exp2(t1);
-          sum2 = add2(sum2, pack_f2(p0, p1));
+          if (j & 2) sum2b = add2(sum2b, pack_f2(p0, p1)); else sum2a = add2(sum2a, pack_f2(p0, p1));
           pk[j >> 1] = pack_half2(p0, p1);
         }
-        tmem_st8(t_lane + c * 8, pk);
+        tmem_st4(t_lane + c * 4, pk);
       }
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(bar_p + s);
       float sa, sb;
-      unpack_f2(sum2, sa, sb);
-      l_run = l_run * alpha + (sa + sb);
-      m_run = m_new;
-      // ---- fold this tile's P V into the running output
-      mbar_wait(bar_o + s, i & 1);
+      unpack_f2(add2(sum2a, sum2b), sa, sb);
+      l_run += sa + sb;
+    }
+
+    // ---- stream epilogue: fetch the accumulated O from TMEM
+    float o_acc[D];
+    if (my_tiles > 0) {
+      mbar_wait(bar_o + s, 0, 3);
       tc_fence_after();
 #pragma unroll
       for (int c = 0; c < D / 8; ++c) {
-        uint32_t r[8];
+        uint32_t o[8];
         const int col = c * 8;
-        tmem_ld8_sync(t_lane + Cfg::O_OFF + (col < Cfg::N0 ? col : 64 + (col - Cfg::N0)), r);
+        tmem_ld8_sync(t_lane + Cfg::O_OFF + (col < Cfg::N0 ? col : 64 + (col - Cfg::N0)), o);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o_acc[col + j] = fmaf(o_acc[col + j], alpha, __uint_as_float(r[j]));
+        for (int j = 0; j < 8; ++j) o_acc[col + j] = __uint_as_float(o[j]);
       }
-      tc_fence_before();
+    } else {
+#pragma unroll
+      for (int j = 0; j < D; ++j) o_acc[j] = 0.f;
     }
 
     // ---- merge the two streams (split-KV combine) and store

