@@ -1,40 +1,37 @@
-// FRESCO attention forward (spatial-guided and cross-frame SDPA) for sm_100a -- v2 "dual-stream".
+// FRESCO attention forward (spatial-guided and cross-frame SDPA) for sm_100a -- v4.
 //
 // Replaces the two dense F.scaled_dot_product_attention calls of the reference processor
 // (src/diffusion_hacked.py:281-285 and :303-305).
 //
-// One CTA owns a 128-row query tile of one (batch, head).  K/V are streamed in 64-row tiles; the
-// even tiles feed softmax stream A (warps 0-3), the odd tiles stream B (warps 4-7).  Each stream
-// is a complete online-softmax pipeline of its own (own running max / sum / output accumulator,
-// own S, P and O regions in TMEM, own mbarriers), so the two streams never synchronise per tile;
-// their partial results are merged once at the end (split-KV combine).  Four independent streams
-// per SM (2 CTAs) keep the MUFU and the tensor pipe busy while any one stream waits for its MMAs.
+// One CTA owns a 128-row query tile of one (batch, head) and streams K/V in 64-row tiles.
 //
-//   warp 8   TMA producer   Q once, K/V tiles through a kStages-deep mbarrier ring
-//   warp 9   MMA issuer     S_s = Q K_t^T  (tcgen05.mma SS, M128 N64, fp32 in TMEM)
-//                           O_s = P_s V_t  (tcgen05.mma TS, P read from TMEM, V MN-major)
-//   warps 0-7 softmax       one query row per thread (= one TMEM lane): the 64 scores of the tile are
-//                           read from TMEM once into registers; row max, p = exp2(s*scale*log2e - m)
-//                           with packed fp32x2 math, P written back to TMEM as fp16 over the first
-//                           half of S.  O accumulates in TMEM across tiles; the running max is only
-//                           raised (and O rescaled in TMEM) when it grows by more than 2^8, so the
-//                           common tile costs no O traffic at all.
+//   warps 0-3 softmax       one query row per thread (= one TMEM lane).  The 64 scores of a tile are read
+//                           from TMEM once into registers; row max; p = exp2(s*scale*log2e - m) with packed
+//                           fp32x2 math; P is written to its own TMEM region as fp16.
+//   warp 4    TMA producer  Q once, K/V tiles through a 5-stage mbarrier ring
+//   warp 5    MMA issuer    S_i = Q K_i^T  (tcgen05.mma SS, M128 N64, fp32) into one of TWO S buffers, so the
+//                           scores of tile i+1 are computed while the softmax warps work on tile i;
+//                           O += P_i V_i   (tcgen05.mma TS, P from TMEM, V MN-major), accumulated in TMEM
+//                           across all tiles.
 //
-// Token-major [batch, tokens, heads*head_dim] fp16 tensors are consumed in place: the TMA tensor
-// map views them as {head_dim, heads, tokens, batch}; a {64,1,rows,1} box lands one head's tile
-// in the canonical 128B-swizzled K-major layout; columns >= head_dim and rows >= tokens are
-// hardware zero-filled.
+// The running row max is lazy: it is raised (and O rescaled in TMEM by the owning thread) only when a tile
+// exceeds it by more than 2^8, so the common tile costs no O traffic at all and the softmax warps never wait
+// for an MMA round trip (S and P are both double-buffered).  TMEM: S0 64 + S1 64 + P0 32 + P1 32 + O <= 64
+// columns = 256 -> two CTAs per SM for d <= 64.
+//
+// Token-major [batch, tokens, heads*head_dim] fp16 tensors are consumed in place: the TMA tensor map views
+// them as {head_dim, heads, tokens, batch}; a {64,1,rows,1} box lands one head's tile in the canonical
+// 128B-swizzled K-major layout; columns >= head_dim and rows >= tokens are hardware zero-filled.
 #include "common.cuh"
 #include "fresco_internal.h"
 
 namespace fresco {
 
 constexpr int kTileM = 128;            // query rows per CTA
-constexpr int kTileN = 64;             // kv rows per tile (one stream step)
+constexpr int kTileN = 64;             // kv rows per tile
 constexpr int kQAtomBytes = 128 * 128;  // [128 rows x 64 fp16]
 constexpr int kKVAtomBytes = 64 * 128;  // [ 64 rows x 64 fp16]
-constexpr int kSoftmaxThreads = 256;
-constexpr int kThreads = 320;
+constexpr int kThreads = 192;
 
 template <int D>
 struct AttnCfg {
@@ -43,17 +40,13 @@ struct AttnCfg {
   static constexpr int DPAD = KSTEPS * 16;
   static constexpr int N0 = DPAD < 64 ? DPAD : 64;   // PV columns from atom 0
   static constexpr int N1 = DPAD - N0;               // PV columns from atom 1
-  static constexpr bool SMALL = DPAD <= 64;
-  static constexpr int TMEM_COLS = SMALL ? 256 : 512;
-  static constexpr int STREAM_STRIDE = SMALL ? 128 : 256;   // TMEM columns between the two streams
-  static constexpr int O_OFF = 64;                          // O region inside a stream (after S/P)
-  // even, so that stream s only ever touches ring stages of parity s: the two streams then never wait on each
-  // other's tiles (an odd depth can deadlock the single MMA thread)
-  static constexpr int STAGES = 4;
+  static constexpr int S_OFF0 = 0, S_OFF1 = 64, P_OFF0 = 128, P_OFF1 = 160, O_OFF = 192;
+  static constexpr int TMEM_COLS = (O_OFF + DPAD <= 256) ? 256 : 512;
+  static constexpr int STAGES = NATOM == 1 ? 5 : 4;
   static constexpr int Q_BYTES = NATOM * kQAtomBytes;
   static constexpr int STAGE_BYTES = 2 * NATOM * kKVAtomBytes;
   static constexpr int SMEM_BYTES = 1024 + Q_BYTES + STAGES * STAGE_BYTES + 256;
-  static constexpr int MIN_CTAS = (SMALL && SMEM_BYTES <= 110 * 1024) ? 2 : 1;
+  static constexpr int MIN_CTAS = (TMEM_COLS == 256 && SMEM_BYTES <= 112 * 1024) ? 2 : 1;
 };
 
 struct AttnParams {
@@ -139,10 +132,10 @@ fresco_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   uint64_t* bar_q = bars + 0;
   uint64_t* bar_kv_full = bars + 1;            // [ST]
   uint64_t* bar_kv_empty = bars + 1 + ST;      // [ST]
-  uint64_t* bar_s = bars + 1 + 2 * ST;         // [2]  S_s ready
-  uint64_t* bar_p = bar_s + 2;                 // [2]  P_s written (128 arrivals)
-  uint64_t* bar_o = bar_s + 4;                 // [2]  O_s = P_s V ready
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s + 6);
+  uint64_t* bar_s = bars + 1 + 2 * ST;         // [2]  S buffer b holds tile i (i & 1 == b)
+  uint64_t* bar_p = bar_s + 2;                 // P_i written (128 arrivals)
+  uint64_t* bar_o = bar_s + 3;                 // [2] P_i V_i retired, i & 1 == b (P buffer b free, O stable)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s + 5);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -152,20 +145,20 @@ fresco_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   const int b_kv = b / p.q_per_kv;
   const int n_tiles = (p.kv_len + kTileN - 1) / kTileN;
 
-  if (warp == 9 && lane == 0) {
+  if (warp == 5 && lane == 0) {
     mbar_init(bar_q, 1);
     for (int s = 0; s < ST; ++s) {
       mbar_init(bar_kv_full + s, 1);
       mbar_init(bar_kv_empty + s, 1);
     }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(bar_s + s, 1);
-      mbar_init(bar_p + s, 128);
-      mbar_init(bar_o + s, 1);
-    }
+    mbar_init(bar_s + 0, 1);
+    mbar_init(bar_s + 1, 1);
+    mbar_init(bar_p, 128);
+    mbar_init(bar_o + 0, 1);
+    mbar_init(bar_o + 1, 1);
     fence_barrier_init();
   }
-  if (warp == 8) {
+  if (warp == 4) {
     if (lane == 0) {
       tma_prefetch_desc(&tm_q);
       tma_prefetch_desc(&tm_k);
@@ -179,7 +172,7 @@ fresco_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 8) {
+  if (warp == 4) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       mbar_expect_tx(bar_q, Cfg::Q_BYTES);
@@ -188,7 +181,7 @@ fresco_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         const int st = t % ST;
         if (t >= ST) {
           const uint32_t ph = ((t / ST) - 1) & 1;
-          while (!mbar_try_wait(bar_kv_empty + st, ph)) __nanosleep(64);
+          while (!mbar_try_wait(bar_kv_empty + st, ph)) __nanosleep(40);
         }
         uint8_t* sk = s_kv + st * Cfg::STAGE_BYTES;
         uint8_t* sv = sk + Cfg::NATOM * kKVAtomBytes;
@@ -199,22 +192,19 @@ fresco_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         }
       }
     }
-  } else if (warp == 9) {
-    // ------------------------------------------------------------ MMA issuer (serves both streams)
+  } else if (warp == 5) {
+    // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc_qk = make_idesc_f16(kTileM, kTileN, 0);
       constexpr uint32_t idesc_pv0 = make_idesc_f16(kTileM, Cfg::N0, 1);
       constexpr uint32_t idesc_pv1 = make_idesc_f16(kTileM, Cfg::N1 > 0 ? Cfg::N1 : 16, 1);
       const uint32_t q_addr = smem_u32(s_q);
-      // Non-blocking state machine over the two streams: the single MMA thread never parks on one stream's
-      // barrier while the other stream has work (and the K/V ring can therefore never deadlock).
-      //   state 0: next tile's K/V not yet confirmed in smem -> poll kv_full, then issue S = Q K^T
-      //   state 1: S issued, waiting for the stream's P          -> poll bar_p,  then issue O = P V
-      auto issue_qk = [&](int s, int t) {
+      auto issue_qk = [&](int t) {
         const int st = t % ST;
+        mbar_wait(bar_kv_full + st, (t / ST) & 1, 10);
         tc_fence_after();
         const uint32_t k_addr = smem_u32(s_kv + st * Cfg::STAGE_BYTES);
-        const uint32_t d_tmem = tmem + s * Cfg::STREAM_STRIDE;
+        const uint32_t d_tmem = tmem + ((t & 1) ? Cfg::S_OFF1 : Cfg::S_OFF0);
 #pragma unroll
         for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
           const uint32_t qoff = (ks >> 2) * kQAtomBytes + (ks & 3) * 32;
@@ -222,88 +212,61 @@ fresco_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           umma_ss(d_tmem, make_smem_desc_sw128(q_addr + qoff, 16, 1024), make_smem_desc_sw128(k_addr + koff, 16, 1024),
                   idesc_qk, ks > 0);
         }
-        umma_commit(bar_s + s);
+        umma_commit(bar_s + (t & 1));
       };
-      auto issue_pv = [&](int s, int t, bool first, bool last) {
+      mbar_wait(bar_q, 0, 11);
+      issue_qk(0);
+      if (n_tiles > 1) issue_qk(1);
+      for (int t = 0; t < n_tiles; ++t) {
         const int st = t % ST;
+        mbar_wait(bar_p, t & 1, 12);                       // P_t in TMEM (and S_t fully consumed)
         tc_fence_after();
         const uint32_t v_addr = smem_u32(s_kv + st * Cfg::STAGE_BYTES + Cfg::NATOM * kKVAtomBytes);
-        const uint32_t p_tmem = tmem + s * Cfg::STREAM_STRIDE;
-        const uint32_t o_tmem = p_tmem + Cfg::O_OFF;
 #pragma unroll
         for (int k2 = 0; k2 < kTileN / 16; ++k2) {
-          const uint32_t acc = (k2 > 0 || !first) ? 1u : 0u;      // O accumulates in TMEM across the stream's tiles
-          umma_ts(o_tmem, p_tmem + k2 * 8, make_smem_desc_sw128(v_addr + k2 * 2048, kKVAtomBytes, 1024), idesc_pv0,
+          const uint32_t acc = (k2 > 0 || t > 0) ? 1u : 0u;  // O accumulates in TMEM across all tiles
+          const uint32_t p_tmem = tmem + ((t & 1) ? Cfg::P_OFF1 : Cfg::P_OFF0) + k2 * 8;
+          umma_ts(tmem + Cfg::O_OFF, p_tmem, make_smem_desc_sw128(v_addr + k2 * 2048, kKVAtomBytes, 1024), idesc_pv0,
                   acc);
           if (Cfg::N1 > 0)
-            umma_ts(o_tmem + 64, p_tmem + k2 * 8,
+            umma_ts(tmem + Cfg::O_OFF + 64, p_tmem,
                     make_smem_desc_sw128(v_addr + kKVAtomBytes + k2 * 2048, kKVAtomBytes, 1024), idesc_pv1, acc);
         }
         umma_commit(bar_kv_empty + st);
-        if (last) umma_commit(bar_o + s);                         // single-phase "stream finished" signal
-      };
-      mbar_wait(bar_q, 0, 1);
-      int it[2] = {0, 0};                     // per-stream step counter; stream s handles tiles s, s+2, ...
-      int state[2] = {0, 0};
-      const int cnt[2] = {(n_tiles + 1) / 2, n_tiles / 2};
-      int remaining = cnt[0] + cnt[1];
-      uint32_t idle = 0;
-      while (remaining > 0) {
-        bool progressed = false;
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          if (it[s] >= cnt[s]) continue;
-          const int t = s + 2 * it[s];
-          if (state[s] == 0) {
-            if (mbar_try_wait(bar_kv_full + (t % ST), (t / ST) & 1)) {
-              issue_qk(s, t);
-              state[s] = 1;
-              progressed = true;
-            }
-          } else if (mbar_try_wait(bar_p + s, it[s] & 1)) {
-            issue_pv(s, t, it[s] == 0, it[s] + 1 == cnt[s]);
-            ++it[s];
-            --remaining;
-            state[s] = 0;
-            progressed = true;
-          }
-        }
-        if (progressed) {
-          idle = 0;
-        } else if (++idle > FRESCO_WATCHDOG_POLLS) {
-          printf("fresco_b200 watchdog: attention MMA issuer stalled, block (%d,%d,%d) it=(%d,%d)/(%d,%d) state=(%d,%d)\n",
-                 blockIdx.x, blockIdx.y, blockIdx.z, it[0], it[1], cnt[0], cnt[1], state[0], state[1]);
-          __trap();
-        }
+        umma_commit(bar_o + (t & 1));
+        if (t + 2 < n_tiles) issue_qk(t + 2);              // reuses S buffer (t & 1), free since P_t arrived
       }
     }
   } else {
-    // ------------------------------------------------------------ softmax streams
-    const int s = warp >> 2;                               // stream: 0 = even tiles, 1 = odd tiles
-    const int row = (warp & 3) * 32 + lane;                // query row inside the tile == TMEM lane
-    const uint32_t t_lane = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16) + s * Cfg::STREAM_STRIDE;
+    // ------------------------------------------------------------ softmax warps
+    const int row = warp * 32 + lane;                      // query row inside the tile == TMEM lane
+    const uint32_t t_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
     const int q_row = q0 + row;
-    const int my_tiles = s == 0 ? (n_tiles + 1) / 2 : n_tiles / 2;
     const int kv_len = p.kv_len;
     const float scale_log2 = p.scale_log2, bias_log2 = p.diag_bias_log2;
     const bool use_bias = bias_log2 != 0.f;
     const unsigned long long scale2 = pack_f2(scale_log2, scale_log2);
     float m_run = -INFINITY, l_run = 0.f;
 
-    for (int i = 0; i < my_tiles; ++i) {
-      const int col0 = (s + 2 * i) * kTileN;
+    bool s_ready = false;                      // result of the early (overlapped) probe of the next S barrier
+    for (int i = 0; i < n_tiles; ++i) {
+      const int col0 = i * kTileN;
       // warp-uniform: does this tile need masking (ragged tail) or the diagonal bias?
       const bool special = (col0 + kTileN > kv_len) ||
-                           (use_bias && (q0 + (warp & 3) * 32) < col0 + kTileN && (q0 + (warp & 3) * 32 + 32) > col0);
-      mbar_wait(bar_s + s, i & 1, 2);          // S_i ready; this also implies the stream's previous P V has retired
+                           (use_bias && (q0 + warp * 32) < col0 + kTileN && (q0 + warp * 32 + 32) > col0);
+      if (!s_ready) mbar_wait(bar_s + (i & 1), (i >> 1) & 1, 2);
       tc_fence_after();
       // ---- the whole 64-column row of scores, once, into registers
+      const uint32_t s_addr = t_lane + ((i & 1) ? Cfg::S_OFF1 : Cfg::S_OFF0);
       uint32_t r[64];
-      tmem_ld16(t_lane + 0, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
-      tmem_ld16(t_lane + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
-      tmem_ld16(t_lane + 32, *reinterpret_cast<uint32_t(*)[16]>(&r[32]));
-      tmem_ld16(t_lane + 48, *reinterpret_cast<uint32_t(*)[16]>(&r[48]));
+      tmem_ld16(s_addr + 0, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+      tmem_ld16(s_addr + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+      tmem_ld16(s_addr + 32, *reinterpret_cast<uint32_t(*)[16]>(&r[32]));
+      tmem_ld16(s_addr + 48, *reinterpret_cast<uint32_t(*)[16]>(&r[48]));
       tmem_ld_wait_dep64(r);
+      // probe S_{i+1} now: it was issued a whole tile ago, and the ~100-cycle latency of a try_wait on an
+      // already-completed barrier hides behind the max / exp work instead of opening the next iteration
+      s_ready = (i + 1 < n_tiles) && mbar_test_wait(bar_s + ((i + 1) & 1), ((i + 1) >> 1) & 1);
       if (special) {                            // rare path: fold mask / bias into the raw scores
 #pragma unroll
         for (int j = 0; j < 64; ++j) {
@@ -323,12 +286,17 @@ fresco_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         mx3 = max3(mx3, __uint_as_float(r[j + 6]), __uint_as_float(r[j + 7]));
       }
       const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
+      // P buffer (i & 1) was last read by P_{i-2} V_{i-2}.  That MMA was issued before S_i = Q K_i^T and
+      // tcgen05.commit tracks every earlier MMA, so the S_i barrier we just passed already implies it retired.
       // ---- lazy running max: raise it (and rescale O in TMEM) only when it grows by more than 2^8
       if (i == 0) {
         m_run = m_tile;
       } else {
         const bool need = m_tile > m_run + 8.0f;
         if (__any_sync(0xffffffffu, need)) {
+          // O may only be touched once P_{i-1} V_{i-1} has retired (rare path, so the wait is affordable)
+          mbar_wait(bar_o + ((i - 1) & 1), ((i - 1) >> 1) & 1, 5);
+          tc_fence_after();
           const float alpha = need ? fast_exp2(m_run - m_tile) : 1.0f;
           if (need) {
             l_run *= alpha;
@@ -346,87 +314,59 @@ fresco_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           }
         }
       }
-      // ---- p = exp2(s*scale - m), packed to fp16 over the first 32 columns of S
+      // ---- p = exp2(s*scale - m): all 64 exponentials are issued back to back (nothing volatile in between,
+      //      so the MUFU pipe is never left idle waiting for a store), then packed to fp16 into the P region
       const unsigned long long negm2 = pack_f2(-m_run, -m_run);
-      unsigned long long sum2a = pack_f2(0.f, 0.f), sum2b = pack_f2(0.f, 0.f);
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        uint32_t pk[4];
-#pragma unroll
-        for (int j = 0; j < 8; j += 2) {
-          float t0, t1;
-          unpack_f2(fma2(pack_f2(__uint_as_float(r[c * 8 + j]), __uint_as_float(r[c * 8 + j + 1])), scale2, negm2), t0, t1);
-          const float p0 = fast_exp2(t0);
-          const float p1 = fast_exp2(t1);
-          if (j & 2) sum2b = add2(sum2b, pack_f2(p0, p1)); else sum2a = add2(sum2a, pack_f2(p0, p1));
-          pk[j >> 1] = pack_half2(p0, p1);
-        }
-        tmem_st4(t_lane + c * 4, pk);
+      for (int j = 0; j < 64; j += 2) {
+        float t0, t1;
+        unpack_f2(fma2(pack_f2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), scale2, negm2), t0, t1);
+        r[j] = __float_as_uint(fast_exp2(t0));
+        r[j + 1] = __float_as_uint(fast_exp2(t1));
       }
+      unsigned long long sum2[4] = {pack_f2(0.f, 0.f), pack_f2(0.f, 0.f), pack_f2(0.f, 0.f), pack_f2(0.f, 0.f)};
+#pragma unroll
+      for (int j = 0; j < 64; j += 2)
+        sum2[(j >> 1) & 3] = add2(sum2[(j >> 1) & 3], pack_f2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])));
+      uint32_t pk[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) pk[j] = pack_half2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+      const uint32_t p_addr = t_lane + ((i & 1) ? Cfg::P_OFF1 : Cfg::P_OFF0);
+      tmem_st16(p_addr, *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
+      tmem_st16(p_addr + 16, *reinterpret_cast<uint32_t(*)[16]>(&pk[16]));
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(bar_p + s);
+      mbar_arrive(bar_p);
       float sa, sb;
-      unpack_f2(add2(sum2a, sum2b), sa, sb);
+      unpack_f2(add2(add2(sum2[0], sum2[1]), add2(sum2[2], sum2[3])), sa, sb);
       l_run += sa + sb;
     }
 
-    // ---- stream epilogue: fetch the accumulated O from TMEM
-    float o_acc[D];
-    if (my_tiles > 0) {
-      mbar_wait(bar_o + s, 0, 3);
-      tc_fence_after();
+    // ---- epilogue: O / l -> fp16 head slice of this row
+    mbar_wait(bar_o + ((n_tiles - 1) & 1), ((n_tiles - 1) >> 1) & 1, 4);
+    tc_fence_after();
+    const float inv = 1.f / l_run;
+    __half* dst = p.out + (static_cast<size_t>(b) * p.q_len + q_row) * (static_cast<size_t>(p.heads) * D) +
+                  static_cast<size_t>(head) * D;
 #pragma unroll
-      for (int c = 0; c < D / 8; ++c) {
-        uint32_t o[8];
-        const int col = c * 8;
-        tmem_ld8_sync(t_lane + Cfg::O_OFF + (col < Cfg::N0 ? col : 64 + (col - Cfg::N0)), o);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o_acc[col + j] = __uint_as_float(o[j]);
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < D; ++j) o_acc[j] = 0.f;
-    }
-
-    // ---- merge the two streams (split-KV combine) and store
-    // all MMAs that read the K/V ring have completed once both streams saw their last bar_o, so the ring is free
-    float* xch = reinterpret_cast<float*>(s_kv);                       // [D + 2][128]
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    if (s == 1) {
-      xch[0 * 128 + row] = m_run;
-      xch[1 * 128 + row] = l_run;
-#pragma unroll
-      for (int i = 0; i < D; ++i) xch[(2 + i) * 128 + row] = o_acc[i];
-    }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    if (s == 0 && q_row < p.q_len) {
-      const float mb = xch[row], lb = xch[128 + row];
-      const float m = fmaxf(m_run, mb);
-      const float wa = fast_exp2(m_run - m);
-      const float wb = (mb == -INFINITY) ? 0.f : fast_exp2(mb - m);
-      const float inv = 1.f / (l_run * wa + lb * wb);
-      const float ca = wa * inv, cb = wb * inv;
-      __half* dst = p.out + (static_cast<size_t>(b) * p.q_len + q_row) * (static_cast<size_t>(p.heads) * D) +
-                    static_cast<size_t>(head) * D;
-#pragma unroll
-      for (int v8 = 0; v8 < D / 8; ++v8) {
-        float o[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = o_acc[v8 * 8 + j] * ca + xch[(2 + v8 * 8 + j) * 128 + row] * cb;
+    for (int c = 0; c < D / 8; ++c) {
+      uint32_t o[8];
+      const int col = c * 8;
+      tmem_ld8_sync(t_lane + Cfg::O_OFF + (col < Cfg::N0 ? col : 64 + (col - Cfg::N0)), o);
+      if (q_row < p.q_len) {
         uint4 pkt;
-        pkt.x = pack_half2(o[0], o[1]);
-        pkt.y = pack_half2(o[2], o[3]);
-        pkt.z = pack_half2(o[4], o[5]);
-        pkt.w = pack_half2(o[6], o[7]);
-        reinterpret_cast<uint4*>(dst)[v8] = pkt;
+        pkt.x = pack_half2(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
+        pkt.y = pack_half2(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
+        pkt.z = pack_half2(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
+        pkt.w = pack_half2(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
+        reinterpret_cast<uint4*>(dst)[c] = pkt;
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc<Cfg::TMEM_COLS>(tmem);
+  if (warp == 4) tmem_dealloc<Cfg::TMEM_COLS>(tmem);
 }
 
 // ---------------------------------------------------------------------------------------------
