@@ -168,11 +168,14 @@ class FRESCOAttnProcessor2_0:
     attention (spatial-guided -> cross-frame -> temporal-guided).
     Call contract of src/diffusion_hacked.py:169-387."""
 
-    def __init__(self, unet_chunk_size=2, controller=None):
+    def __init__(self, unet_chunk_size=2, controller=None, shard=None):
         if not hasattr(F, "scaled_dot_product_attention"):
             raise ImportError("AttnProcessor2_0 requires PyTorch 2.0, to use it, please upgrade PyTorch to 2.0.")
         self.unet_chunk_size = unet_chunk_size
         self.controller = controller
+        # optional frame sharding over the GPUs of one box: (world, rank, process_group); see fresco_b200/dist.py
+        self.shard = shard
+        self._sharded = None
 
     def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None):
         residual = hidden_states
@@ -229,6 +232,18 @@ class FRESCOAttnProcessor2_0:
         q = query.to(torch.float16).contiguous()
         k = key.to(torch.float16).contiguous()
         v = value.to(torch.float16).contiguous()
+        if self.shard is not None and ctrl is not None:
+            if self._sharded is None:
+                from .dist import ShardedFRESCOAttention
+                world, rank, group = self.shard
+                self._sharded = ShardedFRESCOAttention(ctrl, world, rank, self.unet_chunk_size, group)
+            ref_q = ref_k = None
+            if ctrl.use_intraattn:
+                ref = ctrl(None)
+                assert ref.shape == hidden_states.shape
+                ref_q = attn.to_q(ref).to(torch.float16).contiguous()
+                ref_k = attn.to_k(ref).to(torch.float16).contiguous()
+            return self._sharded(q, k, v, heads, ref_q=ref_q, ref_k=ref_k).to(in_dtype)
         B, L, C = q.shape
         chunks = self.unet_chunk_size
         inv_sqrt_d = 1.0 / math.sqrt(head_dim)
@@ -296,10 +311,11 @@ def _default_attn_processor():
         return _SDPAProcessor()
 
 
-def apply_FRESCO_attn(pipe):
+def apply_FRESCO_attn(pipe, shard=None):
     """Install one shared FRESCO processor on every attention of up_blocks.2 / up_blocks.3
-    (src/diffusion_hacked.py:390-403) and return it."""
-    fresco_proc = FRESCOAttnProcessor2_0(2, AttentionControl())
+    (src/diffusion_hacked.py:390-403) and return it.  ``shard=(world, rank, group)`` (not in the
+    reference) runs the batch frame-sharded over the GPUs of one box."""
+    fresco_proc = FRESCOAttnProcessor2_0(2, AttentionControl(), shard=shard)
     plain = _default_attn_processor()
     table = {}
     for name in pipe.unet.attn_processors.keys():

@@ -1,0 +1,115 @@
+"""World-size-2 gloo test of the frame-sharded attention exchange (host logic of fresco_b200/dist.py).
+Compute is injected as a torch backend (the CUDA kernels need a GPU); the result of the two ranks,
+concatenated, must equal the single-process oracle on the full batch."""
+import math
+import os
+import socket
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class TorchBackend:
+    def kv_compact(self, k, v, idx, chunks):
+        B, L, C = k.shape
+        rows = (B // chunks) * L
+        return k.reshape(chunks, rows, C)[:, idx.long()], v.reshape(chunks, rows, C)[:, idx.long()]
+
+    def attn_fwd(self, q, k, v, heads, q_per_kv, softmax_scale, diag_bias=0.0):
+        B, L, C = q.shape
+        d = C // heads
+        k = k.repeat_interleave(q_per_kv, 0)
+        v = v.repeat_interleave(q_per_kv, 0)
+        qh, kh, vh = (t.view(t.shape[0], -1, heads, d).transpose(1, 2) for t in (q, k, v))
+        s = qh @ kh.transpose(-1, -2) * softmax_scale
+        if diag_bias:
+            s = s + torch.eye(L, kh.shape[2]) * diag_bias
+        return (torch.softmax(s, -1) @ vh).transpose(1, 2).reshape(B, L, C)
+
+    def temporal_attn_fwd(self, q, k, v, fwd_map, traj_mask, chunks, heads, scale):
+        B, L, C = q.shape
+        N = B // chunks
+        d = C // heads
+        gi = fwd_map[None, :, :, None, None].expand(chunks, N, L, heads, d)
+        qt = torch.gather(q.view(chunks, N, L, heads, d), 2, gi)
+        kt = torch.gather(k.view(chunks, N, L, heads, d), 2, gi)
+        vt = torch.gather(v.view(chunks, N, L, heads, d), 2, gi)
+        s = torch.einsum("bfphd,bgphd->bphfg", qt, kt) * scale
+        s = s.masked_fill(~traj_mask.bool()[None, :, None], float("-inf"))
+        o = torch.einsum("bphfg,bgphd->bfphd", torch.softmax(s, -1), vt)
+        out = torch.empty_like(o)
+        out.scatter_(2, gi, o)
+        return out.reshape(B, L, C)
+
+
+def _worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from fresco_b200 import diffusion_hacked as dh
+    from fresco_b200.dist import ShardedFRESCOAttention, frame_range
+    from oracle import fresco_oracle as O
+    torch.manual_seed(0)
+    N, chunks, L, heads, C = 4, 2, 64, 2, 16
+    x = torch.randn(chunks * N, L, C)
+    ref = torch.randn(chunks * N, L, C)
+    w = [torch.randn(C, C) * 0.3 for _ in range(4)]
+    bo = torch.randn(C) * 0.1
+    masks = [torch.rand(N, L) > 0.6]
+    masks[0][0] = True
+    perm = torch.stack([torch.randperm(L) for _ in range(N)])
+    perm[0] = torch.arange(L)
+    fm = perm[:, None, :]
+    bm = torch.argsort(perm, dim=1)[:, None, :]
+    im = (torch.rand(L, 1, N, N) > 0.3) | torch.eye(N, dtype=torch.bool)[None, None]
+    for flags in range(8):
+        cf, intra, inter = bool(flags & 1), bool(flags & 2), bool(flags & 4)
+        want = O.fresco_attention(x, w[0], w[1], w[2], w[3], bo, heads, use_cfattn=cf, attn_masks=masks,
+                                  use_intraattn=intra, ref_hidden=ref, use_interattn=inter, fwd_mappings=[fm],
+                                  bwd_mappings=[bm], interattn_masks=[im])
+        ctrl = dh.AttentionControl()
+        if intra:
+            ctrl.stored_attn["decoder_attn"] = [ref]
+            ctrl.enable_intraattn()
+        if inter:
+            ctrl.enable_interattn({"fwd_mappings": [fm], "bwd_mappings": [bm], "interattn_masks": [im]})
+        if cf:
+            ctrl.enable_cfattn(masks)
+        lo, hi = frame_range(N, world, rank)
+        sel = torch.cat([torch.arange(c * N + lo, c * N + hi) for c in range(chunks)])
+        xl, rl = x[sel], ref[sel]
+        sharded = ShardedFRESCOAttention(ctrl, world, rank, chunks, backend=TorchBackend())
+        a = sharded(xl @ w[0].t(), xl @ w[1].t(), xl @ w[2].t(), heads, ref_q=rl @ w[0].t(), ref_k=rl @ w[1].t())
+        got = a @ w[3].t() + bo
+        err = (got - want[sel]).abs().max().item()
+        assert err < 1e-4, (flags, rank, err)
+    if rank == 0:
+        ret.put("ok")
+    dist.destroy_process_group()
+
+
+def test_sharded_attention_world2_gloo():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert ret.get(timeout=5) == "ok"
+
+
+def test_frame_range():
+    sys.path.insert(0, ROOT)
+    from fresco_b200.dist import frame_range
+    assert [frame_range(16, 4, r) for r in range(4)] == [(0, 4), (4, 8), (8, 12), (12, 16)]
