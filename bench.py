@@ -223,8 +223,7 @@ def timed_region(wl, steps, warmup, host_io, world):
 # --------------------------------------------------------------------------------------------
 def cpu_reference_line(args, as_reference_arm):
     from oracle import ref_step
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    cores = ref_step.pick_threads(os.cpu_count() or 1)
     steps = args.steps if as_reference_arm else 1
     warm = args.warmup if as_reference_arm else 0
     res = ref_step.run(n_full=N_FRAMES, n_sample=args.cpu_sample_frames, res=RES, schedule=SCHEDULE,
