@@ -52,6 +52,7 @@ tile_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   uint64_t* bar_acc_empty = bar_acc_full + 2;    // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc_empty + 2);
 
+  if (EPI == EPI_GRAM_SIGN && blockIdx.x < blockIdx.y) return;   // symmetric output: tiles with J < I are mirrored
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * 128;
   const int batch = blockIdx.z;
@@ -170,10 +171,30 @@ tile_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           }
         }
       } else if (EPI == EPI_GRAM_SIGN) {
+        // T is symmetric (T_ij = sign(G_ij - A_ij) + sign(G_ij - A_ji), G symmetric), so only tiles J >= I are
+        // launched; this CTA also writes the mirrored tile T_JI and accounts for its share of the loss.
+        // The direct target tile A[I, J] is staged through shared memory (the operand ring is idle once the last
+        // MMA has retired; n_iter == 1) so that global reads are coalesced; the transposed tile A[J, I] is read
+        // straight from global -- for a fixed j, consecutive lanes read consecutive i.
         const size_t plane = (size_t)batch * p.M * p.M;
-        const float* a_dir = p.target + plane + (size_t)gm * p.M + n0;        // A[i, j0 + c]   (own row)
-        const float* a_tr = p.target + plane + (size_t)n0 * p.M + gm;         // A[j0 + c, i]   (coalesced over lanes)
-        __half* dst = p.tsign + plane + (size_t)gm * p.M + n0;
+        const bool diag_tile = (n0 == m0);
+        constexpr int kLd = 132;                                        // padded row stride (floats), keeps 16 B alignment
+        float* stage = reinterpret_cast<float*>(smem);
+        {
+          const int tid = threadIdx.x;                                   // 0..127
+          for (int it = 0; it < 32; ++it) {
+            const int rr = it * 4 + (tid >> 5);
+            const int c4 = (tid & 31) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m0 + rr < p.M && n0 + c4 < p.M)
+              v = __ldg(reinterpret_cast<const float4*>(p.target + plane + (size_t)(m0 + rr) * p.M + n0 + c4));
+            *reinterpret_cast<float4*>(stage + rr * kLd + c4) = v;
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const float* a_tr = p.target + plane + (size_t)n0 * p.M + gm;         // A[j0 + c, i]
+        __half* dst = p.tsign + plane + (size_t)gm * p.M + n0;                // T[i, j0 + c]
+        __half* dst_tr = p.tsign + plane + (size_t)n0 * p.M + gm;             // T[j0 + c, i]
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
           uint32_t r[32];
@@ -185,16 +206,17 @@ tile_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             for (int i = 0; i < 32; i += 4) {
               const int col = c * 32 + i;
               float tv[4] = {0.f, 0.f, 0.f, 0.f};
-              if (n0 + col < p.M) {                                          // M is a multiple of 4 (checked on the host)
-                const float4 d4 = __ldg(reinterpret_cast<const float4*>(a_dir + col));
+              if (n0 + col < p.M) {                                          // M is a multiple of 8 (checked on the host)
+                const float4 d4 = *reinterpret_cast<const float4*>(stage + row * kLd + col);
                 const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                   const float g = __uint_as_float(r[i + u]);
                   const float d1 = g - dv[u];
                   const float d2 = g - __ldg(a_tr + (size_t)(col + u) * p.M);
-                  loss += fabsf(d1);
+                  loss += fabsf(d1) + (diag_tile ? 0.f : fabsf(d2));
                   tv[u] = (d1 > 0.f ? 1.f : (d1 < 0.f ? -1.f : 0.f)) + (d2 > 0.f ? 1.f : (d2 < 0.f ? -1.f : 0.f));
+                  if (!diag_tile) dst_tr[(size_t)(col + u) * p.M] = __float2half_rn(tv[u]);
                 }
               }
               pk[i >> 1] = pack_half2(tv[0], tv[1]);

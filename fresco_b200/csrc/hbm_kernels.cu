@@ -66,14 +66,20 @@ __global__ void temporal_attn_kernel(const __half* __restrict__ q_raw, const __h
   const uint8_t* mrow = traj_mask + (long long)p * N * N;
   for (int pair = lane; pair < N * N; pair += 32) {
     const int f = pair / N, g = pair % N;
-    const __half2* a = reinterpret_cast<const __half2*>(sq + f * d);
-    const __half2* bb = reinterpret_cast<const __half2*>(sk + g * d);
+    const uint4* a = reinterpret_cast<const uint4*>(sq + f * d);      // 16-byte shared loads: 8 channels each
+    const uint4* bb = reinterpret_cast<const uint4*>(sk + g * d);
     float acc = 0.f;
-    for (int c = 0; c < d / 2; ++c) {
-      const float2 x = __half22float2(a[c]);
-      const float2 y = __half22float2(bb[c]);
-      acc = fmaf(x.x, y.x, acc);
-      acc = fmaf(x.y, y.y, acc);
+    for (int c = 0; c < vpr; ++c) {
+      const uint4 xa = a[c], yb = bb[c];
+      const __half2* xh = reinterpret_cast<const __half2*>(&xa);
+      const __half2* yh = reinterpret_cast<const __half2*>(&yb);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float2 x = __half22float2(xh[u]);
+        const float2 y = __half22float2(yh[u]);
+        acc = fmaf(x.x, y.x, acc);
+        acc = fmaf(x.y, y.y, acc);
+      }
     }
     sc[pair] = mrow[pair] ? acc * scale : -INFINITY;
   }
@@ -92,11 +98,26 @@ __global__ void temporal_attn_kernel(const __half* __restrict__ q_raw, const __h
     for (int g = 0; g < N; ++g) r[g] *= inv;
   }
   __syncwarp();
-  for (int i = lane; i < N * d; i += 32) {
-    const int f = i / d, c = i % d;
-    float acc = 0.f;
-    for (int g = 0; g < N; ++g) acc = fmaf(sc[f * N + g], __half2float(sv[g * d + c]), acc);
-    sq[i] = __float2half_rn(acc);                              // q is dead: reuse as the output staging
+  for (int t = lane; t < nvec; t += 32) {                            // one (frame, 8-channel chunk) per lane
+    const int f = t / vpr, part = t % vpr;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int g = 0; g < N; ++g) {
+      const float pw = sc[f * N + g];
+      const uint4 vv = reinterpret_cast<const uint4*>(sv + g * d)[part];
+      const __half2* vh = reinterpret_cast<const __half2*>(&vv);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float2 y = __half22float2(vh[u]);
+        acc[2 * u] = fmaf(pw, y.x, acc[2 * u]);
+        acc[2 * u + 1] = fmaf(pw, y.y, acc[2 * u + 1]);
+      }
+    }
+    uint4 o;
+    o.x = pack_half2(acc[0], acc[1]);
+    o.y = pack_half2(acc[2], acc[3]);
+    o.z = pack_half2(acc[4], acc[5]);
+    o.w = pack_half2(acc[6], acc[7]);
+    reinterpret_cast<uint4*>(sq)[t] = o;                             // q is dead: reuse as the output staging
   }
   __syncwarp();
   for (int t = lane; t < nvec; t += 32) {
@@ -199,6 +220,7 @@ __global__ void warp_chain_smem_kernel(const T* __restrict__ sample, T* __restri
     const float* fl = bwd_flow + (long long)ii * 2 * hw;
     const float* mk = blend + (long long)ii * hw;
     const bool last = (ii + 2 == frames);
+#pragma unroll 4
     for (int i = threadIdx.x; i < hw; i += blockDim.x) {
       const int x = i % w, y = i / w;
       const Taps tp = make_taps(x + fl[i], y + fl[hw + i], h, w);
@@ -248,20 +270,46 @@ __global__ void warp_blend_step_kernel(const float* __restrict__ src_frames, flo
 
 // =============================================================================================
 // O2  temporal-consistency loss forward + backward  (src/diffusion_hacked.py:461-466)
-// one CTA per (chunk, channel); frame pairs are walked sequentially with both planes and both
-// gradient planes in shared memory, so the bilinear adjoint is a shared-memory scatter-add.
+// one CTA per (chunk, channel); frame pairs are walked sequentially with both planes in shared memory.
+// The backward of the bilinear warp (the adjoint W^T, a scatter-add in autograd) is evaluated as a GATHER:
+// W^T is the same sparse matrix for all chunks*channels planes of a frame pair, so its CSR form
+// (destination pixel -> list of (source pixel, weight)) is built once per batch (warp_taps_kernel + a sort
+// on the host) and every plane just reads it -- no atomics in the per-iteration kernel.
 // =============================================================================================
+__global__ void warp_taps_kernel(const float* __restrict__ flow, int32_t* __restrict__ dest,
+                                 float* __restrict__ weight, int frames, int h, int w) {
+  const int hw = h * w;
+  const long long total = (long long)frames * hw;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(t % hw);
+    const int f = (int)(t / hw);
+    const float* fl = flow + (long long)f * 2 * hw;
+    const Taps tp = make_taps((i % w) + fl[i], (i / w) + fl[hw + i], h, w);
+    const int idx[4] = {tp.i00, tp.i01, tp.i10, tp.i11};
+    const float wt[4] = {tp.w00, tp.w01, tp.w10, tp.w11};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      dest[t * 4 + k] = wt[k] != 0.f ? idx[k] : -1;
+      weight[t * 4 + k] = wt[k];
+    }
+  }
+}
+
 __global__ void warp_loss_kernel(const float* __restrict__ cs, const float* __restrict__ fwd_flow,
                                  const float* __restrict__ bwd_flow, const float* __restrict__ fwd_keep,
-                                 const float* __restrict__ bwd_keep, float* __restrict__ grad,
+                                 const float* __restrict__ bwd_keep, const int32_t* __restrict__ bwd_rowptr,
+                                 const int32_t* __restrict__ bwd_col, const float* __restrict__ bwd_val,
+                                 const int32_t* __restrict__ fwd_rowptr, const int32_t* __restrict__ fwd_col,
+                                 const float* __restrict__ fwd_val, float* __restrict__ grad,
                                  float* __restrict__ loss_acc, int accumulate, int frames, int channels, int h,
                                  int w, float k /* 2 / numel */) {
   extern __shared__ float sm[];
   const int hw = h * w;
   float* c1 = sm;
   float* c2 = sm + hw;
-  float* gA = sm + 2 * hw;
-  float* gB = sm + 3 * hw;
+  float* s1 = sm + 2 * hw;          // sign(c2 - W_bf c1) * keep_b * k
+  float* s2 = sm + 3 * hw;          // sign(c1 - W_ff c2) * keep_f * k
   const int c = blockIdx.x % channels;
   const int b = blockIdx.x / channels;
   auto plane_of = [&](int f) { return ((long long)(b * frames + f) * channels + c) * hw; };
@@ -274,16 +322,13 @@ __global__ void warp_loss_kernel(const float* __restrict__ cs, const float* __re
     c1 = c2;                                                    // previous "next" plane becomes c1
     c2 = t;
     __syncthreads();
-    for (int i = threadIdx.x; i < hw; i += blockDim.x) {
-      c2[i] = cs[plane_of(fn) + i];
-      gA[i] = 0.f;
-      gB[i] = 0.f;
-    }
+    for (int i = threadIdx.x; i < hw; i += blockDim.x) c2[i] = cs[plane_of(fn) + i];
     __syncthreads();
     const float* bf = bwd_flow + (long long)f * 2 * hw;
     const float* ff = fwd_flow + (long long)f * 2 * hw;
     const float* mb = bwd_keep + (long long)f * hw;
     const float* mf = fwd_keep + (long long)f * hw;
+#pragma unroll 2
     for (int i = threadIdx.x; i < hw; i += blockDim.x) {
       const int x = i % w, y = i / w;
       {  // r1 = c2 - W_bf(c1)
@@ -291,41 +336,39 @@ __global__ void warp_loss_kernel(const float* __restrict__ cs, const float* __re
         const float r = c2[i] - sample_taps(c1, tp);
         const float m = mb[i];
         loss += fabsf(r) * m;
-        const float s = (r > 0.f ? 1.f : (r < 0.f ? -1.f : 0.f)) * m * k;
-        if (s != 0.f) {
-          atomicAdd(gB + i, s);
-          if (tp.w00 != 0.f) atomicAdd(gA + tp.i00, -s * tp.w00);
-          if (tp.w01 != 0.f) atomicAdd(gA + tp.i01, -s * tp.w01);
-          if (tp.w10 != 0.f) atomicAdd(gA + tp.i10, -s * tp.w10);
-          if (tp.w11 != 0.f) atomicAdd(gA + tp.i11, -s * tp.w11);
-        }
+        s1[i] = (r > 0.f ? 1.f : (r < 0.f ? -1.f : 0.f)) * m * k;
       }
       {  // r2 = c1 - W_ff(c2)
         const Taps tp = make_taps(x + ff[i], y + ff[hw + i], h, w);
         const float r = c1[i] - sample_taps(c2, tp);
         const float m = mf[i];
         loss += fabsf(r) * m;
-        const float s = (r > 0.f ? 1.f : (r < 0.f ? -1.f : 0.f)) * m * k;
-        if (s != 0.f) {
-          atomicAdd(gA + i, s);
-          if (tp.w00 != 0.f) atomicAdd(gB + tp.i00, -s * tp.w00);
-          if (tp.w01 != 0.f) atomicAdd(gB + tp.i01, -s * tp.w01);
-          if (tp.w10 != 0.f) atomicAdd(gB + tp.i10, -s * tp.w10);
-          if (tp.w11 != 0.f) atomicAdd(gB + tp.i11, -s * tp.w11);
-        }
+        s2[i] = (r > 0.f ? 1.f : (r < 0.f ? -1.f : 0.f)) * m * k;
       }
     }
     __syncthreads();
     const bool a_add = accumulate || f > 0;                     // frame f   : first touched at f == 0
     const bool b_add = accumulate || f == frames - 1;           // frame f+1 : first touched here, except the wrap to 0
+    const int32_t* rp_b = bwd_rowptr + (long long)f * (hw + 1);
+    const int32_t* rp_f = fwd_rowptr + (long long)f * (hw + 1);
+    const int32_t* cb = bwd_col + (long long)f * 4 * hw;
+    const int32_t* cf = fwd_col + (long long)f * 4 * hw;
+    const float* vb = bwd_val + (long long)f * 4 * hw;
+    const float* vf = fwd_val + (long long)f * 4 * hw;
     float* ga = grad + plane_of(f);
     float* gb = grad + plane_of(fn);
-    for (int i = threadIdx.x; i < hw; i += blockDim.x) {
-      ga[i] = a_add ? ga[i] + gA[i] : gA[i];
+    // d/dc1 = s2 - W_bf^T s1      (frame f)
+    for (int q = threadIdx.x; q < hw; q += blockDim.x) {
+      float acc = s2[q];
+      for (int e = rp_b[q]; e < rp_b[q + 1]; ++e) acc = fmaf(-vb[e], s1[cb[e]], acc);
+      ga[q] = a_add ? ga[q] + acc : acc;
     }
-    __syncthreads();                                            // frames == 2: ga and gb can be the same plane pair
-    for (int i = threadIdx.x; i < hw; i += blockDim.x) {
-      gb[i] = b_add ? gb[i] + gB[i] : gB[i];
+    if (frames == 2) __syncthreads();                           // ga / gb alias the same two planes
+    // d/dc2 = s1 - W_ff^T s2      (frame f+1)
+    for (int q = threadIdx.x; q < hw; q += blockDim.x) {
+      float acc = s1[q];
+      for (int e = rp_f[q]; e < rp_f[q + 1]; ++e) acc = fmaf(-vf[e], s2[cf[e]], acc);
+      gb[q] = b_add ? gb[q] + acc : acc;
     }
   }
   if (loss_acc != nullptr) {
@@ -566,11 +609,23 @@ extern "C" int fresco_warp_fuse_chain(const void* sample, void* out, int is_half
   return check_launch("warp_blend_step_kernel");
 }
 
+extern "C" int fresco_warp_taps(const float* flow, int32_t* dest, float* weight, int frames, int h, int w,
+                                void* stream) {
+  if (!flow || !dest || !weight) return set_error(FRESCO_ERR_ARG, "fresco_warp_taps: null pointer");
+  if (frames <= 0 || h <= 0 || w <= 0) return set_error(FRESCO_ERR_ARG, "fresco_warp_taps: bad shape");
+  warp_taps_kernel<<<grid_for((long long)frames * h * w, 256), 256, 0, (cudaStream_t)stream>>>(flow, dest, weight,
+                                                                                              frames, h, w);
+  return check_launch("warp_taps_kernel");
+}
+
 extern "C" int fresco_warp_loss_fwd_bwd(const float* cs, const float* fwd_flow, const float* bwd_flow,
-                                        const float* fwd_keep, const float* bwd_keep, float* grad, float* loss_acc,
+                                        const float* fwd_keep, const float* bwd_keep, const int32_t* bwd_rowptr,
+                                        const int32_t* bwd_col, const float* bwd_val, const int32_t* fwd_rowptr,
+                                        const int32_t* fwd_col, const float* fwd_val, float* grad, float* loss_acc,
                                         int accumulate, int chunks, int frames, int channels, int h, int w,
                                         void* stream) {
-  if (!cs || !fwd_flow || !bwd_flow || !fwd_keep || !bwd_keep || !grad)
+  if (!cs || !fwd_flow || !bwd_flow || !fwd_keep || !bwd_keep || !grad || !bwd_rowptr || !bwd_col || !bwd_val ||
+      !fwd_rowptr || !fwd_col || !fwd_val)
     return set_error(FRESCO_ERR_ARG, "fresco_warp_loss_fwd_bwd: null pointer");
   if (chunks <= 0 || frames < 2 || channels <= 0 || h <= 0 || w <= 0)
     return set_error(FRESCO_ERR_ARG, "fresco_warp_loss_fwd_bwd: bad shape (frames >= 2)");
@@ -584,8 +639,8 @@ extern "C" int fresco_warp_loss_fwd_bwd(const float* cs, const float* fwd_flow, 
   }
   const double numel = (double)chunks * frames * channels * h * w;
   warp_loss_kernel<<<chunks * channels, 256, smem, (cudaStream_t)stream>>>(
-      cs, fwd_flow, bwd_flow, fwd_keep, bwd_keep, grad, loss_acc, accumulate, frames, channels, h, w,
-      (float)(2.0 / numel));
+      cs, fwd_flow, bwd_flow, fwd_keep, bwd_keep, bwd_rowptr, bwd_col, bwd_val, fwd_rowptr, fwd_col, fwd_val, grad,
+      loss_acc, accumulate, frames, channels, h, w, (float)(2.0 / numel));
   return check_launch("warp_loss_kernel");
 }
 

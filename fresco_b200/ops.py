@@ -92,10 +92,36 @@ def warp_fuse_chain(sample, bwd_flow, fwd_flow_last, blend, chunks: int, out=Non
     return out
 
 
-def warp_loss_fwd_bwd(cs, fwd_flow, bwd_flow, fwd_keep, bwd_keep, grad, loss_acc=None, accumulate=False):
+def warp_adjoint_csr(flow: torch.Tensor):
+    """CSR form of the adjoint of the bilinear warp by ``flow`` [F,2,h,w] (per-batch preparation):
+    row_ptr int32 [F, hw+1], col int32 [F, 4hw], val fp32 [F, 4hw]; row = destination pixel."""
+    Fr, _, h, w = flow.shape
+    hw = h * w
+    dest = torch.empty(Fr, hw, 4, dtype=torch.int32, device=flow.device)
+    wgt = torch.empty(Fr, hw, 4, dtype=torch.float32, device=flow.device)
+    L.check(L.lib().fresco_warp_taps(L.ptr(flow), L.ptr(dest), L.ptr(wgt), Fr, h, w, L.stream()), "fresco_warp_taps")
+    dest = dest.reshape(Fr, 4 * hw).long()
+    src = torch.arange(hw, device=flow.device).repeat_interleave(4)[None].expand(Fr, -1)
+    key = torch.where(dest >= 0, dest, torch.full_like(dest, hw))            # tap-less entries sort to the end
+    order = torch.argsort(key, dim=1, stable=True)
+    key_s = torch.gather(key, 1, order)
+    col = torch.gather(src, 1, order).to(torch.int32).contiguous()
+    val = torch.gather(wgt.reshape(Fr, 4 * hw), 1, order).contiguous()
+    bounds = torch.arange(hw + 1, device=flow.device)[None].expand(Fr, -1).contiguous()
+    row_ptr = torch.searchsorted(key_s.contiguous(), bounds).to(torch.int32).contiguous()
+    return row_ptr, col, val
+
+
+def warp_loss_fwd_bwd(cs, fwd_flow, bwd_flow, fwd_keep, bwd_keep, grad, loss_acc=None, accumulate=False,
+                      bwd_csr=None, fwd_csr=None):
     chunks, frames, C, h, w = cs.shape
+    if bwd_csr is None:
+        bwd_csr = warp_adjoint_csr(bwd_flow)
+    if fwd_csr is None:
+        fwd_csr = warp_adjoint_csr(fwd_flow)
     L.check(L.lib().fresco_warp_loss_fwd_bwd(L.ptr(cs), L.ptr(fwd_flow), L.ptr(bwd_flow), L.ptr(fwd_keep),
-                                             L.ptr(bwd_keep), L.ptr(grad),
+                                             L.ptr(bwd_keep), L.ptr(bwd_csr[0]), L.ptr(bwd_csr[1]), L.ptr(bwd_csr[2]),
+                                             L.ptr(fwd_csr[0]), L.ptr(fwd_csr[1]), L.ptr(fwd_csr[2]), L.ptr(grad),
                                              L.ptr(loss_acc) if loss_acc is not None else None,
                                              1 if accumulate else 0, chunks, frames, C, h, w, L.stream()),
             "fresco_warp_loss_fwd_bwd")
