@@ -481,3 +481,60 @@ def gram_targets(features: Sequence[torch.Tensor]):
         v = v / ((v ** 2).sum(dim=2, keepdim=True) ** 0.5)
         out.append(torch.bmm(v, v.transpose(-1, -2)).to(torch.float32))
     return out
+
+
+@torch.no_grad()
+def get_intraframe_paras(pipe, imgs, frescoProc, prompt_embeds, do_classifier_free_guidance=True, seed=0):
+    """Parameters for spatial-guided attention / optimisation (src/diffusion_hacked.py:843-901): one UNet pass
+    on the noised input frames with the controller in store mode (fills
+    ``frescoProc.controller.stored_attn['decoder_attn']``), then the normalised-Gram targets of the four
+    decoder features."""
+    scheduler = pipe.scheduler
+    timestep = scheduler.timesteps[-1]
+    device = pipe._execution_device
+    generator = torch.Generator(device=device).manual_seed(seed)
+    B, C, H, W = imgs.shape
+    ctrl = frescoProc.controller
+    ctrl.disable_controller()
+    disable_FRESCO_opt(pipe)
+    ctrl.clear_store()
+    ctrl.enable_store()
+    latents = pipe.prepare_latents(B, pipe.unet.config.in_channels, H, W, prompt_embeds.dtype, device, generator,
+                                   latents=None)
+    latent_x0 = pipe.vae.config.scaling_factor * pipe.vae.encode(imgs.to(pipe.unet.dtype)).latent_dist.sample()
+    latents = scheduler.add_noise(latent_x0, latents, timestep).detach()
+    model_in = torch.cat([latents] * 2) if do_classifier_free_guidance else latents
+    out = pipe.unet(model_in, timestep, encoder_hidden_states=prompt_embeds, cross_attention_kwargs=None,
+                    return_dict=False)
+    ctrl.disable_store()
+    return gram_targets(out[1:])
+
+
+@torch.no_grad()
+def get_flow_and_interframe_paras(flow_model, imgs, visualize_pipeline=False):
+    """Parameters for temporal-guided attention / optimisation (src/diffusion_hacked.py:905-957): bidirectional
+    GMFlow flow between consecutive keyframes (incl. the wrap-around pair), occlusion masks from flow consistency
+    and photometric error, the cross-frame K/V masks at 3 scales and the FLATTEN trajectories at 2 scales.
+    ``imgs``: list of HxWx3 uint8 arrays.  ``flow_model``: a GMFlow instance (its global correlation can be
+    redirected to fresco_b200.gmflow_matching)."""
+    from .flow_utils import flow_warp, forward_backward_consistency_check, get_mapping_ind
+    dev = next(flow_model.parameters()).device
+    images = torch.stack([torch.from_numpy(im).permute(2, 0, 1).float() for im in imgs], dim=0).to(dev)
+    imgs_torch = images / 127.5 - 1.0                                   # numpy2tensor (src/utils.py:8-12)
+    reshuffle = list(range(1, len(images))) + [0]
+    res = flow_model(images, images[reshuffle], attn_splits_list=[2], corr_radius_list=[-1], prop_radius_list=[-1],
+                     pred_bidir_flow=True)
+    fwd_flows, bwd_flows = res["flow_preds"][-1].chunk(2)
+    fwd_flows, bwd_flows = fwd_flows.contiguous(), bwd_flows.contiguous()
+    fwd_occs, bwd_occs = forward_backward_consistency_check(fwd_flows, bwd_flows)
+    warped1 = flow_warp(images, bwd_flows)
+    bwd_occs = torch.clamp(bwd_occs + (abs(images[reshuffle] - warped1).mean(dim=1) > 255 * 0.25).float(), 0, 1)
+    warped2 = flow_warp(images[reshuffle], fwd_flows)
+    fwd_occs = torch.clamp(fwd_occs + (abs(images - warped2).mean(dim=1) > 255 * 0.25).float(), 0, 1)
+    attn_mask = cross_frame_attn_masks(bwd_occs)
+    fwd_m, bwd_m, masks = [], [], []
+    for scale in (8.0, 16.0):
+        f, b, m = get_mapping_ind(bwd_flows, bwd_occs, imgs_torch, scale=scale)
+        fwd_m.append(f), bwd_m.append(b), masks.append(m)
+    paras = {"fwd_mappings": fwd_m, "bwd_mappings": bwd_m, "interattn_masks": masks}
+    return [fwd_flows, bwd_flows], [fwd_occs, bwd_occs], attn_mask, paras

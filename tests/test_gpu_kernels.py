@@ -423,3 +423,31 @@ def test_gmflow_global_correlation(fb, golden):
     ref, _ = O.global_correlation_softmax(a, b, True)
     got, _ = gmflow_matching.global_correlation_softmax(a.cuda(), b.cuda(), True)
     assert (got.cpu() - ref).abs().max().item() < 0.1
+
+
+def test_get_flow_and_interframe_paras_with_stub_flow_model(fb):
+    """per-batch prep (src/diffusion_hacked.py:905-957) with a stand-in flow model that returns smooth flows:
+    masks / mappings must equal the oracle's on the same flows (bit-exact integer path)."""
+    N, H, W = 3, 128, 128
+    flows, _ = O.synth_flows(N, H, W, seed=5, mag=10.0)
+
+    class StubFlow(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.p = torch.nn.Parameter(torch.zeros(1))
+
+        def forward(self, a, b, **kw):
+            return {"flow_preds": [torch.cat([flows[0], flows[1]]).to(a.device)]}
+
+    g = torch.Generator().manual_seed(0)
+    imgs = [(torch.rand(H, W, 3, generator=g) * 255).to(torch.uint8).numpy() for _ in range(N)]
+    fl, oc, masks, paras = fb.dh.get_flow_and_interframe_paras(StubFlow().cuda(), imgs)
+    images = torch.stack([torch.from_numpy(im).permute(2, 0, 1).float() for im in imgs])
+    resh = list(range(1, N)) + [0]
+    fo, bo = O.forward_backward_consistency_check(flows[0], flows[1])
+    bo = torch.clamp(bo + ((images[resh] - O.flow_warp(images, flows[1])).abs().mean(1) > 255 * 0.25).float(), 0, 1)
+    assert (oc[1].cpu() != bo).float().mean().item() < 2e-3
+    ref_masks = O.cross_frame_masks(oc[1].cpu())
+    assert all(torch.equal(a.cpu(), b) for a, b in zip(masks, ref_masks))
+    fm, bm, im = O.mapping_ind(fl[1].cpu(), oc[1].cpu(), images / 127.5 - 1.0, 8.0)
+    assert torch.equal(paras["fwd_mappings"][0].cpu(), fm) and torch.equal(paras["interattn_masks"][0].cpu(), im)
