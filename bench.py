@@ -112,7 +112,7 @@ class ClockSampler:
 # workload construction (fresco arm)
 # --------------------------------------------------------------------------------------------
 class Workload:
-    def __init__(self, device, seed=0, n_frames=N_FRAMES, res=RES):
+    def __init__(self, device, seed=0, n_frames=N_FRAMES, res=RES, optimise=False):
         from fresco_b200 import diffusion_hacked as dh
         from fresco_b200 import flow_utils as fu
         from fresco_b200.harness import synth
@@ -151,10 +151,21 @@ class Workload:
             self.pipe.unet(torch.cat([self.latents] * 2), TIMESTEPS[-1], encoder_hidden_states=self.prompt,
                            return_dict=False)
         ctrl.disable_store()
-        # warp-only decoder fusion on the optimisation steps (optimize_feature early-outs: no Gram targets,
-        # optimize_temporal=False)
-        dh.apply_FRESCO_opt(self.pipe, steps=OPT_STEPS, flows=self.flows, occs=self.occs, correlation_matrix=[],
-                            optimize_temporal=False, saliency=self.saliency)
+        if optimise:
+            # BASELINE configs[2]: FRESCO feature optimisation (20 Adam iterations, temporal + Gram-L1 loss) on the 4
+            # decoder features on the optimisation steps, Gram targets from the reference pass (get_intraframe_paras)
+            with torch.no_grad():
+                feats = self.pipe.unet(torch.cat([self.latents] * 2), TIMESTEPS[-1], encoder_hidden_states=self.prompt,
+                                       return_dict=False)[1:]
+            self.gram = dh.gram_targets(feats)
+            dh.apply_FRESCO_opt(self.pipe, steps=OPT_STEPS, flows=self.flows, occs=self.occs,
+                                correlation_matrix=self.gram, intra_weight=1e2, iters=20, optimize_temporal=True,
+                                saliency=self.saliency)
+        else:
+            # BASELINE configs[1]: warp-only decoder fusion on the optimisation steps (optimize_feature early-outs:
+            # no Gram targets, optimize_temporal=False)
+            dh.apply_FRESCO_opt(self.pipe, steps=OPT_STEPS, flows=self.flows, occs=self.occs, correlation_matrix=[],
+                                optimize_temporal=False, saliency=self.saliency)
         self.kv_len = {int(m.shape[1]): int(m.sum().item()) for m in self.attn_mask}
 
     def set_schedule_state(self, i):
@@ -241,6 +252,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-frames", type=int, default=2)
     ap.add_argument("--cpu-budget-s", type=float, default=150.0)
+    ap.add_argument("--workload", default="config2", choices=["config2", "config3"],
+                    help="config2 (default, the headline): FRESCO attention + warp fusion; config3: + feature "
+                         "optimisation (apply_FRESCO_opt with Gram targets, 20 Adam iterations on 10 of 15 steps)")
     ap.add_argument("--profile-mode", action="store_true",
                     help="for ncu captures only: 1 warm-up + --steps, no e2e / cpu baseline; never a bench value")
     args = ap.parse_args()
@@ -273,7 +287,9 @@ def main():
     device = torch.device("cuda", local)
     from fresco_b200 import _lib, ops
     _lib.lib()
-    wl = Workload(device, seed=rank)
+    wl = Workload(device, seed=rank, optimise=args.workload == "config3")
+    if args.workload == "config3":
+        config["workload"] += "; + optimize_feature (20 Adam iters, temporal + Gram-L1) on 4 decoder features, 10 of 15 steps"
 
     # ---- value: inputs resident in HBM
     sampler = ClockSampler(local)
