@@ -173,61 +173,83 @@ tile_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       } else if (EPI == EPI_GRAM_SIGN) {
         // T is symmetric (T_ij = sign(G_ij - A_ij) + sign(G_ij - A_ji), G symmetric), so only tiles J >= I are
         // launched; this CTA also writes the mirrored tile T_JI and accounts for its share of the loss.
-        // The direct target tile A[I, J] is staged through shared memory (the operand ring is idle once the last
-        // MMA has retired; n_iter == 1) so that global reads are coalesced; the transposed tile A[J, I] is read
-        // straight from global -- for a fixed j, consecutive lanes read consecutive i.
+        // Both target tiles -- A[I, J] (read along this thread's row) and A[J, I] (read along a column) -- and the
+        // mirrored output are staged through shared memory in two 64-column halves (the operand ring is idle once
+        // the last MMA has retired; n_iter == 1), so every global access is a coalesced 16-byte vector with many
+        // loads in flight per thread.
         const size_t plane = (size_t)batch * p.M * p.M;
         const bool diag_tile = (n0 == m0);
-        constexpr int kLd = 132;                                        // padded row stride (floats), keeps 16 B alignment
-        float* stage = reinterpret_cast<float*>(smem);
-        {
-          const int tid = threadIdx.x;                                   // 0..127
-          for (int it = 0; it < 32; ++it) {
-            const int rr = it * 4 + (tid >> 5);
-            const int c4 = (tid & 31) * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (m0 + rr < p.M && n0 + c4 < p.M)
-              v = __ldg(reinterpret_cast<const float4*>(p.target + plane + (size_t)(m0 + rr) * p.M + n0 + c4));
-            *reinterpret_cast<float4*>(stage + rr * kLd + c4) = v;
-          }
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        const float* a_tr = p.target + plane + (size_t)n0 * p.M + gm;         // A[j0 + c, i]
-        __half* dst = p.tsign + plane + (size_t)gm * p.M + n0;                // T[i, j0 + c]
-        __half* dst_tr = p.tsign + plane + (size_t)n0 * p.M + gm;             // T[j0 + c, i]
+        constexpr int kLdD = 68;                                         // direct half  [128 i][64 j] (+pad), floats
+        constexpr int kLdT = 132;                                        // transposed   [ 64 j][128 i] (+pad), floats
+        constexpr int kLdO = 136;                                        // mirrored out [ 64 j][128 i] (+pad), halves
+        float* st_d = reinterpret_cast<float*>(smem);
+        float* st_t = st_d + 128 * kLdD;
+        __half* st_o = reinterpret_cast<__half*>(st_t + 64 * kLdT);
+        const int tid = threadIdx.x;                                     // 0..127
+        __half* dst = p.tsign + plane + (size_t)gm * p.M + n0;            // T[i, j0 + c]
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t r[32];
-          tmem_ld32(acc + c * 32, r);
-          tmem_ld_wait();
-          if (gm < p.M) {
+        for (int half = 0; half < 2; ++half) {
+          const int j0 = n0 + half * 64;
+          // ---- coalesced loads: direct half tile (rows i) and transposed half tile (rows j)
+#pragma unroll 4
+          for (int it = 0; it < 16; ++it) {                               // 128 rows x 16 float4
+            const int rr = it * 8 + (tid >> 4), c4 = (tid & 15) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m0 + rr < p.M && j0 + c4 < p.M)
+              v = __ldg(reinterpret_cast<const float4*>(p.target + plane + (size_t)(m0 + rr) * p.M + j0 + c4));
+            *reinterpret_cast<float4*>(st_d + rr * kLdD + c4) = v;
+          }
+#pragma unroll 4
+          for (int it = 0; it < 16; ++it) {                               // 64 rows x 32 float4
+            const int rr = it * 4 + (tid >> 5), c4 = (tid & 31) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j0 + rr < p.M && m0 + c4 < p.M)
+              v = __ldg(reinterpret_cast<const float4*>(p.target + plane + (size_t)(j0 + rr) * p.M + m0 + c4));
+            *reinterpret_cast<float4*>(st_t + rr * kLdT + c4) = v;
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            uint32_t r[32];
+            tmem_ld32(acc + half * 64 + c * 32, r);
+            tmem_ld_wait();
             uint32_t pk[16];
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const int col = c * 32 + i;
-              float tv[4] = {0.f, 0.f, 0.f, 0.f};
-              if (n0 + col < p.M) {                                          // M is a multiple of 8 (checked on the host)
-                const float4 d4 = *reinterpret_cast<const float4*>(stage + row * kLd + col);
-                const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+            for (int i = 0; i < 32; i += 2) {
+              float tv[2];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  const float g = __uint_as_float(r[i + u]);
-                  const float d1 = g - dv[u];
-                  const float d2 = g - __ldg(a_tr + (size_t)(col + u) * p.M);
-                  loss += fabsf(d1) + (diag_tile ? 0.f : fabsf(d2));
-                  tv[u] = (d1 > 0.f ? 1.f : (d1 < 0.f ? -1.f : 0.f)) + (d2 > 0.f ? 1.f : (d2 < 0.f ? -1.f : 0.f));
-                  if (!diag_tile) dst_tr[(size_t)(col + u) * p.M] = __float2half_rn(tv[u]);
-                }
+              for (int u = 0; u < 2; ++u) {
+                const int jj = c * 32 + i + u;                             // column inside the half tile
+                const float g = __uint_as_float(r[i + u]);
+                const float d1 = g - st_d[row * kLdD + jj];
+                const float d2 = g - st_t[jj * kLdT + row];
+                const bool live = (gm < p.M) && (j0 + jj < p.M);
+                if (live) loss += fabsf(d1) + (diag_tile ? 0.f : fabsf(d2));
+                tv[u] = (d1 > 0.f ? 1.f : (d1 < 0.f ? -1.f : 0.f)) + (d2 > 0.f ? 1.f : (d2 < 0.f ? -1.f : 0.f));
+                st_o[jj * kLdO + row] = __float2half_rn(tv[u]);
               }
               pk[i >> 1] = pack_half2(tv[0], tv[1]);
-              pk[(i >> 1) + 1] = pack_half2(tv[2], tv[3]);
             }
+            if (gm < p.M) {
 #pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4)
-              if (n0 + c * 32 + q4 * 8 < p.M)
-                *reinterpret_cast<uint4*>(dst + c * 32 + q4 * 8) =
-                    make_uint4(pk[q4 * 4], pk[q4 * 4 + 1], pk[q4 * 4 + 2], pk[q4 * 4 + 3]);
+              for (int q4 = 0; q4 < 4; ++q4)
+                if (j0 + c * 32 + q4 * 8 < p.M)
+                  *reinterpret_cast<uint4*>(dst + half * 64 + c * 32 + q4 * 8) =
+                      make_uint4(pk[q4 * 4], pk[q4 * 4 + 1], pk[q4 * 4 + 2], pk[q4 * 4 + 3]);
+            }
           }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (!diag_tile) {
+            // mirrored tile T[j0 + jj, m0 + i]: 64 rows x 16 sixteen-byte vectors, coalesced
+#pragma unroll 4
+            for (int it = 0; it < 8; ++it) {
+              const int jj = it * 8 + (tid >> 4), c8 = (tid & 15) * 8;
+              if (j0 + jj < p.M && m0 + c8 < p.M)
+                *reinterpret_cast<uint4*>(p.tsign + plane + (size_t)(j0 + jj) * p.M + m0 + c8) =
+                    *reinterpret_cast<const uint4*>(st_o + jj * kLdO + c8);
+            }
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");                  // staging is reused by the next half
         }
       } else {  // EPI_GMFLOW: online softmax with V = (x, y) pixel coordinates of the key token
         float m_tile = -INFINITY;

@@ -272,9 +272,10 @@ __global__ void warp_blend_step_kernel(const float* __restrict__ src_frames, flo
 // O2  temporal-consistency loss forward + backward  (src/diffusion_hacked.py:461-466)
 // one CTA per (chunk, channel); frame pairs are walked sequentially with both planes in shared memory.
 // The backward of the bilinear warp (the adjoint W^T, a scatter-add in autograd) is evaluated as a GATHER:
-// W^T is the same sparse matrix for all chunks*channels planes of a frame pair, so its CSR form
-// (destination pixel -> list of (source pixel, weight)) is built once per batch (warp_taps_kernel + a sort
-// on the host) and every plane just reads it -- no atomics in the per-iteration kernel.
+// W^T is the same sparse matrix for all chunks*channels planes of a frame pair, so it is built once per batch
+// (warp_taps_kernel + a sort on the host) in ELL form -- 8 packed (source:u16, weight:unorm16) slots per
+// destination pixel, 32 bytes per row -- and every plane just reads it: no atomics and no data-dependent loop
+// in the per-iteration kernel.  Destinations hit by more than 8 taps go to a small overflow list.
 // =============================================================================================
 __global__ void warp_taps_kernel(const float* __restrict__ flow, int32_t* __restrict__ dest,
                                  float* __restrict__ weight, int frames, int h, int w) {
@@ -298,12 +299,10 @@ __global__ void warp_taps_kernel(const float* __restrict__ flow, int32_t* __rest
 
 __global__ void warp_loss_kernel(const float* __restrict__ cs, const float* __restrict__ fwd_flow,
                                  const float* __restrict__ bwd_flow, const float* __restrict__ fwd_keep,
-                                 const float* __restrict__ bwd_keep, const int32_t* __restrict__ bwd_rowptr,
-                                 const int32_t* __restrict__ bwd_col, const float* __restrict__ bwd_val,
-                                 const int32_t* __restrict__ fwd_rowptr, const int32_t* __restrict__ fwd_col,
-                                 const float* __restrict__ fwd_val, float* __restrict__ grad,
-                                 float* __restrict__ loss_acc, int accumulate, int frames, int channels, int h,
-                                 int w, float k /* 2 / numel */) {
+                                 const float* __restrict__ bwd_keep, const uint4* __restrict__ bwd_ell,
+                                 const uint4* __restrict__ fwd_ell, const int32_t* __restrict__ ovf /*[2][frames][n_ovf][3]*/,
+                                 int n_ovf, float* __restrict__ grad, float* __restrict__ loss_acc, int accumulate,
+                                 int frames, int channels, int h, int w, float k /* 2 / numel */) {
   extern __shared__ float sm[];
   const int hw = h * w;
   float* c1 = sm;
@@ -349,26 +348,40 @@ __global__ void warp_loss_kernel(const float* __restrict__ cs, const float* __re
     __syncthreads();
     const bool a_add = accumulate || f > 0;                     // frame f   : first touched at f == 0
     const bool b_add = accumulate || f == frames - 1;           // frame f+1 : first touched here, except the wrap to 0
-    const int32_t* rp_b = bwd_rowptr + (long long)f * (hw + 1);
-    const int32_t* rp_f = fwd_rowptr + (long long)f * (hw + 1);
-    const int32_t* cb = bwd_col + (long long)f * 4 * hw;
-    const int32_t* cf = fwd_col + (long long)f * 4 * hw;
-    const float* vb = bwd_val + (long long)f * 4 * hw;
-    const float* vf = fwd_val + (long long)f * 4 * hw;
+    // adjoint as a gather: 8 packed (source, weight) slots per destination pixel (ELL), two 16-byte loads per row
+    const uint4* eb = bwd_ell + (long long)f * hw * 2;
+    const uint4* ef = fwd_ell + (long long)f * hw * 2;
     float* ga = grad + plane_of(f);
     float* gb = grad + plane_of(fn);
+    auto gather8 = [&](const uint4* ell, int q, const float* sv) {
+      const uint4 e0 = __ldg(ell + 2 * q), e1 = __ldg(ell + 2 * q + 1);
+      const uint32_t e[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc = fmaf((float)(e[j] >> 16) * (1.0f / 65535.0f), sv[e[j] & 0xffffu], acc);
+      return acc;
+    };
     // d/dc1 = s2 - W_bf^T s1      (frame f)
+#pragma unroll 4
     for (int q = threadIdx.x; q < hw; q += blockDim.x) {
-      float acc = s2[q];
-      for (int e = rp_b[q]; e < rp_b[q + 1]; ++e) acc = fmaf(-vb[e], s1[cb[e]], acc);
+      const float acc = s2[q] - gather8(eb, q, s1);
       ga[q] = a_add ? ga[q] + acc : acc;
     }
     if (frames == 2) __syncthreads();                           // ga / gb alias the same two planes
     // d/dc2 = s1 - W_ff^T s2      (frame f+1)
+#pragma unroll 4
     for (int q = threadIdx.x; q < hw; q += blockDim.x) {
-      float acc = s1[q];
-      for (int e = rp_f[q]; e < rp_f[q + 1]; ++e) acc = fmaf(-vf[e], s2[cf[e]], acc);
+      const float acc = s1[q] - gather8(ef, q, s2);
       gb[q] = b_add ? gb[q] + acc : acc;
+    }
+    if (n_ovf > 0) {                                            // destinations hit by more than 8 taps (rare)
+      __syncthreads();
+      const int32_t* ob = ovf + ((long long)0 * frames + f) * n_ovf * 3;
+      const int32_t* of = ovf + ((long long)1 * frames + f) * n_ovf * 3;
+      for (int e = threadIdx.x; e < n_ovf; e += blockDim.x) {
+        if (ob[3 * e] >= 0) atomicAdd(ga + ob[3 * e], -__int_as_float(ob[3 * e + 2]) * s1[ob[3 * e + 1]]);
+        if (of[3 * e] >= 0) atomicAdd(gb + of[3 * e], -__int_as_float(of[3 * e + 2]) * s2[of[3 * e + 1]]);
+      }
     }
   }
   if (loss_acc != nullptr) {
@@ -619,16 +632,15 @@ extern "C" int fresco_warp_taps(const float* flow, int32_t* dest, float* weight,
 }
 
 extern "C" int fresco_warp_loss_fwd_bwd(const float* cs, const float* fwd_flow, const float* bwd_flow,
-                                        const float* fwd_keep, const float* bwd_keep, const int32_t* bwd_rowptr,
-                                        const int32_t* bwd_col, const float* bwd_val, const int32_t* fwd_rowptr,
-                                        const int32_t* fwd_col, const float* fwd_val, float* grad, float* loss_acc,
-                                        int accumulate, int chunks, int frames, int channels, int h, int w,
-                                        void* stream) {
-  if (!cs || !fwd_flow || !bwd_flow || !fwd_keep || !bwd_keep || !grad || !bwd_rowptr || !bwd_col || !bwd_val ||
-      !fwd_rowptr || !fwd_col || !fwd_val)
+                                        const float* fwd_keep, const float* bwd_keep, const void* bwd_ell,
+                                        const void* fwd_ell, const int32_t* overflow, int n_overflow, float* grad,
+                                        float* loss_acc, int accumulate, int chunks, int frames, int channels, int h,
+                                        int w, void* stream) {
+  if (!cs || !fwd_flow || !bwd_flow || !fwd_keep || !bwd_keep || !grad || !bwd_ell || !fwd_ell)
     return set_error(FRESCO_ERR_ARG, "fresco_warp_loss_fwd_bwd: null pointer");
-  if (chunks <= 0 || frames < 2 || channels <= 0 || h <= 0 || w <= 0)
-    return set_error(FRESCO_ERR_ARG, "fresco_warp_loss_fwd_bwd: bad shape (frames >= 2)");
+  if (n_overflow > 0 && !overflow) return set_error(FRESCO_ERR_ARG, "fresco_warp_loss_fwd_bwd: overflow list missing");
+  if (chunks <= 0 || frames < 2 || channels <= 0 || h <= 0 || w <= 0 || h * w > 65535)
+    return set_error(FRESCO_ERR_ARG, "fresco_warp_loss_fwd_bwd: bad shape (frames >= 2, h*w <= 65535)");
   const size_t smem = (size_t)4 * h * w * sizeof(float);
   if (smem > 200 * 1024) return set_error(FRESCO_ERR_UNSUPPORTED, "fresco_warp_loss_fwd_bwd: plane too large for shared memory");
   static bool attr_set = false;
@@ -639,8 +651,8 @@ extern "C" int fresco_warp_loss_fwd_bwd(const float* cs, const float* fwd_flow, 
   }
   const double numel = (double)chunks * frames * channels * h * w;
   warp_loss_kernel<<<chunks * channels, 256, smem, (cudaStream_t)stream>>>(
-      cs, fwd_flow, bwd_flow, fwd_keep, bwd_keep, bwd_rowptr, bwd_col, bwd_val, fwd_rowptr, fwd_col, fwd_val, grad,
-      loss_acc, accumulate, frames, channels, h, w, (float)(2.0 / numel));
+      cs, fwd_flow, bwd_flow, fwd_keep, bwd_keep, (const uint4*)bwd_ell, (const uint4*)fwd_ell, overflow, n_overflow,
+      grad, loss_acc, accumulate, frames, channels, h, w, (float)(2.0 / numel));
   return check_launch("warp_loss_kernel");
 }
 

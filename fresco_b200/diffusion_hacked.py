@@ -354,7 +354,7 @@ def optimize_feature(sample, flows, occs, correlation_matrix=[], intra_weight=1e
         _, fwd_flow, bwd_flow, fwd_occ, bwd_occ = resize_flows_occs(flows, occs, h)
         fwd_keep = (1 - fwd_occ).reshape(n, h, w).contiguous()
         bwd_keep = (1 - bwd_occ).reshape(n, h, w).contiguous()
-        bwd_csr, fwd_csr = adjoint_csr(flows, occs, h)          # per-batch: cached on the flow tensors
+        adjoint = adjoint_csr(flows, occs, h)                   # per-batch: cached on the flow tensors
     target = None
     for tmp in correlation_matrix:
         if h * w == tmp.shape[1]:
@@ -369,7 +369,7 @@ def optimize_feature(sample, flows, occs, correlation_matrix=[], intra_weight=1e
             loss_acc.zero_()
         if have_temporal:
             ops.warp_loss_fwd_bwd(cs, fwd_flow, bwd_flow, fwd_keep, bwd_keep, grad, loss_acc, accumulate=False,
-                                  bwd_csr=bwd_csr, fwd_csr=fwd_csr)
+                                  adjoint=adjoint)
         else:
             grad.zero_()
         if spatial:

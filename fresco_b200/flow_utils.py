@@ -82,10 +82,10 @@ def _resize_flows_occs(flows, occs, size_h):
 
 
 def adjoint_csr(flows, occs, size_h: int):
-    """CSR matrices of the warp adjoints (backward of flow_warp) at a feature resolution, cached per batch."""
+    """ELL matrices of the warp adjoints (backward of flow_warp) at a feature resolution, cached per batch."""
     def make():
         _, fwd_flow, bwd_flow, _, _ = resize_flows_occs(flows, occs, size_h)
-        return ops.warp_adjoint_csr(bwd_flow), ops.warp_adjoint_csr(fwd_flow)
+        return ops.warp_adjoint_pair(bwd_flow, fwd_flow)
     key = ("adjoint", size_h) + tuple(_tensor_key(t) for t in (flows[0], flows[1]))
     return _cache_get(key, make)
 

@@ -92,40 +92,75 @@ def warp_fuse_chain(sample, bwd_flow, fwd_flow_last, blend, chunks: int, out=Non
     return out
 
 
-def warp_adjoint_csr(flow: torch.Tensor):
-    """CSR form of the adjoint of the bilinear warp by ``flow`` [F,2,h,w] (per-batch preparation):
-    row_ptr int32 [F, hw+1], col int32 [F, 4hw], val fp32 [F, 4hw]; row = destination pixel."""
+ELL_SLOTS = 8
+
+
+def warp_adjoint_ell(flow: torch.Tensor):
+    """ELL form of the adjoint of the bilinear warp by ``flow`` [F,2,h,w] (per-batch preparation).
+    Returns (ell uint32-as-int32 [F, hw, 8], overflow int32 [F, n_ovf, 3]); row = destination pixel, entry =
+    (round(w*65535) << 16) | source; destinations with more than 8 taps spill to the overflow list."""
     Fr, _, h, w = flow.shape
     hw = h * w
-    dest = torch.empty(Fr, hw, 4, dtype=torch.int32, device=flow.device)
-    wgt = torch.empty(Fr, hw, 4, dtype=torch.float32, device=flow.device)
+    dev = flow.device
+    dest = torch.empty(Fr, hw, 4, dtype=torch.int32, device=dev)
+    wgt = torch.empty(Fr, hw, 4, dtype=torch.float32, device=dev)
     L.check(L.lib().fresco_warp_taps(L.ptr(flow), L.ptr(dest), L.ptr(wgt), Fr, h, w, L.stream()), "fresco_warp_taps")
     dest = dest.reshape(Fr, 4 * hw).long()
-    src = torch.arange(hw, device=flow.device).repeat_interleave(4)[None].expand(Fr, -1)
+    wgt = wgt.reshape(Fr, 4 * hw)
+    src = torch.arange(hw, device=dev).repeat_interleave(4)[None].expand(Fr, -1)
     key = torch.where(dest >= 0, dest, torch.full_like(dest, hw))            # tap-less entries sort to the end
     order = torch.argsort(key, dim=1, stable=True)
-    key_s = torch.gather(key, 1, order)
-    col = torch.gather(src, 1, order).to(torch.int32).contiguous()
-    val = torch.gather(wgt.reshape(Fr, 4 * hw), 1, order).contiguous()
-    bounds = torch.arange(hw + 1, device=flow.device)[None].expand(Fr, -1).contiguous()
-    row_ptr = torch.searchsorted(key_s.contiguous(), bounds).to(torch.int32).contiguous()
-    return row_ptr, col, val
+    key_s = torch.gather(key, 1, order).contiguous()
+    src_s = torch.gather(src, 1, order)
+    w_s = torch.gather(wgt, 1, order)
+    bounds = torch.arange(hw + 1, device=dev)[None].expand(Fr, -1).contiguous()
+    row_ptr = torch.searchsorted(key_s, bounds)                               # [F, hw+1]
+    valid = key_s < hw
+    rank = torch.arange(4 * hw, device=dev)[None] - torch.gather(row_ptr, 1, key_s.clamp(max=hw - 1))
+    packed = ((w_s * 65535.0).round().long() << 16) | src_s
+    ell = torch.zeros(Fr, hw * ELL_SLOTS, dtype=torch.int64, device=dev)
+    in_ell = valid & (rank < ELL_SLOTS)
+    slot = (key_s.clamp(max=hw - 1) * ELL_SLOTS + rank.clamp(0, ELL_SLOTS - 1))
+    ell.scatter_(1, torch.where(in_ell, slot, torch.zeros_like(slot)),
+                 torch.where(in_ell, packed, torch.zeros_like(packed)), reduce="add")   # slot 0 of row 0 gets +0 for the rest
+    # uint32 payload stored in an int32 tensor (two's complement wrap)
+    ell = torch.where(ell >= 2 ** 31, ell - 2 ** 32, ell).to(torch.int32).reshape(Fr, hw, ELL_SLOTS).contiguous()
+    over = valid & (rank >= ELL_SLOTS)
+    n_ovf = int(over.sum(1).max().item())
+    ovf = torch.full((Fr, max(n_ovf, 1), 3), -1, dtype=torch.int32, device=dev)
+    if n_ovf > 0:
+        for f in range(Fr):
+            sel = torch.nonzero(over[f]).reshape(-1)
+            ovf[f, :sel.numel(), 0] = key_s[f, sel].to(torch.int32)
+            ovf[f, :sel.numel(), 1] = src_s[f, sel].to(torch.int32)
+            ovf[f, :sel.numel(), 2] = w_s[f, sel].contiguous().view(torch.int32)
+    return ell, ovf, n_ovf
 
 
 def warp_loss_fwd_bwd(cs, fwd_flow, bwd_flow, fwd_keep, bwd_keep, grad, loss_acc=None, accumulate=False,
-                      bwd_csr=None, fwd_csr=None):
+                      adjoint=None):
+    """``adjoint`` = (bwd_ell, fwd_ell, overflow [2, F, n, 3], n) from :func:`warp_adjoint_pair` (cached per batch)."""
     chunks, frames, C, h, w = cs.shape
-    if bwd_csr is None:
-        bwd_csr = warp_adjoint_csr(bwd_flow)
-    if fwd_csr is None:
-        fwd_csr = warp_adjoint_csr(fwd_flow)
+    if adjoint is None:
+        adjoint = warp_adjoint_pair(bwd_flow, fwd_flow)
+    bwd_ell, fwd_ell, ovf, n_ovf = adjoint
     L.check(L.lib().fresco_warp_loss_fwd_bwd(L.ptr(cs), L.ptr(fwd_flow), L.ptr(bwd_flow), L.ptr(fwd_keep),
-                                             L.ptr(bwd_keep), L.ptr(bwd_csr[0]), L.ptr(bwd_csr[1]), L.ptr(bwd_csr[2]),
-                                             L.ptr(fwd_csr[0]), L.ptr(fwd_csr[1]), L.ptr(fwd_csr[2]), L.ptr(grad),
-                                             L.ptr(loss_acc) if loss_acc is not None else None,
+                                             L.ptr(bwd_keep), L.ptr(bwd_ell), L.ptr(fwd_ell), L.ptr(ovf), int(n_ovf),
+                                             L.ptr(grad), L.ptr(loss_acc) if loss_acc is not None else None,
                                              1 if accumulate else 0, chunks, frames, C, h, w, L.stream()),
             "fresco_warp_loss_fwd_bwd")
     return grad
+
+
+def warp_adjoint_pair(bwd_flow, fwd_flow):
+    b_ell, b_ovf, nb = warp_adjoint_ell(bwd_flow)
+    f_ell, f_ovf, nf = warp_adjoint_ell(fwd_flow)
+    n = max(nb, nf)
+    Fr = bwd_flow.shape[0]
+    ovf = torch.full((2, Fr, max(n, 1), 3), -1, dtype=torch.int32, device=bwd_flow.device)
+    ovf[0, :, :b_ovf.shape[1]] = b_ovf
+    ovf[1, :, :f_ovf.shape[1]] = f_ovf
+    return b_ell, f_ell, ovf.contiguous(), n
 
 
 def gram_normalize(cs_bcl: torch.Tensor):

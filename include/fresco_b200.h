@@ -85,18 +85,18 @@ int fresco_warp_fuse_chain(const void* sample, void* out, int is_half, const flo
  * replaces src/diffusion_hacked.py:461-466 and its autograd backward.
  * cs, grad float [chunks, frames, channels, h, w]; fwd_flow/bwd_flow float [frames,2,h,w];
  * fwd_keep/bwd_keep float [frames,h,w] (= 1 - occlusion).  The adjoint of the bilinear warp is applied as a
- * gather through a per-frame CSR matrix (destination pixel -> (source pixel, weight)), built once per batch from
- * fresco_warp_taps + a sort by destination: *_rowptr int32 [frames, h*w+1], *_col int32 [frames, 4*h*w],
- * *_val float [frames, 4*h*w].  grad is overwritten (accumulate=0) or added to; *loss_acc (device float, may be
- * null) gets the loss value added.
+ * gather through a per-frame ELL matrix built once per batch from fresco_warp_taps + a sort by destination:
+ * *_ell uint32 [frames, h*w, 8], entry = (round(weight*65535) << 16) | source pixel (0 = empty slot);
+ * overflow int32 [2 (bwd,fwd), frames, n_overflow, 3] = (destination | -1, source, float bits of weight) for
+ * destinations with more than 8 taps.  h*w <= 65535.  grad is overwritten (accumulate=0) or added to;
+ * *loss_acc (device float, may be null) gets the loss value added.
  * fresco_warp_taps: the 4 bilinear taps of every source pixel: dest int32 [frames, h*w, 4] (-1 = no tap),
  * weight float [frames, h*w, 4].                                                                 */
 int fresco_warp_taps(const float* flow, int32_t* dest, float* weight, int frames, int h, int w, void* stream);
 int fresco_warp_loss_fwd_bwd(const float* cs, const float* fwd_flow, const float* bwd_flow, const float* fwd_keep,
-                             const float* bwd_keep, const int32_t* bwd_rowptr, const int32_t* bwd_col,
-                             const float* bwd_val, const int32_t* fwd_rowptr, const int32_t* fwd_col,
-                             const float* fwd_val, float* grad, float* loss_acc, int accumulate, int chunks,
-                             int frames, int channels, int h, int w, void* stream);
+                             const float* bwd_keep, const void* bwd_ell, const void* fwd_ell, const int32_t* overflow,
+                             int n_overflow, float* grad, float* loss_acc, int accumulate, int chunks, int frames,
+                             int channels, int h, int w, void* stream);
 
 /* ---- O3: spatial-consistency (normalised Gram, L1) loss, forward + backward -----------------
  * replaces src/diffusion_hacked.py:469-476 and its backward.

@@ -49,9 +49,9 @@ def main():
         _, ff, bf, fo, bo = dh.resize_flows_occs(flows, occs, h)
         gr = torch.empty_like(cs)
         from fresco_b200.flow_utils import adjoint_csr
-        bcsr, fcsr = adjoint_csr(flows, occs, h)
+        adj = adjoint_csr(flows, occs, h)
         kf, kb = (1 - fo).reshape(N, h, h).contiguous(), (1 - bo).reshape(N, h, h).contiguous()
-        t_warp = timeit(lambda: ops.warp_loss_fwd_bwd(cs, ff, bf, kf, kb, gr, bwd_csr=bcsr, fwd_csr=fcsr), 5)
+        t_warp = timeit(lambda: ops.warp_loss_fwd_bwd(cs, ff, bf, kf, kb, gr, adjoint=adj), 5)
         m = torch.zeros_like(cs)
         v = torch.zeros_like(cs)
         t_adam = timeit(lambda: ops.adam_step(cs, gr, m, v, 1), 5)
