@@ -146,6 +146,20 @@ tile_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const uint32_t t_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
     float loss = 0.f;
     float m_run = -INFINITY, l_run = 0.f, ax = 0.f, ay = 0.f;     // EPI_GMFLOW online-softmax state
+    if (EPI == EPI_GRAM_SIGN) {
+      // The epilogue warps are idle during the K loop: pull this CTA's two target tiles (A[I,J] and A[J,I],
+      // 64 KB each) into L2 now so that the staging loads after the last MMA hit L2 instead of HBM.
+      const int n0p = n_tile0 * 128;
+      const size_t planep = (size_t)batch * p.M * p.M;
+#pragma unroll
+      for (int k2 = 0; k2 < 8; ++k2) {                              // 128 rows x 4 lines (128 B) per tile
+        const int idx = k2 * 128 + threadIdx.x, rr = idx >> 2, ln = (idx & 3) * 32;
+        if (m0 + rr < p.M && n0p + ln < p.M)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(p.target + planep + (size_t)(m0 + rr) * p.M + n0p + ln));
+        if (n0p + rr < p.M && m0 + ln < p.M)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(p.target + planep + (size_t)(n0p + rr) * p.M + m0 + ln));
+      }
+    }
     for (int t = 0; t < p.n_iter; ++t) {
       const int buf = t & 1;
       const int n0 = (n_tile0 + t) * 128;
@@ -191,21 +205,28 @@ tile_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         for (int half = 0; half < 2; ++half) {
           const int j0 = n0 + half * 64;
           // ---- coalesced loads: direct half tile (rows i) and transposed half tile (rows j)
-#pragma unroll 4
-          for (int it = 0; it < 16; ++it) {                               // 128 rows x 16 float4
-            const int rr = it * 8 + (tid >> 4), c4 = (tid & 15) * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (m0 + rr < p.M && j0 + c4 < p.M)
-              v = __ldg(reinterpret_cast<const float4*>(p.target + plane + (size_t)(m0 + rr) * p.M + j0 + c4));
-            *reinterpret_cast<float4*>(st_d + rr * kLdD + c4) = v;
-          }
-#pragma unroll 4
-          for (int it = 0; it < 16; ++it) {                               // 64 rows x 32 float4
-            const int rr = it * 4 + (tid >> 5), c4 = (tid & 31) * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (j0 + rr < p.M && m0 + c4 < p.M)
-              v = __ldg(reinterpret_cast<const float4*>(p.target + plane + (size_t)(j0 + rr) * p.M + m0 + c4));
-            *reinterpret_cast<float4*>(st_t + rr * kLdT + c4) = v;
+          {
+            float4 v[16];
+#pragma unroll
+            for (int it = 0; it < 16; ++it) {                             // 128 rows x 16 float4, all in flight
+              const int rr = it * 8 + (tid >> 4), c4 = (tid & 15) * 4;
+              v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (m0 + rr < p.M && j0 + c4 < p.M)
+                v[it] = __ldg(reinterpret_cast<const float4*>(p.target + plane + (size_t)(m0 + rr) * p.M + j0 + c4));
+            }
+#pragma unroll
+            for (int it = 0; it < 16; ++it)
+              *reinterpret_cast<float4*>(st_d + (it * 8 + (tid >> 4)) * kLdD + (tid & 15) * 4) = v[it];
+#pragma unroll
+            for (int it = 0; it < 16; ++it) {                             // 64 rows x 32 float4
+              const int rr = it * 4 + (tid >> 5), c4 = (tid & 31) * 4;
+              v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (j0 + rr < p.M && m0 + c4 < p.M)
+                v[it] = __ldg(reinterpret_cast<const float4*>(p.target + plane + (size_t)(j0 + rr) * p.M + m0 + c4));
+            }
+#pragma unroll
+            for (int it = 0; it < 16; ++it)
+              *reinterpret_cast<float4*>(st_t + (it * 4 + (tid >> 5)) * kLdT + (tid & 31) * 4) = v[it];
           }
           asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll 1

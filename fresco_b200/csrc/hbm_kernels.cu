@@ -327,9 +327,15 @@ __global__ void warp_loss_kernel(const float* __restrict__ cs, const float* __re
     const float* ff = fwd_flow + (long long)f * 2 * hw;
     const float* mb = bwd_keep + (long long)f * hw;
     const float* mf = fwd_keep + (long long)f * hw;
+    // pixel coordinates advance incrementally (no integer division in the loop)
+    const int dx = blockDim.x % w, dy = blockDim.x / w;
+    int x = threadIdx.x % w, y = threadIdx.x / w;
 #pragma unroll 2
-    for (int i = threadIdx.x; i < hw; i += blockDim.x) {
-      const int x = i % w, y = i / w;
+    for (int i = threadIdx.x; i < hw; i += blockDim.x, x += dx, y += dy) {
+      if (x >= w) {
+        x -= w;
+        ++y;
+      }
       {  // r1 = c2 - W_bf(c1)
         const Taps tp = make_taps(x + bf[i], y + bf[hw + i], h, w);
         const float r = c2[i] - sample_taps(c1, tp);
