@@ -32,6 +32,10 @@ constexpr int kTileN = 64;             // kv rows per tile
 constexpr int kQAtomBytes = 128 * 128;  // [128 rows x 64 fp16]
 constexpr int kKVAtomBytes = 64 * 128;  // [ 64 rows x 64 fp16]
 constexpr int kThreads = 192;
+#ifndef FRESCO_ATTN_POLY_EVERY
+#define FRESCO_ATTN_POLY_EVERY 0
+#endif
+constexpr int kPolyEvery = FRESCO_ATTN_POLY_EVERY;   // every N-th pair of scores uses the FMA-pipe exp2 (0 = never)
 
 template <int D>
 struct AttnCfg {
@@ -78,6 +82,29 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
   return d;
+}
+
+// exp2 on the FMA pipe for a fraction of the scores (the MUFU pipe, 16 ex2/clk/SM, is the busiest unit of this
+// kernel): Cody-Waite split x = n + f, f in [-0.5, 0.5], degree-3 minimax polynomial for 2^f (max relative error
+// 7.5e-5, well inside the fp16 rounding of P), exponent patched in with an integer add.  Two scores at a time so
+// the range reduction and Horner steps are packed fp32x2 instructions.
+__device__ __forceinline__ void exp2_poly_x2(float t0, float t1, float& p0, float& p1) {
+  t0 = fmaxf(t0, -126.0f);
+  t1 = fmaxf(t1, -126.0f);
+  const unsigned long long t2 = pack_f2(t0, t1);
+  const unsigned long long magic = pack_f2(12582912.0f, 12582912.0f);            // 1.5 * 2^23
+  const unsigned long long r2 = add2(t2, magic);                                  // integer part in the low mantissa bits
+  const unsigned long long n2 = add2(r2, pack_f2(-12582912.0f, -12582912.0f));
+  const unsigned long long f2 = fma2(n2, pack_f2(-1.0f, -1.0f), t2);
+  unsigned long long q2 = fma2(pack_f2(0.05517164617776871f, 0.05517164617776871f), f2,
+                               pack_f2(0.2426111251115799f, 0.2426111251115799f));
+  q2 = fma2(q2, f2, pack_f2(0.6932609677314758f, 0.6932609677314758f));
+  q2 = fma2(q2, f2, pack_f2(0.9999280571937561f, 0.9999280571937561f));
+  float q0, q1, r0, r1;
+  unpack_f2(q2, q0, q1);
+  unpack_f2(r2, r0, r1);
+  p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(r0) << 23));
+  p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(r1) << 23));
 }
 
 __device__ __forceinline__ void tmem_ld16_sync(uint32_t taddr, uint32_t (&r)[16]) {
@@ -133,9 +160,12 @@ fresco_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   uint64_t* bar_kv_full = bars + 1;            // [ST]
   uint64_t* bar_kv_empty = bars + 1 + ST;      // [ST]
   uint64_t* bar_s = bars + 1 + 2 * ST;         // [2]  S buffer b holds tile i (i & 1 == b)
-  uint64_t* bar_p = bar_s + 2;                 // P_i written (128 arrivals)
-  uint64_t* bar_o = bar_s + 3;                 // [2] P_i V_i retired, i & 1 == b (P buffer b free, O stable)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s + 5);
+  // every barrier below exists once per TMEM buffer (index i & 1, phase (i >> 1) & 1): a parity wait is only sound
+  // if the waited barrier cannot complete two phases before the waiter looks at it
+  uint64_t* bar_p = bar_s + 2;                 // [2] P_i written (128 arrivals)
+  uint64_t* bar_o = bar_s + 4;                 // [2] P_i V_i retired (P buffer free, O stable)
+  uint64_t* bar_c = bar_s + 6;                 // [2] S_i copied to registers by all 128 softmax threads (S buffer free)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s + 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -153,9 +183,12 @@ fresco_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     }
     mbar_init(bar_s + 0, 1);
     mbar_init(bar_s + 1, 1);
-    mbar_init(bar_p, 128);
+    mbar_init(bar_p + 0, 128);
+    mbar_init(bar_p + 1, 128);
     mbar_init(bar_o + 0, 1);
     mbar_init(bar_o + 1, 1);
+    mbar_init(bar_c + 0, 128);
+    mbar_init(bar_c + 1, 128);
     fence_barrier_init();
   }
   if (warp == 4) {
@@ -219,7 +252,15 @@ fresco_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       if (n_tiles > 1) issue_qk(1);
       for (int t = 0; t < n_tiles; ++t) {
         const int st = t % ST;
-        mbar_wait(bar_p, t & 1, 12);                       // P_t in TMEM (and S_t fully consumed)
+        if (t + 2 < n_tiles) {
+          // S buffer (t & 1) is free as soon as the softmax threads hold S_t in registers -- long before P_t is
+          // written -- so the scores of tile t+2 are issued now and are ready well ahead of their consumer
+          // (one barrier per S buffer: the softmax warps can run ahead of this thread, and a parity wait is only
+          //  sound if the waited barrier cannot complete two phases in the meantime)
+          mbar_wait(bar_c + (t & 1), (t >> 1) & 1, 13);
+          issue_qk(t + 2);
+        }
+        mbar_wait(bar_p + (t & 1), (t >> 1) & 1, 12);      // P_t in TMEM
         tc_fence_after();
         const uint32_t v_addr = smem_u32(s_kv + st * Cfg::STAGE_BYTES + Cfg::NATOM * kKVAtomBytes);
 #pragma unroll
@@ -234,7 +275,6 @@ fresco_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         }
         umma_commit(bar_kv_empty + st);
         umma_commit(bar_o + (t & 1));
-        if (t + 2 < n_tiles) issue_qk(t + 2);              // reuses S buffer (t & 1), free since P_t arrived
       }
     }
   } else {
@@ -264,6 +304,10 @@ fresco_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       tmem_ld16(s_addr + 32, *reinterpret_cast<uint32_t(*)[16]>(&r[32]));
       tmem_ld16(s_addr + 48, *reinterpret_cast<uint32_t(*)[16]>(&r[48]));
       tmem_ld_wait_dep64(r);
+      tc_fence_before();
+      mbar_arrive(bar_c + (i & 1));              // S buffer (i & 1) may be overwritten by Q K_{i+2}^T
+      // P buffer (i & 1) was last read by P_{i-2} V_{i-2}; probe its retirement now, wait (rarely) before the stores
+      const bool p_free = (i < 2) || mbar_test_wait(bar_o + (i & 1), ((i - 2) >> 1) & 1);
       // probe S_{i+1} now: it was issued a whole tile ago, and the ~100-cycle latency of a try_wait on an
       // already-completed barrier hides behind the max / exp work instead of opening the next iteration
       s_ready = (i + 1 < n_tiles) && mbar_test_wait(bar_s + ((i + 1) & 1), ((i + 1) >> 1) & 1);
@@ -286,8 +330,10 @@ fresco_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         mx3 = max3(mx3, __uint_as_float(r[j + 6]), __uint_as_float(r[j + 7]));
       }
       const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
-      // P buffer (i & 1) was last read by P_{i-2} V_{i-2}.  That MMA was issued before S_i = Q K_i^T and
-      // tcgen05.commit tracks every earlier MMA, so the S_i barrier we just passed already implies it retired.
+      if (!p_free) {
+        mbar_wait(bar_o + (i & 1), ((i - 2) >> 1) & 1, 3);
+        tc_fence_after();
+      }
       // ---- lazy running max: raise it (and rescale O in TMEM) only when it grows by more than 2^8
       if (i == 0) {
         m_run = m_tile;
@@ -321,8 +367,15 @@ fresco_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       for (int j = 0; j < 64; j += 2) {
         float t0, t1;
         unpack_f2(fma2(pack_f2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), scale2, negm2), t0, t1);
-        r[j] = __float_as_uint(fast_exp2(t0));
-        r[j + 1] = __float_as_uint(fast_exp2(t1));
+        if (kPolyEvery > 0 && ((j >> 1) % (kPolyEvery > 0 ? kPolyEvery : 1)) == (kPolyEvery - 1)) {
+          float p0, p1;
+          exp2_poly_x2(t0, t1, p0, p1);                    // FMA-pipe exponential for every kPolyEvery-th pair
+          r[j] = __float_as_uint(p0);
+          r[j + 1] = __float_as_uint(p1);
+        } else {
+          r[j] = __float_as_uint(fast_exp2(t0));
+          r[j + 1] = __float_as_uint(fast_exp2(t1));
+        }
       }
       unsigned long long sum2[4] = {pack_f2(0.f, 0.f), pack_f2(0.f, 0.f), pack_f2(0.f, 0.f), pack_f2(0.f, 0.f)};
 #pragma unroll
@@ -336,7 +389,7 @@ fresco_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       tmem_st16(p_addr + 16, *reinterpret_cast<uint32_t(*)[16]>(&pk[16]));
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(bar_p);
+      mbar_arrive(bar_p + (i & 1));
       float sa, sb;
       unpack_f2(add2(add2(sum2[0], sum2[1]), add2(sum2[2], sum2[3])), sa, sb);
       l_run += sa + sb;
