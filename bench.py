@@ -57,6 +57,18 @@ def load_peaks():
     return {"tflops": 1400.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
 
 
+def load_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed
+    `ncu --set full` capture of this same workload (profiles/r01_attn_traffic.json); None if absent."""
+    p = os.path.join(ROOT, "profiles", "r01_attn_traffic.json")
+    try:
+        with open(p) as f:
+            d = json.load(f)
+        return {"bytes_per_launch": d["traffic_bytes_per_launch"], "unit": "B", "source": d["source"]}
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -333,7 +345,7 @@ def main():
         share = sum(t for _, t in ent) / ((args.steps + args.warmup) / args.steps * ms)
         roof = {"kernel": "fresco_attn_kernel<40> (cross-frame, L=%d, Lk=%d, B=16, 8 heads)" % (L_b, wl.kv_len[L_b]),
                 "bound": "tensor", "achieved": round(ach, 2), "peak": peaks["tflops"], "unit": "TFLOP/s",
-                "frac": round(ach / peaks["tflops"], 4), "traffic": None, "peak_source": peaks["source"],
+                "frac": round(ach / peaks["tflops"], 4), "traffic": load_traffic(), "peak_source": peaks["source"],
                 "algorithmic_flops_per_launch": flops, "avg_launch_ms": round(avg_ms, 4),
                 "launches_timed": len(ent), "share_of_step_time": round(share, 4),
                 "all_attention_ms_per_step": round(total_attn_ms / (args.steps + args.warmup), 3)}
