@@ -22,6 +22,8 @@
 // Token-major [batch, tokens, heads*head_dim] fp16 tensors are consumed in place: the TMA tensor map views
 // them as {head_dim, heads, tokens, batch}; a {64,1,rows,1} box lands one head's tile in the canonical
 // 128B-swizzled K-major layout; columns >= head_dim and rows >= tokens are hardware zero-filled.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "fresco_internal.h"
 
@@ -32,6 +34,11 @@ constexpr int kTileN = 64;             // kv rows per tile
 constexpr int kQAtomBytes = 128 * 128;  // [128 rows x 64 fp16]
 constexpr int kKVAtomBytes = 64 * 128;  // [ 64 rows x 64 fp16]
 constexpr int kThreads = 192;
+#ifdef FRESCO_ATTN_ABLATE_BUILD
+#define ABL(p, bit) ((p).ablate & (bit))
+#else
+#define ABL(p, bit) 0
+#endif
 #ifndef FRESCO_ATTN_POLY_EVERY
 #define FRESCO_ATTN_POLY_EVERY 0
 #endif
@@ -58,6 +65,10 @@ struct AttnParams {
   int q_len, kv_len, heads, q_per_kv;
   float scale_log2;        // softmax_scale * log2(e)
   float diag_bias_log2;    // bias added where kv index == query index, * log2(e)
+  int ablate;              // profiling aid, only honoured when built with -DFRESCO_ATTN_ABLATE_BUILD (results are
+                           // WRONG when non-zero; env FRESCO_ATTN_ABLATE selects the bits): bit0 no exp2,
+                           // bit1 no S load from TMEM, bit2 no P store, bit3 no P V MMA, bit4 no row max,
+                           // bit5 no Q K^T MMA (commit only), bit6 K/V tiles loaded once per ring stage only
 };
 
 __device__ __forceinline__ unsigned long long pack_f2(float lo, float hi) {
@@ -218,6 +229,10 @@ fresco_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         }
         uint8_t* sk = s_kv + st * Cfg::STAGE_BYTES;
         uint8_t* sv = sk + Cfg::NATOM * kKVAtomBytes;
+        if (ABL(p, 64) && t >= ST) {
+          mbar_arrive(bar_kv_full + st);                      // ablation: reuse whatever the stage holds
+          continue;
+        }
         mbar_expect_tx(bar_kv_full + st, Cfg::STAGE_BYTES);
         for (int a = 0; a < Cfg::NATOM; ++a) {
           tma_load_4d(sk + a * kKVAtomBytes, &tm_k, bar_kv_full + st, a * 64, head, t * kTileN, b_kv);
@@ -239,7 +254,7 @@ fresco_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         const uint32_t k_addr = smem_u32(s_kv + st * Cfg::STAGE_BYTES);
         const uint32_t d_tmem = tmem + ((t & 1) ? Cfg::S_OFF1 : Cfg::S_OFF0);
 #pragma unroll
-        for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
+        for (int ks = 0; ks < (ABL(p, 32) ? 0 : Cfg::KSTEPS); ++ks) {
           const uint32_t qoff = (ks >> 2) * kQAtomBytes + (ks & 3) * 32;
           const uint32_t koff = (ks >> 2) * kKVAtomBytes + (ks & 3) * 32;
           umma_ss(d_tmem, make_smem_desc_sw128(q_addr + qoff, 16, 1024), make_smem_desc_sw128(k_addr + koff, 16, 1024),
@@ -264,7 +279,7 @@ fresco_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         tc_fence_after();
         const uint32_t v_addr = smem_u32(s_kv + st * Cfg::STAGE_BYTES + Cfg::NATOM * kKVAtomBytes);
 #pragma unroll
-        for (int k2 = 0; k2 < kTileN / 16; ++k2) {
+        for (int k2 = 0; k2 < (ABL(p, 8) ? 0 : kTileN / 16); ++k2) {
           const uint32_t acc = (k2 > 0 || t > 0) ? 1u : 0u;  // O accumulates in TMEM across all tiles
           const uint32_t p_tmem = tmem + ((t & 1) ? Cfg::P_OFF1 : Cfg::P_OFF0) + k2 * 8;
           umma_ts(tmem + Cfg::O_OFF, p_tmem, make_smem_desc_sw128(v_addr + k2 * 2048, kKVAtomBytes, 1024), idesc_pv0,
@@ -299,10 +314,15 @@ fresco_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       // ---- the whole 64-column row of scores, once, into registers
       const uint32_t s_addr = t_lane + ((i & 1) ? Cfg::S_OFF1 : Cfg::S_OFF0);
       uint32_t r[64];
-      tmem_ld16(s_addr + 0, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
-      tmem_ld16(s_addr + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
-      tmem_ld16(s_addr + 32, *reinterpret_cast<uint32_t(*)[16]>(&r[32]));
-      tmem_ld16(s_addr + 48, *reinterpret_cast<uint32_t(*)[16]>(&r[48]));
+      if (!ABL(p, 2)) {
+        tmem_ld16(s_addr + 0, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+        tmem_ld16(s_addr + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+        tmem_ld16(s_addr + 32, *reinterpret_cast<uint32_t(*)[16]>(&r[32]));
+        tmem_ld16(s_addr + 48, *reinterpret_cast<uint32_t(*)[16]>(&r[48]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 64; ++j) r[j] = 0x3a83126fu + ((uint32_t)(j ^ i) << 8);   // ~1e-3, no conversions
+      }
       tmem_ld_wait_dep64(r);
       tc_fence_before();
       mbar_arrive(bar_c + (i & 1));              // S buffer (i & 1) may be overwritten by Q K_{i+2}^T
@@ -329,7 +349,7 @@ fresco_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         mx2 = max3(mx2, __uint_as_float(r[j + 4]), __uint_as_float(r[j + 5]));
         mx3 = max3(mx3, __uint_as_float(r[j + 6]), __uint_as_float(r[j + 7]));
       }
-      const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
+      const float m_tile = ABL(p, 16) ? 0.f : fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
       if (!p_free) {
         mbar_wait(bar_o + (i & 1), ((i - 2) >> 1) & 1, 3);
         tc_fence_after();
@@ -372,6 +392,9 @@ fresco_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           exp2_poly_x2(t0, t1, p0, p1);                    // FMA-pipe exponential for every kPolyEvery-th pair
           r[j] = __float_as_uint(p0);
           r[j + 1] = __float_as_uint(p1);
+        } else if (ABL(p, 1)) {
+          r[j] = __float_as_uint(t0 * 0.001f);
+          r[j + 1] = __float_as_uint(t1 * 0.001f);
         } else {
           r[j] = __float_as_uint(fast_exp2(t0));
           r[j + 1] = __float_as_uint(fast_exp2(t1));
@@ -385,8 +408,12 @@ fresco_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 #pragma unroll
       for (int j = 0; j < 32; ++j) pk[j] = pack_half2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
       const uint32_t p_addr = t_lane + ((i & 1) ? Cfg::P_OFF1 : Cfg::P_OFF0);
-      tmem_st16(p_addr, *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
-      tmem_st16(p_addr + 16, *reinterpret_cast<uint32_t(*)[16]>(&pk[16]));
+      if (!ABL(p, 4)) {
+        tmem_st16(p_addr, *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
+        tmem_st16(p_addr + 16, *reinterpret_cast<uint32_t(*)[16]>(&pk[16]));
+      } else if (pk[0] == 0x12345678u && pk[31] == 0x9abcdef0u) {
+        tmem_st16(p_addr, *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));      // keeps pk live
+      }
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(bar_p + (i & 1));
@@ -462,6 +489,8 @@ static int launch_attn(const void* q, const void* k, const void* v, void* out, i
   p.q_per_kv = q_per_kv;
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
   p.diag_bias_log2 = diag_bias * 1.4426950408889634f;
+  static const int ablate = getenv("FRESCO_ATTN_ABLATE") ? atoi(getenv("FRESCO_ATTN_ABLATE")) : 0;
+  p.ablate = ablate;
   dim3 grid((q_len + kTileM - 1) / kTileM, heads, batch_q);
   fresco_attn_kernel<D><<<grid, kThreads, Cfg::SMEM_BYTES, stream>>>(tq, tk, tv, p);
   return check_launch("fresco_attn_kernel");
