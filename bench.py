@@ -273,7 +273,9 @@ def main():
     if args.impl == "fresco" and not args.profile_mode:
         args.warmup = max(args.warmup, 3)
 
-    world, rank, local = dist_setup(args.gpus)
+    if args.impl == "reference" and int(os.environ.get("RANK", "0")) != 0:
+        return                                   # under torchrun only rank 0 runs (and prints) the CPU arm
+    world, rank, local = (1, 0, 0) if args.impl == "reference" else dist_setup(args.gpus)
     config = {"workload": "N=8 keyframes 512x512 (CFG batch 16), SD1.5-shaped random-init fp16 UNet, FRESCO "
                           "attention (cross-frame + spatial step 0 + temporal t>=350) on 6 decoder layers + "
                           "warp_tensor fusion on 4 decoder features; 15-step DDPM schedule t=700..0 walked cyclically",
@@ -281,8 +283,7 @@ def main():
               "l2": "working set (1.7 GB weights + activations) >> 126 MB L2, no explicit flush"}
 
     if args.impl == "reference":
-        if rank != 0:
-            return
+        config["parallelism"] = "host cores only (rank 0); n_gpus echoes --gpus"
         cb, res = cpu_reference_line(args, True)
         line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
                 "steps": res["steps"], "warmup": res["warmup"], "ms_per_step": 1000.0 / cb["value"],
