@@ -225,7 +225,7 @@ fresco_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         const int st = t % ST;
         if (t >= ST) {
           const uint32_t ph = ((t / ST) - 1) & 1;
-          while (!mbar_try_wait(bar_kv_empty + st, ph)) __nanosleep(40);
+          mbar_wait_backoff(bar_kv_empty + st, ph, 500, 14);
         }
         uint8_t* sk = s_kv + st * Cfg::STAGE_BYTES;
         uint8_t* sv = sk + Cfg::NATOM * kKVAtomBytes;
@@ -272,10 +272,10 @@ fresco_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           // written -- so the scores of tile t+2 are issued now and are ready well ahead of their consumer
           // (one barrier per S buffer: the softmax warps can run ahead of this thread, and a parity wait is only
           //  sound if the waited barrier cannot complete two phases in the meantime)
-          mbar_wait(bar_c + (t & 1), (t >> 1) & 1, 13);
+          mbar_wait_backoff(bar_c + (t & 1), (t >> 1) & 1, 100, 13);
           issue_qk(t + 2);
         }
-        mbar_wait(bar_p + (t & 1), (t >> 1) & 1, 12);      // P_t in TMEM
+        mbar_wait_backoff(bar_p + (t & 1), (t >> 1) & 1, 100, 12);   // P_t in TMEM
         tc_fence_after();
         const uint32_t v_addr = smem_u32(s_kv + st * Cfg::STAGE_BYTES + Cfg::NATOM * kKVAtomBytes);
 #pragma unroll

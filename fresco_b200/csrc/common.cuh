@@ -81,6 +81,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
     if (++polls > FRESCO_WATCHDOG_POLLS) mbar_timeout(bar, parity, tag);
   }
 }
+// Wait for threads that share a scheduler with busy math warps (TMA producer, MMA issuer): back off between probes
+// so the polling loop does not steal issue slots from them.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t ns, int tag = 0) {
+  uint32_t polls = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(ns);
+    if (++polls > FRESCO_WATCHDOG_POLLS) mbar_timeout(bar, parity, tag);
+  }
+}
 // Latency-critical waits spin on the non-blocking test_wait: measured on B200, a thread parked by try_wait resumes
 // ~0.8 us after the phase completes, which made the attention pipeline's per-tile barrier round trips (not its math)
 // the critical path.

@@ -451,3 +451,31 @@ def test_get_flow_and_interframe_paras_with_stub_flow_model(fb):
     assert all(torch.equal(a.cpu(), b) for a, b in zip(masks, ref_masks))
     fm, bm, im = O.mapping_ind(fl[1].cpu(), oc[1].cpu(), images / 127.5 - 1.0, 8.0)
     assert torch.equal(paras["fwd_mappings"][0].cpu(), fm) and torch.equal(paras["interattn_masks"][0].cpu(), im)
+
+
+def test_sharded_attention_world1_matches_processor(fb, golden):
+    """fresco_b200/dist.py on one GPU (world size 1, no collective) must reproduce the plain processor path:
+    same kernels, same K/V order, for all 8 mode combinations of the golden attention fixture."""
+    from fresco_b200.dist import ShardedFRESCOAttention
+    g = golden("attention")
+    attn = FakeAttn(g).cuda().half()
+    x = T(g["x"]).half()
+    ref_hidden = T(g["ref_hidden"]).half()
+    masks = [T(g[f"attn_mask{i}"]) for i in range(3)]
+    paras = {"fwd_mappings": [T(g["fwd_map"])], "bwd_mappings": [T(g["bwd_map"])],
+             "interattn_masks": [T(g["inter_mask"])]}
+    for flags in range(8):
+        outs = []
+        for shard in (None, (1, 0, None)):
+            ctrl = fb.dh.AttentionControl()
+            proc = fb.dh.FRESCOAttnProcessor2_0(2, ctrl, shard=shard)
+            if flags & 2:
+                ctrl.stored_attn["decoder_attn"] = [ref_hidden.clone()]
+                ctrl.enable_intraattn()
+            if flags & 4:
+                ctrl.enable_interattn(paras)
+            if flags & 1:
+                ctrl.enable_cfattn(masks)
+            with torch.no_grad():
+                outs.append(proc(attn, x.clone()))
+        assert torch.equal(outs[0], outs[1]), flags
