@@ -124,7 +124,9 @@ class ClockSampler:
 # workload construction (fresco arm)
 # --------------------------------------------------------------------------------------------
 class Workload:
-    def __init__(self, device, seed=0, n_frames=N_FRAMES, res=RES, optimise=False):
+    def __init__(self, device, seed=0, n_frames=N_FRAMES, res=RES, optimise=False, shard=None):
+        """shard = (world, rank): frame-sharded batch (config 4); n_frames is then the GLOBAL frame count and this
+        rank feeds frames [rank*n/world, (rank+1)*n/world) of both CFG chunks through the UNet."""
         from fresco_b200 import diffusion_hacked as dh
         from fresco_b200 import flow_utils as fu
         from fresco_b200.harness import synth
@@ -135,15 +137,22 @@ class Workload:
         torch.manual_seed(seed)
         unet = SD15UNet().to(device=device, dtype=torch.float16).eval()
         self.pipe = FakePipe(unet)
-        self.proc = dh.apply_FRESCO_attn(self.pipe)
+        self.shard = shard
+        if shard is not None:
+            world, rk = shard
+            self.lo, self.hi = rk * n_frames // world, (rk + 1) * n_frames // world
+        else:
+            self.lo, self.hi = 0, n_frames
+        n_local = self.hi - self.lo
+        self.proc = dh.apply_FRESCO_attn(self.pipe, shard=None if shard is None else (shard[0], shard[1], None))
         ctrl = self.proc.controller
         ctrl.disable_controller()
         dh.disable_FRESCO_opt(self.pipe)
         lat = res // 8
         g = torch.Generator().manual_seed(seed + 1)
-        self.latents_host = torch.randn(n_frames, 4, lat, lat, generator=g).half().pin_memory()
-        self.prompt_host = torch.randn(CHUNKS * n_frames, 77, 768, generator=g).half().pin_memory()
-        self.out_host = torch.empty(CHUNKS * n_frames, 4, lat, lat, dtype=torch.float16).pin_memory()
+        self.latents_host = torch.randn(n_frames, 4, lat, lat, generator=g)[self.lo:self.hi].half().pin_memory()
+        self.prompt_host = torch.randn(CHUNKS * n_local, 77, 768, generator=g).half().pin_memory()
+        self.out_host = torch.empty(CHUNKS * n_local, 4, lat, lat, dtype=torch.float16).pin_memory()
         self.latents = self.latents_host.to(device)
         self.prompt = self.prompt_host.to(device)
         # per-batch FRESCO parameters (what get_flow_and_interframe_paras produces, with synthetic flow)
@@ -156,6 +165,7 @@ class Workload:
             f, b, m = fu.get_mapping_ind(self.flows[1], self.occs[1], imgs, scale=scale)
             fm.append(f), bm.append(b), im.append(m)
         self.interattn_paras = {"fwd_mappings": fm, "bwd_mappings": bm, "interattn_masks": im}
+        self.kv_len = {int(m.shape[1]): int(m.sum().item()) for m in self.attn_mask}
         # reference pass: store the 6 decoder self-attention inputs (get_intraframe_paras, store=True)
         ctrl.clear_store()
         ctrl.enable_store()
@@ -163,6 +173,8 @@ class Workload:
             self.pipe.unet(torch.cat([self.latents] * 2), TIMESTEPS[-1], encoder_hidden_states=self.prompt,
                            return_dict=False)
         ctrl.disable_store()
+        if shard is not None:
+            return                         # config 4: attention only (warp_tensor is a sequential frame chain)
         if optimise:
             # BASELINE configs[2]: FRESCO feature optimisation (20 Adam iterations, temporal + Gram-L1 loss) on the 4
             # decoder features on the optimisation steps, Gram targets from the reference pass (get_intraframe_paras)
@@ -178,8 +190,6 @@ class Workload:
             # no Gram targets, optimize_temporal=False)
             dh.apply_FRESCO_opt(self.pipe, steps=OPT_STEPS, flows=self.flows, occs=self.occs, correlation_matrix=[],
                                 optimize_temporal=False, saliency=self.saliency)
-        self.kv_len = {int(m.shape[1]): int(m.sum().item()) for m in self.attn_mask}
-
     def set_schedule_state(self, i):
         """flag toggles of pipe_FRESCO.inference (src/pipe_FRESCO.py:171-174)"""
         ctrl = self.proc.controller
@@ -264,9 +274,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-frames", type=int, default=2)
     ap.add_argument("--cpu-budget-s", type=float, default=150.0)
-    ap.add_argument("--workload", default="config2", choices=["config2", "config3"],
+    ap.add_argument("--workload", default="config2", choices=["config2", "config3", "config4"],
                     help="config2 (default, the headline): FRESCO attention + warp fusion; config3: + feature "
-                         "optimisation (apply_FRESCO_opt with Gram targets, 20 Adam iterations on 10 of 15 steps)")
+                         "optimisation (apply_FRESCO_opt with Gram targets, 20 Adam iterations on 10 of 15 steps); "
+                         "config4: ONE N=16 keyframe batch frame-sharded over the ranks, K/V all-gather per FRESCO "
+                         "layer (strong scaling; attention only, no warp fusion)")
     ap.add_argument("--profile-mode", action="store_true",
                     help="for ncu captures only: 1 warm-up + --steps, no e2e / cpu baseline; never a bench value")
     args = ap.parse_args()
@@ -300,7 +312,15 @@ def main():
     device = torch.device("cuda", local)
     from fresco_b200 import _lib, ops
     _lib.lib()
-    wl = Workload(device, seed=rank, optimise=args.workload == "config3")
+    if args.workload == "config4":
+        # every rank must build the same per-batch parameters (same seed); only the frame slice differs
+        wl = Workload(device, seed=0, n_frames=16, shard=(world, rank))
+        config.update({"workload": "ONE batch of N=16 keyframes 512x512 (CFG batch 32) frame-sharded over the ranks, SD1.5-"
+                       "shaped random-init fp16 UNet, FRESCO attention on 6 decoder layers with one NCCL all-gather of "
+                       "the compacted K/V per layer (+ q/k/out gathers while temporal-guided attention is on)",
+                       "frames": 16, "parallelism": "frame-sharded x%d" % world})
+    else:
+        wl = Workload(device, seed=rank, optimise=args.workload == "config3")
     if args.workload == "config3":
         config["workload"] += "; + optimize_feature (20 Adam iters, temporal + Gram-L1) on 4 decoder features, 10 of 15 steps"
 
@@ -323,14 +343,16 @@ def main():
     # ---- e2e: pinned-host inputs / outputs copied inside the timed region
     ms_e2e = timed_region(wl, args.steps, 1, True, world)
 
-    value = world * args.steps / (ms / 1000.0)
-    e2e_value = world * args.steps / (ms_e2e / 1000.0)
+    jobs = 1 if args.workload == "config4" else world      # config 4: all ranks work on the same batch
+    value = jobs * args.steps / (ms / 1000.0)
+    e2e_value = jobs * args.steps / (ms_e2e / 1000.0)
     h2d = wl.latents_host.numel() * 2 + wl.prompt_host.numel() * 2
     d2h = wl.out_host.numel() * 2
 
     # ---- roofline of the dominant kernel: cross-frame attention at level B (L=4096, d=40)
     peaks = load_peaks()
     L_b = (RES // 8) ** 2
+    n_q = 2 * (wl.hi - wl.lo)
     by_tag = {}
     for tag, work, a, b in prof:
         by_tag.setdefault(tag, []).append((work, a.elapsed_time(b)))
@@ -344,7 +366,7 @@ def main():
         ach = flops / (avg_ms * 1e-3) / 1e12
         total_attn_ms = sum(t for e in by_tag.values() for _, t in e)
         share = sum(t for _, t in ent) / ((args.steps + args.warmup) / args.steps * ms)
-        roof = {"kernel": "fresco_attn_kernel<40> (cross-frame, L=%d, Lk=%d, B=16, 8 heads)" % (L_b, wl.kv_len[L_b]),
+        roof = {"kernel": "fresco_attn_kernel<40> (cross-frame, L=%d, Lk=%d, B=%d, 8 heads)" % (L_b, wl.kv_len[L_b], n_q),
                 "bound": "tensor", "achieved": round(ach, 2), "peak": peaks["tflops"], "unit": "TFLOP/s",
                 "frac": round(ach / peaks["tflops"], 4), "traffic": load_traffic(), "peak_source": peaks["source"],
                 "algorithmic_flops_per_launch": flops, "avg_launch_ms": round(avg_ms, 4),
@@ -353,8 +375,8 @@ def main():
 
     line = {"metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic", "config": config,
-            "clocks": clocks,
+            "scaling": "strong" if args.workload == "config4" else "weak", "vs_baseline": None, "dtype": "f16",
+            "data": "synthetic", "config": config, "clocks": clocks,
             "e2e": {"value": round(e2e_value, 4), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": round(ms_e2e / args.steps, 3)},
             "gpu_launches": gpu_launches, "roofline": roof,

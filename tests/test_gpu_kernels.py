@@ -479,3 +479,34 @@ def test_sharded_attention_world1_matches_processor(fb, golden):
             with torch.no_grad():
                 outs.append(proc(attn, x.clone()))
         assert torch.equal(outs[0], outs[1]), flags
+
+
+def test_config5_resolution_768(fb):
+    """BASELINE configs[4] shapes (768x768: L = 9216 / 2304, masks at 96^2 / 48^2): attention spot rows +
+    properties at L=9216, warp_tensor and the pixel mapping at 96x96 against the oracle."""
+    g = torch.Generator(device="cuda").manual_seed(21)
+    N, chunks, L, heads, d = 4, 2, 9216, 8, 40
+    C = heads * d
+    Lk = L + 5000
+    q = torch.randn(chunks * N, L, C, device="cuda", generator=g).half()
+    k = torch.randn(chunks, Lk, C, device="cuda", generator=g).half()
+    v = torch.randn(chunks, Lk, C, device="cuda", generator=g).half()
+    out = fb.ops.attn_fwd(q, k, v, heads, N).float()
+    rows = [0, 127, 128, 4607, 9215]
+    for b in (0, 5):
+        ref = sdpa_ref(q[b:b + 1, rows], k[b // N:b // N + 1], v[b // N:b // N + 1], heads)
+        assert (out[b, rows] - ref[0]).abs().max().item() < 2e-3 * ref.abs().max().item()
+    oc = fb.ops.attn_fwd(q, k, torch.full_like(v, -0.5), heads, N).float()
+    assert (oc + 0.5).abs().max().item() < 1e-3
+    # decoder features at 96x96 (768 / 8) and the image-resolution mapping at scale 8
+    Nf, H = 3, 768
+    flows, occs = O.synth_flows(Nf, H, H, seed=6, mag=12.0)
+    sal = torch.rand(Nf, 1, 384, 384, generator=torch.Generator().manual_seed(0))
+    feat = torch.randn(2 * Nf, 16, 96, 96, generator=torch.Generator().manual_seed(1))
+    ref_w = O.warp_tensor(feat, flows, occs, sal, 2)
+    got_w = fb.fu.warp_tensor(feat.cuda(), [f.cuda() for f in flows], [o.cuda() for o in occs], sal.cuda(), 2)
+    assert (got_w.cpu() - ref_w).abs().max().item() < 5e-5
+    imgs = torch.rand(Nf, 3, H, H, generator=torch.Generator().manual_seed(2)) * 2 - 1
+    fm_ref, bm_ref, mk_ref = O.mapping_ind(flows[1], occs[1], imgs, 8.0)
+    fm, bm, mk = fb.fu.get_mapping_ind(flows[1].cuda(), occs[1].cuda(), imgs.cuda(), 8.0)
+    assert torch.equal(fm.cpu(), fm_ref) and torch.equal(bm.cpu(), bm_ref) and torch.equal(mk.cpu(), mk_ref)
