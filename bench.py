@@ -17,6 +17,9 @@ pinned-host inputs/outputs copied inside the timed region; `roofline` = the domi
 (cross-frame attention, level B) timed per launch with CUDA events; `cpu_baseline` = the CPU
 oracle on a bounded sample.  With --gpus N > 1 (torchrun) every rank runs an independent
 8-keyframe batch (the reference's own batching unit): weak scaling, no data-path collective.
+Other workloads (never the headline): --workload config3 adds the feature optimisation,
+--workload config4 frame-shards ONE N=16 batch over the ranks (K/V all-gather per layer,
+strong scaling).
 """
 from __future__ import annotations
 

@@ -21,6 +21,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--use_fast_math=false",
          "-Xptxas", "-v", "-I", os.path.join(os.path.dirname(HERE), "include")]
 FLAGS = [f for f in FLAGS if f != "--use_fast_math=false"]
+FLAGS += os.environ.get("FRESCO_NVCC_EXTRA", "").split()      # profiling builds only (-DFRESCO_ATTN_TRACE ...)
 
 
 def sources():

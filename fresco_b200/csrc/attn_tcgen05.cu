@@ -1,18 +1,23 @@
-// FRESCO attention forward (spatial-guided and cross-frame SDPA) for sm_100a -- v4.
+// FRESCO attention forward (spatial-guided and cross-frame SDPA) for sm_100a.
 //
 // Replaces the two dense F.scaled_dot_product_attention calls of the reference processor
 // (src/diffusion_hacked.py:281-285 and :303-305).
 //
-// One CTA owns a 128-row query tile of one (batch, head) and streams K/V in 64-row tiles.
+// Pipelined kernel (all head dims): one CTA owns a 128-row query tile of one (batch, head) and streams K/V in 64-row
+// tiles.
 //
-//   warps 0-3 softmax       one query row per thread (= one TMEM lane).  The 64 scores of a tile are read
-//                           from TMEM once into registers; row max; p = exp2(s*scale*log2e - m) with packed
-//                           fp32x2 math; P is written to its own TMEM region as fp16.
-//   warp 4    TMA producer  Q once, K/V tiles through a 5-stage mbarrier ring
-//   warp 5    MMA issuer    S_i = Q K_i^T  (tcgen05.mma SS, M128 N64, fp32) into one of TWO S buffers, so the
-//                           scores of tile i+1 are computed while the softmax warps work on tile i;
-//                           O += P_i V_i   (tcgen05.mma TS, P from TMEM, V MN-major), accumulated in TMEM
-//                           across all tiles.
+//   warps 0-3   softmax       one query row per thread (= one TMEM lane).  The 64 scores of a tile are read from
+//                             TMEM once into registers; row max; p = exp2(s*scale*log2e - m) with packed fp32x2
+//                             math; P is written to its own TMEM region as fp16.
+//   producer    TMA           Q once, K/V tiles through a 4/5-stage mbarrier ring
+//   QK issuer   tcgen05.mma   S_i = Q K_i^T (SS, M128 N64, fp32) into one of TWO S buffers, issued as soon as the
+//                             softmax threads hold S_{i-2} in registers, so scores are always ready ahead of time
+//   PV issuer   tcgen05.mma   O += P_i V_i (TS, P from TMEM, V MN-major), accumulated in TMEM across all tiles; for
+//                             head_dim 40 one more N=16 MMA per K-step against a tile of ones yields the row sums
+//
+// With one CTA per SM (head_dim 80/128) each of the three roles has its own warp (224 threads).  With two CTAs per
+// SM (head_dim 40/64) a seventh warp would cost the softmax threads the 168 registers they need, so the producer
+// shares a thread with the QK issuer and refills the ring without ever blocking (192 threads).
 //
 // The running row max is lazy: it is raised (and O rescaled in TMEM by the owning thread) only when a tile
 // exceeds it by more than 2^8, so the common tile costs no O traffic at all and the softmax warps never wait
@@ -22,6 +27,13 @@
 // Token-major [batch, tokens, heads*head_dim] fp16 tensors are consumed in place: the TMA tensor map views
 // them as {head_dim, heads, tokens, batch}; a {64,1,rows,1} box lands one head's tile in the canonical
 // 128B-swizzled K-major layout; columns >= head_dim and rows >= tokens are hardware zero-filled.
+//
+// What bounds it (measured, tools/pipe_probe.cu, tools/softmax_mix_probe.cu, tools/trace_attn.py): at head_dim 40 a
+// tile is 192 tensor-core clocks but 512 MUFU clocks, and a warp cannot overlap its own MUFU.EX2 (8 clk) with its
+// half-rate max / fma2 / add2 / pack instructions (2 clk each): the bare arithmetic of a tile costs 854 clk with one
+// softmax warp per sub-partition, 671 with two (this kernel; 820 measured with TMEM traffic and barriers) and 562
+// with four.  The "narrow" kernel further down trades the pipelining for four CTAs per SM; it lands at the same
+// speed and is kept as a selectable variant.
 #include <cstdlib>
 
 #include "common.cuh"
@@ -33,18 +45,29 @@ constexpr int kTileM = 128;            // query rows per CTA
 constexpr int kTileN = 64;             // kv rows per tile
 constexpr int kQAtomBytes = 128 * 128;  // [128 rows x 64 fp16]
 constexpr int kKVAtomBytes = 64 * 128;  // [ 64 rows x 64 fp16]
-constexpr int kThreads = 192;
 #ifdef FRESCO_ATTN_ABLATE_BUILD
 #define ABL(p, bit) ((p).ablate & (bit))
 #else
 #define ABL(p, bit) 0
 #endif
-#ifndef FRESCO_ATTN_POLY_EVERY
-#define FRESCO_ATTN_POLY_EVERY 0
-#endif
-constexpr int kPolyEvery = FRESCO_ATTN_POLY_EVERY;   // every N-th pair of scores uses the FMA-pipe exp2 (0 = never)
 
-template <int D>
+// Profiling aid (-DFRESCO_ATTN_TRACE): SM-clock stamps of one CTA's pipeline stages for tiles [64, 96), read back with
+// fresco_debug_attn_trace().  Never part of the product build.
+#ifdef FRESCO_ATTN_TRACE
+__device__ long long g_attn_trace[32 * 16];
+#define TRACE(i, slot, dep)                                                                       \
+  do {                                                                                            \
+    if (trace_cta && (i) >= 64 && (i) < 96) {                                                     \
+      long long t_;                                                                               \
+      asm volatile("mov.u64 %0, %%clock64;" : "=l"(t_) : "r"(dep) : "memory");                    \
+      g_attn_trace[((i) - 64) * 16 + (slot)] = t_;                                                \
+    }                                                                                             \
+  } while (0)
+#else
+#define TRACE(i, slot, dep) do { } while (0)
+#endif
+
+template <int D, bool ROWSUM = false>
 struct AttnCfg {
   static constexpr int NATOM = (D + 63) / 64;
   static constexpr int KSTEPS = (D + 15) / 16;
@@ -54,10 +77,22 @@ struct AttnCfg {
   static constexpr int S_OFF0 = 0, S_OFF1 = 64, P_OFF0 = 128, P_OFF1 = 160, O_OFF = 192;
   static constexpr int TMEM_COLS = (O_OFF + DPAD <= 256) ? 256 : 512;
   static constexpr int STAGES = NATOM == 1 ? 5 : 4;
+  // Row sums l = sum_j p_j come out of the tensor core when the O region has 16 spare columns (d = 40: O uses 48 of
+  // its 64): every K-step issues one extra N=16 MMA of P against a constant tile of ones into O columns [48, 64).
+  // That removes the add.f32x2 chain (about 10 % of the softmax warps' instructions) from the issue-bound loop.
+  static constexpr bool MMA_ROWSUM = ROWSUM && (DPAD + 16 <= 64);
+  static constexpr int L_COL = 48;
+  static constexpr int ONES_BYTES = MMA_ROWSUM ? 2048 : 0;
   static constexpr int Q_BYTES = NATOM * kQAtomBytes;
   static constexpr int STAGE_BYTES = 2 * NATOM * kKVAtomBytes;
-  static constexpr int SMEM_BYTES = 1024 + Q_BYTES + STAGES * STAGE_BYTES + 256;
+  static constexpr int SMEM_BYTES = 1024 + Q_BYTES + STAGES * STAGE_BYTES + ONES_BYTES + 256;
   static constexpr int MIN_CTAS = (TMEM_COLS == 256 && SMEM_BYTES <= 112 * 1024) ? 2 : 1;
+  // Warp roles.  With one CTA per SM there are registers to spare, so the TMA producer, the score-MMA issuer and the
+  // P V issuer each get a warp (SPLIT).  With two CTAs per SM a seventh warp would push the softmax threads under the
+  // 168 registers they need, so the producer shares a thread with the score-MMA issuer.
+  static constexpr bool SPLIT = MIN_CTAS == 1;
+  static constexpr int THREADS = SPLIT ? 224 : 192;
+  static constexpr int QK_WARP = SPLIT ? 5 : 4, PV_WARP = SPLIT ? 6 : 5;
 };
 
 struct AttnParams {
@@ -156,17 +191,19 @@ __device__ __forceinline__ void tmem_ld_wait_dep64(uint32_t (&r)[64]) {
 #undef FR8
 }
 
-template <int D>
-__global__ void __launch_bounds__(kThreads, AttnCfg<D>::MIN_CTAS)
+// POLY: every POLY-th pair of scores takes the FMA-pipe exp2 instead of MUFU.EX2 (0 = never)
+template <int D, int POLY, bool ROWSUM>
+__global__ void __launch_bounds__(AttnCfg<D>::THREADS, AttnCfg<D>::MIN_CTAS)
 fresco_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                    const __grid_constant__ CUtensorMap tm_v, const AttnParams p) {
-  using Cfg = AttnCfg<D>;
+  using Cfg = AttnCfg<D, ROWSUM>;
   constexpr int ST = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* s_q = smem;
   uint8_t* s_kv = smem + Cfg::Q_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::Q_BYTES + ST * Cfg::STAGE_BYTES);
+  uint8_t* s_ones = smem + Cfg::Q_BYTES + ST * Cfg::STAGE_BYTES;      // [16 kv rows x 128 B] of fp16 1.0 (MMA_ROWSUM)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ones + Cfg::ONES_BYTES);
   uint64_t* bar_q = bars + 0;
   uint64_t* bar_kv_full = bars + 1;            // [ST]
   uint64_t* bar_kv_empty = bars + 1 + ST;      // [ST]
@@ -185,21 +222,24 @@ fresco_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   const int b = blockIdx.z;
   const int b_kv = b / p.q_per_kv;
   const int n_tiles = (p.kv_len + kTileN - 1) / kTileN;
+#ifdef FRESCO_ATTN_TRACE
+  const bool trace_cta = blockIdx.x == 3 && blockIdx.y == 2 && blockIdx.z == 0 && lane == 0 && (warp == 0 || warp >= 4);
+#endif
 
   if (warp == 5 && lane == 0) {
     mbar_init(bar_q, 1);
     for (int s = 0; s < ST; ++s) {
       mbar_init(bar_kv_full + s, 1);
-      mbar_init(bar_kv_empty + s, 1);
+      mbar_init(bar_kv_empty + s, 2);          // released by the QK issuer (K read) and by the PV issuer (V read)
     }
     mbar_init(bar_s + 0, 1);
     mbar_init(bar_s + 1, 1);
-    mbar_init(bar_p + 0, 128);
-    mbar_init(bar_p + 1, 128);
+    mbar_init(bar_p + 0, 4);                     // one elected arrival per softmax warp: 128 per-thread arrivals on one
+    mbar_init(bar_p + 1, 4);                     // shared-memory word serialise (each is an atomic on the same address)
     mbar_init(bar_o + 0, 1);
     mbar_init(bar_o + 1, 1);
-    mbar_init(bar_c + 0, 128);
-    mbar_init(bar_c + 1, 128);
+    mbar_init(bar_c + 0, 4);
+    mbar_init(bar_c + 1, 4);
     fence_barrier_init();
   }
   if (warp == 4) {
@@ -211,45 +251,64 @@ fresco_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     __syncwarp();
     tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
   }
+  if (Cfg::MMA_ROWSUM) {
+    for (int i = threadIdx.x; i < Cfg::ONES_BYTES / 4; i += Cfg::THREADS) reinterpret_cast<uint32_t*>(s_ones)[i] = 0x3C003C00u;
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 4) {
-    // ------------------------------------------------------------ TMA producer
+  // K/V tile t -> ring stage t % ST (the caller has made sure that the stage is free)
+  auto load_kv_tile = [&](int t) {
+    const int st = t % ST;
+    uint8_t* sk = s_kv + st * Cfg::STAGE_BYTES;
+    uint8_t* sv = sk + Cfg::NATOM * kKVAtomBytes;
+    mbar_expect_tx(bar_kv_full + st, Cfg::STAGE_BYTES);
+    for (int a = 0; a < Cfg::NATOM; ++a) {
+      tma_load_4d(sk + a * kKVAtomBytes, &tm_k, bar_kv_full + st, a * 64, head, t * kTileN, b_kv);
+      tma_load_4d(sv + a * kKVAtomBytes, &tm_v, bar_kv_full + st, a * 64, head, t * kTileN, b_kv);
+    }
+  };
+  auto load_q = [&]() {
+    mbar_expect_tx(bar_q, Cfg::Q_BYTES);
+    for (int a = 0; a < Cfg::NATOM; ++a) tma_load_4d(s_q + a * kQAtomBytes, &tm_q, bar_q, a * 64, head, q0, b);
+  };
+
+  if (Cfg::SPLIT && warp == 4) {
+    // ------------------------------------------------------------ TMA producer (own warp)
     if (lane == 0) {
-      mbar_expect_tx(bar_q, Cfg::Q_BYTES);
-      for (int a = 0; a < Cfg::NATOM; ++a) tma_load_4d(s_q + a * kQAtomBytes, &tm_q, bar_q, a * 64, head, q0, b);
+      load_q();
       for (int t = 0; t < n_tiles; ++t) {
-        const int st = t % ST;
-        if (t >= ST) {
-          const uint32_t ph = ((t / ST) - 1) & 1;
-          mbar_wait_backoff(bar_kv_empty + st, ph, 500, 14);
-        }
-        uint8_t* sk = s_kv + st * Cfg::STAGE_BYTES;
-        uint8_t* sv = sk + Cfg::NATOM * kKVAtomBytes;
-        if (ABL(p, 64) && t >= ST) {
-          mbar_arrive(bar_kv_full + st);                      // ablation: reuse whatever the stage holds
-          continue;
-        }
-        mbar_expect_tx(bar_kv_full + st, Cfg::STAGE_BYTES);
-        for (int a = 0; a < Cfg::NATOM; ++a) {
-          tma_load_4d(sk + a * kKVAtomBytes, &tm_k, bar_kv_full + st, a * 64, head, t * kTileN, b_kv);
-          tma_load_4d(sv + a * kKVAtomBytes, &tm_v, bar_kv_full + st, a * 64, head, t * kTileN, b_kv);
-        }
+        if (t >= ST) mbar_wait(bar_kv_empty + t % ST, ((t / ST) - 1) & 1, 1);
+        load_kv_tile(t);
       }
     }
-  } else if (warp == 5) {
-    // ------------------------------------------------------------ MMA issuer
+  } else if (warp == Cfg::QK_WARP) {
+    // ------------------------------------------------------------ score-MMA issuer (+ TMA producer when !SPLIT)
+    // tcgen05.mma issue is a serial affair for the issuing thread; with 7 small MMAs and 3 commits per 128x64 tile a
+    // single issuer thread sat on the critical path.  The score MMAs are therefore issued here and the P V MMAs by
+    // another warp.  Without a producer warp of its own this thread also refills the K/V ring, never blocking on it.
     if (lane == 0) {
       constexpr uint32_t idesc_qk = make_idesc_f16(kTileM, kTileN, 0);
-      constexpr uint32_t idesc_pv0 = make_idesc_f16(kTileM, Cfg::N0, 1);
-      constexpr uint32_t idesc_pv1 = make_idesc_f16(kTileM, Cfg::N1 > 0 ? Cfg::N1 : 16, 1);
       const uint32_t q_addr = smem_u32(s_q);
+      int next_load = 0;
+      auto refill = [&]() {                     // issue every K/V tile load whose ring stage is free; never blocks
+        if (Cfg::SPLIT) return;
+        while (next_load < n_tiles) {
+          if (next_load >= ST && !mbar_test_wait(bar_kv_empty + next_load % ST, ((next_load / ST) - 1) & 1)) break;
+          load_kv_tile(next_load);
+          ++next_load;
+        }
+      };
       auto issue_qk = [&](int t) {
         const int st = t % ST;
-        mbar_wait(bar_kv_full + st, (t / ST) & 1, 10);
+        uint32_t polls = 0;
+        while (!mbar_try_wait(bar_kv_full + st, (t / ST) & 1)) {   // keep the ring moving while waiting for K_t
+          refill();
+          if (++polls > FRESCO_WATCHDOG_POLLS) mbar_timeout(bar_kv_full + st, (t / ST) & 1, 10);
+        }
         tc_fence_after();
         const uint32_t k_addr = smem_u32(s_kv + st * Cfg::STAGE_BYTES);
         const uint32_t d_tmem = tmem + ((t & 1) ? Cfg::S_OFF1 : Cfg::S_OFF0);
@@ -261,21 +320,38 @@ fresco_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                   idesc_qk, ks > 0);
         }
         umma_commit(bar_s + (t & 1));
+        umma_commit(bar_kv_empty + st);          // K_t consumed (second arrival comes from the PV issuer)
       };
+      if (!Cfg::SPLIT) load_q();
+      refill();
       mbar_wait(bar_q, 0, 11);
       issue_qk(0);
       if (n_tiles > 1) issue_qk(1);
+      for (int t = 0; t + 2 < n_tiles; ++t) {
+        refill();
+        // S buffer (t & 1) is free as soon as the softmax threads hold S_t in registers
+        uint32_t polls = 0;
+        while (!mbar_try_wait(bar_c + (t & 1), (t >> 1) & 1)) {
+          refill();
+          if (++polls > FRESCO_WATCHDOG_POLLS) mbar_timeout(bar_c + (t & 1), (t >> 1) & 1, 13);
+        }
+        TRACE(t, 9, polls);
+        issue_qk(t + 2);
+        TRACE(t, 10, polls);
+      }
+      while (!Cfg::SPLIT && next_load < n_tiles) refill();   // (every tile is loaded by now unless n_tiles <= 2)
+    }
+  } else if (warp == Cfg::PV_WARP) {
+    // ------------------------------------------------------------ P V MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_pv0 = make_idesc_f16(kTileM, Cfg::N0, 1);
+      constexpr uint32_t idesc_pv1 = make_idesc_f16(kTileM, Cfg::N1 > 0 ? Cfg::N1 : 16, 1);
+      constexpr uint32_t idesc_ones = make_idesc_f16(kTileM, 16, 1);
       for (int t = 0; t < n_tiles; ++t) {
         const int st = t % ST;
-        if (t + 2 < n_tiles) {
-          // S buffer (t & 1) is free as soon as the softmax threads hold S_t in registers -- long before P_t is
-          // written -- so the scores of tile t+2 are issued now and are ready well ahead of their consumer
-          // (one barrier per S buffer: the softmax warps can run ahead of this thread, and a parity wait is only
-          //  sound if the waited barrier cannot complete two phases in the meantime)
-          mbar_wait_backoff(bar_c + (t & 1), (t >> 1) & 1, 100, 13);
-          issue_qk(t + 2);
-        }
-        mbar_wait_backoff(bar_p + (t & 1), (t >> 1) & 1, 100, 12);   // P_t in TMEM
+        mbar_wait_backoff(bar_p + (t & 1), (t >> 1) & 1, 20, 12);   // P_t in TMEM
+        TRACE(t, 11, st);
+        mbar_wait(bar_kv_full + st, (t / ST) & 1, 15);              // V_t landed long ago; observe it for visibility
         tc_fence_after();
         const uint32_t v_addr = smem_u32(s_kv + st * Cfg::STAGE_BYTES + Cfg::NATOM * kKVAtomBytes);
 #pragma unroll
@@ -287,12 +363,16 @@ fresco_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           if (Cfg::N1 > 0)
             umma_ts(tmem + Cfg::O_OFF + 64, p_tmem,
                     make_smem_desc_sw128(v_addr + kKVAtomBytes + k2 * 2048, kKVAtomBytes, 1024), idesc_pv1, acc);
+          if (Cfg::MMA_ROWSUM)      // l += P_t * ones  (every element of the constant tile is 1.0, so its layout is moot)
+            umma_ts(tmem + Cfg::O_OFF + Cfg::L_COL, p_tmem, make_smem_desc_sw128(smem_u32(s_ones), 2048, 1024),
+                    idesc_ones, acc);
         }
         umma_commit(bar_kv_empty + st);
         umma_commit(bar_o + (t & 1));
+        TRACE(t, 12, st);
       }
     }
-  } else {
+  } else if (warp < 4) {
     // ------------------------------------------------------------ softmax warps
     const int row = warp * 32 + lane;                      // query row inside the tile == TMEM lane
     const uint32_t t_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
@@ -309,8 +389,10 @@ fresco_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       // warp-uniform: does this tile need masking (ragged tail) or the diagonal bias?
       const bool special = (col0 + kTileN > kv_len) ||
                            (use_bias && (q0 + warp * 32) < col0 + kTileN && (q0 + warp * 32 + 32) > col0);
+      TRACE(i, 0, col0);
       if (!s_ready) mbar_wait(bar_s + (i & 1), (i >> 1) & 1, 2);
       tc_fence_after();
+      TRACE(i, 1, col0);
       // ---- the whole 64-column row of scores, once, into registers
       const uint32_t s_addr = t_lane + ((i & 1) ? Cfg::S_OFF1 : Cfg::S_OFF0);
       uint32_t r[64];
@@ -324,13 +406,16 @@ fresco_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         for (int j = 0; j < 64; ++j) r[j] = 0x3a83126fu + ((uint32_t)(j ^ i) << 8);   // ~1e-3, no conversions
       }
       tmem_ld_wait_dep64(r);
+      TRACE(i, 2, r[63]);
       tc_fence_before();
-      mbar_arrive(bar_c + (i & 1));              // S buffer (i & 1) may be overwritten by Q K_{i+2}^T
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_c + (i & 1));   // S buffer (i & 1) may be overwritten by Q K_{i+2}^T
       // P buffer (i & 1) was last read by P_{i-2} V_{i-2}; probe its retirement now, wait (rarely) before the stores
       const bool p_free = (i < 2) || mbar_test_wait(bar_o + (i & 1), ((i - 2) >> 1) & 1);
       // probe S_{i+1} now: it was issued a whole tile ago, and the ~100-cycle latency of a try_wait on an
       // already-completed barrier hides behind the max / exp work instead of opening the next iteration
       s_ready = (i + 1 < n_tiles) && mbar_test_wait(bar_s + ((i + 1) & 1), ((i + 1) >> 1) & 1);
+      TRACE(i, 3, (int)s_ready + (int)p_free);
       if (special) {                            // rare path: fold mask / bias into the raw scores
 #pragma unroll
         for (int j = 0; j < 64; ++j) {
@@ -350,6 +435,7 @@ fresco_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         mx3 = max3(mx3, __uint_as_float(r[j + 6]), __uint_as_float(r[j + 7]));
       }
       const float m_tile = ABL(p, 16) ? 0.f : fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
+      TRACE(i, 4, __float_as_uint(m_tile));
       if (!p_free) {
         mbar_wait(bar_o + (i & 1), ((i - 2) >> 1) & 1, 3);
         tc_fence_after();
@@ -369,10 +455,12 @@ fresco_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
             m_run = m_tile;
           }
 #pragma unroll
-          for (int c = 0; c < D / 8; ++c) {
+          for (int c = 0; c < D / 8 + (Cfg::MMA_ROWSUM ? 1 : 0); ++c) {
             uint32_t o[8];
+            const bool lchunk = Cfg::MMA_ROWSUM && c == D / 8;                          // last chunk: the row-sum column
             const int col = c * 8;
-            const uint32_t addr = t_lane + Cfg::O_OFF + (col < Cfg::N0 ? col : 64 + (col - Cfg::N0));
+            const uint32_t addr = t_lane + Cfg::O_OFF +
+                                  (lchunk ? Cfg::L_COL : (col < Cfg::N0 ? col : 64 + (col - Cfg::N0)));
             tmem_ld8_sync(addr, o);
 #pragma unroll
             for (int j = 0; j < 8; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
@@ -387,9 +475,9 @@ fresco_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       for (int j = 0; j < 64; j += 2) {
         float t0, t1;
         unpack_f2(fma2(pack_f2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), scale2, negm2), t0, t1);
-        if (kPolyEvery > 0 && ((j >> 1) % (kPolyEvery > 0 ? kPolyEvery : 1)) == (kPolyEvery - 1)) {
+        if (POLY > 0 && ((j >> 1) % (POLY > 0 ? POLY : 1)) == (POLY - 1)) {
           float p0, p1;
-          exp2_poly_x2(t0, t1, p0, p1);                    // FMA-pipe exponential for every kPolyEvery-th pair
+          exp2_poly_x2(t0, t1, p0, p1);                    // FMA-pipe exponential for every POLY-th pair
           r[j] = __float_as_uint(p0);
           r[j + 1] = __float_as_uint(p1);
         } else if (ABL(p, 1)) {
@@ -401,12 +489,15 @@ fresco_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         }
       }
       unsigned long long sum2[4] = {pack_f2(0.f, 0.f), pack_f2(0.f, 0.f), pack_f2(0.f, 0.f), pack_f2(0.f, 0.f)};
+      if (!Cfg::MMA_ROWSUM) {
 #pragma unroll
-      for (int j = 0; j < 64; j += 2)
-        sum2[(j >> 1) & 3] = add2(sum2[(j >> 1) & 3], pack_f2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])));
+        for (int j = 0; j < 64; j += 2)
+          sum2[(j >> 1) & 3] = add2(sum2[(j >> 1) & 3], pack_f2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])));
+      }
       uint32_t pk[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) pk[j] = pack_half2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+      TRACE(i, 5, pk[31] ^ pk[0] ^ pk[15]);
       const uint32_t p_addr = t_lane + ((i & 1) ? Cfg::P_OFF1 : Cfg::P_OFF0);
       if (!ABL(p, 4)) {
         tmem_st16(p_addr, *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
@@ -414,9 +505,13 @@ fresco_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       } else if (pk[0] == 0x12345678u && pk[31] == 0x9abcdef0u) {
         tmem_st16(p_addr, *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));      // keeps pk live
       }
+      TRACE(i, 6, i);
       tmem_st_wait();
+      TRACE(i, 7, i);
       tc_fence_before();
-      mbar_arrive(bar_p + (i & 1));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p + (i & 1));
+      TRACE(i, 8, i);
       float sa, sb;
       unpack_f2(add2(add2(sum2[0], sum2[1]), add2(sum2[2], sum2[3])), sa, sb);
       l_run += sa + sb;
@@ -425,6 +520,11 @@ fresco_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     // ---- epilogue: O / l -> fp16 head slice of this row
     mbar_wait(bar_o + ((n_tiles - 1) & 1), ((n_tiles - 1) >> 1) & 1, 4);
     tc_fence_after();
+    if (Cfg::MMA_ROWSUM) {
+      uint32_t lcol[8];
+      tmem_ld8_sync(t_lane + Cfg::O_OFF + Cfg::L_COL, lcol);
+      l_run = __uint_as_float(lcol[0]);
+    }
     const float inv = 1.f / l_run;
     __half* dst = p.out + (static_cast<size_t>(b) * p.q_len + q_row) * (static_cast<size_t>(p.heads) * D) +
                   static_cast<size_t>(head) * D;
@@ -433,6 +533,277 @@ fresco_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       uint32_t o[8];
       const int col = c * 8;
       tmem_ld8_sync(t_lane + Cfg::O_OFF + (col < Cfg::N0 ? col : 64 + (col - Cfg::N0)), o);
+      if (q_row < p.q_len) {
+        uint4 pkt;
+        pkt.x = pack_half2(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
+        pkt.y = pack_half2(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
+        pkt.z = pack_half2(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
+        pkt.w = pack_half2(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
+        reinterpret_cast<uint4*>(dst)[c] = pkt;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc<Cfg::TMEM_COLS>(tmem);
+}
+
+// ---------------------------------------------------------------------------------------------
+// head_dim <= 64: the "narrow" kernel
+// ---------------------------------------------------------------------------------------------
+// At head_dim 40 a 128x64 tile is 192 tensor-core clocks but 512 MUFU clocks (8192 ex2 at 16/clk/SM): the kernel is
+// bound by the ex2 pipe, and a softmax warp runs a serial chain per tile (wait S, TMEM load, row max, 64 ex2, pack,
+// TMEM store, arrive) in which it keeps that pipe busy only about a third of the time.  The pipelined kernel above has
+// two softmax warps per SM sub-partition and measured 64 % ex2-pipe utilisation.  This kernel goes for occupancy
+// instead of per-CTA pipelining: every CTA is as small as possible so that FOUR fit on an SM (four softmax warps per
+// sub-partition keep the ex2 pipe fed while the others sit in their non-ex2 phases or wait for an MMA round trip).
+//
+//   TMEM  128 columns per CTA: S [0,64) fp32, O [64,128) fp32.  P (fp16, 32 columns) overwrites the upper half of S
+//         once those scores are in registers: keys 32..63 -> columns [32,48), keys 0..31 -> columns [48,64).
+//   regs  a thread never holds more than 32 scores: the row is read twice from TMEM (max pass, exp pass; the second
+//         half stays in registers across the two), which keeps the kernel under 100 registers.
+//   smem  Q 16 KB + a 2-stage K/V ring of 16 KB stages.
+//   warps 0-3 softmax, warp 4 (one thread) TMA producer + both MMAs, strictly serial per tile:
+//         S_t = Q K_t^T -> softmax -> O += P_t V_t ; S_{t+1} ...   (tcgen05.mma executes in issue order, so S_{t+1}
+//         may be issued right behind P_t V_t although it overwrites the columns P_t is read from; the commit that
+//         publishes S_{t+1} also covers P_t V_t, hence O is stable whenever a softmax thread holds S_{t+1}.)
+template <int D, int CTAS>
+struct NarrowCfg {
+  static_assert(D <= 64, "narrow kernel: one 64-wide atom per head");
+  static constexpr int KSTEPS = (D + 15) / 16;
+  static constexpr int DPAD = KSTEPS * 16;
+  static constexpr int O_OFF = 64, P_HI = 32, P_LO = 48, TMEM_COLS = 128;
+  static constexpr int STAGES = CTAS >= 4 ? 2 : 3;
+  static constexpr int Q_BYTES = kQAtomBytes;
+  static constexpr int STAGE_BYTES = 2 * kKVAtomBytes;
+  static constexpr int SMEM_BYTES = 1024 + Q_BYTES + STAGES * STAGE_BYTES + 128;
+  static constexpr int THREADS = 160;
+};
+
+__device__ __forceinline__ void tmem_ld_wait_dep32(uint32_t (&r)[32]) {
+#define FR8(b) "+r"(r[b]), "+r"(r[b + 1]), "+r"(r[b + 2]), "+r"(r[b + 3]), "+r"(r[b + 4]), "+r"(r[b + 5]), "+r"(r[b + 6]), "+r"(r[b + 7])
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : FR8(0), FR8(8), FR8(16), FR8(24) : : "memory");
+#undef FR8
+}
+
+template <int D, int CTAS>
+__global__ void __launch_bounds__(NarrowCfg<D, CTAS>::THREADS, CTAS)
+fresco_attn_narrow_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                          const __grid_constant__ CUtensorMap tm_v, const AttnParams p) {
+  using Cfg = NarrowCfg<D, CTAS>;
+  constexpr int ST = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_q = smem;
+  uint8_t* s_kv = smem + Cfg::Q_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_kv + ST * Cfg::STAGE_BYTES);
+  uint64_t* bar_q = bars + 0;
+  uint64_t* bar_kv_full = bars + 1;            // [ST]
+  uint64_t* bar_kv_empty = bars + 1 + ST;      // [ST]
+  uint64_t* bar_s = bars + 1 + 2 * ST;         // S_t ready (and every MMA issued before it retired); phase t & 1
+  uint64_t* bar_p = bar_s + 1;                 // P_t written, one elected arrival per softmax warp; phase t & 1
+  uint64_t* bar_o = bar_s + 2;                 // last P V retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s + 3);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kTileM;
+  const int head = blockIdx.y;
+  const int b = blockIdx.z;
+  const int b_kv = b / p.q_per_kv;
+  const int n_tiles = (p.kv_len + kTileN - 1) / kTileN;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_init(bar_q, 1);
+      for (int s = 0; s < ST; ++s) {
+        mbar_init(bar_kv_full + s, 1);
+        mbar_init(bar_kv_empty + s, 1);
+      }
+      mbar_init(bar_s, 1);
+      mbar_init(bar_p, 4);
+      mbar_init(bar_o, 1);
+      fence_barrier_init();
+      tma_prefetch_desc(&tm_q);
+      tma_prefetch_desc(&tm_k);
+      tma_prefetch_desc(&tm_v);
+    }
+    __syncwarp();
+    tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 4) {
+    // ------------------------------------------------------------ TMA producer + MMA issuer (one thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = make_idesc_f16(kTileM, kTileN, 0);
+      constexpr uint32_t idesc_pv = make_idesc_f16(kTileM, Cfg::DPAD, 1);
+      const uint32_t q_addr = smem_u32(s_q);
+      int next_load = 0;
+      auto refill = [&]() {                     // issue every K/V tile load whose ring stage is free; never blocks
+        while (next_load < n_tiles) {
+          const int st = next_load % ST;
+          if (next_load >= ST && !mbar_test_wait(bar_kv_empty + st, ((next_load / ST) - 1) & 1)) break;
+          uint8_t* sk = s_kv + st * Cfg::STAGE_BYTES;
+          mbar_expect_tx(bar_kv_full + st, Cfg::STAGE_BYTES);
+          tma_load_4d(sk, &tm_k, bar_kv_full + st, 0, head, next_load * kTileN, b_kv);
+          tma_load_4d(sk + kKVAtomBytes, &tm_v, bar_kv_full + st, 0, head, next_load * kTileN, b_kv);
+          ++next_load;
+        }
+      };
+      auto wait_poll = [&](uint64_t* bar, uint32_t parity, int tag) {   // wait, keeping the K/V ring moving
+        uint32_t polls = 0;
+        while (!mbar_try_wait(bar, parity)) {
+          refill();
+          if (++polls > FRESCO_WATCHDOG_POLLS) mbar_timeout(bar, parity, tag);
+        }
+      };
+      auto issue_qk = [&](int t) {
+        const int st = t % ST;
+        wait_poll(bar_kv_full + st, (t / ST) & 1, 20);
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(s_kv + st * Cfg::STAGE_BYTES);
+#pragma unroll
+        for (int ks = 0; ks < Cfg::KSTEPS; ++ks)
+          umma_ss(tmem, make_smem_desc_sw128(q_addr + ks * 32, 16, 1024), make_smem_desc_sw128(k_addr + ks * 32, 16, 1024),
+                  idesc_qk, ks > 0);
+        umma_commit(bar_s);
+      };
+      mbar_expect_tx(bar_q, Cfg::Q_BYTES);
+      tma_load_4d(s_q, &tm_q, bar_q, 0, head, q0, b);
+      refill();
+      mbar_wait(bar_q, 0, 21);
+      issue_qk(0);
+      for (int t = 0; t < n_tiles; ++t) {
+        const int st = t % ST;
+        wait_poll(bar_p, t & 1, 22);                                   // P_t in TMEM
+        tc_fence_after();
+        const uint32_t v_addr = smem_u32(s_kv + st * Cfg::STAGE_BYTES + kKVAtomBytes);
+#pragma unroll
+        for (int k2 = 0; k2 < kTileN / 16; ++k2) {
+          const uint32_t p_col = k2 < 2 ? Cfg::P_LO + k2 * 8 : Cfg::P_HI + (k2 - 2) * 8;
+          umma_ts(tmem + Cfg::O_OFF, tmem + p_col, make_smem_desc_sw128(v_addr + k2 * 2048, kKVAtomBytes, 1024), idesc_pv,
+                  (k2 > 0 || t > 0) ? 1u : 0u);
+        }
+        umma_commit(bar_kv_empty + st);                                // K_t and V_t consumed
+        if (t + 1 < n_tiles) issue_qk(t + 1);
+        else umma_commit(bar_o);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ softmax warps
+    const int row = warp * 32 + lane;                      // query row inside the tile == TMEM lane
+    const uint32_t t_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+    const int q_row = q0 + row;
+    const int kv_len = p.kv_len;
+    const float scale_log2 = p.scale_log2, bias_log2 = p.diag_bias_log2;
+    const bool use_bias = bias_log2 != 0.f;
+    const unsigned long long scale2 = pack_f2(scale_log2, scale_log2);
+    float m_run = -INFINITY, l_run = 0.f;
+
+    for (int i = 0; i < n_tiles; ++i) {
+      const int col0 = i * kTileN;
+      // warp-uniform: does this tile need masking (ragged tail) or the diagonal bias?
+      const bool special = (col0 + kTileN > kv_len) ||
+                           (use_bias && (q0 + warp * 32) < col0 + kTileN && (q0 + warp * 32 + 32) > col0);
+      auto fixup = [&](uint32_t (&r)[32], int cbase) {     // rare path: fold mask / bias into the raw scores
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int col = cbase + j;
+          float v = __uint_as_float(r[j]);
+          if (use_bias && col == q_row) v += bias_log2 / scale_log2;
+          if (col >= kv_len) v = -INFINITY;
+          r[j] = __float_as_uint(v);
+        }
+      };
+      auto row_max = [&](const uint32_t (&r)[32]) {
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          mx0 = max3(mx0, __uint_as_float(r[j]), __uint_as_float(r[j + 1]));
+          mx1 = max3(mx1, __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+          mx2 = max3(mx2, __uint_as_float(r[j + 4]), __uint_as_float(r[j + 5]));
+          mx3 = max3(mx3, __uint_as_float(r[j + 6]), __uint_as_float(r[j + 7]));
+        }
+        return fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      };
+      mbar_wait(bar_s, i & 1, 2);
+      tc_fence_after();
+      uint32_t r[32];
+      // ---- pass 1: row max over keys 0..31, then 32..63 (the second half stays in registers)
+      tmem_ld32(t_lane, r);
+      tmem_ld_wait_dep32(r);
+      if (special) fixup(r, col0);
+      const float mx_lo = row_max(r);
+      tmem_ld32(t_lane + 32, r);
+      tmem_ld_wait_dep32(r);
+      if (special) fixup(r, col0 + 32);
+      const float m_tile = fmaxf(mx_lo, row_max(r)) * scale_log2;
+      // ---- lazy running max: raise it (and rescale O in TMEM) only when it grows by more than 2^8.  O is stable here:
+      //      the commit that published S_i was issued after P_{i-1} V_{i-1}.
+      if (i == 0) {
+        m_run = m_tile;
+      } else {
+        const bool need = m_tile > m_run + 8.0f;
+        if (__any_sync(0xffffffffu, need)) {
+          const float alpha = need ? fast_exp2(m_run - m_tile) : 1.0f;
+          if (need) {
+            l_run *= alpha;
+            m_run = m_tile;
+          }
+#pragma unroll
+          for (int c = 0; c < D / 8; ++c) {
+            uint32_t o[8];
+            tmem_ld8_sync(t_lane + Cfg::O_OFF + c * 8, o);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
+            tmem_st8(t_lane + Cfg::O_OFF + c * 8, o);
+          }
+        }
+      }
+      // ---- pass 2: p = exp2(s*scale - m), packed to fp16 over the upper half of S
+      const unsigned long long negm2 = pack_f2(-m_run, -m_run);
+      unsigned long long sum2[4] = {pack_f2(0.f, 0.f), pack_f2(0.f, 0.f), pack_f2(0.f, 0.f), pack_f2(0.f, 0.f)};
+      auto exp_half = [&](uint32_t (&r)[32], uint32_t p_col) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float t0, t1;
+          unpack_f2(fma2(pack_f2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), scale2, negm2), t0, t1);
+          const float e0 = fast_exp2(t0), e1 = fast_exp2(t1);
+          sum2[(j >> 1) & 3] = add2(sum2[(j >> 1) & 3], pack_f2(e0, e1));
+          pk[j >> 1] = pack_half2(e0, e1);
+        }
+        tmem_st16(t_lane + p_col, pk);
+      };
+      exp_half(r, Cfg::P_HI);                   // keys 32..63 -> columns [32,48) (their scores are in registers)
+      tmem_ld32(t_lane, r);                     // keys 0..31 again (columns [0,32) are untouched so far)
+      tmem_ld_wait_dep32(r);
+      if (special) fixup(r, col0);
+      exp_half(r, Cfg::P_LO);                   // -> columns [48,64)
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p);
+      float sa, sb;
+      unpack_f2(add2(add2(sum2[0], sum2[1]), add2(sum2[2], sum2[3])), sa, sb);
+      l_run += sa + sb;
+    }
+
+    // ---- epilogue: O / l -> fp16 head slice of this row
+    mbar_wait(bar_o, 0, 4);
+    tc_fence_after();
+    const float inv = 1.f / l_run;
+    __half* dst = p.out + (static_cast<size_t>(b) * p.q_len + q_row) * (static_cast<size_t>(p.heads) * D) +
+                  static_cast<size_t>(head) * D;
+#pragma unroll
+    for (int c = 0; c < D / 8; ++c) {
+      uint32_t o[8];
+      tmem_ld8_sync(t_lane + Cfg::O_OFF + c * 8, o);
       if (q_row < p.q_len) {
         uint4 pkt;
         pkt.x = pack_half2(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
@@ -465,6 +836,49 @@ static int make_head_tile_map(CUtensorMap* map, const void* base, int head_dim, 
                           CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
+// Tuning knobs (read on every call so that tests can flip them): which head_dim <= 64 kernel, and how many of the
+// exponentials go to the FMA pipe.  The defaults are the measured best on B200 (attention).
+constexpr int kNarrowDefault = 0;
+constexpr int kPolyDefault = 0;
+constexpr int kRowsumDefault = 1;    // row sums from the tensor core (head_dim 40 only: needs 16 spare O columns)
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+template <int D, int POLY, bool ROWSUM>
+static int launch_pipelined(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
+                            dim3 grid, cudaStream_t stream) {
+  using Cfg = AttnCfg<D, ROWSUM>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(fresco_attn_kernel<D, POLY, ROWSUM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(attn)");
+    attr_set = true;
+  }
+  fresco_attn_kernel<D, POLY, ROWSUM><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tq, tk, tv, p);
+  return check_launch("fresco_attn_kernel");
+}
+
+template <int D, int CTAS>
+static int launch_narrow(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, dim3 grid,
+                         cudaStream_t stream) {
+  using Cfg = NarrowCfg<D, CTAS>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(fresco_attn_narrow_kernel<D, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(fresco_attn_narrow_kernel<D, CTAS>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                               cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(attn narrow)");
+    attr_set = true;
+  }
+  fresco_attn_narrow_kernel<D, CTAS><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tq, tk, tv, p);
+  return check_launch("fresco_attn_narrow_kernel");
+}
+
 template <int D>
 static int launch_attn(const void* q, const void* k, const void* v, void* out, int batch_q, int q_len, int kv_len,
                        int heads, int q_per_kv, float softmax_scale, float diag_bias, cudaStream_t stream) {
@@ -474,13 +888,6 @@ static int launch_attn(const void* q, const void* k, const void* v, void* out, i
   if (make_head_tile_map(&tq, q, D, heads, q_len, batch_q, kTileM)) return FRESCO_ERR_TENSORMAP;
   if (make_head_tile_map(&tk, k, D, heads, kv_len, batch_kv, kTileN)) return FRESCO_ERR_TENSORMAP;
   if (make_head_tile_map(&tv, v, D, heads, kv_len, batch_kv, kTileN)) return FRESCO_ERR_TENSORMAP;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(fresco_attn_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(attn)");
-    attr_set = true;
-  }
   AttnParams p;
   p.out = static_cast<__half*>(out);
   p.q_len = q_len;
@@ -492,13 +899,34 @@ static int launch_attn(const void* q, const void* k, const void* v, void* out, i
   static const int ablate = getenv("FRESCO_ATTN_ABLATE") ? atoi(getenv("FRESCO_ATTN_ABLATE")) : 0;
   p.ablate = ablate;
   dim3 grid((q_len + kTileM - 1) / kTileM, heads, batch_q);
-  fresco_attn_kernel<D><<<grid, kThreads, Cfg::SMEM_BYTES, stream>>>(tq, tk, tv, p);
-  return check_launch("fresco_attn_kernel");
+  if constexpr (D == 40) {   // (the narrow kernel is written for any head_dim <= 64 but has only been validated at 40)
+    // FRESCO_ATTN_NARROW = 0 (pipelined kernel), 3 or 4 (narrow kernel, that many CTAs per SM)
+    const int narrow = env_int("FRESCO_ATTN_NARROW", kNarrowDefault);
+    if (narrow == 3) return launch_narrow<D, 3>(tq, tk, tv, p, grid, stream);
+    if (narrow == 4) return launch_narrow<D, 4>(tq, tk, tv, p, grid, stream);
+  }
+  const int poly = env_int("FRESCO_ATTN_POLY", kPolyDefault);
+  if constexpr (AttnCfg<D, true>::MMA_ROWSUM) {
+    if (env_int("FRESCO_ATTN_ROWSUM", kRowsumDefault)) {
+      if (poly == 4) return launch_pipelined<D, 4, true>(tq, tk, tv, p, grid, stream);
+      if (poly == 8) return launch_pipelined<D, 8, true>(tq, tk, tv, p, grid, stream);
+      return launch_pipelined<D, 0, true>(tq, tk, tv, p, grid, stream);
+    }
+  }
+  if (poly == 4) return launch_pipelined<D, 4, false>(tq, tk, tv, p, grid, stream);
+  if (poly == 8) return launch_pipelined<D, 8, false>(tq, tk, tv, p, grid, stream);
+  return launch_pipelined<D, 0, false>(tq, tk, tv, p, grid, stream);
 }
 
 }  // namespace fresco
 
 using namespace fresco;
+
+#ifdef FRESCO_ATTN_TRACE
+extern "C" int fresco_debug_attn_trace(long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, g_attn_trace, sizeof(long long) * 32 * 16) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 extern "C" int fresco_attn_fwd(const void* q, const void* k, const void* v, void* out, int batch_q, int q_len,
                                int kv_len, int heads, int head_dim, int q_per_kv, float softmax_scale,

@@ -90,16 +90,6 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity
     if (++polls > FRESCO_WATCHDOG_POLLS) mbar_timeout(bar, parity, tag);
   }
 }
-// Latency-critical waits spin on the non-blocking test_wait: measured on B200, a thread parked by try_wait resumes
-// ~0.8 us after the phase completes, which made the attention pipeline's per-tile barrier round trips (not its math)
-// the critical path.
-__device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity, int tag = 0) {
-  uint32_t polls = 0;
-  while (!mbar_test_wait(bar, parity)) {
-    if (++polls > (FRESCO_WATCHDOG_POLLS << 4)) mbar_timeout(bar, parity, tag);
-  }
-}
-
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

@@ -121,8 +121,8 @@ def warp_adjoint_ell(flow: torch.Tensor):
     ell = torch.zeros(Fr, hw * ELL_SLOTS, dtype=torch.int64, device=dev)
     in_ell = valid & (rank < ELL_SLOTS)
     slot = (key_s.clamp(max=hw - 1) * ELL_SLOTS + rank.clamp(0, ELL_SLOTS - 1))
-    ell.scatter_(1, torch.where(in_ell, slot, torch.zeros_like(slot)),
-                 torch.where(in_ell, packed, torch.zeros_like(packed)), reduce="add")   # slot 0 of row 0 gets +0 for the rest
+    ell.scatter_add_(1, torch.where(in_ell, slot, torch.zeros_like(slot)),
+                     torch.where(in_ell, packed, torch.zeros_like(packed)))           # slot 0 of row 0 gets +0 for the rest
     # uint32 payload stored in an int32 tensor (two's complement wrap)
     ell = torch.where(ell >= 2 ** 31, ell - 2 ** 32, ell).to(torch.int32).reshape(Fr, hw, ELL_SLOTS).contiguous()
     over = valid & (rank >= ELL_SLOTS)
