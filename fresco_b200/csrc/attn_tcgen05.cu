@@ -821,6 +821,300 @@ fresco_attn_narrow_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
 }
 
 // ---------------------------------------------------------------------------------------------
+// head_dim <= 64: the "wide" kernel -- EXPERIMENTAL, compiled but not yet run on hardware (FRESCO_ATTN_WIDE=1)
+// ---------------------------------------------------------------------------------------------
+// Written from the round-1 measurements (attention): the arithmetic of a tile costs 671 SM clocks with two
+// softmax warps per sub-partition and 562 with four, and the pipelined kernel cannot have four because a thread that
+// holds a whole 64-score row needs 168 registers.  Here every query row is shared by TWO threads (warps w and w + 4,
+// which may touch the same TMEM lanes), each owning 32 of a tile's 64 keys -- and nothing else is shared: each half
+// keeps its own running max, its own row sum and its own O accumulator, exactly as if the keys had been split over
+// two kernels (split-KV), and the two partial results are merged once, in the epilogue:
+//     O = (2^(m0-m) O_0 + 2^(m1-m) O_1) / (2^(m0-m) l_0 + 2^(m1-m) l_1),   m = max(m0, m1).
+// So the halves never talk to each other per tile, a thread holds 32 scores (<= 112 registers), and two CTAs of
+// eight softmax warps each put four softmax warps on every sub-partition while S stays double-buffered.
+//
+//   TMEM  256 columns: S0 [0,64), S1 [64,128) fp32; O_0 [128,192), O_1 [192,256) fp32 (head_dim columns + padding;
+//         at head_dim <= 48 columns [48,64) of each hold the tensor-core row sums).  P_h (fp16, 16 columns)
+//         overwrites the first half of the 32 S columns its thread has just read.
+//   warps 0-7 softmax (lane quarter w & 3, key half w >> 2); warp 8, one thread: TMA producer + every MMA, in the order
+//         ... P V(t), Q K(t+2)^T ... : tcgen05.mma executes in issue order, so S_{t+2} may be issued right behind
+//         P_t V_t although it overwrites the columns P_t is read from.
+template <int D>
+struct WideCfg {
+  static_assert(D <= 64, "wide kernel: one 64-wide atom per head");
+  static constexpr int KSTEPS = (D + 15) / 16;
+  static constexpr int DPAD = KSTEPS * 16;
+  static constexpr int S_OFF0 = 0, S_OFF1 = 64, O_OFF = 128, O_STRIDE = 64, TMEM_COLS = 256;
+  static constexpr bool MMA_ROWSUM = DPAD + 16 <= 64;
+  static constexpr int L_COL = 48;
+  static constexpr int ONES_BYTES = MMA_ROWSUM ? 2048 : 0;
+  static constexpr int STAGES = 5;
+  static constexpr int Q_BYTES = kQAtomBytes;
+  static constexpr int STAGE_BYTES = 2 * kKVAtomBytes;
+  static constexpr int SMEM_BYTES = 1024 + Q_BYTES + STAGES * STAGE_BYTES + ONES_BYTES + 2 * 128 * 8 + 256;
+  static constexpr int THREADS = 288;
+};
+
+template <int D>
+__global__ void __launch_bounds__(WideCfg<D>::THREADS, 2)
+fresco_attn_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                        const __grid_constant__ CUtensorMap tm_v, const AttnParams p) {
+  using Cfg = WideCfg<D>;
+  constexpr int ST = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_q = smem;
+  uint8_t* s_kv = smem + Cfg::Q_BYTES;
+  uint8_t* s_ones = s_kv + ST * Cfg::STAGE_BYTES;                     // [16 kv rows x 128 B] of fp16 1.0
+  float2* s_ml = reinterpret_cast<float2*>(s_ones + Cfg::ONES_BYTES);  // [2 halves][128 rows] {running max, row sum}
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ml + 2 * 128);
+  uint64_t* bar_q = bars + 0;
+  uint64_t* bar_kv_full = bars + 1;            // [ST]
+  uint64_t* bar_kv_empty = bars + 1 + ST;      // [ST]
+  uint64_t* bar_s = bars + 1 + 2 * ST;         // [2] S_t ready in buffer t & 1; phase (t >> 1) & 1
+  uint64_t* bar_p = bar_s + 2;                 // [2] both halves of P_t written (one elected arrival per softmax warp)
+  uint64_t* bar_o = bar_s + 4;                 // [2] P_t V_t retired (O_0, O_1 stable up to tile t)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s + 6);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kTileM;
+  const int head = blockIdx.y;
+  const int b = blockIdx.z;
+  const int b_kv = b / p.q_per_kv;
+  const int n_tiles = (p.kv_len + kTileN - 1) / kTileN;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      mbar_init(bar_q, 1);
+      for (int s = 0; s < ST; ++s) {
+        mbar_init(bar_kv_full + s, 1);
+        mbar_init(bar_kv_empty + s, 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(bar_s + i, 1);
+        mbar_init(bar_p + i, 8);
+        mbar_init(bar_o + i, 1);
+      }
+      fence_barrier_init();
+      tma_prefetch_desc(&tm_q);
+      tma_prefetch_desc(&tm_k);
+      tma_prefetch_desc(&tm_v);
+    }
+    __syncwarp();
+    tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  }
+  if (Cfg::MMA_ROWSUM) {
+    for (int i = threadIdx.x; i < Cfg::ONES_BYTES / 4; i += Cfg::THREADS) reinterpret_cast<uint32_t*>(s_ones)[i] = 0x3C003C00u;
+    fence_proxy_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 8) {
+    // ------------------------------------------------------------ TMA producer + MMA issuer (one thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = make_idesc_f16(kTileM, kTileN, 0);
+      constexpr uint32_t idesc_pv = make_idesc_f16(kTileM, Cfg::DPAD, 1);
+      constexpr uint32_t idesc_ones = make_idesc_f16(kTileM, 16, 1);
+      const uint32_t q_addr = smem_u32(s_q);
+      int next_load = 0;
+      auto refill = [&]() {                     // issue every K/V tile load whose ring stage is free; never blocks
+        while (next_load < n_tiles) {
+          const int st = next_load % ST;
+          if (next_load >= ST && !mbar_test_wait(bar_kv_empty + st, ((next_load / ST) - 1) & 1)) break;
+          uint8_t* sk = s_kv + st * Cfg::STAGE_BYTES;
+          mbar_expect_tx(bar_kv_full + st, Cfg::STAGE_BYTES);
+          tma_load_4d(sk, &tm_k, bar_kv_full + st, 0, head, next_load * kTileN, b_kv);
+          tma_load_4d(sk + kKVAtomBytes, &tm_v, bar_kv_full + st, 0, head, next_load * kTileN, b_kv);
+          ++next_load;
+        }
+      };
+      auto wait_poll = [&](uint64_t* bar, uint32_t parity, int tag) {   // wait, keeping the K/V ring moving
+        uint32_t polls = 0;
+        while (!mbar_try_wait(bar, parity)) {
+          refill();
+          if (++polls > FRESCO_WATCHDOG_POLLS) mbar_timeout(bar, parity, tag);
+        }
+      };
+      auto issue_qk = [&](int t) {
+        const int st = t % ST;
+        wait_poll(bar_kv_full + st, (t / ST) & 1, 30);
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(s_kv + st * Cfg::STAGE_BYTES);
+        const uint32_t d_tmem = tmem + ((t & 1) ? Cfg::S_OFF1 : Cfg::S_OFF0);
+#pragma unroll
+        for (int ks = 0; ks < Cfg::KSTEPS; ++ks)
+          umma_ss(d_tmem, make_smem_desc_sw128(q_addr + ks * 32, 16, 1024), make_smem_desc_sw128(k_addr + ks * 32, 16, 1024),
+                  idesc_qk, ks > 0);
+        umma_commit(bar_s + (t & 1));
+      };
+      mbar_expect_tx(bar_q, Cfg::Q_BYTES);
+      tma_load_4d(s_q, &tm_q, bar_q, 0, head, q0, b);
+      refill();
+      mbar_wait(bar_q, 0, 31);
+      issue_qk(0);
+      if (n_tiles > 1) issue_qk(1);
+      for (int t = 0; t < n_tiles; ++t) {
+        const int st = t % ST;
+        wait_poll(bar_p + (t & 1), (t >> 1) & 1, 32);                  // both halves of P_t in TMEM
+        tc_fence_after();
+        const uint32_t v_addr = smem_u32(s_kv + st * Cfg::STAGE_BYTES + kKVAtomBytes);
+        const uint32_t s_buf = tmem + ((t & 1) ? Cfg::S_OFF1 : Cfg::S_OFF0);
+#pragma unroll
+        for (int k2 = 0; k2 < kTileN / 16; ++k2) {
+          const int h = k2 >> 1;                                       // key half == accumulator
+          const uint32_t p_tmem = s_buf + 32 * h + (k2 & 1) * 8;       // P_h: 16 columns at the start of its S half
+          const uint32_t o_tmem = tmem + Cfg::O_OFF + h * Cfg::O_STRIDE;
+          const uint32_t acc = (t > 0 || (k2 & 1)) ? 1u : 0u;
+          umma_ts(o_tmem, p_tmem, make_smem_desc_sw128(v_addr + k2 * 2048, kKVAtomBytes, 1024), idesc_pv, acc);
+          if (Cfg::MMA_ROWSUM)      // l_h += P_h * ones (every element of the constant tile is 1.0, so its layout is moot)
+            umma_ts(o_tmem + Cfg::L_COL, p_tmem, make_smem_desc_sw128(smem_u32(s_ones), 2048, 1024), idesc_ones, acc);
+        }
+        umma_commit(bar_kv_empty + st);                                // K_t and V_t consumed
+        umma_commit(bar_o + (t & 1));
+        if (t + 2 < n_tiles) issue_qk(t + 2);                          // overwrites S/P buffer t & 1, behind P_t V_t
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ softmax warps: (row, key half)
+    const int quarter = warp & 3, half = warp >> 2;
+    const int row = quarter * 32 + lane;                   // query row inside the tile == TMEM lane
+    const uint32_t t_lane = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
+    const uint32_t o_mine = t_lane + Cfg::O_OFF + half * Cfg::O_STRIDE;
+    const int q_row = q0 + row;
+    const int kv_len = p.kv_len;
+    const float scale_log2 = p.scale_log2, bias_log2 = p.diag_bias_log2;
+    const bool use_bias = bias_log2 != 0.f;
+    const unsigned long long scale2 = pack_f2(scale_log2, scale_log2);
+    float m_run = -INFINITY, l_run = 0.f;
+
+    for (int i = 0; i < n_tiles; ++i) {
+      const int col0 = i * kTileN + 32 * half;             // first key of this thread's half tile
+      // warp-uniform: does this half tile need masking (ragged tail) or the diagonal bias?
+      const bool special = (col0 + 32 > kv_len) ||
+                           (use_bias && (q0 + quarter * 32) < col0 + 32 && (q0 + quarter * 32 + 32) > col0);
+      mbar_wait(bar_s + (i & 1), (i >> 1) & 1, 2);
+      tc_fence_after();
+      const uint32_t s_addr = t_lane + ((i & 1) ? Cfg::S_OFF1 : Cfg::S_OFF0) + 32 * half;
+      uint32_t r[32];
+      tmem_ld32(s_addr, r);
+      tmem_ld_wait_dep32(r);
+      if (special) {                                        // rare path: fold mask / bias into the raw scores
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int col = col0 + j;
+          float v = __uint_as_float(r[j]);
+          if (use_bias && col == q_row) v += bias_log2 / scale_log2;
+          if (col >= kv_len) v = -INFINITY;
+          r[j] = __float_as_uint(v);
+        }
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        mx0 = max3(mx0, __uint_as_float(r[j]), __uint_as_float(r[j + 1]));
+        mx1 = max3(mx1, __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+        mx2 = max3(mx2, __uint_as_float(r[j + 4]), __uint_as_float(r[j + 5]));
+        mx3 = max3(mx3, __uint_as_float(r[j + 6]), __uint_as_float(r[j + 7]));
+      }
+      const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
+      // ---- lazy running max of THIS half: raise it (and rescale O_h in TMEM) only when it grows by more than 2^8.
+      //      (m_run stays -inf while every key of this half has been masked; exp2(-inf) = 0 keeps P, l and O at zero.)
+      if (i == 0) {
+        m_run = m_tile;
+      } else {
+        const bool need = m_tile > m_run + 8.0f;           // also true for the first unmasked tile after m_run = -inf
+        if (__any_sync(0xffffffffu, need)) {
+          // O_h may only be touched once P_{i-1} V_{i-1} has retired (rare path, so the wait is affordable)
+          mbar_wait(bar_o + ((i - 1) & 1), ((i - 1) >> 1) & 1, 5);
+          tc_fence_after();
+          const float alpha = need ? fast_exp2(m_run - m_tile) : 1.0f;   // 0 when m_run was -inf (O_h, l_h are 0 then)
+          if (need) {
+            l_run *= alpha;
+            m_run = m_tile;
+          }
+#pragma unroll
+          for (int c = 0; c < D / 8 + (Cfg::MMA_ROWSUM ? 1 : 0); ++c) {
+            uint32_t o[8];
+            const uint32_t addr = o_mine + ((Cfg::MMA_ROWSUM && c == D / 8) ? Cfg::L_COL : c * 8);
+            tmem_ld8_sync(addr, o);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
+            tmem_st8(addr, o);
+          }
+        }
+      }
+      // ---- p = exp2(s*scale - m), packed to fp16 over the first 16 of the 32 columns just read
+      const float neg_m = (m_run == -INFINITY) ? 0.f : -m_run;           // all-masked so far: s = -inf -> p = 0, not NaN
+      const unsigned long long negm2 = pack_f2(neg_m, neg_m);
+      unsigned long long sum2[2] = {pack_f2(0.f, 0.f), pack_f2(0.f, 0.f)};
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        float t0, t1;
+        unpack_f2(fma2(pack_f2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), scale2, negm2), t0, t1);
+        const float e0 = fast_exp2(t0), e1 = fast_exp2(t1);
+        if (!Cfg::MMA_ROWSUM) sum2[(j >> 1) & 1] = add2(sum2[(j >> 1) & 1], pack_f2(e0, e1));
+        pk[j >> 1] = pack_half2(e0, e1);
+      }
+      tmem_st16(s_addr, pk);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p + (i & 1));
+      if (!Cfg::MMA_ROWSUM) {
+        float sa, sb;
+        unpack_f2(add2(sum2[0], sum2[1]), sa, sb);
+        l_run += sa + sb;
+      }
+    }
+
+    // ---- epilogue: merge the two halves of every row, O / l -> fp16 head slice
+    mbar_wait(bar_o + ((n_tiles - 1) & 1), ((n_tiles - 1) >> 1) & 1, 4);
+    tc_fence_after();
+    if (Cfg::MMA_ROWSUM) {
+      uint32_t lcol[8];
+      tmem_ld8_sync(o_mine + Cfg::L_COL, lcol);
+      l_run = __uint_as_float(lcol[0]);
+    }
+    s_ml[half * 128 + row] = make_float2(m_run, l_run);
+    asm volatile("bar.sync 1, 256;" ::: "memory");          // the eight softmax warps only
+    const float2 other = s_ml[(half ^ 1) * 128 + row];
+    const float m_all = fmaxf(m_run, other.x);              // finite: at least one key of the row is unmasked
+    const float w_mine = fast_exp2(m_run - m_all), w_other = fast_exp2(other.x - m_all);
+    const float inv = 1.f / (w_mine * l_run + w_other * other.y);
+    const float w0 = (half == 0 ? w_mine : w_other) * inv, w1 = (half == 0 ? w_other : w_mine) * inv;
+    __half* dst = p.out + (static_cast<size_t>(b) * p.q_len + q_row) * (static_cast<size_t>(p.heads) * D) +
+                  static_cast<size_t>(head) * D;
+#pragma unroll
+    for (int c = 0; c < D / 8; ++c) {
+      if ((c & 1) != half) continue;                        // the two threads of a row split its 16-byte chunks
+      uint32_t o0[8], o1[8];
+      tmem_ld8_sync(t_lane + Cfg::O_OFF + c * 8, o0);
+      tmem_ld8_sync(t_lane + Cfg::O_OFF + Cfg::O_STRIDE + c * 8, o1);
+      if (q_row < p.q_len) {
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(o0[j]) * w0 + __uint_as_float(o1[j]) * w1;
+        uint4 pkt;
+        pkt.x = pack_half2(f[0], f[1]);
+        pkt.y = pack_half2(f[2], f[3]);
+        pkt.z = pack_half2(f[4], f[5]);
+        pkt.w = pack_half2(f[6], f[7]);
+        reinterpret_cast<uint4*>(dst)[c] = pkt;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc<Cfg::TMEM_COLS>(tmem);
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 
@@ -880,6 +1174,21 @@ static int launch_narrow(const CUtensorMap& tq, const CUtensorMap& tk, const CUt
 }
 
 template <int D>
+static int launch_wide(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, dim3 grid,
+                       cudaStream_t stream) {
+  using Cfg = WideCfg<D>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(fresco_attn_wide_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(attn wide)");
+    attr_set = true;
+  }
+  fresco_attn_wide_kernel<D><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tq, tk, tv, p);
+  return check_launch("fresco_attn_wide_kernel");
+}
+
+template <int D>
 static int launch_attn(const void* q, const void* k, const void* v, void* out, int batch_q, int q_len, int kv_len,
                        int heads, int q_per_kv, float softmax_scale, float diag_bias, cudaStream_t stream) {
   using Cfg = AttnCfg<D>;
@@ -899,6 +1208,9 @@ static int launch_attn(const void* q, const void* k, const void* v, void* out, i
   static const int ablate = getenv("FRESCO_ATTN_ABLATE") ? atoi(getenv("FRESCO_ATTN_ABLATE")) : 0;
   p.ablate = ablate;
   dim3 grid((q_len + kTileM - 1) / kTileM, heads, batch_q);
+  if constexpr (D <= 64) {   // EXPERIMENTAL, see the kernel: off unless asked for
+    if (env_int("FRESCO_ATTN_WIDE", 0) == 1) return launch_wide<D>(tq, tk, tv, p, grid, stream);
+  }
   if constexpr (D == 40) {   // (the narrow kernel is written for any head_dim <= 64 but has only been validated at 40)
     // FRESCO_ATTN_NARROW = 0 (pipelined kernel), 3 or 4 (narrow kernel, that many CTAs per SM)
     const int narrow = env_int("FRESCO_ATTN_NARROW", kNarrowDefault);
