@@ -74,8 +74,94 @@ def smooth_flows(n, H, W, seed, mag):
     return fwd, bwd
 
 
+def scenario_b(dh, fu, geometry, matching, ut):
+    """Second fixture set (``python tests/golden/make_golden.py --set b``): an ODD number of frames, a NON-SQUARE
+    plane and head_dim 80 (SD1.5 level A), so that nothing in the oracle or the kernels can silently rely on
+    N being even, h == w or d == 40.  Same reference entry points as set A."""
+    torch.manual_seed(1)
+    torch.set_grad_enabled(False)
+    N, H, W = 3, 64, 96
+    fwd, bwd = smooth_flows(N, H, W, 21, 4.0)
+    fo, bo = geometry.forward_backward_consistency_check(fwd, bwd)
+    imgs = torch.rand(N, 3, H, W) * 2 - 1
+    bocc = torch.clamp(bo + (torch.rand(N, H, W) > 0.85).float(), 0, 1)
+    res = {"fwd": fwd.numpy(), "bwd": bwd.numpy(), "fwd_occ": fo.numpy(), "bwd_occ": bocc.numpy(), "imgs": imgs.numpy()}
+
+    # mapping at scale 8 (8 x 12 tokens)
+    fm, bm, im = fu.get_mapping_ind(bwd, bocc, imgs, scale=8.0)
+    res.update(fwd_map=fm.numpy(), bwd_map=bm.numpy(), inter_mask=im.numpy())
+
+    # attention, all 8 flag combinations, C = 160 / 2 heads => head_dim 80
+    C, heads, chunks = 160, 2, 2
+    L = (H // 8) * (W // 8)
+    attn = FakeAttn(C, heads, 5)
+    x = torch.randn(chunks * N, L, C)
+    ref_hidden = torch.randn(chunks * N, L, C)
+    attn_mask = []
+    for scale in [8.0, 16.0, 32.0]:
+        o_ = F.interpolate(bocc[:-1].unsqueeze(1), scale_factor=1. / scale, mode='bilinear')
+        attn_mask += [torch.cat((o_[0:1].reshape(1, -1) > -1, o_.reshape(o_.shape[0], -1) > 0.5), dim=0)]
+    paras = {"fwd_mappings": [fm], "bwd_mappings": [bm], "interattn_masks": [im]}
+    res.update(x=x.numpy(), ref_hidden=ref_hidden.numpy(), heads=np.int64(heads), wq=attn.to_q.weight.numpy(),
+               wk=attn.to_k.weight.numpy(), wv=attn.to_v.weight.numpy(), wo=attn.to_out[0].weight.numpy(),
+               bo=attn.to_out[0].bias.numpy())
+    for i, m in enumerate(attn_mask):
+        res[f"attn_mask{i}"] = m.numpy()
+    for flags in (0, 1, 6, 7):     # set A holds all eight; here: none, cross-frame only, intra+inter, all
+        cf, intra, inter = bool(flags & 1), bool(flags & 2), bool(flags & 4)
+        ctrl = dh.AttentionControl()
+        proc = dh.FRESCOAttnProcessor2_0(chunks, ctrl)
+        if intra:
+            ctrl.stored_attn['decoder_attn'] = [ref_hidden.clone()]
+            ctrl.enable_intraattn()
+        if inter:
+            ctrl.enable_interattn(paras)
+        if cf:
+            ctrl.enable_cfattn(attn_mask)
+        res[f"out_{flags}"] = proc(attn, x.clone()).numpy()
+
+    # warp_tensor: decoder feature (2 chunks) and image (Dilate(13) path)
+    sal = torch.rand(N, 1, 32, 48)
+    s_feat = torch.randn(2 * N, 6, 8, 12)
+    s_img = torch.randn(N, 3, H, W)
+    res.update(saliency=sal.numpy(), sample_feat=s_feat.numpy(), sample_img=s_img.numpy(),
+               out_feat=fu.warp_tensor(s_feat.clone(), [fwd, bwd], [fo, bocc], sal, 2).numpy(),
+               out_img=fu.warp_tensor(s_img.clone(), [fwd, bwd], [fo, bocc], sal, 1).numpy())
+
+    # optimize_feature, 2 iterations, on an 8 x 12 plane
+    Cc, h, w = 16, 8, 12
+    sample = torch.randn(2 * N, Cc, h, w)
+    other = sample + 0.5 * torch.randn(2 * N, Cc, h, w)
+    lv = other.reshape(2 * N, Cc, h * w).transpose(1, 2)
+    lv = lv / ((lv ** 2).sum(dim=2, keepdim=True) ** 0.5)
+    target = torch.bmm(lv, lv.transpose(-1, -2))
+    losses = []
+    orig_step = torch.optim.Adam.step
+
+    def rec_step(self, closure=None):
+        r = orig_step(self, closure)
+        losses.append(float(r))
+        return r
+
+    torch.optim.Adam.step = rec_step
+    try:
+        for tag, kw in {"full1": dict(iters=1), "full3": dict(iters=3)}.items():
+            losses.clear()
+            o = dh.optimize_feature(sample.clone(), [fwd, bwd], [fo, bocc], correlation_matrix=[target],
+                                    intra_weight=1e2, **kw)
+            res[f"opt_{tag}_out"] = o.detach().numpy()
+            res[f"opt_{tag}_losses"] = np.array(losses, dtype=np.float64)
+    finally:
+        torch.optim.Adam.step = orig_step
+    res.update(opt_sample=sample.numpy(), opt_target=target.numpy())
+    np.savez_compressed(os.path.join(HERE, "set_b.npz"), **res)
+    print("golden fixture set B written to", HERE)
+
+
 def main():
     dh, fu, geometry, matching, ut = import_reference()
+    if "--set" in sys.argv and sys.argv[sys.argv.index("--set") + 1] == "b":
+        return scenario_b(dh, fu, geometry, matching, ut)
     torch.manual_seed(0)
     torch.set_grad_enabled(False)
 

@@ -106,3 +106,36 @@ def test_gmflow_global_correlation(golden):
     assert (pb - T(g["prob_bidir"])).abs().max() < 1e-5
     fu, _ = O.global_correlation_softmax(f0, f1, False)
     assert (fu - T(g["flow_uni"])).abs().max() < 1e-4
+
+
+def test_set_b_odd_frames_nonsquare_head_dim_80(golden):
+    """Fixture set B (N = 3 frames, 64 x 96 plane, head_dim 80): mapping, attention, warp_tensor, optimize_feature."""
+    g = golden("set_b")
+    fwd, bwd, fo, bocc, imgs = (T(g[k]) for k in ("fwd", "bwd", "fwd_occ", "bwd_occ", "imgs"))
+    fo_, _ = O.forward_backward_consistency_check(fwd, bwd)
+    assert torch.equal(fo_, fo)
+    fm, bm, mask = O.mapping_ind(bwd, bocc, imgs, 8.0)
+    assert torch.equal(fm, T(g["fwd_map"])) and torch.equal(bm, T(g["bwd_map"])) and torch.equal(mask, T(g["inter_mask"]))
+    base, masks = _attn_args(g)
+    assert base["x"].shape[2] // base["heads"] == 80
+    for flags in (0, 1, 6, 7):
+        out = O.fresco_attention(
+            **base, use_cfattn=bool(flags & 1), attn_masks=masks,
+            use_intraattn=bool(flags & 2), ref_hidden=T(g["ref_hidden"]),
+            use_interattn=bool(flags & 4), fwd_mappings=[fm], bwd_mappings=[bm], interattn_masks=[mask])
+        ref = T(g[f"out_{flags}"])
+        assert (out - ref).abs().max().item() < 2e-5 * max(1.0, ref.abs().max().item()), flags
+    flows, occs = [fwd, bwd], [fo, bocc]
+    o = O.warp_tensor(T(g["sample_feat"]), flows, occs, T(g["saliency"]), 2)
+    assert (o - T(g["out_feat"])).abs().max() < 1e-5
+    o = O.warp_tensor(T(g["sample_img"]), flows, occs, T(g["saliency"]), 1)
+    assert (o - T(g["out_img"])).abs().max() < 1e-5
+    for tag, iters in (("full1", 1), ("full3", 3)):
+        out, trace = O.optimize_feature(T(g["opt_sample"]), flows, occs, correlation_matrix=[T(g["opt_target"])],
+                                        intra_weight=1e2, iters=iters, return_trace=True)
+        assert np.allclose(np.array([t["loss"] for t in trace]), g[f"opt_{tag}_losses"], rtol=2e-4), tag
+        ref = T(g[f"opt_{tag}_out"])
+        if iters == 1:
+            assert (out - ref).abs().max() < 1e-4
+        else:
+            assert (out - ref).abs().mean() / ref.abs().mean() < 5e-2
