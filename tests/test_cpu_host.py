@@ -140,3 +140,93 @@ def test_hook_surface_on_harness_unet():
     from fresco_b200.harness.sd15_unet import PlainProcessor
     with torch.no_grad():
         assert torch.allclose(proc(attn2, h, encoder_hidden_states=e), PlainProcessor()(attn2, h, e), atol=1e-6)
+
+
+class _TorchOps:
+    """fp32 torch stand-ins for the three kernels the processor calls (same signatures as fresco_b200.ops); the
+    results are rounded to fp16 like the kernels' outputs.  Lets the processor's HOST logic run without a GPU."""
+
+    @staticmethod
+    def kv_compact(k, v, idx, chunks):
+        B, L, C = k.shape
+        rows = (B // chunks) * L
+        return k.reshape(chunks, rows, C)[:, idx.long()].contiguous(), v.reshape(chunks, rows, C)[:, idx.long()].contiguous()
+
+    @staticmethod
+    def attn_fwd(q, k, v, heads, q_per_kv=1, softmax_scale=None, diag_bias=0.0, out=None):
+        B, L, C = q.shape
+        d = C // heads
+        qf, kf, vf = q.float(), k.float().repeat_interleave(q_per_kv, 0), v.float().repeat_interleave(q_per_kv, 0)
+        qh, kh, vh = (t.view(t.shape[0], -1, heads, d).transpose(1, 2) for t in (qf, kf, vf))
+        s = qh @ kh.transpose(-1, -2) * (softmax_scale if softmax_scale is not None else d ** -0.5)
+        if diag_bias:
+            s = s + torch.eye(L, kh.shape[2]) * diag_bias
+        return (torch.softmax(s, -1) @ vh).transpose(1, 2).reshape(B, L, C).to(q.dtype)
+
+    @staticmethod
+    def temporal_attn_fwd(q, k, v, fwd_map, traj_mask, chunks, heads, scale):
+        B, L, C = q.shape
+        N, d = B // chunks, C // heads
+        gi = fwd_map[None, :, :, None, None].expand(chunks, N, L, heads, d)
+        qt, kt, vt = (torch.gather(t.float().view(chunks, N, L, heads, d), 2, gi) for t in (q, k, v))
+        s = torch.einsum("bfphd,bgphd->bphfg", qt, kt) * scale
+        s = s.masked_fill(~traj_mask.bool()[None, :, None], float("-inf"))
+        o = torch.einsum("bphfg,bgphd->bfphd", torch.softmax(s, -1), vt)
+        out = torch.empty_like(o)
+        out.scatter_(2, gi, o)
+        return out.reshape(B, L, C).to(v.dtype)
+
+
+class _GoldenAttn(torch.nn.Module):
+    def __init__(self, g):
+        super().__init__()
+        c = g["wq"].shape[0]
+        self.heads = int(g["heads"])
+        self.spatial_norm = self.group_norm = None
+        self.norm_cross = self.residual_connection = False
+        self.rescale_output_factor = 1.0
+        self.to_q, self.to_k, self.to_v = (torch.nn.Linear(c, c, bias=False) for _ in range(3))
+        self.to_out = torch.nn.ModuleList([torch.nn.Linear(c, c), torch.nn.Dropout(0.0)])
+        with torch.no_grad():
+            for lin, key in ((self.to_q, "wq"), (self.to_k, "wk"), (self.to_v, "wv"), (self.to_out[0], "wo")):
+                lin.weight.copy_(torch.from_numpy(g[key]))
+            self.to_out[0].bias.copy_(torch.from_numpy(g["bo"]))
+
+
+@pytest.mark.parametrize("fixture,flag_sets", [("attention", range(8)), ("set_b", (0, 1, 6, 7))])
+def test_processor_host_logic_against_reference_outputs(golden, monkeypatch, fixture, flag_sets):
+    """The product processor (mask -> K/V row indices, frame-0 fallback, query replacement by the spatial-guided
+    pass, trajectory tables, scale factors, chunk / frame layout) reproduces the REFERENCE's outputs when its three
+    kernel calls are served by fp32 torch stand-ins: set A (N=4, 64 tokens, head_dim 40, all 8 mode combinations) and
+    set B (N=3 frames, 8 x 12 tokens, head_dim 80).  Bound: fp16 rounding of q / k / v / attention output, as in the
+    -m gpu test of the same fixtures."""
+    from fresco_b200 import diffusion_hacked as dh
+    monkeypatch.setattr(dh, "ops", _TorchOps)
+    g = golden(fixture)
+    attn = _GoldenAttn(g)
+    x, ref_hidden = torch.from_numpy(g["x"]), torch.from_numpy(g["ref_hidden"])
+    masks = [torch.from_numpy(g[f"attn_mask{i}"]) for i in range(3)]
+    paras = {"fwd_mappings": [torch.from_numpy(g["fwd_map"])], "bwd_mappings": [torch.from_numpy(g["bwd_map"])],
+             "interattn_masks": [torch.from_numpy(g["inter_mask"])]}
+    for flags in flag_sets:
+        ctrl = dh.AttentionControl()
+        proc = dh.FRESCOAttnProcessor2_0(2, ctrl)
+        if flags & 2:
+            ctrl.stored_attn["decoder_attn"] = [ref_hidden.clone()]
+            ctrl.enable_intraattn()
+        if flags & 4:
+            ctrl.enable_interattn(paras)
+        if flags & 1:
+            ctrl.enable_cfattn(masks)
+        with torch.no_grad():
+            out = proc(attn, x.clone())
+        ref = torch.from_numpy(g[f"out_{flags}"])
+        assert (out - ref).abs().max().item() < 1e-2 * ref.abs().max().item(), (fixture, flags)
+    if fixture == "attention":          # cross-frame attention without a mask of this resolution: frame-0 K/V
+        ctrl = dh.AttentionControl()
+        proc = dh.FRESCOAttnProcessor2_0(2, ctrl)
+        ctrl.enable_cfattn([masks[1]])
+        with torch.no_grad():
+            out = proc(attn, x.clone())
+        ref = torch.from_numpy(g["out_cf_nomask"])
+        assert (out - ref).abs().max().item() < 1e-2 * ref.abs().max().item()
