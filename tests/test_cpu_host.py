@@ -230,3 +230,67 @@ def test_processor_host_logic_against_reference_outputs(golden, monkeypatch, fix
             out = proc(attn, x.clone())
         ref = torch.from_numpy(g["out_cf_nomask"])
         assert (out - ref).abs().max().item() < 1e-2 * ref.abs().max().item()
+
+
+class _TorchWarpOps:
+    """fp32 stand-ins (built on the oracle's flow_warp / single_mapping_ind, test-side only) for the kernels that
+    flow_utils.warp_tensor and get_mapping_ind call, so that their HOST code (flow / occlusion / saliency resizing,
+    dilation, blend weights, cache keys, mapping chain and trajectory cuts) runs on CPU."""
+
+    @staticmethod
+    def flow_warp(src, flow):
+        from oracle import fresco_oracle as O
+        return O.flow_warp(src, flow[torch.arange(src.shape[0]) % flow.shape[0]])
+
+    @staticmethod
+    def warp_fuse_chain(sample, bwd_flow, fwd_flow_last, blend, chunks, out=None):
+        from oracle import fresco_oracle as O
+        z = sample.float().clone()
+        n = sample.shape[0] // chunks
+        for j in range(chunks):
+            base = n * j
+            for ii in range(n - 1):
+                m = blend[ii:ii + 1]
+                z[base + ii + 1] = (z[base + ii + 1:base + ii + 2] * (1 - m) + O.flow_warp(z[base + ii:base + ii + 1], bwd_flow[ii:ii + 1]) * m)[0]
+            m = blend[n - 1:n]
+            z[base + n - 1] = (z[base + n - 1:base + n] * (1 - m) + O.flow_warp(z[base:base + 1], fwd_flow_last[None]) * m)[0]
+        return z.to(sample.dtype)
+
+    @staticmethod
+    def mapping_single(bwd_flow, bwd_occ, imgs, scale):
+        from oracle import fresco_oracle as O
+        return O.single_mapping_ind(bwd_flow, bwd_occ, imgs, float(scale))
+
+
+@pytest.mark.parametrize("fixture", ["set_a", "set_b"])
+def test_warp_tensor_and_mapping_host_logic_against_reference_outputs(golden, monkeypatch, fixture):
+    """flow_utils.warp_tensor / get_mapping_ind with their kernel calls served by CPU stand-ins reproduce the
+    REFERENCE's outputs: square N=4 fixtures (set A) and the N=3, 64 x 96 fixture (set B)."""
+    from fresco_b200 import flow_utils as fu
+    monkeypatch.setattr(fu, "ops", _TorchWarpOps)
+    fu._PREP_CACHE.clear()
+    T = torch.from_numpy
+    if fixture == "set_a":
+        g = golden("warp_tensor")
+        flows, occs, sal = [T(g["fwd"]), T(g["bwd"])], [T(g["fwd_occ"]), T(g["bwd_occ"])], T(g["saliency"])
+    else:
+        g = golden("set_b")
+        flows, occs, sal = [T(g["fwd"]), T(g["bwd"])], [T(g["fwd_occ"]), T(g["bwd_occ"])], T(g["saliency"])
+    feat = T(g["sample_feat"])
+    keep = feat.clone()
+    o = fu.warp_tensor(feat, flows, occs, sal, 2)
+    assert torch.equal(feat, keep)                                   # never mutates its input
+    assert (o - T(g["out_feat"])).abs().max().item() < 1e-5
+    o = fu.warp_tensor(T(g["sample_img"]), flows, occs, sal, 1)     # image resolution: Dilate(13) path
+    assert (o - T(g["out_img"])).abs().max().item() < 1e-5
+    if fixture == "set_a":
+        m = golden("mapping")
+        for tag in "abc":
+            fm, bm, mask = fu.get_mapping_ind(T(m[f"{tag}_bwd_flows"]), T(m[f"{tag}_bwd_occs"]), T(m[f"{tag}_imgs"]),
+                                              scale=float(m[f"{tag}_scale"]))
+            assert torch.equal(fm, T(m[f"{tag}_fwd_map"])) and torch.equal(bm, T(m[f"{tag}_bwd_map"]))
+            assert torch.equal(mask, T(m[f"{tag}_mask"]))
+    else:
+        fm, bm, mask = fu.get_mapping_ind(flows[1], occs[1], T(g["imgs"]), scale=8.0)
+        assert torch.equal(fm, T(g["fwd_map"])) and torch.equal(bm, T(g["bwd_map"])) and torch.equal(mask, T(g["inter_mask"]))
+    fu._PREP_CACHE.clear()
