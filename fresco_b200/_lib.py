@@ -20,6 +20,7 @@ _SIGNATURES = {
     "fresco_abi_version": (c_int, []),
     "fresco_last_error": (c_char_p, []),
     "fresco_launch_count": (c_longlong, []),
+    "fresco_set_option": (c_int, [c_char_p, c_int]),
     "fresco_kv_compact": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "fresco_attn_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, _P]),
     "fresco_temporal_attn_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float, _P]),
@@ -87,6 +88,11 @@ def ptr(t: torch.Tensor) -> int:
 
 def stream() -> int:
     return torch.cuda.current_stream().cuda_stream
+
+
+def set_option(name: str, value: int) -> None:
+    """Override a tuning option (named like its environment variable); value < 0 restores the default."""
+    check(lib().fresco_set_option(name.encode(), int(value)), "fresco_set_option")
 
 
 def launch_count() -> int:

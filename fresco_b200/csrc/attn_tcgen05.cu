@@ -34,8 +34,6 @@
 // softmax warp per sub-partition, 671 with two (this kernel; 820 measured with TMEM traffic and barriers) and 562
 // with four.  The "narrow" kernel further down trades the pipelining for four CTAs per SM; it lands at the same
 // speed and is kept as a selectable variant.
-#include <cstdlib>
-
 #include "common.cuh"
 #include "fresco_internal.h"
 
@@ -821,42 +819,50 @@ fresco_attn_narrow_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
 }
 
 // ---------------------------------------------------------------------------------------------
-// head_dim <= 64: the "wide" kernel -- EXPERIMENTAL, compiled but not yet run on hardware (FRESCO_ATTN_WIDE=1)
+// the "wide" kernel: two threads per query row (split-KV inside the CTA), every head_dim
 // ---------------------------------------------------------------------------------------------
-// Written from the round-1 measurements (attention): the arithmetic of a tile costs 671 SM clocks with two
-// softmax warps per sub-partition and 562 with four, and the pipelined kernel cannot have four because a thread that
-// holds a whole 64-score row needs 168 registers.  Here every query row is shared by TWO threads (warps w and w + 4,
-// which may touch the same TMEM lanes), each owning 32 of a tile's 64 keys -- and nothing else is shared: each half
-// keeps its own running max, its own row sum and its own O accumulator, exactly as if the keys had been split over
-// two kernels (split-KV), and the two partial results are merged once, in the epilogue:
+// Written from the round-1 measurements (attention): a softmax warp runs a serial chain per tile (wait S,
+// TMEM load, row max, 64 ex2, pack, TMEM store, arrive) of about 1600 SM clocks, so the kernel's speed is set by how
+// many softmax warps share an SM sub-partition: the bare arithmetic of a tile costs 854 clocks with one warp per
+// sub-partition, 671 with two and 562 with four.  The pipelined kernel above cannot have more than two (one at
+// head_dim 80/128) because a thread that holds a whole 64-score row needs 168 registers.  Here every query row is shared
+// by TWO threads (warps w and w + 4, which may touch the same TMEM lanes), each owning 32 of a tile's 64 keys -- and
+// nothing else is shared: each half keeps its own running max, its own row sum and its own O accumulator, exactly as
+// if the keys had been split over two kernels (split-KV), and the two partial results are merged once, in the epilogue:
 //     O = (2^(m0-m) O_0 + 2^(m1-m) O_1) / (2^(m0-m) l_0 + 2^(m1-m) l_1),   m = max(m0, m1).
-// So the halves never talk to each other per tile, a thread holds 32 scores (<= 112 registers), and two CTAs of
-// eight softmax warps each put four softmax warps on every sub-partition while S stays double-buffered.
+// So the halves never talk to each other per tile and a thread holds 32 scores (<= 112 registers): head_dim <= 48 runs
+// two CTAs of eight softmax warps per SM (four softmax warps per sub-partition), head_dim 64..128 one CTA (two per
+// sub-partition), and S stays double-buffered in both.
 //
-//   TMEM  256 columns: S0 [0,64), S1 [64,128) fp32; O_0 [128,192), O_1 [192,256) fp32 (head_dim columns + padding;
-//         at head_dim <= 48 columns [48,64) of each hold the tensor-core row sums).  P_h (fp16, 16 columns)
-//         overwrites the first half of the 32 S columns its thread has just read.
+//   TMEM  S0 [0,64), S1 [64,128) fp32; O_0, O_1 from column 128, O_STRIDE apart (head_dim columns, then -- except at
+//         head_dim 64 -- 16 columns of tensor-core row sums).  P_h (fp16, 16 columns) overwrites the first half of the
+//         32 S columns its thread has just read.  256 columns at head_dim <= 64, 512 above.
 //   warps 0-7 softmax (lane quarter w & 3, key half w >> 2); warp 8, one thread: TMA producer + every MMA, in the order
 //         ... P V(t), Q K(t+2)^T ... : tcgen05.mma executes in issue order, so S_{t+2} may be issued right behind
 //         P_t V_t although it overwrites the columns P_t is read from.
 template <int D>
 struct WideCfg {
-  static_assert(D <= 64, "wide kernel: one 64-wide atom per head");
+  static constexpr int NATOM = (D + 63) / 64;
   static constexpr int KSTEPS = (D + 15) / 16;
   static constexpr int DPAD = KSTEPS * 16;
-  static constexpr int S_OFF0 = 0, S_OFF1 = 64, O_OFF = 128, O_STRIDE = 64, TMEM_COLS = 256;
-  static constexpr bool MMA_ROWSUM = DPAD + 16 <= 64;
-  static constexpr int L_COL = 48;
+  static constexpr int N0 = DPAD < 64 ? DPAD : 64;    // P V columns from V atom 0
+  static constexpr int N1 = DPAD - N0;                // ... from V atom 1
+  static constexpr bool MMA_ROWSUM = DPAD != 64;      // (head_dim 64 would need 16 more columns than 256 has)
+  static constexpr int L_COL = DPAD;                  // row-sum columns, relative to the start of O_h
+  static constexpr int O_STRIDE = MMA_ROWSUM ? (DPAD + 16 <= 64 ? 64 : DPAD + 16) : 64;
+  static constexpr int S_OFF0 = 0, S_OFF1 = 64, O_OFF = 128;
+  static constexpr int TMEM_COLS = (O_OFF + 2 * O_STRIDE <= 256) ? 256 : 512;
+  static constexpr int CTAS = TMEM_COLS == 256 ? 2 : 1;
   static constexpr int ONES_BYTES = MMA_ROWSUM ? 2048 : 0;
-  static constexpr int STAGES = 5;
-  static constexpr int Q_BYTES = kQAtomBytes;
-  static constexpr int STAGE_BYTES = 2 * kKVAtomBytes;
+  static constexpr int STAGES = NATOM == 1 ? 5 : 4;
+  static constexpr int Q_BYTES = NATOM * kQAtomBytes;
+  static constexpr int STAGE_BYTES = 2 * NATOM * kKVAtomBytes;
   static constexpr int SMEM_BYTES = 1024 + Q_BYTES + STAGES * STAGE_BYTES + ONES_BYTES + 2 * 128 * 8 + 256;
   static constexpr int THREADS = 288;
 };
 
-template <int D>
-__global__ void __launch_bounds__(WideCfg<D>::THREADS, 2)
+template <int D, int POLY>
+__global__ void __launch_bounds__(WideCfg<D>::THREADS, WideCfg<D>::CTAS)
 fresco_attn_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                         const __grid_constant__ CUtensorMap tm_v, const AttnParams p) {
   using Cfg = WideCfg<D>;
@@ -917,7 +923,8 @@ fresco_attn_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     // ------------------------------------------------------------ TMA producer + MMA issuer (one thread)
     if (lane == 0) {
       constexpr uint32_t idesc_qk = make_idesc_f16(kTileM, kTileN, 0);
-      constexpr uint32_t idesc_pv = make_idesc_f16(kTileM, Cfg::DPAD, 1);
+      constexpr uint32_t idesc_pv0 = make_idesc_f16(kTileM, Cfg::N0, 1);
+      constexpr uint32_t idesc_pv1 = make_idesc_f16(kTileM, Cfg::N1 > 0 ? Cfg::N1 : 16, 1);
       constexpr uint32_t idesc_ones = make_idesc_f16(kTileM, 16, 1);
       const uint32_t q_addr = smem_u32(s_q);
       int next_load = 0;
@@ -926,9 +933,13 @@ fresco_attn_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
           const int st = next_load % ST;
           if (next_load >= ST && !mbar_test_wait(bar_kv_empty + st, ((next_load / ST) - 1) & 1)) break;
           uint8_t* sk = s_kv + st * Cfg::STAGE_BYTES;
+          uint8_t* sv = sk + Cfg::NATOM * kKVAtomBytes;
           mbar_expect_tx(bar_kv_full + st, Cfg::STAGE_BYTES);
-          tma_load_4d(sk, &tm_k, bar_kv_full + st, 0, head, next_load * kTileN, b_kv);
-          tma_load_4d(sk + kKVAtomBytes, &tm_v, bar_kv_full + st, 0, head, next_load * kTileN, b_kv);
+#pragma unroll
+          for (int a = 0; a < Cfg::NATOM; ++a) {
+            tma_load_4d(sk + a * kKVAtomBytes, &tm_k, bar_kv_full + st, a * 64, head, next_load * kTileN, b_kv);
+            tma_load_4d(sv + a * kKVAtomBytes, &tm_v, bar_kv_full + st, a * 64, head, next_load * kTileN, b_kv);
+          }
           ++next_load;
         }
       };
@@ -946,13 +957,17 @@ fresco_attn_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         const uint32_t k_addr = smem_u32(s_kv + st * Cfg::STAGE_BYTES);
         const uint32_t d_tmem = tmem + ((t & 1) ? Cfg::S_OFF1 : Cfg::S_OFF0);
 #pragma unroll
-        for (int ks = 0; ks < Cfg::KSTEPS; ++ks)
-          umma_ss(d_tmem, make_smem_desc_sw128(q_addr + ks * 32, 16, 1024), make_smem_desc_sw128(k_addr + ks * 32, 16, 1024),
+        for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
+          const uint32_t qoff = (ks >> 2) * kQAtomBytes + (ks & 3) * 32;
+          const uint32_t koff = (ks >> 2) * kKVAtomBytes + (ks & 3) * 32;
+          umma_ss(d_tmem, make_smem_desc_sw128(q_addr + qoff, 16, 1024), make_smem_desc_sw128(k_addr + koff, 16, 1024),
                   idesc_qk, ks > 0);
+        }
         umma_commit(bar_s + (t & 1));
       };
       mbar_expect_tx(bar_q, Cfg::Q_BYTES);
-      tma_load_4d(s_q, &tm_q, bar_q, 0, head, q0, b);
+#pragma unroll
+      for (int a = 0; a < Cfg::NATOM; ++a) tma_load_4d(s_q + a * kQAtomBytes, &tm_q, bar_q, a * 64, head, q0, b);
       refill();
       mbar_wait(bar_q, 0, 31);
       issue_qk(0);
@@ -961,7 +976,7 @@ fresco_attn_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         const int st = t % ST;
         wait_poll(bar_p + (t & 1), (t >> 1) & 1, 32);                  // both halves of P_t in TMEM
         tc_fence_after();
-        const uint32_t v_addr = smem_u32(s_kv + st * Cfg::STAGE_BYTES + kKVAtomBytes);
+        const uint32_t v_addr = smem_u32(s_kv + st * Cfg::STAGE_BYTES + Cfg::NATOM * kKVAtomBytes);
         const uint32_t s_buf = tmem + ((t & 1) ? Cfg::S_OFF1 : Cfg::S_OFF0);
 #pragma unroll
         for (int k2 = 0; k2 < kTileN / 16; ++k2) {
@@ -969,7 +984,10 @@ fresco_attn_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
           const uint32_t p_tmem = s_buf + 32 * h + (k2 & 1) * 8;       // P_h: 16 columns at the start of its S half
           const uint32_t o_tmem = tmem + Cfg::O_OFF + h * Cfg::O_STRIDE;
           const uint32_t acc = (t > 0 || (k2 & 1)) ? 1u : 0u;
-          umma_ts(o_tmem, p_tmem, make_smem_desc_sw128(v_addr + k2 * 2048, kKVAtomBytes, 1024), idesc_pv, acc);
+          umma_ts(o_tmem, p_tmem, make_smem_desc_sw128(v_addr + k2 * 2048, kKVAtomBytes, 1024), idesc_pv0, acc);
+          if (Cfg::N1 > 0)
+            umma_ts(o_tmem + 64, p_tmem, make_smem_desc_sw128(v_addr + kKVAtomBytes + k2 * 2048, kKVAtomBytes, 1024),
+                    idesc_pv1, acc);
           if (Cfg::MMA_ROWSUM)      // l_h += P_h * ones (every element of the constant tile is 1.0, so its layout is moot)
             umma_ts(o_tmem + Cfg::L_COL, p_tmem, make_smem_desc_sw128(smem_u32(s_ones), 2048, 1024), idesc_ones, acc);
         }
@@ -1037,14 +1055,14 @@ fresco_attn_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
             m_run = m_tile;
           }
 #pragma unroll
-          for (int c = 0; c < D / 8 + (Cfg::MMA_ROWSUM ? 1 : 0); ++c) {
+          for (int c = 0; c < Cfg::DPAD / 8 + (Cfg::MMA_ROWSUM ? 1 : 0); ++c) {   // (L_COL == DPAD: the chunk after O)
             uint32_t o[8];
-            const uint32_t addr = o_mine + ((Cfg::MMA_ROWSUM && c == D / 8) ? Cfg::L_COL : c * 8);
-            tmem_ld8_sync(addr, o);
+            tmem_ld8_sync(o_mine + c * 8, o);
 #pragma unroll
             for (int j = 0; j < 8; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
-            tmem_st8(addr, o);
+            tmem_st8(o_mine + c * 8, o);
           }
+          tmem_st_wait();
         }
       }
       // ---- p = exp2(s*scale - m), packed to fp16 over the first 16 of the 32 columns just read
@@ -1054,9 +1072,14 @@ fresco_attn_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       uint32_t pk[16];
 #pragma unroll
       for (int j = 0; j < 32; j += 2) {
-        float t0, t1;
+        float t0, t1, e0, e1;
         unpack_f2(fma2(pack_f2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), scale2, negm2), t0, t1);
-        const float e0 = fast_exp2(t0), e1 = fast_exp2(t1);
+        if (POLY > 0 && ((j >> 1) % (POLY > 0 ? POLY : 1)) == (POLY - 1)) {
+          exp2_poly_x2(t0, t1, e0, e1);                    // FMA-pipe exponential for every POLY-th pair
+        } else {
+          e0 = fast_exp2(t0);
+          e1 = fast_exp2(t1);
+        }
         if (!Cfg::MMA_ROWSUM) sum2[(j >> 1) & 1] = add2(sum2[(j >> 1) & 1], pack_f2(e0, e1));
         pk[j >> 1] = pack_half2(e0, e1);
       }
@@ -1118,27 +1141,55 @@ fresco_attn_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
 // host side
 // ---------------------------------------------------------------------------------------------
 
-// {head_dim, heads, tokens, batch} view of a token-major [batch, tokens, heads*head_dim] fp16 tensor
+// {head_dim, heads, tokens, batch} view of a token-major [batch, tokens, heads*head_dim] fp16 tensor.
+// cuTensorMapEncodeTiled costs a few microseconds and the same (pointer, shape) comes back every denoise step (torch's
+// caching allocator), so encoded maps are kept in a small direct-mapped table.
+struct MapKey {
+  const void* base;
+  int head_dim, heads, tokens, batch, box_rows;
+  bool operator==(const MapKey& o) const {
+    return base == o.base && head_dim == o.head_dim && heads == o.heads && tokens == o.tokens && batch == o.batch &&
+           box_rows == o.box_rows;
+  }
+};
 static int make_head_tile_map(CUtensorMap* map, const void* base, int head_dim, int heads, int tokens, int batch,
                               int box_rows) {
+  constexpr int kSlots = 64;
+  static thread_local MapKey keys[kSlots];
+  static thread_local CUtensorMap maps[kSlots];
+  static thread_local bool valid[kSlots];
+  const MapKey key = {base, head_dim, heads, tokens, batch, box_rows};
+  const size_t h = (reinterpret_cast<uintptr_t>(base) >> 9) * 0x9E3779B97F4A7C15ull + (size_t)tokens * 31 + box_rows;
+  const int slot = (int)((h >> 32) % kSlots);
+  if (valid[slot] && keys[slot] == key) {
+    *map = maps[slot];
+    return 0;
+  }
   const cuuint64_t dims[4] = {(cuuint64_t)head_dim, (cuuint64_t)heads, (cuuint64_t)tokens, (cuuint64_t)batch};
   const cuuint64_t strides[3] = {(cuuint64_t)head_dim * 2, (cuuint64_t)heads * head_dim * 2,
                                  (cuuint64_t)tokens * heads * head_dim * 2};
   const cuuint32_t box[4] = {64, 1, (cuuint32_t)box_rows, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
-  return encode_tiled_map(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                          CU_TENSOR_MAP_SWIZZLE_128B);
+  const int rc = encode_tiled_map(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box,
+                                  estr, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc == 0) {
+    keys[slot] = key;
+    maps[slot] = *map;
+    valid[slot] = true;
+  }
+  return rc;
 }
 
-// Tuning knobs (read on every call so that tests can flip them): which head_dim <= 64 kernel, and how many of the
-// exponentials go to the FMA pipe.  The defaults are the measured best on B200 (attention).
+// Tuning knobs (fresco_internal.h: option(); environment variable of the same name read once, fresco_set_option()
+// overrides): which kernel, and how many of the exponentials go to the FMA pipe.  Defaults = measured best on B200.
+//   FRESCO_ATTN_WIDE    1 = wide kernel (two threads per row), 0 = pipelined kernel
+//   FRESCO_ATTN_NARROW  3 | 4 = narrow kernel with that many CTAs per SM (head_dim 40 only; 0 = off)
+//   FRESCO_ATTN_POLY    0 | 4 | 8: every n-th pair of exponentials on the FMA pipe
+//   FRESCO_ATTN_ROWSUM  pipelined kernel, head_dim 40: row sums from the tensor core
+constexpr int kWideDefault = 1;
 constexpr int kNarrowDefault = 0;
 constexpr int kPolyDefault = 0;
-constexpr int kRowsumDefault = 1;    // row sums from the tensor core (head_dim 40 only: needs 16 spare O columns)
-static int env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return v ? atoi(v) : dflt;
-}
+constexpr int kRowsumDefault = 1;
 
 template <int D, int POLY, bool ROWSUM>
 static int launch_pipelined(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
@@ -1173,18 +1224,18 @@ static int launch_narrow(const CUtensorMap& tq, const CUtensorMap& tk, const CUt
   return check_launch("fresco_attn_narrow_kernel");
 }
 
-template <int D>
+template <int D, int POLY>
 static int launch_wide(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, dim3 grid,
                        cudaStream_t stream) {
   using Cfg = WideCfg<D>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(fresco_attn_wide_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(fresco_attn_wide_kernel<D, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(attn wide)");
     attr_set = true;
   }
-  fresco_attn_wide_kernel<D><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tq, tk, tv, p);
+  fresco_attn_wide_kernel<D, POLY><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tq, tk, tv, p);
   return check_launch("fresco_attn_wide_kernel");
 }
 
@@ -1205,21 +1256,21 @@ static int launch_attn(const void* q, const void* k, const void* v, void* out, i
   p.q_per_kv = q_per_kv;
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
   p.diag_bias_log2 = diag_bias * 1.4426950408889634f;
-  static const int ablate = getenv("FRESCO_ATTN_ABLATE") ? atoi(getenv("FRESCO_ATTN_ABLATE")) : 0;
-  p.ablate = ablate;
+  p.ablate = option(OPT_ATTN_ABLATE, 0);
   dim3 grid((q_len + kTileM - 1) / kTileM, heads, batch_q);
-  if constexpr (D <= 64) {   // EXPERIMENTAL, see the kernel: off unless asked for
-    if (env_int("FRESCO_ATTN_WIDE", 0) == 1) return launch_wide<D>(tq, tk, tv, p, grid, stream);
-  }
+  const int poly = option(OPT_ATTN_POLY, kPolyDefault);
   if constexpr (D == 40) {   // (the narrow kernel is written for any head_dim <= 64 but has only been validated at 40)
-    // FRESCO_ATTN_NARROW = 0 (pipelined kernel), 3 or 4 (narrow kernel, that many CTAs per SM)
-    const int narrow = env_int("FRESCO_ATTN_NARROW", kNarrowDefault);
+    const int narrow = option(OPT_ATTN_NARROW, kNarrowDefault);
     if (narrow == 3) return launch_narrow<D, 3>(tq, tk, tv, p, grid, stream);
     if (narrow == 4) return launch_narrow<D, 4>(tq, tk, tv, p, grid, stream);
   }
-  const int poly = env_int("FRESCO_ATTN_POLY", kPolyDefault);
+  if (option(OPT_ATTN_WIDE, kWideDefault) == 1) {
+    if (poly == 4) return launch_wide<D, 4>(tq, tk, tv, p, grid, stream);
+    if (poly == 8) return launch_wide<D, 8>(tq, tk, tv, p, grid, stream);
+    return launch_wide<D, 0>(tq, tk, tv, p, grid, stream);
+  }
   if constexpr (AttnCfg<D, true>::MMA_ROWSUM) {
-    if (env_int("FRESCO_ATTN_ROWSUM", kRowsumDefault)) {
+    if (option(OPT_ATTN_ROWSUM, kRowsumDefault)) {
       if (poly == 4) return launch_pipelined<D, 4, true>(tq, tk, tv, p, grid, stream);
       if (poly == 8) return launch_pipelined<D, 8, true>(tq, tk, tv, p, grid, stream);
       return launch_pipelined<D, 0, true>(tq, tk, tv, p, grid, stream);

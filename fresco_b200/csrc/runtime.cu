@@ -1,6 +1,7 @@
 // Error state, launch accounting and the driver-API entry point for TMA tensor maps.
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "fresco_internal.h"
@@ -64,6 +65,22 @@ int encode_tiled_map(CUtensorMap* map, CUtensorMapDataType dtype, int rank, void
   return FRESCO_OK;
 }
 
+static const char* const kOptionNames[OPT_COUNT] = {"FRESCO_ATTN_WIDE", "FRESCO_ATTN_NARROW", "FRESCO_ATTN_POLY",
+                                                    "FRESCO_ATTN_ROWSUM", "FRESCO_ATTN_ABLATE", "FRESCO_TEMPORAL_V"};
+static std::atomic<int> g_opt_state[OPT_COUNT];      // 0 = not looked at, 1 = unset (use the default), 2 = set
+static std::atomic<int> g_opt_value[OPT_COUNT];
+
+int option(Option which, int dflt) {
+  int st = g_opt_state[which].load(std::memory_order_acquire);
+  if (st == 0) {
+    const char* v = getenv(kOptionNames[which]);
+    if (v) g_opt_value[which].store(atoi(v), std::memory_order_relaxed);
+    st = v ? 2 : 1;
+    g_opt_state[which].store(st, std::memory_order_release);
+  }
+  return st == 2 ? g_opt_value[which].load(std::memory_order_relaxed) : dflt;
+}
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -80,3 +97,18 @@ int sm_count() {
 extern "C" int fresco_abi_version(void) { return FRESCO_ABI_VERSION; }
 extern "C" const char* fresco_last_error(void) { return fresco::g_err; }
 extern "C" long long fresco_launch_count(void) { return fresco::g_launches.load(); }
+extern "C" int fresco_set_option(const char* name, int value) {
+  using namespace fresco;
+  if (!name) return set_error(FRESCO_ERR_ARG, "fresco_set_option: null name");
+  for (int i = 0; i < OPT_COUNT; ++i)
+    if (strcmp(name, kOptionNames[i]) == 0) {
+      if (value < 0) {                       // negative: back to the built-in default
+        g_opt_state[i].store(1, std::memory_order_release);
+      } else {
+        g_opt_value[i].store(value, std::memory_order_relaxed);
+        g_opt_state[i].store(2, std::memory_order_release);
+      }
+      return FRESCO_OK;
+    }
+  return set_error(FRESCO_ERR_ARG, "fresco_set_option: unknown option");
+}

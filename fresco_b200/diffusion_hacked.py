@@ -23,7 +23,7 @@ import torch.nn.functional as F
 
 from . import ops
 from ._lib import FrescoError
-from .flow_utils import adjoint_csr, resize_flows_occs, warp_tensor
+from .flow_utils import adjoint_csr, clear_prep_cache, resize_flows_occs, warp_tensor
 
 
 # =============================================================================
@@ -334,6 +334,15 @@ class OptimizeTrace:
         self.losses: List[float] = []
 
 
+def spatial_loss_grad(cs_bcl, target, intra_weight, grad_bcl, loss_acc=None):
+    """One evaluation of the spatial-consistency term (src/diffusion_hacked.py:469-476) and its gradient:
+    ``grad_bcl += d/dcs [ intra_weight * l1_loss(Xh Xh^T, target) ]`` for cs [2N, C, L] fp32 (channel-major, as the
+    UNet holds it); ``loss_acc`` (device float or None) gets the loss value added."""
+    xhat, norms = ops.gram_normalize(cs_bcl)
+    tsign = ops.gram_sign(xhat, target, intra_weight, loss_acc)
+    ops.gram_grad(tsign, xhat, norms, grad_bcl, intra_weight)
+
+
 @torch.no_grad()
 def optimize_feature(sample, flows, occs, correlation_matrix=[], intra_weight=1e2, iters=20, unet_chunk_size=2,
                      optimize_temporal=True, trace: Optional[OptimizeTrace] = None):
@@ -373,10 +382,8 @@ def optimize_feature(sample, flows, occs, correlation_matrix=[], intra_weight=1e
         else:
             grad.zero_()
         if spatial:
-            cs_bcl = cs.view(unet_chunk_size * n, C, h * w)
-            xhat, norms = ops.gram_normalize(cs_bcl)
-            tsign = ops.gram_sign(xhat, target, intra_weight, loss_acc)
-            ops.gram_grad(tsign, xhat, norms, grad.view(unet_chunk_size * n, C, h * w), intra_weight)
+            spatial_loss_grad(cs.view(unet_chunk_size * n, C, h * w), target, intra_weight,
+                              grad.view(unet_chunk_size * n, C, h * w), loss_acc)
         ops.adam_step(cs, grad, exp_avg, exp_avg_sq, it, lr=0.2)
         if trace is not None:
             trace.losses.append(float(loss_acc.item()))
@@ -446,7 +453,9 @@ def my_forward(self, steps=[], layers=[0, 1, 2, 3], flows=None, occs=None, corre
 
 def apply_FRESCO_opt(pipe, steps=[], layers=[0, 1, 2, 3], flows=None, occs=None, correlation_matrix=[],
                      intra_weight=1e2, iters=20, optimize_temporal=True, saliency=None):
-    """src/diffusion_hacked.py:819-825."""
+    """src/diffusion_hacked.py:819-825.  Called once per keyframe batch (run_fresco.py:232-234): per-batch
+    preparation cached for the previous batch's flows is dropped here."""
+    clear_prep_cache()
     pipe.unet.forward = my_forward(pipe.unet, steps, layers, flows, occs, correlation_matrix, intra_weight, iters,
                                    optimize_temporal, saliency)
 

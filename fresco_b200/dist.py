@@ -109,14 +109,19 @@ class ShardedFRESCOAttention:
         self._plans = {}
 
     def _plan(self, tokens: int) -> Optional[ShardedKVExchange]:
-        if tokens not in self._plans:
-            chosen = None
-            if self.ctrl.attn_mask is not None:
-                for m in self.ctrl.attn_mask:
-                    if m.shape[1] == tokens:
-                        chosen = m
-            self._plans[tokens] = None if chosen is None else ShardedKVExchange(chosen, self.world, self.rank, self.group)
-        return self._plans[tokens]
+        """Exchange plan for the mask with ``shape[1] == tokens``; rebuilt whenever the controller holds a different
+        mask tensor (enable_cfattn(new_mask) for the next keyframe batch), validated by identity."""
+        chosen = None
+        if self.ctrl.attn_mask is not None:
+            for m in self.ctrl.attn_mask:
+                if m.shape[1] == tokens:
+                    chosen = m
+        hit = self._plans.get(tokens)
+        if hit is None or hit[0] is not chosen:
+            plan = None if chosen is None else ShardedKVExchange(chosen, self.world, self.rank, self.group)
+            hit = (chosen, plan)
+            self._plans[tokens] = hit
+        return hit[1]
 
     def __call__(self, q, k, v, heads: int, ref_q=None, ref_k=None):
         """q, k, v: [chunks * N_local, L, C] projections of the local frames; ref_q / ref_k: projections of the
@@ -137,7 +142,8 @@ class ShardedFRESCOAttention:
                 v0 = v.view(chunks, n_local, L, C)[:, 0].contiguous()
                 if self.world > 1:
                     kv = torch.stack([k0, v0])
-                    dist.broadcast(kv, src=0, group=self.group)
+                    src = dist.get_global_rank(self.group, 0) if self.group is not None else 0
+                    dist.broadcast(kv, src=src, group=self.group)
                     k0, v0 = kv[0], kv[1]
                 k_att, v_att = k0, v0
             else:

@@ -43,32 +43,41 @@ def _dilate(x: torch.Tensor, k: int) -> torch.Tensor:
     return torch.clamp(F.conv2d(x, torch.ones(1, 1, k, k, dtype=x.dtype, device=x.device)), 0, 1)
 
 
-_PREP_CACHE: dict = {}
-_PREP_CACHE_MAX = 32
+_PREP_CACHE: "dict" = {}
+_PREP_CACHE_MAX = 16
 
 
 def _tensor_key(t: torch.Tensor):
-    return (t.data_ptr(), t._version, tuple(t.shape), t.dtype)
+    return (id(t), t._version)
 
 
-def _cache_get(key, make):
-    """Per-batch preparation (resized flows, pooled masks, blend weights) depends only on the flow /
-    occlusion / saliency tensors, which are constant over the denoise steps of a batch: the reference
-    recomputes it at every call (flow_utils.py:24-39); we key it on tensor identity + version."""
+def clear_prep_cache() -> None:
+    """Drop every cached per-batch preparation (called when a new keyframe batch is installed)."""
+    _PREP_CACHE.clear()
+
+
+def _cache_get(tag, tensors, make):
+    """Per-batch preparation (resized flows, pooled masks, blend weights, warp adjoints) depends only on the flow /
+    occlusion / saliency tensors, which are constant over the denoise steps of a batch: the reference recomputes it at
+    every call (flow_utils.py:24-39).  An entry is keyed on the IDENTITY (and in-place version counter) of those
+    tensors and keeps a reference to them, so a hit is validated with ``is`` -- an address the allocator hands out
+    again for the next batch's flows can never alias a live entry."""
+    key = (tag,) + tuple(_tensor_key(t) for t in tensors)
     hit = _PREP_CACHE.get(key)
-    if hit is None:
-        if len(_PREP_CACHE) >= _PREP_CACHE_MAX:
-            _PREP_CACHE.clear()
-        hit = make()
-        _PREP_CACHE[key] = hit
-    return hit
+    if hit is not None and len(hit[0]) == len(tensors) and all(a is b for a, b in zip(hit[0], tensors)):
+        return hit[1]
+    if len(_PREP_CACHE) >= _PREP_CACHE_MAX:
+        _PREP_CACHE.pop(next(iter(_PREP_CACHE)))            # oldest entry (insertion order)
+    value = make()
+    _PREP_CACHE[key] = (tuple(tensors), value)
+    return value
 
 
 def resize_flows_occs(flows: Sequence[torch.Tensor], occs: Sequence[torch.Tensor], size_h: int):
     """Flows / occlusions at the resolution of a feature map.
     src/flow_utils.py:24-33 == src/diffusion_hacked.py:437-442."""
-    key = ("resize", size_h) + tuple(_tensor_key(t) for t in (flows[0], flows[1], occs[0], occs[1]))
-    return _cache_get(key, lambda: _resize_flows_occs(flows, occs, size_h))
+    return _cache_get(("resize", size_h), (flows[0], flows[1], occs[0], occs[1]),
+                      lambda: _resize_flows_occs(flows, occs, size_h))
 
 
 def _resize_flows_occs(flows, occs, size_h):
@@ -86,8 +95,7 @@ def adjoint_csr(flows, occs, size_h: int):
     def make():
         _, fwd_flow, bwd_flow, _, _ = resize_flows_occs(flows, occs, size_h)
         return ops.warp_adjoint_pair(bwd_flow, fwd_flow)
-    key = ("adjoint", size_h) + tuple(_tensor_key(t) for t in (flows[0], flows[1]))
-    return _cache_get(key, make)
+    return _cache_get(("adjoint", size_h), (flows[0], flows[1], occs[0], occs[1]), make)
 
 
 # --------------------------------------------------------------------------- warp_tensor
@@ -114,10 +122,13 @@ def warp_tensor(sample, flows, occs, saliency, unet_chunk_size):
         blend[n - 1:] = (1 - fwd_occ[n - 1:n]) * sal[n - 1:n] * warp_sal_last      # :50
         return bwd_flow, fwd_flow[n - 1].contiguous(), blend.contiguous()
 
-    key = ("warp_tensor", n, h, w) + tuple(_tensor_key(t) for t in (flows[0], flows[1], occs[0], occs[1], saliency))
-    bwd_flow, fwd_flow_last, blend = _cache_get(key, prepare)
+    bwd_flow, fwd_flow_last, blend = _cache_get(("warp_tensor", n, h, w),
+                                                 (flows[0], flows[1], occs[0], occs[1], saliency), prepare)
     x = sample.contiguous()
-    if x.dtype not in (torch.float16, torch.float32):
+    # the shared-memory chain kernel takes fp16 or fp32 planes up to 100 KB; image-resolution planes (background
+    # smoothing, src/pipe_FRESCO.py:46, fp16 VAE output) run the per-step kernel, which works on fp32 like the
+    # reference's own `.to(torch.float32)` copy (flow_utils.py:36)
+    if x.dtype not in (torch.float16, torch.float32) or 2 * h * w * 4 > 200 * 1024:
         x = x.float()
     out = ops.warp_fuse_chain(x, bwd_flow, fwd_flow_last, blend, unet_chunk_size)
     return out.to(sample.dtype)

@@ -35,6 +35,10 @@ int fresco_abi_version(void);
 const char* fresco_last_error(void);
 /* number of kernels launched by this library in this process (for bench.py's gpu_launches) */
 long long fresco_launch_count(void);
+/* tuning option by the name of its environment variable (FRESCO_ATTN_WIDE, FRESCO_ATTN_NARROW, FRESCO_ATTN_POLY,
+ * FRESCO_ATTN_ROWSUM, FRESCO_ATTN_ABLATE, FRESCO_TEMPORAL_V); the environment is read once, this overrides it;
+ * value < 0 restores the built-in default. */
+int fresco_set_option(const char* name, int value);
 
 /* ---- A2: cross-frame K/V selection --------------------------------------------------------
  * replaces src/diffusion_hacked.py:234-247 (`key[:, attn_mask]` + `repeat(...)`).

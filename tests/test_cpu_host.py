@@ -294,3 +294,47 @@ def test_warp_tensor_and_mapping_host_logic_against_reference_outputs(golden, mo
         fm, bm, mask = fu.get_mapping_ind(flows[1], occs[1], T(g["imgs"]), scale=8.0)
         assert torch.equal(fm, T(g["fwd_map"])) and torch.equal(bm, T(g["bwd_map"])) and torch.equal(mask, T(g["inter_mask"]))
     fu._PREP_CACHE.clear()
+
+
+def test_prep_cache_never_serves_another_batch(monkeypatch):
+    """per-batch preparation was keyed on (data_ptr, version, shape); the allocator hands the same
+    address to the next batch's flows, so batch k could silently get batch j's resized flows.  Entries are now keyed on
+    tensor identity and hold a reference: two same-shape batches, the first one freed before the second is made."""
+    from fresco_b200 import flow_utils as fu
+    from oracle import fresco_oracle as O
+    monkeypatch.setattr(fu, "ops", _TorchWarpOps)
+    fu.clear_prep_cache()
+    outs, wants = [], []
+    for seed in (1, 2, 3, 4, 5, 6):
+        flows, occs = O.synth_flows(3, 64, 64, seed=seed, mag=6.0)
+        sal = torch.rand(3, 1, 32, 32, generator=torch.Generator().manual_seed(seed))
+        feat = torch.randn(6, 4, 8, 8, generator=torch.Generator().manual_seed(100 + seed))
+        outs.append(fu.warp_tensor(feat, flows, occs, sal, 2))
+        outs.append(fu.warp_tensor(feat, flows, occs, sal, 2))          # second call of the batch: served from the cache
+        fu_fresh = O.warp_tensor(feat.clone(), flows, occs, sal, 2)
+        wants += [fu_fresh, fu_fresh]
+        del flows, occs, sal                                             # the next batch may reuse these addresses
+    for o, w in zip(outs, wants):
+        assert (o - w).abs().max().item() < 1e-5
+    assert len(fu._PREP_CACHE) <= fu._PREP_CACHE_MAX
+    fu.clear_prep_cache()
+
+
+def test_sharded_plan_follows_the_mask_tensor():
+    """the sharded K/V exchange plan was cached per token count forever; it must be rebuilt when
+    enable_cfattn installs the next batch's mask."""
+    from fresco_b200 import diffusion_hacked as dh
+    from fresco_b200.dist import ShardedFRESCOAttention
+    ctrl = dh.AttentionControl()
+    sh = ShardedFRESCOAttention(ctrl, world=1, rank=0, backend=object())
+    m1 = torch.zeros(4, 64, dtype=torch.bool)
+    m1[0] = True
+    m1[1, :5] = True
+    ctrl.enable_cfattn([m1])
+    p1 = sh._plan(64)
+    assert p1.total == 64 + 5 and sh._plan(64) is p1
+    m2 = m1.clone()
+    m2[2, :7] = True
+    ctrl.enable_cfattn([m2])
+    p2 = sh._plan(64)
+    assert p2 is not p1 and p2.total == 64 + 5 + 7

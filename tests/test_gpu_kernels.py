@@ -24,7 +24,8 @@ def T(a, device="cuda"):
 
 @pytest.fixture(scope="module")
 def fb():
-    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    if not torch.cuda.is_available():
+        pytest.skip("GPU tests need a CUDA device")
     import fresco_b200
     from fresco_b200 import _lib, diffusion_hacked, flow_utils, ops
     _lib.lib()      # fails loudly if the extension is missing
@@ -73,35 +74,6 @@ def test_attn_fwd_vs_fp32(fb, d, heads, B, Lq, Lk, qpk, gain):
     ref = sdpa_ref(q, k, v, heads, qpk)
     err = (out.float() - ref).abs().max().item()
     assert err < 2e-3 * max(1.0, ref.abs().max().item()), err
-
-
-@pytest.mark.parametrize("knobs", [
-    dict(FRESCO_ATTN_NARROW="0", FRESCO_ATTN_POLY="0", FRESCO_ATTN_ROWSUM="0"),   # pipelined kernel, plain
-    dict(FRESCO_ATTN_NARROW="0", FRESCO_ATTN_POLY="0", FRESCO_ATTN_ROWSUM="1"),   # row sums from the tensor core
-    dict(FRESCO_ATTN_NARROW="0", FRESCO_ATTN_POLY="4", FRESCO_ATTN_ROWSUM="1"),   # + FMA-pipe exp2 for every 4th pair
-    dict(FRESCO_ATTN_NARROW="0", FRESCO_ATTN_POLY="8", FRESCO_ATTN_ROWSUM="0"),
-    dict(FRESCO_ATTN_NARROW="3"),                                                  # narrow kernel, 3 CTAs / SM
-    dict(FRESCO_ATTN_NARROW="4"),                                                  # narrow kernel, 4 CTAs / SM
-])
-def test_attn_fwd_tuning_variants(fb, monkeypatch, knobs):
-    """Every compiled variant of the head_dim 40 attention kernel (selected by the FRESCO_ATTN_* knobs, read on
-    every call) meets the same fp32 bound, incl. ragged q / kv tails, shared K/V, the diagonal bias and a peaky
-    softmax that exercises the lazy rescale (same cases as tools/check_attn_knobs.py)."""
-    d = 40
-    for k_, v_ in knobs.items():
-        monkeypatch.setenv(k_, v_)
-    g = torch.Generator(device="cuda").manual_seed(17 + d)
-    B, Lq, Lk, heads, qpk = 4, 300, 1000, 2, 2
-    q = (torch.randn(B, Lq, heads * d, device="cuda", generator=g) * 4.0).half()
-    k = torch.randn(B // qpk, Lk, heads * d, device="cuda", generator=g).half()
-    v = torch.randn(B // qpk, Lk, heads * d, device="cuda", generator=g).half()
-    out = fb.ops.attn_fwd(q, k, v, heads, qpk)
-    ref = sdpa_ref(q, k, v, heads, qpk)
-    assert (out.float() - ref).abs().max().item() < 2e-3 * max(1.0, ref.abs().max().item())
-    qs, ks, vs = q[:2, :256].contiguous(), k[:1, :256].repeat(2, 1, 1), v[:1, :256].repeat(2, 1, 1)
-    out = fb.ops.attn_fwd(qs, ks, vs, heads, 1, softmax_scale=0.2 / math.sqrt(d), diag_bias=1.5)
-    ref = sdpa_ref(qs, ks, vs, heads, 1, 0.2 / math.sqrt(d), 1.5)
-    assert (out.float() - ref).abs().max().item() < 2e-3 * ref.abs().max().item()
 
 
 def test_attn_fwd_scale_and_diag_bias(fb):
