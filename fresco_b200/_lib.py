@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_int64, c_longlong, c_size_t, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_longlong, c_size_t, c_void_p
 
 import torch
 
@@ -23,6 +23,12 @@ _SIGNATURES = {
     "fresco_set_option": (c_int, [c_char_p, c_int]),
     "fresco_kv_compact": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "fresco_attn_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, _P]),
+    "fresco_attn_fwd_kv_strided": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_longlong, c_longlong,
+                                           c_float, c_float, _P]),
+    "fresco_kv_compact_packed": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
+    "fresco_rows_gather": (c_int, [_P, _P, _P, c_longlong, c_int, c_int, c_int, _P]),
+    "fresco_rows_scatter": (c_int, [_P, _P, _P, c_longlong, c_int, _P]),
+    "fresco_temporal_attn_fwd_strided": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, _P]),
     "fresco_temporal_attn_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float, _P]),
     "fresco_flow_warp": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "fresco_warp_fuse_chain": (c_int, [_P, _P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
@@ -32,7 +38,7 @@ _SIGNATURES = {
     "fresco_gram_sign": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_float, _P]),
     "fresco_gram_grad": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_float, _P, c_size_t, _P]),
     "fresco_gram_grad_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
-    "fresco_adam_step": (c_int, [_P, _P, _P, _P, c_longlong, c_int, c_float, c_float, c_float, c_float, _P]),
+    "fresco_adam_step": (c_int, [_P, _P, _P, _P, c_longlong, c_int, c_double, c_double, c_double, c_double, _P]),
     "fresco_adain": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P]),
     "gmflow_global_corr_softmax": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
     "fresco_gmflow_corr_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),

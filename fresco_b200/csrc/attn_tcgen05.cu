@@ -819,68 +819,92 @@ fresco_attn_narrow_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
 }
 
 // ---------------------------------------------------------------------------------------------
-// the "wide" kernel: two threads per query row (split-KV inside the CTA), every head_dim
+// the "wide" kernel: SPLIT threads per query row (split-KV inside the CTA), every head_dim
 // ---------------------------------------------------------------------------------------------
-// Written from the round-1 measurements (attention): a softmax warp runs a serial chain per tile (wait S,
-// TMEM load, row max, 64 ex2, pack, TMEM store, arrive) of about 1600 SM clocks, so the kernel's speed is set by how
-// many softmax warps share an SM sub-partition: the bare arithmetic of a tile costs 854 clocks with one warp per
-// sub-partition, 671 with two and 562 with four.  The pipelined kernel above cannot have more than two (one at
-// head_dim 80/128) because a thread that holds a whole 64-score row needs 168 registers.  Here every query row is shared
-// by TWO threads (warps w and w + 4, which may touch the same TMEM lanes), each owning 32 of a tile's 64 keys -- and
-// nothing else is shared: each half keeps its own running max, its own row sum and its own O accumulator, exactly as
-// if the keys had been split over two kernels (split-KV), and the two partial results are merged once, in the epilogue:
-//     O = (2^(m0-m) O_0 + 2^(m1-m) O_1) / (2^(m0-m) l_0 + 2^(m1-m) l_1),   m = max(m0, m1).
-// So the halves never talk to each other per tile and a thread holds 32 scores (<= 112 registers): head_dim <= 48 runs
-// two CTAs of eight softmax warps per SM (four softmax warps per sub-partition), head_dim 64..128 one CTA (two per
-// sub-partition), and S stays double-buffered in both.
+// Written from two measurements (attention).  (1) A softmax warp runs a serial chain per tile (wait S, TMEM
+// load, row max, ex2, pack, TMEM store, arrive) of about 1600 SM clocks for 64 scores per thread, of which the ex2 pipe
+// is busy 512: the kernel's speed is set by how many softmax warps share an SM sub-partition (854 clocks of bare
+// arithmetic per tile with one, 671 with two, 562 with four), and the pipelined kernel above cannot have more than two
+// (one at head_dim 80/128) because a thread that holds a whole 64-score row needs 168 registers.  (2) Issuing a
+// tcgen05.mma costs the issuing thread 60-70 clocks whatever its shape, so a single issuer thread caps a CTA at about
+// one tile per 65 * (MMAs per tile) clocks: the first version of this kernel (one thread issuing everything) was
+// slower than the pipelined kernel for that reason alone.
 //
-//   TMEM  S0 [0,64), S1 [64,128) fp32; O_0, O_1 from column 128, O_STRIDE apart (head_dim columns, then -- except at
-//         head_dim 64 -- 16 columns of tensor-core row sums).  P_h (fp16, 16 columns) overwrites the first half of the
-//         32 S columns its thread has just read.  256 columns at head_dim <= 64, 512 above.
-//   warps 0-7 softmax (lane quarter w & 3, key half w >> 2); warp 8, one thread: TMA producer + every MMA, in the order
-//         ... P V(t), Q K(t+2)^T ... : tcgen05.mma executes in issue order, so S_{t+2} may be issued right behind
-//         P_t V_t although it overwrites the columns P_t is read from.
-template <int D>
+// Here every query row is shared by SPLIT threads (warps w, w + 4, ...; the same TMEM lane quarter), each owning
+// 64 / SPLIT of a tile's keys -- and nothing else is shared: each part keeps its own running max, its own row sum
+// and its own O accumulator, exactly as if the keys had been split over SPLIT kernels (split-KV), and the partial
+// results are merged once, in the epilogue:   O = sum_p 2^(m_p - m) O_p / sum_p 2^(m_p - m) l_p,   m = max_p m_p.
+// head_dim <= 48 runs two CTAs of eight softmax warps per SM (four per sub-partition), larger head dims one CTA of
+// eight (SPLIT 2) or sixteen (SPLIT 4) softmax warps.  The TMA producer, the score-MMA issuer and one or two P V issuers
+// are single threads in warps of their own.
+//
+//   TMEM  S0 [0,64), S1 [64,128) fp32 (double-buffered scores); P (fp16, 32 columns per buffer; two buffers when the
+//         CTA has TMEM to itself) at 128; O_0 .. O_{SPLIT-1}, DPAD columns each, behind it.  Row sums are accumulated by
+//         the softmax threads (fp32), so a tile costs ceil(d/16) + 4 * ceil(d/64) MMA instructions and nothing else.
+template <int D, int SPLIT_>
 struct WideCfg {
+  static constexpr int SPLIT = SPLIT_;
+  static constexpr int KEYS = kTileN / SPLIT;         // keys per softmax thread and tile
   static constexpr int NATOM = (D + 63) / 64;
   static constexpr int KSTEPS = (D + 15) / 16;
   static constexpr int DPAD = KSTEPS * 16;
   static constexpr int N0 = DPAD < 64 ? DPAD : 64;    // P V columns from V atom 0
   static constexpr int N1 = DPAD - N0;                // ... from V atom 1
-  static constexpr bool MMA_ROWSUM = DPAD != 64;      // (head_dim 64 would need 16 more columns than 256 has)
-  static constexpr int L_COL = DPAD;                  // row-sum columns, relative to the start of O_h
-  static constexpr int O_STRIDE = MMA_ROWSUM ? (DPAD + 16 <= 64 ? 64 : DPAD + 16) : 64;
-  static constexpr int S_OFF0 = 0, S_OFF1 = 64, O_OFF = 128;
-  static constexpr int TMEM_COLS = (O_OFF + 2 * O_STRIDE <= 256) ? 256 : 512;
-  static constexpr int CTAS = TMEM_COLS == 256 ? 2 : 1;
-  static constexpr int ONES_BYTES = MMA_ROWSUM ? 2048 : 0;
+  static constexpr int S_OFF0 = 0, S_OFF1 = 64, P_OFF = 128;
+  static constexpr bool SMALL = 128 + 32 + SPLIT * DPAD <= 256;      // fits half of TMEM: two CTAs per SM
+  static constexpr int PBUF = SMALL ? 1 : 2;          // P buffers
+  static constexpr int O_OFF = P_OFF + 32 * PBUF;
+  static constexpr int TMEM_COLS = SMALL ? 256 : 512;
+  static_assert(O_OFF + SPLIT * DPAD <= TMEM_COLS, "TMEM budget");
+  static constexpr int CTAS = SMALL ? 2 : 1;
+  static constexpr int NPV = (NATOM > 1) ? 2 : 1;     // P V issuer threads (each owns SPLIT / NPV accumulators)
   static constexpr int STAGES = NATOM == 1 ? 5 : 4;
   static constexpr int Q_BYTES = NATOM * kQAtomBytes;
   static constexpr int STAGE_BYTES = 2 * NATOM * kKVAtomBytes;
-  static constexpr int SMEM_BYTES = 1024 + Q_BYTES + STAGES * STAGE_BYTES + ONES_BYTES + 2 * 128 * 8 + 256;
-  static constexpr int THREADS = 288;
+  static constexpr int SMEM_BYTES = 1024 + Q_BYTES + STAGES * STAGE_BYTES + SPLIT * 128 * 8 + 512;
+  static constexpr int SOFTMAX_WARPS = 4 * SPLIT;
+  static constexpr int TMA_WARP = SOFTMAX_WARPS, QK_WARP = SOFTMAX_WARPS + 1, PV_WARP0 = SOFTMAX_WARPS + 2;
+  static constexpr int THREADS = (SOFTMAX_WARPS + 2 + NPV) * 32;
 };
 
-template <int D, int POLY>
-__global__ void __launch_bounds__(WideCfg<D>::THREADS, WideCfg<D>::CTAS)
+template <int N>
+__device__ __forceinline__ void tmem_ld_keys(uint32_t taddr, uint32_t (&r)[N]) {
+  if constexpr (N == 32) {
+    tmem_ld32(taddr, r);
+    tmem_ld_wait_dep32(r);
+  } else {
+    static_assert(N == 16, "16 or 32 keys per thread");
+    tmem_ld16_sync(taddr, r);
+  }
+}
+template <int N>
+__device__ __forceinline__ void tmem_st_half(uint32_t taddr, const uint32_t (&r)[N]) {
+  if constexpr (N == 16) tmem_st16(taddr, r);
+  else tmem_st8(taddr, r);
+}
+
+template <int D, int SPLIT, int POLY>
+__global__ void __launch_bounds__(WideCfg<D, SPLIT>::THREADS, WideCfg<D, SPLIT>::CTAS)
 fresco_attn_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                         const __grid_constant__ CUtensorMap tm_v, const AttnParams p) {
-  using Cfg = WideCfg<D>;
+  using Cfg = WideCfg<D, SPLIT>;
   constexpr int ST = Cfg::STAGES;
+  constexpr int KEYS = Cfg::KEYS;
+  constexpr int PB = Cfg::PBUF;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* s_q = smem;
   uint8_t* s_kv = smem + Cfg::Q_BYTES;
-  uint8_t* s_ones = s_kv + ST * Cfg::STAGE_BYTES;                     // [16 kv rows x 128 B] of fp16 1.0
-  float2* s_ml = reinterpret_cast<float2*>(s_ones + Cfg::ONES_BYTES);  // [2 halves][128 rows] {running max, row sum}
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ml + 2 * 128);
+  float2* s_ml = reinterpret_cast<float2*>(s_kv + ST * Cfg::STAGE_BYTES);   // [SPLIT][128] {running max, row sum}
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ml + SPLIT * 128);
   uint64_t* bar_q = bars + 0;
   uint64_t* bar_kv_full = bars + 1;            // [ST]
-  uint64_t* bar_kv_empty = bars + 1 + ST;      // [ST]
-  uint64_t* bar_s = bars + 1 + 2 * ST;         // [2] S_t ready in buffer t & 1; phase (t >> 1) & 1
-  uint64_t* bar_p = bar_s + 2;                 // [2] both halves of P_t written (one elected arrival per softmax warp)
-  uint64_t* bar_o = bar_s + 4;                 // [2] P_t V_t retired (O_0, O_1 stable up to tile t)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s + 6);
+  uint64_t* bar_kv_empty = bars + 1 + ST;      // [ST]  1 (score issuer) + NPV arrivals
+  uint64_t* bar_s = bars + 1 + 2 * ST;         // [2]   S_t ready in buffer t & 1; phase (t >> 1) & 1
+  uint64_t* bar_c = bar_s + 2;                 // [2]   S_t copied to registers by every softmax warp (buffer free)
+  uint64_t* bar_p = bar_s + 4;                 // [PB][NPV] the P columns of issuer j's parts written for tile t
+  uint64_t* bar_o = bar_s + 8;                 // [PB][NPV] P V of those parts retired (P buffer free, O stable)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s + 12);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -889,20 +913,26 @@ fresco_attn_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   const int b = blockIdx.z;
   const int b_kv = b / p.q_per_kv;
   const int n_tiles = (p.kv_len + kTileN - 1) / kTileN;
+  constexpr int PARTS_PER_PV = SPLIT / Cfg::NPV;       // accumulators (= key parts) per P V issuer
 
-  if (warp == 8) {
+  if (warp == Cfg::QK_WARP && lane == 0) {
+    mbar_init(bar_q, 1);
+    for (int s = 0; s < ST; ++s) {
+      mbar_init(bar_kv_full + s, 1);
+      mbar_init(bar_kv_empty + s, 1 + Cfg::NPV);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_s + i, 1);
+      mbar_init(bar_c + i, Cfg::SOFTMAX_WARPS);
+    }
+    for (int i = 0; i < PB * Cfg::NPV; ++i) {
+      mbar_init(bar_p + i, 4 * PARTS_PER_PV);            // one elected arrival per softmax warp of those parts
+      mbar_init(bar_o + i, 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == Cfg::TMA_WARP) {
     if (lane == 0) {
-      mbar_init(bar_q, 1);
-      for (int s = 0; s < ST; ++s) {
-        mbar_init(bar_kv_full + s, 1);
-        mbar_init(bar_kv_empty + s, 1);
-      }
-      for (int i = 0; i < 2; ++i) {
-        mbar_init(bar_s + i, 1);
-        mbar_init(bar_p + i, 8);
-        mbar_init(bar_o + i, 1);
-      }
-      fence_barrier_init();
       tma_prefetch_desc(&tm_q);
       tma_prefetch_desc(&tm_k);
       tma_prefetch_desc(&tm_v);
@@ -910,49 +940,40 @@ fresco_attn_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     __syncwarp();
     tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
   }
-  if (Cfg::MMA_ROWSUM) {
-    for (int i = threadIdx.x; i < Cfg::ONES_BYTES / 4; i += Cfg::THREADS) reinterpret_cast<uint32_t*>(s_ones)[i] = 0x3C003C00u;
-    fence_proxy_async_smem();
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 8) {
-    // ------------------------------------------------------------ TMA producer + MMA issuer (one thread)
+  if (warp == Cfg::TMA_WARP) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(bar_q, Cfg::Q_BYTES);
+#pragma unroll
+      for (int a = 0; a < Cfg::NATOM; ++a) tma_load_4d(s_q + a * kQAtomBytes, &tm_q, bar_q, a * 64, head, q0, b);
+      for (int t = 0; t < n_tiles; ++t) {
+        const int st = t % ST;
+        if (t >= ST) mbar_wait_backoff(bar_kv_empty + st, ((t / ST) - 1) & 1, 32, 40);
+        uint8_t* sk = s_kv + st * Cfg::STAGE_BYTES;
+        uint8_t* sv = sk + Cfg::NATOM * kKVAtomBytes;
+        mbar_expect_tx(bar_kv_full + st, Cfg::STAGE_BYTES);
+#pragma unroll
+        for (int a = 0; a < Cfg::NATOM; ++a) {
+          tma_load_4d(sk + a * kKVAtomBytes, &tm_k, bar_kv_full + st, a * 64, head, t * kTileN, b_kv);
+          tma_load_4d(sv + a * kKVAtomBytes, &tm_v, bar_kv_full + st, a * 64, head, t * kTileN, b_kv);
+        }
+      }
+    }
+  } else if (warp == Cfg::QK_WARP) {
+    // ------------------------------------------------------------ score-MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc_qk = make_idesc_f16(kTileM, kTileN, 0);
-      constexpr uint32_t idesc_pv0 = make_idesc_f16(kTileM, Cfg::N0, 1);
-      constexpr uint32_t idesc_pv1 = make_idesc_f16(kTileM, Cfg::N1 > 0 ? Cfg::N1 : 16, 1);
-      constexpr uint32_t idesc_ones = make_idesc_f16(kTileM, 16, 1);
       const uint32_t q_addr = smem_u32(s_q);
-      int next_load = 0;
-      auto refill = [&]() {                     // issue every K/V tile load whose ring stage is free; never blocks
-        while (next_load < n_tiles) {
-          const int st = next_load % ST;
-          if (next_load >= ST && !mbar_test_wait(bar_kv_empty + st, ((next_load / ST) - 1) & 1)) break;
-          uint8_t* sk = s_kv + st * Cfg::STAGE_BYTES;
-          uint8_t* sv = sk + Cfg::NATOM * kKVAtomBytes;
-          mbar_expect_tx(bar_kv_full + st, Cfg::STAGE_BYTES);
-#pragma unroll
-          for (int a = 0; a < Cfg::NATOM; ++a) {
-            tma_load_4d(sk + a * kKVAtomBytes, &tm_k, bar_kv_full + st, a * 64, head, next_load * kTileN, b_kv);
-            tma_load_4d(sv + a * kKVAtomBytes, &tm_v, bar_kv_full + st, a * 64, head, next_load * kTileN, b_kv);
-          }
-          ++next_load;
-        }
-      };
-      auto wait_poll = [&](uint64_t* bar, uint32_t parity, int tag) {   // wait, keeping the K/V ring moving
-        uint32_t polls = 0;
-        while (!mbar_try_wait(bar, parity)) {
-          refill();
-          if (++polls > FRESCO_WATCHDOG_POLLS) mbar_timeout(bar, parity, tag);
-        }
-      };
-      auto issue_qk = [&](int t) {
+      mbar_wait(bar_q, 0, 41);
+      for (int t = 0; t < n_tiles; ++t) {
         const int st = t % ST;
-        wait_poll(bar_kv_full + st, (t / ST) & 1, 30);
+        if (t >= 2) mbar_wait(bar_c + (t & 1), ((t - 2) >> 1) & 1, 42);     // S buffer t & 1 is in registers
+        mbar_wait(bar_kv_full + st, (t / ST) & 1, 43);
         tc_fence_after();
         const uint32_t k_addr = smem_u32(s_kv + st * Cfg::STAGE_BYTES);
         const uint32_t d_tmem = tmem + ((t & 1) ? Cfg::S_OFF1 : Cfg::S_OFF0);
@@ -964,44 +985,49 @@ fresco_attn_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
                   idesc_qk, ks > 0);
         }
         umma_commit(bar_s + (t & 1));
-      };
-      mbar_expect_tx(bar_q, Cfg::Q_BYTES);
-#pragma unroll
-      for (int a = 0; a < Cfg::NATOM; ++a) tma_load_4d(s_q + a * kQAtomBytes, &tm_q, bar_q, a * 64, head, q0, b);
-      refill();
-      mbar_wait(bar_q, 0, 31);
-      issue_qk(0);
-      if (n_tiles > 1) issue_qk(1);
+        umma_commit(bar_kv_empty + st);                                    // K_t consumed
+      }
+    }
+  } else if (warp >= Cfg::PV_WARP0) {
+    // ------------------------------------------------------------ P V issuer j: accumulators [j*PPV, (j+1)*PPV)
+    if (lane == 0) {
+      const int j = warp - Cfg::PV_WARP0;
+      constexpr uint32_t idesc_pv0 = make_idesc_f16(kTileM, Cfg::N0, 1);
+      constexpr uint32_t idesc_pv1 = make_idesc_f16(kTileM, Cfg::N1 > 0 ? Cfg::N1 : 16, 1);
+      constexpr int KS_PER_PART = (kTileN / 16) / SPLIT;                   // 16-key MMA steps per key part
       for (int t = 0; t < n_tiles; ++t) {
         const int st = t % ST;
-        wait_poll(bar_p + (t & 1), (t >> 1) & 1, 32);                  // both halves of P_t in TMEM
+        const int pb = t % PB;
+        mbar_wait_backoff(bar_p + pb * Cfg::NPV + j, (t / PB) & 1, 20, 44);   // P_t of my parts in TMEM
+        mbar_wait(bar_kv_full + st, (t / ST) & 1, 45);                     // V_t landed long ago; observe it
         tc_fence_after();
         const uint32_t v_addr = smem_u32(s_kv + st * Cfg::STAGE_BYTES + Cfg::NATOM * kKVAtomBytes);
-        const uint32_t s_buf = tmem + ((t & 1) ? Cfg::S_OFF1 : Cfg::S_OFF0);
 #pragma unroll
-        for (int k2 = 0; k2 < kTileN / 16; ++k2) {
-          const int h = k2 >> 1;                                       // key half == accumulator
-          const uint32_t p_tmem = s_buf + 32 * h + (k2 & 1) * 8;       // P_h: 16 columns at the start of its S half
-          const uint32_t o_tmem = tmem + Cfg::O_OFF + h * Cfg::O_STRIDE;
-          const uint32_t acc = (t > 0 || (k2 & 1)) ? 1u : 0u;
-          umma_ts(o_tmem, p_tmem, make_smem_desc_sw128(v_addr + k2 * 2048, kKVAtomBytes, 1024), idesc_pv0, acc);
-          if (Cfg::N1 > 0)
-            umma_ts(o_tmem + 64, p_tmem, make_smem_desc_sw128(v_addr + kKVAtomBytes + k2 * 2048, kKVAtomBytes, 1024),
-                    idesc_pv1, acc);
-          if (Cfg::MMA_ROWSUM)      // l_h += P_h * ones (every element of the constant tile is 1.0, so its layout is moot)
-            umma_ts(o_tmem + Cfg::L_COL, p_tmem, make_smem_desc_sw128(smem_u32(s_ones), 2048, 1024), idesc_ones, acc);
+        for (int pp = 0; pp < PARTS_PER_PV; ++pp) {
+          const int part = j * PARTS_PER_PV + pp;
+          const uint32_t o_tmem = tmem + Cfg::O_OFF + part * Cfg::DPAD;
+#pragma unroll
+          for (int kk = 0; kk < KS_PER_PART; ++kk) {
+            const int k2 = part * KS_PER_PART + kk;                        // 16-key step inside the tile
+            const uint32_t p_tmem = tmem + Cfg::P_OFF + pb * 32 + k2 * 8;
+            const uint32_t acc = (t > 0 || kk > 0) ? 1u : 0u;
+            umma_ts(o_tmem, p_tmem, make_smem_desc_sw128(v_addr + k2 * 2048, kKVAtomBytes, 1024), idesc_pv0, acc);
+            if (Cfg::N1 > 0)
+              umma_ts(o_tmem + 64, p_tmem, make_smem_desc_sw128(v_addr + kKVAtomBytes + k2 * 2048, kKVAtomBytes, 1024),
+                      idesc_pv1, acc);
+          }
         }
-        umma_commit(bar_kv_empty + st);                                // K_t and V_t consumed
-        umma_commit(bar_o + (t & 1));
-        if (t + 2 < n_tiles) issue_qk(t + 2);                          // overwrites S/P buffer t & 1, behind P_t V_t
+        umma_commit(bar_kv_empty + st);                                    // V_t consumed (my share)
+        umma_commit(bar_o + pb * Cfg::NPV + j);
       }
     }
   } else {
-    // ------------------------------------------------------------ softmax warps: (row, key half)
-    const int quarter = warp & 3, half = warp >> 2;
+    // ------------------------------------------------------------ softmax warps: (row, key part)
+    const int quarter = warp & 3, part = warp >> 2;
+    const int jpv = part / PARTS_PER_PV;                   // the P V issuer that owns this part's accumulator
     const int row = quarter * 32 + lane;                   // query row inside the tile == TMEM lane
     const uint32_t t_lane = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
-    const uint32_t o_mine = t_lane + Cfg::O_OFF + half * Cfg::O_STRIDE;
+    const uint32_t o_mine = t_lane + Cfg::O_OFF + part * Cfg::DPAD;
     const int q_row = q0 + row;
     const int kv_len = p.kv_len;
     const float scale_log2 = p.scale_log2, bias_log2 = p.diag_bias_log2;
@@ -1010,19 +1036,21 @@ fresco_attn_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     float m_run = -INFINITY, l_run = 0.f;
 
     for (int i = 0; i < n_tiles; ++i) {
-      const int col0 = i * kTileN + 32 * half;             // first key of this thread's half tile
-      // warp-uniform: does this half tile need masking (ragged tail) or the diagonal bias?
-      const bool special = (col0 + 32 > kv_len) ||
-                           (use_bias && (q0 + quarter * 32) < col0 + 32 && (q0 + quarter * 32 + 32) > col0);
+      const int col0 = i * kTileN + KEYS * part;           // first key of this thread's part of the tile
+      const int pb = i % PB;
+      // warp-uniform: does this part of the tile need masking (ragged tail) or the diagonal bias?
+      const bool special = (col0 + KEYS > kv_len) ||
+                           (use_bias && (q0 + quarter * 32) < col0 + KEYS && (q0 + quarter * 32 + 32) > col0);
       mbar_wait(bar_s + (i & 1), (i >> 1) & 1, 2);
       tc_fence_after();
-      const uint32_t s_addr = t_lane + ((i & 1) ? Cfg::S_OFF1 : Cfg::S_OFF0) + 32 * half;
-      uint32_t r[32];
-      tmem_ld32(s_addr, r);
-      tmem_ld_wait_dep32(r);
+      uint32_t r[KEYS];
+      tmem_ld_keys<KEYS>(t_lane + ((i & 1) ? Cfg::S_OFF1 : Cfg::S_OFF0) + KEYS * part, r);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_c + (i & 1));         // S buffer i & 1 may be overwritten by Q K_{i+2}^T
       if (special) {                                        // rare path: fold mask / bias into the raw scores
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
+        for (int j = 0; j < KEYS; ++j) {
           const int col = col0 + j;
           float v = __uint_as_float(r[j]);
           if (use_bias && col == q_row) v += bias_log2 / scale_log2;
@@ -1032,46 +1060,45 @@ fresco_attn_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       }
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) {
+      for (int j = 0; j < KEYS; j += 8) {
         mx0 = max3(mx0, __uint_as_float(r[j]), __uint_as_float(r[j + 1]));
         mx1 = max3(mx1, __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
         mx2 = max3(mx2, __uint_as_float(r[j + 4]), __uint_as_float(r[j + 5]));
         mx3 = max3(mx3, __uint_as_float(r[j + 6]), __uint_as_float(r[j + 7]));
       }
       const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
-      // ---- lazy running max of THIS half: raise it (and rescale O_h in TMEM) only when it grows by more than 2^8.
-      //      (m_run stays -inf while every key of this half has been masked; exp2(-inf) = 0 keeps P, l and O at zero.)
+      // ---- lazy running max of THIS part: raise it (and rescale O_part in TMEM) only when it grows by more than 2^8.
+      //      (m_run stays -inf while every key of this part has been masked; exp2(-inf) = 0 keeps P, l and O at zero.)
       if (i == 0) {
         m_run = m_tile;
       } else {
         const bool need = m_tile > m_run + 8.0f;           // also true for the first unmasked tile after m_run = -inf
         if (__any_sync(0xffffffffu, need)) {
-          // O_h may only be touched once P_{i-1} V_{i-1} has retired (rare path, so the wait is affordable)
-          mbar_wait(bar_o + ((i - 1) & 1), ((i - 1) >> 1) & 1, 5);
+          // O_part may only be touched once P_{i-1} V_{i-1} has retired (rare path, so the wait is affordable)
+          mbar_wait(bar_o + ((i - 1) % PB) * Cfg::NPV + jpv, ((i - 1) / PB) & 1, 5);
           tc_fence_after();
-          const float alpha = need ? fast_exp2(m_run - m_tile) : 1.0f;   // 0 when m_run was -inf (O_h, l_h are 0 then)
+          const float alpha = need ? fast_exp2(m_run - m_tile) : 1.0f;   // 0 when m_run was -inf (O, l are 0 then)
           if (need) {
             l_run *= alpha;
             m_run = m_tile;
           }
 #pragma unroll
-          for (int c = 0; c < Cfg::DPAD / 8 + (Cfg::MMA_ROWSUM ? 1 : 0); ++c) {   // (L_COL == DPAD: the chunk after O)
+          for (int c = 0; c < Cfg::DPAD / 8; ++c) {
             uint32_t o[8];
             tmem_ld8_sync(o_mine + c * 8, o);
 #pragma unroll
             for (int j = 0; j < 8; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
             tmem_st8(o_mine + c * 8, o);
           }
-          tmem_st_wait();
         }
       }
-      // ---- p = exp2(s*scale - m), packed to fp16 over the first 16 of the 32 columns just read
+      // ---- p = exp2(s*scale - m) -> fp16 into this part's columns of the P buffer; row sum in fp32
       const float neg_m = (m_run == -INFINITY) ? 0.f : -m_run;           // all-masked so far: s = -inf -> p = 0, not NaN
       const unsigned long long negm2 = pack_f2(neg_m, neg_m);
       unsigned long long sum2[2] = {pack_f2(0.f, 0.f), pack_f2(0.f, 0.f)};
-      uint32_t pk[16];
+      uint32_t pk[KEYS / 2];
 #pragma unroll
-      for (int j = 0; j < 32; j += 2) {
+      for (int j = 0; j < KEYS; j += 2) {
         float t0, t1, e0, e1;
         unpack_f2(fma2(pack_f2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), scale2, negm2), t0, t1);
         if (POLY > 0 && ((j >> 1) % (POLY > 0 ? POLY : 1)) == (POLY - 1)) {
@@ -1080,48 +1107,60 @@ fresco_attn_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
           e0 = fast_exp2(t0);
           e1 = fast_exp2(t1);
         }
-        if (!Cfg::MMA_ROWSUM) sum2[(j >> 1) & 1] = add2(sum2[(j >> 1) & 1], pack_f2(e0, e1));
+        sum2[(j >> 1) & 1] = add2(sum2[(j >> 1) & 1], pack_f2(e0, e1));
         pk[j >> 1] = pack_half2(e0, e1);
       }
-      tmem_st16(s_addr, pk);
+      // the P buffer was last read by P V of tile i - PB: its retirement is almost always long past
+      if (i >= PB) {
+        mbar_wait(bar_o + pb * Cfg::NPV + jpv, ((i - PB) / PB) & 1, 3);
+        tc_fence_after();
+      }
+      tmem_st_half<KEYS / 2>(t_lane + Cfg::P_OFF + pb * 32 + (KEYS / 2) * part, pk);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_p + (i & 1));
-      if (!Cfg::MMA_ROWSUM) {
-        float sa, sb;
-        unpack_f2(add2(sum2[0], sum2[1]), sa, sb);
-        l_run += sa + sb;
-      }
+      if (lane == 0) mbar_arrive(bar_p + pb * Cfg::NPV + jpv);
+      float sa, sb;
+      unpack_f2(add2(sum2[0], sum2[1]), sa, sb);
+      l_run += sa + sb;
     }
 
-    // ---- epilogue: merge the two halves of every row, O / l -> fp16 head slice
-    mbar_wait(bar_o + ((n_tiles - 1) & 1), ((n_tiles - 1) >> 1) & 1, 4);
+    // ---- epilogue: merge the SPLIT parts of every row, O / l -> fp16 head slice
+    mbar_wait(bar_o + ((n_tiles - 1) % PB) * Cfg::NPV + jpv, ((n_tiles - 1) / PB) & 1, 4);
     tc_fence_after();
-    if (Cfg::MMA_ROWSUM) {
-      uint32_t lcol[8];
-      tmem_ld8_sync(o_mine + Cfg::L_COL, lcol);
-      l_run = __uint_as_float(lcol[0]);
+    s_ml[part * 128 + row] = make_float2(m_run, l_run);
+    // every accumulator of the row is read below: wait for the other issuers' last P V as well
+#pragma unroll
+    for (int j = 0; j < Cfg::NPV; ++j)
+      if (j != jpv) mbar_wait(bar_o + ((n_tiles - 1) % PB) * Cfg::NPV + j, ((n_tiles - 1) / PB) & 1, 6);
+    tc_fence_after();
+    asm volatile("bar.sync 1, %0;" ::"n"(Cfg::SOFTMAX_WARPS * 32) : "memory");          // the softmax warps only
+    float m_all = -INFINITY;
+#pragma unroll
+    for (int q = 0; q < SPLIT; ++q) m_all = fmaxf(m_all, s_ml[q * 128 + row].x);   // finite: some key of the row is unmasked
+    float wgt[SPLIT], denom = 0.f;
+#pragma unroll
+    for (int q = 0; q < SPLIT; ++q) {
+      const float2 ml = s_ml[q * 128 + row];
+      wgt[q] = fast_exp2(ml.x - m_all);
+      denom += wgt[q] * ml.y;
     }
-    s_ml[half * 128 + row] = make_float2(m_run, l_run);
-    asm volatile("bar.sync 1, 256;" ::: "memory");          // the eight softmax warps only
-    const float2 other = s_ml[(half ^ 1) * 128 + row];
-    const float m_all = fmaxf(m_run, other.x);              // finite: at least one key of the row is unmasked
-    const float w_mine = fast_exp2(m_run - m_all), w_other = fast_exp2(other.x - m_all);
-    const float inv = 1.f / (w_mine * l_run + w_other * other.y);
-    const float w0 = (half == 0 ? w_mine : w_other) * inv, w1 = (half == 0 ? w_other : w_mine) * inv;
+    const float inv = 1.f / denom;
     __half* dst = p.out + (static_cast<size_t>(b) * p.q_len + q_row) * (static_cast<size_t>(p.heads) * D) +
                   static_cast<size_t>(head) * D;
 #pragma unroll
     for (int c = 0; c < D / 8; ++c) {
-      if ((c & 1) != half) continue;                        // the two threads of a row split its 16-byte chunks
-      uint32_t o0[8], o1[8];
-      tmem_ld8_sync(t_lane + Cfg::O_OFF + c * 8, o0);
-      tmem_ld8_sync(t_lane + Cfg::O_OFF + Cfg::O_STRIDE + c * 8, o1);
-      if (q_row < p.q_len) {
-        float f[8];
+      if ((c % SPLIT) != part) continue;                    // the SPLIT threads of a row share its 16-byte chunks
+      float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(o0[j]) * w0 + __uint_as_float(o1[j]) * w1;
+      for (int q = 0; q < SPLIT; ++q) {
+        uint32_t o[8];
+        tmem_ld8_sync(t_lane + Cfg::O_OFF + q * Cfg::DPAD + c * 8, o);
+        const float wq = wgt[q] * inv;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = fmaf(__uint_as_float(o[j]), wq, f[j]);
+      }
+      if (q_row < p.q_len) {
         uint4 pkt;
         pkt.x = pack_half2(f[0], f[1]);
         pkt.y = pack_half2(f[2], f[3]);
@@ -1134,7 +1173,7 @@ fresco_attn_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc<Cfg::TMEM_COLS>(tmem);
+  if (warp == Cfg::TMA_WARP) tmem_dealloc<Cfg::TMEM_COLS>(tmem);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1147,18 +1186,20 @@ fresco_attn_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
 struct MapKey {
   const void* base;
   int head_dim, heads, tokens, batch, box_rows;
+  long long row_stride, batch_stride;
   bool operator==(const MapKey& o) const {
     return base == o.base && head_dim == o.head_dim && heads == o.heads && tokens == o.tokens && batch == o.batch &&
-           box_rows == o.box_rows;
+           box_rows == o.box_rows && row_stride == o.row_stride && batch_stride == o.batch_stride;
   }
 };
+// row_stride / batch_stride in elements (dense: heads*head_dim and tokens*heads*head_dim)
 static int make_head_tile_map(CUtensorMap* map, const void* base, int head_dim, int heads, int tokens, int batch,
-                              int box_rows) {
+                              int box_rows, long long row_stride, long long batch_stride) {
   constexpr int kSlots = 64;
   static thread_local MapKey keys[kSlots];
   static thread_local CUtensorMap maps[kSlots];
   static thread_local bool valid[kSlots];
-  const MapKey key = {base, head_dim, heads, tokens, batch, box_rows};
+  const MapKey key = {base, head_dim, heads, tokens, batch, box_rows, row_stride, batch_stride};
   const size_t h = (reinterpret_cast<uintptr_t>(base) >> 9) * 0x9E3779B97F4A7C15ull + (size_t)tokens * 31 + box_rows;
   const int slot = (int)((h >> 32) % kSlots);
   if (valid[slot] && keys[slot] == key) {
@@ -1166,8 +1207,7 @@ static int make_head_tile_map(CUtensorMap* map, const void* base, int head_dim, 
     return 0;
   }
   const cuuint64_t dims[4] = {(cuuint64_t)head_dim, (cuuint64_t)heads, (cuuint64_t)tokens, (cuuint64_t)batch};
-  const cuuint64_t strides[3] = {(cuuint64_t)head_dim * 2, (cuuint64_t)heads * head_dim * 2,
-                                 (cuuint64_t)tokens * heads * head_dim * 2};
+  const cuuint64_t strides[3] = {(cuuint64_t)head_dim * 2, (cuuint64_t)row_stride * 2, (cuuint64_t)batch_stride * 2};
   const cuuint32_t box[4] = {64, 1, (cuuint32_t)box_rows, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   const int rc = encode_tiled_map(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box,
@@ -1186,7 +1226,7 @@ static int make_head_tile_map(CUtensorMap* map, const void* base, int head_dim, 
 //   FRESCO_ATTN_NARROW  3 | 4 = narrow kernel with that many CTAs per SM (head_dim 40 only; 0 = off)
 //   FRESCO_ATTN_POLY    0 | 4 | 8: every n-th pair of exponentials on the FMA pipe
 //   FRESCO_ATTN_ROWSUM  pipelined kernel, head_dim 40: row sums from the tensor core
-constexpr int kWideDefault = 1;
+constexpr int kWideDefault = 2;
 constexpr int kNarrowDefault = 0;
 constexpr int kPolyDefault = 0;
 constexpr int kRowsumDefault = 1;
@@ -1224,30 +1264,31 @@ static int launch_narrow(const CUtensorMap& tq, const CUtensorMap& tk, const CUt
   return check_launch("fresco_attn_narrow_kernel");
 }
 
-template <int D, int POLY>
+template <int D, int SPLIT, int POLY>
 static int launch_wide(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, dim3 grid,
                        cudaStream_t stream) {
-  using Cfg = WideCfg<D>;
+  using Cfg = WideCfg<D, SPLIT>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(fresco_attn_wide_kernel<D, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(fresco_attn_wide_kernel<D, SPLIT, POLY>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(attn wide)");
     attr_set = true;
   }
-  fresco_attn_wide_kernel<D, POLY><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tq, tk, tv, p);
+  fresco_attn_wide_kernel<D, SPLIT, POLY><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tq, tk, tv, p);
   return check_launch("fresco_attn_wide_kernel");
 }
 
 template <int D>
 static int launch_attn(const void* q, const void* k, const void* v, void* out, int batch_q, int q_len, int kv_len,
-                       int heads, int q_per_kv, float softmax_scale, float diag_bias, cudaStream_t stream) {
-  using Cfg = AttnCfg<D>;
+                       int heads, int q_per_kv, long long kv_row_stride, long long kv_batch_stride, float softmax_scale,
+                       float diag_bias, cudaStream_t stream) {
   CUtensorMap tq, tk, tv;
   const int batch_kv = batch_q / q_per_kv;
-  if (make_head_tile_map(&tq, q, D, heads, q_len, batch_q, kTileM)) return FRESCO_ERR_TENSORMAP;
-  if (make_head_tile_map(&tk, k, D, heads, kv_len, batch_kv, kTileN)) return FRESCO_ERR_TENSORMAP;
-  if (make_head_tile_map(&tv, v, D, heads, kv_len, batch_kv, kTileN)) return FRESCO_ERR_TENSORMAP;
+  const long long C = (long long)heads * D;
+  if (make_head_tile_map(&tq, q, D, heads, q_len, batch_q, kTileM, C, C * q_len)) return FRESCO_ERR_TENSORMAP;
+  if (make_head_tile_map(&tk, k, D, heads, kv_len, batch_kv, kTileN, kv_row_stride, kv_batch_stride)) return FRESCO_ERR_TENSORMAP;
+  if (make_head_tile_map(&tv, v, D, heads, kv_len, batch_kv, kTileN, kv_row_stride, kv_batch_stride)) return FRESCO_ERR_TENSORMAP;
   AttnParams p;
   p.out = static_cast<__half*>(out);
   p.q_len = q_len;
@@ -1264,10 +1305,18 @@ static int launch_attn(const void* q, const void* k, const void* v, void* out, i
     if (narrow == 3) return launch_narrow<D, 3>(tq, tk, tv, p, grid, stream);
     if (narrow == 4) return launch_narrow<D, 4>(tq, tk, tv, p, grid, stream);
   }
-  if (option(OPT_ATTN_WIDE, kWideDefault) == 1) {
-    if (poly == 4) return launch_wide<D, 4>(tq, tk, tv, p, grid, stream);
-    if (poly == 8) return launch_wide<D, 8>(tq, tk, tv, p, grid, stream);
-    return launch_wide<D, 0>(tq, tk, tv, p, grid, stream);
+  // FRESCO_ATTN_WIDE = 2 | 4: that many threads per query row (4 needs head_dim > 48: one CTA per SM)
+  const int wide = option(OPT_ATTN_WIDE, kWideDefault);
+  if (wide == 4) {
+    if constexpr (D > 48 && D <= 80) {
+      if (poly == 4) return launch_wide<D, 4, 4>(tq, tk, tv, p, grid, stream);
+      return launch_wide<D, 4, 0>(tq, tk, tv, p, grid, stream);
+    }
+  }
+  if (wide >= 1) {
+    if (poly == 4) return launch_wide<D, 2, 4>(tq, tk, tv, p, grid, stream);
+    if (poly == 8) return launch_wide<D, 2, 8>(tq, tk, tv, p, grid, stream);
+    return launch_wide<D, 2, 0>(tq, tk, tv, p, grid, stream);
   }
   if constexpr (AttnCfg<D, true>::MMA_ROWSUM) {
     if (option(OPT_ATTN_ROWSUM, kRowsumDefault)) {
@@ -1294,16 +1343,32 @@ extern "C" int fresco_debug_attn_trace(long long* host_out) {
 extern "C" int fresco_attn_fwd(const void* q, const void* k, const void* v, void* out, int batch_q, int q_len,
                                int kv_len, int heads, int head_dim, int q_per_kv, float softmax_scale,
                                float diag_bias, void* stream) {
+  return fresco_attn_fwd_kv_strided(q, k, v, out, batch_q, q_len, kv_len, heads, head_dim, q_per_kv,
+                                    (long long)heads * head_dim, (long long)kv_len * heads * head_dim, softmax_scale,
+                                    diag_bias, stream);
+}
+
+extern "C" int fresco_attn_fwd_kv_strided(const void* q, const void* k, const void* v, void* out, int batch_q, int q_len,
+                                          int kv_len, int heads, int head_dim, int q_per_kv, long long kv_row_stride,
+                                          long long kv_batch_stride, float softmax_scale, float diag_bias, void* stream) {
   if (!q || !k || !v || !out) return set_error(FRESCO_ERR_ARG, "fresco_attn_fwd: null pointer");
   if (batch_q <= 0 || q_len <= 0 || kv_len <= 0 || heads <= 0 || q_per_kv <= 0 || batch_q % q_per_kv != 0)
     return set_error(FRESCO_ERR_ARG, "fresco_attn_fwd: bad shape");
+  if (kv_row_stride < (long long)heads * head_dim || kv_row_stride % 8 != 0 || kv_batch_stride % 8 != 0 ||
+      kv_batch_stride < kv_row_stride)
+    return set_error(FRESCO_ERR_ARG, "fresco_attn_fwd: K/V strides must be multiples of 8 elements and cover a row");
   if (softmax_scale <= 0.f) return set_error(FRESCO_ERR_ARG, "fresco_attn_fwd: softmax_scale must be > 0");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+#define ATTN_CASE(DD)                                                                                                 \
+  case DD:                                                                                                             \
+    return launch_attn<DD>(q, k, v, out, batch_q, q_len, kv_len, heads, q_per_kv, kv_row_stride, kv_batch_stride,      \
+                           softmax_scale, diag_bias, s)
   switch (head_dim) {
-    case 40: return launch_attn<40>(q, k, v, out, batch_q, q_len, kv_len, heads, q_per_kv, softmax_scale, diag_bias, s);
-    case 64: return launch_attn<64>(q, k, v, out, batch_q, q_len, kv_len, heads, q_per_kv, softmax_scale, diag_bias, s);
-    case 80: return launch_attn<80>(q, k, v, out, batch_q, q_len, kv_len, heads, q_per_kv, softmax_scale, diag_bias, s);
-    case 128: return launch_attn<128>(q, k, v, out, batch_q, q_len, kv_len, heads, q_per_kv, softmax_scale, diag_bias, s);
+    ATTN_CASE(40);
+    ATTN_CASE(64);
+    ATTN_CASE(80);
+    ATTN_CASE(128);
     default: return set_error(FRESCO_ERR_UNSUPPORTED, "fresco_attn_fwd: head_dim must be one of 40, 64, 80, 128");
   }
+#undef ATTN_CASE
 }

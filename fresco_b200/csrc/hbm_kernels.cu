@@ -27,10 +27,189 @@ __global__ void kv_compact_kernel(const uint4* __restrict__ k, const uint4* __re
   }
 }
 
+// K and V rows of the selected tokens side by side in one 2C-wide row: the send buffer of the cross-frame K/V exchange
+// (fresco_b200/dist.py), [chunks, out_rows, 2C] with rows [0, n_sel) written
+__global__ void kv_compact_packed_kernel(const uint4* __restrict__ k, const uint4* __restrict__ v,
+                                         const int32_t* __restrict__ idx, uint4* __restrict__ kv_out, int chunks,
+                                         long long rows_per_chunk, int n_sel, int out_rows, int vec_per_row) {
+  const long long total = (long long)chunks * n_sel * vec_per_row;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int part = (int)(t % vec_per_row);
+    const long long row = t / vec_per_row;
+    const int i = (int)(row % n_sel);
+    const int c = (int)(row / n_sel);
+    const long long src = ((long long)c * rows_per_chunk + idx[i]) * vec_per_row + part;
+    const long long dst = ((long long)c * out_rows + i) * 2 * vec_per_row + part;
+    kv_out[dst] = __ldg(k + src);
+    kv_out[dst + vec_per_row] = __ldg(v + src);
+  }
+}
+
+// dst row r (at byte offset dst_off inside a dst_stride-wide row) = src row idx[r]: 16-byte vectors, coalesced along rows
+__global__ void rows_gather_kernel(const uint4* __restrict__ src, const int32_t* __restrict__ idx,
+                                   uint4* __restrict__ dst, long long n_rows, int vec_per_row, int dst_stride_vec,
+                                   int dst_off_vec) {
+  const long long total = n_rows * vec_per_row;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int part = (int)(t % vec_per_row);
+    const long long r = t / vec_per_row;
+    dst[r * dst_stride_vec + dst_off_vec + part] = __ldg(src + (long long)idx[r] * vec_per_row + part);
+  }
+}
+// dst row idx[r] = src row r
+__global__ void rows_scatter_kernel(const uint4* __restrict__ src, const int32_t* __restrict__ idx,
+                                    uint4* __restrict__ dst, long long n_rows, int vec_per_row) {
+  const long long total = n_rows * vec_per_row;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int part = (int)(t % vec_per_row);
+    const long long r = t / vec_per_row;
+    dst[(long long)idx[r] * vec_per_row + part] = __ldg(src + t);
+  }
+}
+
 // =============================================================================================
 // A5  temporal-guided attention  (src/diffusion_hacked.py:320-367)
-// one CTA per (chunk, trajectory); one warp per head
 // =============================================================================================
+// The reference gathers q_raw / k_raw / attention-output rows along each flow trajectory into [2L, heads, N, d] tensors,
+// runs an N x N masked SDPA per (trajectory, head) and gathers the result back -- about twelve full passes over
+// [2N, L, C] tensors.  Here one CTA owns TPB trajectories of one CFG chunk: their 3 x N token rows (all heads, C halves
+// each, contiguous in the token-major layout) are gathered into shared memory with fully coalesced 16-byte loads that
+// are ALL in flight before anything is used (HBM-bound kernel: bytes in flight are what counts), every thread then
+// computes ONE output row -- (trajectory, frame f, head h): N dot products of length d, a softmax over N held in
+// registers, N x d accumulation -- and the rows go back through shared memory with coalesced 16-byte stores to the
+// token the trajectory visits in frame f (fwd_map is a permutation, so every output row is written exactly once).
+// Algorithmic traffic: 3 reads + 1 write of [2N, L, C] fp16 + 8 B of index and N B of mask per (trajectory, frame).
+template <int D, int NMAX>
+__global__ void __launch_bounds__(256)
+temporal_attn_rows_kernel(const __half* __restrict__ q_raw, const __half* __restrict__ k_raw,
+                          const __half* __restrict__ v_src, __half* __restrict__ out,
+                          const int64_t* __restrict__ fwd_map, const uint8_t* __restrict__ traj_mask, int frames,
+                          int tokens, int heads, int tpb, float scale_log2, int in_row_vecs /* 16-byte vectors between
+                          consecutive token rows of q/k/v (C/8 when dense) */) {
+  extern __shared__ uint4 smem_rows[];
+  constexpr int VPR = D / 8;                                   // 16-byte vectors per head row
+  const int N = frames;
+  const int C = heads * D;
+  const int row_vecs = heads * VPR;                            // vectors per token row (all heads)
+  const int traj_vecs = N * row_vecs;                          // vectors per trajectory per tensor
+  const int blocks_per_chunk = (tokens + tpb - 1) / tpb;
+  const int b = blockIdx.x / blocks_per_chunk;
+  const int p0 = (blockIdx.x % blocks_per_chunk) * tpb;
+  const int n_traj = min(tpb, tokens - p0);
+  uint4* sq = smem_rows;                                       // [tpb][N][row_vecs]   (reused for the output rows)
+  uint4* sk = sq + tpb * traj_vecs;
+  uint4* sv = sk + tpb * traj_vecs;
+  int* spos = reinterpret_cast<int*>(sv + tpb * traj_vecs);    // [tpb][N] token visited in frame f
+
+  for (int i = threadIdx.x; i < n_traj * N; i += blockDim.x) {
+    const int tr = i / N, f = i % N;
+    spos[tr * N + f] = (int)fwd_map[(long long)f * tokens + p0 + tr];
+  }
+  __syncthreads();
+  // ---- gather: consecutive threads read consecutive 16-byte pieces of a 2C-byte token row
+  const int total_vecs = n_traj * traj_vecs;
+  for (int i = threadIdx.x; i < total_vecs; i += blockDim.x) {
+    const int tr = i / traj_vecs, rem = i % traj_vecs;
+    const int f = rem / row_vecs, part = rem % row_vecs;
+    const long long src = (((long long)b * N + f) * tokens + spos[tr * N + f]) * in_row_vecs + part;
+    sq[i] = __ldg(reinterpret_cast<const uint4*>(q_raw) + src);
+    sk[i] = __ldg(reinterpret_cast<const uint4*>(k_raw) + src);
+    sv[i] = __ldg(reinterpret_cast<const uint4*>(v_src) + src);
+  }
+  __syncthreads();
+  // ---- one output row per thread: (trajectory tr, frame f, head h)
+  const int rows = n_traj * N * heads;
+  for (int r = threadIdx.x; r < rows; r += blockDim.x) {       // (one trip when blockDim == tpb * N * heads)
+    const int tr = r / (N * heads), fh = r % (N * heads);
+    const int f = fh / heads, h = fh % heads;
+    const uint4* qrow = sq + tr * traj_vecs + f * row_vecs + h * VPR;
+    float2 qv[D / 2];
+#pragma unroll
+    for (int c = 0; c < VPR; ++c) {
+      const uint4 x = qrow[c];
+      const __half2* xh = reinterpret_cast<const __half2*>(&x);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) qv[c * 4 + u] = __half22float2(xh[u]);
+    }
+    const uint8_t* mrow = traj_mask + ((long long)(p0 + tr) * N + f) * N;
+    float sc[NMAX];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int g = 0; g < NMAX; ++g) {
+      sc[g] = -INFINITY;
+      if (g < N) {
+        const uint4* krow = sk + tr * traj_vecs + g * row_vecs + h * VPR;
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < VPR; ++c) {
+          const uint4 y = krow[c];
+          const __half2* yh = reinterpret_cast<const __half2*>(&y);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float2 yy = __half22float2(yh[u]);
+            a0 = fmaf(qv[c * 4 + u].x, yy.x, a0);
+            a1 = fmaf(qv[c * 4 + u].y, yy.y, a1);
+          }
+        }
+        if (mrow[g]) sc[g] = (a0 + a1) * scale_log2;
+        mx = fmaxf(mx, sc[g]);
+      }
+    }
+    float l = 0.f;
+#pragma unroll
+    for (int g = 0; g < NMAX; ++g) {
+      sc[g] = (g < N) ? fast_exp2(sc[g] - mx) : 0.f;             // (the diagonal is never masked: mx is finite)
+      l += sc[g];
+    }
+    const float inv = 1.f / l;
+    float2 acc[D / 2];
+#pragma unroll
+    for (int c = 0; c < D / 2; ++c) acc[c] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int g = 0; g < NMAX; ++g) {
+      if (g < N) {
+        const uint4* vrow = sv + tr * traj_vecs + g * row_vecs + h * VPR;
+        const float pw = sc[g] * inv;
+#pragma unroll
+        for (int c = 0; c < VPR; ++c) {
+          const uint4 y = vrow[c];
+          const __half2* yh = reinterpret_cast<const __half2*>(&y);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float2 yy = __half22float2(yh[u]);
+            acc[c * 4 + u].x = fmaf(pw, yy.x, acc[c * 4 + u].x);
+            acc[c * 4 + u].y = fmaf(pw, yy.y, acc[c * 4 + u].y);
+          }
+        }
+      }
+    }
+    // q row (tr, f, h) is read by this thread only: reuse it as the output staging
+    uint4* orow = sq + tr * traj_vecs + f * row_vecs + h * VPR;
+#pragma unroll
+    for (int c = 0; c < VPR; ++c) {
+      uint4 o;
+      o.x = pack_half2(acc[c * 4 + 0].x, acc[c * 4 + 0].y);
+      o.y = pack_half2(acc[c * 4 + 1].x, acc[c * 4 + 1].y);
+      o.z = pack_half2(acc[c * 4 + 2].x, acc[c * 4 + 2].y);
+      o.w = pack_half2(acc[c * 4 + 3].x, acc[c * 4 + 3].y);
+      orow[c] = o;
+    }
+  }
+  __syncthreads();
+  // ---- scatter back to the tokens the trajectories visit
+  for (int i = threadIdx.x; i < total_vecs; i += blockDim.x) {
+    const int tr = i / traj_vecs, rem = i % traj_vecs;
+    const int f = rem / row_vecs, part = rem % row_vecs;
+    const long long dst = (((long long)b * N + f) * tokens + spos[tr * N + f]) * (C / 8) + part;
+    reinterpret_cast<uint4*>(out)[dst] = sq[i];
+  }
+}
+
+// any frames <= 64 / head_dim % 8 == 0: one CTA per (chunk, trajectory), one warp per head (round-1 kernel; kept for
+// the shapes the row kernel is not instantiated for)
 __global__ void temporal_attn_kernel(const __half* __restrict__ q_raw, const __half* __restrict__ k_raw,
                                      const __half* __restrict__ v_src, __half* __restrict__ out,
                                      const int64_t* __restrict__ fwd_map, const uint8_t* __restrict__ traj_mask,
@@ -84,8 +263,8 @@ __global__ void temporal_attn_kernel(const __half* __restrict__ q_raw, const __h
     sc[pair] = mrow[pair] ? acc * scale : -INFINITY;
   }
   __syncwarp();
-  if (lane < N) {
-    float* r = sc + lane * N;
+  for (int f = lane; f < N; f += 32) {                               // one softmax row per lane (frames may exceed 32)
+    float* r = sc + f * N;
     float m = -INFINITY;
     for (int g = 0; g < N; ++g) m = fmaxf(m, r[g]);
     float s = 0.f;
@@ -248,6 +427,83 @@ __global__ void warp_chain_smem_kernel(const T* __restrict__ sample, T* __restri
   }
 }
 
+// Channel-grouped variant: the per-pixel work that does not depend on the channel (two flow loads, the four bilinear
+// taps, the blend weight) is done ONCE per pixel and applied to K planes; K (chunk, channel) planes per CTA keep their
+// running frames in shared memory.  Same arithmetic, same order of operations per element as the kernel above.
+template <typename T, int K>
+__global__ void __launch_bounds__(512)
+warp_chain_group_kernel(const T* __restrict__ sample, T* __restrict__ out, const float* __restrict__ bwd_flow,
+                        const float* __restrict__ fwd_flow_last, const float* __restrict__ blend, int frames,
+                        int channels, int planes_total, int h, int w) {
+  extern __shared__ float planes[];
+  const int hw = h * w;
+  float* cur = planes;                     // [K][hw]
+  float* nxt = planes + K * hw;            // [K][hw]
+  long long base[K];                       // offset of frame 0 of plane kk; frames are channels*hw apart
+  bool live[K];
+#pragma unroll
+  for (int kk = 0; kk < K; ++kk) {
+    const int pl = blockIdx.x * K + kk;
+    live[kk] = pl < planes_total;
+    const int j = live[kk] ? pl / channels : 0, c = live[kk] ? pl % channels : 0;
+    base[kk] = ((long long)j * frames * channels + c) * hw;
+  }
+  const long long fstride = (long long)channels * hw;
+
+  for (int i = threadIdx.x; i < hw; i += blockDim.x) {
+#pragma unroll
+    for (int kk = 0; kk < K; ++kk) {
+      if (!live[kk]) continue;
+      const float v = ld_as_float(sample + base[kk] + i);
+      cur[kk * hw + i] = v;
+      st_from_float(out + base[kk] + i, v);
+    }
+  }
+  __syncthreads();
+  for (int ii = 0; ii + 1 < frames; ++ii) {
+    const float* fl = bwd_flow + (long long)ii * 2 * hw;
+    const float* mk = blend + (long long)ii * hw;
+    const bool last = (ii + 2 == frames);
+    const long long foff = (long long)(ii + 1) * fstride;
+    for (int i = threadIdx.x; i < hw; i += blockDim.x) {
+      const int x = i % w, y = i / w;
+      const Taps tp = make_taps(x + fl[i], y + fl[hw + i], h, w);
+      const float m = mk[i];
+      float z[K];
+#pragma unroll
+      for (int kk = 0; kk < K; ++kk) z[kk] = live[kk] ? ld_as_float(sample + base[kk] + foff + i) : 0.f;
+#pragma unroll
+      for (int kk = 0; kk < K; ++kk) {
+        const float v = z[kk] * (1.f - m) + sample_taps(cur + kk * hw, tp) * m;
+        nxt[kk * hw + i] = v;
+        if (!last && live[kk]) st_from_float(out + base[kk] + foff + i, v);
+      }
+    }
+    __syncthreads();
+    float* t = cur;
+    cur = nxt;
+    nxt = t;
+  }
+  // closing blend: frame N-1 <- warp(frame 0, fwd_flow[N-1])  (flow_utils.py:47-51)
+  for (int i = threadIdx.x; i < hw; i += blockDim.x) {
+#pragma unroll
+    for (int kk = 0; kk < K; ++kk) nxt[kk * hw + i] = live[kk] ? ld_as_float(sample + base[kk] + i) : 0.f;
+  }
+  __syncthreads();
+  const float* mk = blend + (long long)(frames - 1) * hw;
+  const long long loff = (long long)(frames - 1) * fstride;
+  for (int i = threadIdx.x; i < hw; i += blockDim.x) {
+    const int x = i % w, y = i / w;
+    const Taps tp = make_taps(x + fwd_flow_last[i], y + fwd_flow_last[hw + i], h, w);
+    const float m = mk[i];
+#pragma unroll
+    for (int kk = 0; kk < K; ++kk) {
+      const float v = cur[kk * hw + i] * (1.f - m) + sample_taps(nxt + kk * hw, tp) * m;
+      if (live[kk]) st_from_float(out + base[kk] + loff + i, v);
+    }
+  }
+}
+
 // planes too large for shared memory (image resolution): one launch per chain step, fp32 scratch
 __global__ void warp_blend_step_kernel(const float* __restrict__ src_frames, float* __restrict__ dst_frames,
                                        const float* __restrict__ flow, const float* __restrict__ mask, int chunks,
@@ -389,6 +645,212 @@ __global__ void warp_loss_kernel(const float* __restrict__ cs, const float* __re
         if (of[3 * e] >= 0) atomicAdd(gb + of[3 * e], -__int_as_float(of[3 * e + 2]) * s2[of[3 * e + 1]]);
       }
     }
+  }
+  if (loss_acc != nullptr) {
+    __shared__ float red[32];
+    loss = warp_sum(loss);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = loss;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+      v = warp_sum(v);
+      if (threadIdx.x == 0) atomicAdd(loss_acc, v * k);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Channel-grouped temporal-consistency loss (the kernel optimize_feature runs).
+// Everything that depends on the pixel but not on the channel -- two flows, eight bilinear taps, two keep masks and the
+// two ELL rows of the warp adjoints (88 bytes per pixel and frame pair) -- is fetched and decoded ONCE per pixel and
+// applied to KT planes held by the same thread; a CTA walks the N frame pairs of K = KT * G (chunk, channel) planes with
+// four shared-memory planes per channel (frame f, frame f+1 in fp32; the two masked sign planes in fp16 -- exact for the
+// {0,1} keep masks the reference produces, 2^-11 relative otherwise).  Every cs plane is read once and every grad plane
+// is written once: the contribution a frame receives as the "next" frame of pair f is carried IN REGISTERS to pair f+1,
+// where the same thread owns the same (pixel, plane) elements (frame 0 alone gets a second, read-modify-write pass for
+// the wrap-around pair).  Algorithmic traffic: 8 bytes per element (read cs, write grad) + 1/N of that for frame 0.
+//   thread mapping: hw >= blockDim: thread t owns pixels t + pp * blockDim (pp < P) of KT planes;
+//                   hw <  blockDim: G = blockDim / hw sub-groups; thread (q = t % hw, g = t / hw) owns pixel q of planes
+//                   kk * G + g (kk < KT).
+// ---------------------------------------------------------------------------------------------
+template <int P, int KT>
+__global__ void __launch_bounds__(512, 2)
+warp_loss_group_kernel(const float* __restrict__ cs, const float* __restrict__ fwd_flow,
+                       const float* __restrict__ bwd_flow, const float* __restrict__ fwd_keep,
+                       const float* __restrict__ bwd_keep, const uint4* __restrict__ bwd_ell,
+                       const uint4* __restrict__ fwd_ell, const int32_t* __restrict__ ovf /*[2][frames][n_ovf][3]*/,
+                       int n_ovf, float* __restrict__ grad, float* __restrict__ loss_acc, int accumulate, int frames,
+                       int channels, int planes_total, int h, int w, int G, float k /* 2 / numel */) {
+  extern __shared__ float sm[];
+  const int hw = h * w;
+  const int K = KT * G;
+  float* cur = sm;                                            // [K][hw] frame f
+  float* nxt = sm + K * hw;                                   // [K][hw] frame f + 1
+  __half* s1 = reinterpret_cast<__half*>(sm + 2 * K * hw);    // [K][hw] sign(c2 - W_bf c1) * keep_b
+  __half* s2 = s1 + K * hw;                                   // [K][hw] sign(c1 - W_ff c2) * keep_f
+  const int T = blockDim.x;
+  const int t = threadIdx.x;
+  const int g = (G > 1) ? t / hw : 0;
+  const int q0 = (G > 1) ? t % hw : t;
+  const bool active = g < G;
+  const long long fstride = (long long)channels * hw;
+  // global offset of frame 0 of the planes this thread owns, and of every plane of the CTA (for the cooperative loads)
+  long long own_base[KT];
+  bool own_live[KT];
+#pragma unroll
+  for (int kk = 0; kk < KT; ++kk) {
+    const int slot = kk * G + g;
+    const int pl = blockIdx.x * K + slot;
+    own_live[kk] = active && pl < planes_total;
+    const int b = own_live[kk] ? pl / channels : 0, c = own_live[kk] ? pl % channels : 0;
+    own_base[kk] = ((long long)b * frames * channels + c) * hw;
+  }
+  auto load_plane = [&](float* dst, int f) {                  // frame f of all K planes -> dst (coalesced along pixels)
+    for (int idx = t; idx < K * hw; idx += T) {
+      const int slot = idx / hw, i = idx - slot * hw;
+      const int pl = blockIdx.x * K + slot;
+      float v = 0.f;
+      if (pl < planes_total) {
+        const int b = pl / channels, c = pl % channels;
+        v = cs[((long long)(b * frames + f) * channels + c) * hw + i];
+      }
+      dst[idx] = v;
+    }
+  };
+  float carry[P * KT];
+#pragma unroll
+  for (int j = 0; j < P * KT; ++j) carry[j] = 0.f;
+  float loss = 0.f;
+
+  load_plane(cur, 0);
+  for (int f = 0; f < frames; ++f) {
+    const int fn = (f + 1 == frames) ? 0 : f + 1;
+    load_plane(nxt, fn);
+    __syncthreads();
+    // ---- residuals of pair (f, fn): taps once per pixel, applied to the KT planes of this thread
+    {
+      const float* bf = bwd_flow + (long long)f * 2 * hw;
+      const float* ff = fwd_flow + (long long)f * 2 * hw;
+      const float* mbp = bwd_keep + (long long)f * hw;
+      const float* mfp = fwd_keep + (long long)f * hw;
+#pragma unroll
+      for (int pp = 0; pp < P; ++pp) {
+        const int q = q0 + pp * T;
+        if (!active || q >= hw) continue;
+        const int x = q % w, y = q / w;
+        const Taps tb = make_taps(x + bf[q], y + bf[hw + q], h, w);
+        const Taps tf = make_taps(x + ff[q], y + ff[hw + q], h, w);
+        const float mb = mbp[q], mf = mfp[q];
+#pragma unroll
+        for (int kk = 0; kk < KT; ++kk) {
+          const int slot = kk * G + g;
+          const float* c1 = cur + slot * hw;
+          const float* c2 = nxt + slot * hw;
+          const float r1 = c2[q] - sample_taps(c1, tb);       // c2 - W_bf(c1)
+          const float r2 = c1[q] - sample_taps(c2, tf);       // c1 - W_ff(c2)
+          loss += fabsf(r1) * mb + fabsf(r2) * mf;
+          s1[slot * hw + q] = __float2half_rn((r1 > 0.f ? 1.f : (r1 < 0.f ? -1.f : 0.f)) * mb);
+          s2[slot * hw + q] = __float2half_rn((r2 > 0.f ? 1.f : (r2 < 0.f ? -1.f : 0.f)) * mf);
+        }
+      }
+    }
+    __syncthreads();
+    // ---- destinations hit by more than 8 taps of the forward-flow warp (rare): their extra terms of d/dc2 go
+    //      through the dead frame-f planes, which the gather below adds in
+    if (n_ovf > 0) {
+      for (int idx = t; idx < K * hw; idx += T) cur[idx] = 0.f;
+      __syncthreads();
+      const int32_t* of = ovf + ((long long)1 * frames + f) * n_ovf * 3;
+      for (int e = t; e < n_ovf; e += T) {
+        if (of[3 * e] < 0) continue;
+        const float wgt = __int_as_float(of[3 * e + 2]);
+        for (int slot = 0; slot < K; ++slot)
+          atomicAdd(cur + slot * hw + of[3 * e], -wgt * __half2float(s2[slot * hw + of[3 * e + 1]]));
+      }
+      __syncthreads();
+    }
+    // ---- adjoints as gathers (8 packed (source, weight) ELL slots per destination pixel), decoded once per pixel
+    const uint4* ebp = bwd_ell + (long long)f * hw * 2;
+    const uint4* efp = fwd_ell + (long long)f * hw * 2;
+    const long long goff_a = (long long)f * fstride;
+#pragma unroll
+    for (int pp = 0; pp < P; ++pp) {
+      const int q = q0 + pp * T;
+      if (!active || q >= hw) continue;
+      float ga[KT], gb[KT];
+#pragma unroll
+      for (int kk = 0; kk < KT; ++kk) {
+        const int slot = kk * G + g;
+        ga[kk] = __half2float(s2[slot * hw + q]);             // d/dc1 = s2 - W_bf^T s1   (frame f)
+        gb[kk] = __half2float(s1[slot * hw + q]);             // d/dc2 = s1 - W_ff^T s2   (frame fn)
+        if (n_ovf > 0) gb[kk] += cur[slot * hw + q];
+      }
+      {
+        const uint4 e0 = __ldg(ebp + 2 * q), e1 = __ldg(ebp + 2 * q + 1);
+        const uint32_t e[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (e[j] >> 16) {                                    // empty slots carry weight 0
+            const float wj = (float)(e[j] >> 16) * (1.0f / 65535.0f);
+            const int src = e[j] & 0xffffu;
+#pragma unroll
+            for (int kk = 0; kk < KT; ++kk) ga[kk] = fmaf(-wj, __half2float(s1[(kk * G + g) * hw + src]), ga[kk]);
+          }
+        }
+      }
+      {
+        const uint4 e0 = __ldg(efp + 2 * q), e1 = __ldg(efp + 2 * q + 1);
+        const uint32_t e[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (e[j] >> 16) {
+            const float wj = (float)(e[j] >> 16) * (1.0f / 65535.0f);
+            const int src = e[j] & 0xffffu;
+#pragma unroll
+            for (int kk = 0; kk < KT; ++kk) gb[kk] = fmaf(-wj, __half2float(s2[(kk * G + g) * hw + src]), gb[kk]);
+          }
+        }
+      }
+#pragma unroll
+      for (int kk = 0; kk < KT; ++kk) {
+        if (own_live[kk]) {
+          float* dst = grad + own_base[kk] + goff_a + q;
+          const float val = (carry[pp * KT + kk] + ga[kk]) * k;   // frame f: its term as "next" of pair f-1 + this pair
+          *dst = accumulate ? *dst + val : val;
+        }
+        carry[pp * KT + kk] = gb[kk];
+      }
+    }
+    __syncthreads();                                           // s1 / s2 / cur are rewritten by the next pair
+    // ---- destinations with more than 8 taps of the backward-flow warp: extra terms of d/dc1, frame f is final in
+    //      global memory now
+    if (n_ovf > 0) {
+      const int32_t* ob = ovf + ((long long)0 * frames + f) * n_ovf * 3;
+      for (int e = t; e < n_ovf; e += T) {
+        if (ob[3 * e] < 0) continue;
+        const float wgt = __int_as_float(ob[3 * e + 2]);
+        for (int slot = 0; slot < K; ++slot) {
+          const int pl = blockIdx.x * K + slot;
+          if (pl >= planes_total) break;
+          const int b = pl / channels, c = pl % channels;
+          atomicAdd(grad + ((long long)(b * frames + f) * channels + c) * hw + ob[3 * e],
+                    -wgt * __half2float(s1[slot * hw + ob[3 * e + 1]]) * k);
+        }
+      }
+      __syncthreads();
+    }
+    float* tmp = cur;                                          // frame fn becomes frame f of the next pair
+    cur = nxt;
+    nxt = tmp;
+  }
+  // ---- wrap-around: what frame 0 receives as the "next" frame of pair N-1
+#pragma unroll
+  for (int pp = 0; pp < P; ++pp) {
+    const int q = q0 + pp * T;
+    if (!active || q >= hw) continue;
+#pragma unroll
+    for (int kk = 0; kk < KT; ++kk)
+      if (own_live[kk]) grad[own_base[kk] + q] += carry[pp * KT + kk] * k;
   }
   if (loss_acc != nullptr) {
     __shared__ float red[32];
@@ -546,14 +1008,103 @@ extern "C" int fresco_kv_compact(const void* k, const void* v, const int32_t* id
   return check_launch("kv_compact_kernel");
 }
 
+extern "C" int fresco_kv_compact_packed(const void* k, const void* v, const int32_t* idx, void* kv_out, int chunks,
+                                        int rows_per_chunk, int n_sel, int out_rows, int channels, void* stream) {
+  if (!k || !v || !idx || !kv_out) return set_error(FRESCO_ERR_ARG, "fresco_kv_compact_packed: null pointer");
+  if (chunks <= 0 || rows_per_chunk <= 0 || n_sel <= 0 || out_rows < n_sel || channels <= 0 || channels % 8 != 0)
+    return set_error(FRESCO_ERR_ARG, "fresco_kv_compact_packed: bad shape (channels must be a multiple of 8)");
+  const int vpr = channels / 8;
+  const long long total = (long long)chunks * n_sel * vpr;
+  kv_compact_packed_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const uint4*)k, (const uint4*)v, idx, (uint4*)kv_out, chunks, rows_per_chunk, n_sel, out_rows, vpr);
+  return check_launch("kv_compact_packed_kernel");
+}
+
+extern "C" int fresco_rows_gather(const void* src, const int32_t* idx, void* dst, long long n_rows, int row_bytes,
+                                  int dst_stride_bytes, int dst_offset_bytes, void* stream) {
+  if (!src || !idx || !dst) return set_error(FRESCO_ERR_ARG, "fresco_rows_gather: null pointer");
+  if (n_rows <= 0 || row_bytes <= 0 || row_bytes % 16 || dst_stride_bytes % 16 || dst_offset_bytes % 16 ||
+      dst_offset_bytes + row_bytes > dst_stride_bytes)
+    return set_error(FRESCO_ERR_ARG, "fresco_rows_gather: rows / strides / offsets must be multiples of 16 bytes");
+  rows_gather_kernel<<<grid_for(n_rows * (row_bytes / 16), 256), 256, 0, (cudaStream_t)stream>>>(
+      (const uint4*)src, idx, (uint4*)dst, n_rows, row_bytes / 16, dst_stride_bytes / 16, dst_offset_bytes / 16);
+  return check_launch("rows_gather_kernel");
+}
+
+extern "C" int fresco_rows_scatter(const void* src, const int32_t* idx, void* dst, long long n_rows, int row_bytes,
+                                   void* stream) {
+  if (!src || !idx || !dst) return set_error(FRESCO_ERR_ARG, "fresco_rows_scatter: null pointer");
+  if (n_rows <= 0 || row_bytes <= 0 || row_bytes % 16)
+    return set_error(FRESCO_ERR_ARG, "fresco_rows_scatter: rows must be multiples of 16 bytes");
+  rows_scatter_kernel<<<grid_for(n_rows * (row_bytes / 16), 256), 256, 0, (cudaStream_t)stream>>>(
+      (const uint4*)src, idx, (uint4*)dst, n_rows, row_bytes / 16);
+  return check_launch("rows_scatter_kernel");
+}
+
+template <int D, int NMAX>
+static int launch_temporal_rows(const void* q_raw, const void* k_raw, const void* v_src, void* out, const int64_t* fwd_map,
+                                const uint8_t* traj_mask, int chunks, int frames, int tokens, int heads, float scale,
+                                int in_row_stride, cudaStream_t s) {
+  // trajectories per CTA: one thread per output row, up to 256 threads; shared memory 3 * N * 2C bytes per trajectory
+  const int rows_per_traj = frames * heads;
+  int tpb = 256 / rows_per_traj;
+  if (tpb < 1) tpb = 1;
+  const size_t per_traj = (size_t)3 * frames * heads * D * sizeof(__half) + (size_t)frames * sizeof(int);
+  while (tpb > 1 && tpb * per_traj > 64 * 1024) --tpb;
+  const size_t smem = tpb * per_traj;
+  if (smem > 200 * 1024) return FRESCO_ERR_UNSUPPORTED;
+  int threads = tpb * rows_per_traj;
+  threads = (threads + 31) / 32 * 32;
+  if (threads > 256) threads = 256;
+  static size_t attr_smem = 0;
+  if (smem > 48 * 1024 && smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(temporal_attn_rows_kernel<D, NMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(temporal_attn_rows)");
+    attr_smem = smem;
+  }
+  const int blocks = chunks * ((tokens + tpb - 1) / tpb);
+  temporal_attn_rows_kernel<D, NMAX><<<blocks, threads, smem, s>>>(
+      (const __half*)q_raw, (const __half*)k_raw, (const __half*)v_src, (__half*)out, fwd_map, traj_mask, frames, tokens,
+      heads, tpb, scale * 1.4426950408889634f, in_row_stride / 8);
+  return check_launch("temporal_attn_rows_kernel");
+}
+
 extern "C" int fresco_temporal_attn_fwd(const void* q_raw, const void* k_raw, const void* v_src, void* out,
                                         const int64_t* fwd_map, const uint8_t* traj_mask, int chunks, int frames,
                                         int tokens, int heads, int head_dim, float scale, void* stream) {
+  return fresco_temporal_attn_fwd_strided(q_raw, k_raw, v_src, out, fwd_map, traj_mask, chunks, frames, tokens, heads,
+                                          head_dim, heads * head_dim, scale, stream);
+}
+
+extern "C" int fresco_temporal_attn_fwd_strided(const void* q_raw, const void* k_raw, const void* v_src, void* out,
+                                                const int64_t* fwd_map, const uint8_t* traj_mask, int chunks,
+                                                int frames, int tokens, int heads, int head_dim, int in_row_stride,
+                                                float scale, void* stream) {
   if (!q_raw || !k_raw || !v_src || !out || !fwd_map || !traj_mask)
     return set_error(FRESCO_ERR_ARG, "fresco_temporal_attn_fwd: null pointer");
   if (chunks <= 0 || frames <= 0 || tokens <= 0 || heads <= 0 || heads > 32 || head_dim % 8 != 0 || frames > 64)
     return set_error(FRESCO_ERR_ARG, "fresco_temporal_attn_fwd: bad shape");
   if (out == v_src) return set_error(FRESCO_ERR_ARG, "fresco_temporal_attn_fwd: out must not alias v_src");
+  if (in_row_stride < heads * head_dim || in_row_stride % 8 != 0)
+    return set_error(FRESCO_ERR_ARG, "fresco_temporal_attn_fwd: bad input row stride");
+  cudaStream_t s = (cudaStream_t)stream;
+  // row kernel (one output row per thread) for the head dims / frame counts of the BASELINE configs
+  const bool dense = in_row_stride == heads * head_dim;
+  if (frames <= 16 && (option(OPT_TEMPORAL_V, 2) == 2 || !dense)) {
+    int rc = FRESCO_ERR_UNSUPPORTED;
+#define ROWS(DD)                                                                                                      \
+  rc = frames <= 8 ? launch_temporal_rows<DD, 8>(q_raw, k_raw, v_src, out, fwd_map, traj_mask, chunks, frames, tokens, \
+                                                 heads, scale, in_row_stride, s)                                       \
+                   : launch_temporal_rows<DD, 16>(q_raw, k_raw, v_src, out, fwd_map, traj_mask, chunks, frames, tokens,\
+                                                  heads, scale, in_row_stride, s)
+    if (head_dim == 40) ROWS(40);
+    else if (head_dim == 64) ROWS(64);
+    else if (head_dim == 80) ROWS(80);
+#undef ROWS
+    if (rc != FRESCO_ERR_UNSUPPORTED) return rc;
+  }
+  if (!dense) return set_error(FRESCO_ERR_UNSUPPORTED, "fresco_temporal_attn_fwd: strided inputs need frames <= 16 and head_dim 40/64/80");
   const size_t per_warp =
       (((size_t)3 * frames * head_dim * sizeof(__half) + (size_t)frames * frames * sizeof(float)) + 15) & ~size_t(15);
   const size_t smem = per_warp * heads;
@@ -562,7 +1113,7 @@ extern "C" int fresco_temporal_attn_fwd(const void* q_raw, const void* k_raw, co
     cudaError_t e = cudaFuncSetAttribute(temporal_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(temporal_attn)");
   }
-  temporal_attn_kernel<<<chunks * tokens, 32 * heads, smem, (cudaStream_t)stream>>>(
+  temporal_attn_kernel<<<chunks * tokens, 32 * heads, smem, s>>>(
       (const __half*)q_raw, (const __half*)k_raw, (const __half*)v_src, (__half*)out, fwd_map, traj_mask, frames,
       tokens, heads, head_dim, scale);
   return check_launch("temporal_attn_kernel");
@@ -578,20 +1129,34 @@ extern "C" int fresco_flow_warp(const float* src, const float* flow, float* dst,
   return check_launch("flow_warp_kernel");
 }
 
+template <typename T, int K>
+static int launch_chain_group(const void* sample, void* out, const float* bwd_flow, const float* fwd_flow_last,
+                              const float* blend, int chunks, int frames, int channels, int h, int w, cudaStream_t s) {
+  const size_t smem = (size_t)2 * K * h * w * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(warp_chain_group_kernel<T, K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         200 * 1024);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(warp_chain_group)");
+    attr_set = true;
+  }
+  const int planes = chunks * channels;
+  warp_chain_group_kernel<T, K><<<(planes + K - 1) / K, 512, smem, s>>>((const T*)sample, (T*)out, bwd_flow, fwd_flow_last,
+                                                                       blend, frames, channels, planes, h, w);
+  return check_launch("warp_chain_group_kernel");
+}
+
 template <typename T>
 static int launch_chain(const void* sample, void* out, const float* bwd_flow, const float* fwd_flow_last,
                         const float* blend, int chunks, int frames, int channels, int h, int w, cudaStream_t s) {
-  const size_t smem = (size_t)2 * h * w * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(warp_chain_smem_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         200 * 1024);
-    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(warp_chain)");
-    attr_set = true;
-  }
-  warp_chain_smem_kernel<T><<<chunks * channels, 256, smem, s>>>((const T*)sample, (T*)out, bwd_flow, fwd_flow_last,
-                                                                 blend, frames, channels, h, w);
-  return check_launch("warp_chain_smem_kernel");
+  // planes per CTA: as many as keep two CTAs on an SM (<= ~100 KB of shared memory each) and the grid above two waves
+  const size_t plane2 = (size_t)2 * h * w * sizeof(float);
+  const int planes = chunks * channels;
+  if (8 * plane2 <= 100 * 1024 && planes / 8 >= 296)
+    return launch_chain_group<T, 8>(sample, out, bwd_flow, fwd_flow_last, blend, chunks, frames, channels, h, w, s);
+  if (3 * plane2 <= 100 * 1024 && planes / 3 >= 296)
+    return launch_chain_group<T, 3>(sample, out, bwd_flow, fwd_flow_last, blend, chunks, frames, channels, h, w, s);
+  return launch_chain_group<T, 1>(sample, out, bwd_flow, fwd_flow_last, blend, chunks, frames, channels, h, w, s);
 }
 
 extern "C" int fresco_warp_fuse_chain(const void* sample, void* out, int is_half, const float* bwd_flow,
@@ -647,6 +1212,55 @@ extern "C" int fresco_warp_loss_fwd_bwd(const float* cs, const float* fwd_flow, 
   if (n_overflow > 0 && !overflow) return set_error(FRESCO_ERR_ARG, "fresco_warp_loss_fwd_bwd: overflow list missing");
   if (chunks <= 0 || frames < 2 || channels <= 0 || h <= 0 || w <= 0 || h * w > 65535)
     return set_error(FRESCO_ERR_ARG, "fresco_warp_loss_fwd_bwd: bad shape (frames >= 2, h*w <= 65535)");
+  const double numel = (double)chunks * frames * channels * h * w;
+  const float kk = (float)(2.0 / numel);
+  cudaStream_t s = (cudaStream_t)stream;
+  // ---- channel-grouped kernel: 512 threads; P pixel slots x KT planes per thread (carried in registers)
+  {
+    const int T = 512, hw = h * w, planes = chunks * channels;
+    const int P = hw > T ? (hw + T - 1) / T : 1;
+    const int G = hw >= T ? 1 : T / hw;
+    int KT = 0;
+    for (int cand = 4; cand >= 1; cand >>= 1) {        // (8 planes per thread spill at 64 registers)
+      const size_t smem_c = (size_t)cand * G * hw * 12;
+      if (P * cand > 18 || smem_c > 100 * 1024) continue;
+      if (cand > 1 && (planes + cand * G - 1) / (cand * G) < 296) continue;     // keep the grid above two waves
+      KT = cand;
+      break;
+    }
+    if (KT == 0 && P == 18 && (size_t)G * hw * 12 <= 200 * 1024) KT = 1;
+    int rc = FRESCO_ERR_UNSUPPORTED;
+    if (KT > 0) {
+      const int K = KT * G;
+      const size_t smem = (size_t)K * hw * 12;
+      const int grid = (planes + K - 1) / K;
+#define LOSS_CASE(PP, KK)                                                                                               \
+  if (P == PP && KT == KK) {                                                                                            \
+    static bool attr_set = false;                                                                                       \
+    if (!attr_set) {                                                                                                    \
+      cudaError_t e = cudaFuncSetAttribute(warp_loss_group_kernel<PP, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                           200 * 1024);                                                                 \
+      if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(warp_loss_group)");                          \
+      attr_set = true;                                                                                                  \
+    }                                                                                                                   \
+    warp_loss_group_kernel<PP, KK><<<grid, T, smem, s>>>(cs, fwd_flow, bwd_flow, fwd_keep, bwd_keep,                    \
+                                                         (const uint4*)bwd_ell, (const uint4*)fwd_ell, overflow,        \
+                                                         n_overflow, grad, loss_acc, accumulate, frames, channels,      \
+                                                         planes, h, w, G, kk);                                          \
+    rc = check_launch("warp_loss_group_kernel");                                                                        \
+  }
+      LOSS_CASE(1, 1) LOSS_CASE(1, 2) LOSS_CASE(1, 4)
+      LOSS_CASE(2, 1) LOSS_CASE(2, 2) LOSS_CASE(2, 4)
+      LOSS_CASE(3, 1) LOSS_CASE(3, 2) LOSS_CASE(3, 4)
+      LOSS_CASE(4, 1) LOSS_CASE(4, 2) LOSS_CASE(4, 4)
+      LOSS_CASE(5, 1) LOSS_CASE(5, 2)
+      LOSS_CASE(8, 1) LOSS_CASE(8, 2)
+      LOSS_CASE(18, 1)
+#undef LOSS_CASE
+    }
+    if (rc != FRESCO_ERR_UNSUPPORTED) return rc;
+  }
+  // ---- any other plane size: one CTA per plane (round-1 kernel)
   const size_t smem = (size_t)4 * h * w * sizeof(float);
   if (smem > 200 * 1024) return set_error(FRESCO_ERR_UNSUPPORTED, "fresco_warp_loss_fwd_bwd: plane too large for shared memory");
   static bool attr_set = false;
@@ -655,27 +1269,30 @@ extern "C" int fresco_warp_loss_fwd_bwd(const float* cs, const float* fwd_flow, 
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(warp_loss)");
     attr_set = true;
   }
-  const double numel = (double)chunks * frames * channels * h * w;
-  warp_loss_kernel<<<chunks * channels, 256, smem, (cudaStream_t)stream>>>(
+  warp_loss_kernel<<<chunks * channels, 256, smem, s>>>(
       cs, fwd_flow, bwd_flow, fwd_keep, bwd_keep, (const uint4*)bwd_ell, (const uint4*)fwd_ell, overflow, n_overflow,
-      grad, loss_acc, accumulate, frames, channels, h, w, (float)(2.0 / numel));
+      grad, loss_acc, accumulate, frames, channels, h, w, kk);
   return check_launch("warp_loss_kernel");
 }
 
 extern "C" int fresco_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
-                                int step, float lr, float beta1, float beta2, float eps, void* stream) {
+                                int step, double lr, double beta1, double beta2, double eps, void* stream) {
   if (!param || !grad || !exp_avg || !exp_avg_sq) return set_error(FRESCO_ERR_ARG, "fresco_adam_step: null pointer");
   if (n <= 0 || step <= 0) return set_error(FRESCO_ERR_ARG, "fresco_adam_step: bad n/step");
   double bc1 = 1.0, bc2 = 1.0, p1 = 1.0, p2 = 1.0;
   for (int i = 0; i < step; ++i) {
-    p1 *= (double)beta1;
-    p2 *= (double)beta2;
+    p1 *= beta1;
+    p2 *= beta2;
   }
   bc1 = 1.0 - p1;
   bc2 = 1.0 - p2;
   double sq = bc2 > 0 ? 1.0 / __builtin_sqrt(bc2) : 1.0;
-  adam_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, 1.f - beta1,
-                                                                  beta2, 1.f - beta2, (float)(lr / bc1), (float)sq, eps);
+  // hyper-parameters arrive as doubles (python floats) and are rounded to fp32 one by one, as torch.optim.Adam does
+  // with its python scalars: (float)(1 - beta2) is NOT 1.f - (float)beta2
+  adam_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n,
+                                                                  (float)(1.0 - beta1), (float)beta2,
+                                                                  (float)(1.0 - beta2), (float)(lr / bc1), (float)sq,
+                                                                  (float)eps);
   return check_launch("adam_kernel");
 }
 

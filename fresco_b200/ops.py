@@ -41,6 +41,66 @@ def kv_compact(k: torch.Tensor, v: torch.Tensor, idx: torch.Tensor, chunks: int)
     return k_out, v_out
 
 
+def kv_compact_packed(k: torch.Tensor, v: torch.Tensor, idx: torch.Tensor, kv_out: torch.Tensor, chunks: int):
+    """Selected K and V rows side by side into rows [0, n_sel) of kv_out [chunks, out_rows, 2C] (exchange send buffer)."""
+    B, tokens, C = k.shape
+    rows = (B // chunks) * tokens
+    L.check(L.lib().fresco_kv_compact_packed(L.ptr(k), L.ptr(v), L.ptr(idx), L.ptr(kv_out), chunks, rows, idx.numel(),
+                                             kv_out.shape[1], C, L.stream()), "fresco_kv_compact_packed")
+    return kv_out
+
+
+def rows_gather(src: torch.Tensor, idx: torch.Tensor, dst: torch.Tensor, dst_col: int = 0):
+    """dst[r, dst_col : dst_col + W] = src[idx[r], :] for 2-D row views (src [*, W], dst [n, >= dst_col + W])."""
+    W = src.shape[-1]
+    es = src.element_size()
+    L.check(L.lib().fresco_rows_gather(L.ptr(src), L.ptr(idx), L.ptr(dst), idx.numel(), W * es, dst.shape[-1] * es,
+                                       dst_col * es, L.stream()), "fresco_rows_gather")
+    return dst
+
+
+def rows_scatter(src: torch.Tensor, idx: torch.Tensor, dst: torch.Tensor):
+    """dst[idx[r], :] = src[r, :]."""
+    W = src.shape[-1]
+    L.check(L.lib().fresco_rows_scatter(L.ptr(src), L.ptr(idx), L.ptr(dst), idx.numel(), W * src.element_size(),
+                                        L.stream()), "fresco_rows_scatter")
+    return dst
+
+
+def attn_fwd_kv_packed(q: torch.Tensor, kv: torch.Tensor, heads: int, q_per_kv: int, softmax_scale: float,
+                       out: Optional[torch.Tensor] = None):
+    """q [Bq, Lq, C]; kv [Bq/q_per_kv, Lk, 2C] with K in columns [0, C) and V in [C, 2C) of every row."""
+    Bq, Lq, C = q.shape
+    d = C // heads
+    Lk = kv.shape[1]
+    if q.dtype != torch.float16 or kv.dtype != torch.float16 or kv.shape[2] != 2 * C:
+        raise L.FrescoError("attn_fwd_kv_packed: fp16 q [B,L,C] and kv [B/q_per_kv, Lk, 2C] expected")
+    if out is None:
+        out = torch.empty_like(q)
+    ev = _prof_begin()
+    kp = L.ptr(kv)
+    L.check(L.lib().fresco_attn_fwd_kv_strided(L.ptr(q), kp, kp + C * 2, L.ptr(out), Bq, Lq, Lk, heads, d, q_per_kv,
+                                               2 * C, Lk * 2 * C, float(softmax_scale), 0.0, L.stream()),
+            "fresco_attn_fwd_kv_strided")
+    _prof_end(ev, "attn_d%d_L%d_Lk%d" % (d, Lq, Lk), 4.0 * Bq * Lq * Lk * C)
+    return out
+
+
+def temporal_attn_fwd_packed(qkv: torch.Tensor, fwd_map, traj_mask, chunks: int, heads: int, scale: float):
+    """qkv [chunks*frames, tokens, 3C] with q | k | v side by side in every row -> out [chunks*frames, tokens, C]."""
+    B, tokens, C3 = qkv.shape
+    C = C3 // 3
+    frames = B // chunks
+    out = torch.empty(B, tokens, C, dtype=qkv.dtype, device=qkv.device)
+    base = L.ptr(qkv)
+    ev = _prof_begin()
+    L.check(L.lib().fresco_temporal_attn_fwd_strided(base, base + 2 * C, base + 4 * C, L.ptr(out), L.ptr(fwd_map),
+                                                     L.ptr(traj_mask), chunks, frames, tokens, heads, C // heads, C3,
+                                                     float(scale), L.stream()), "fresco_temporal_attn_fwd_strided")
+    _prof_end(ev, "temporal_d%d_L%d_N%d" % (C // heads, tokens, frames), 8.0 * B * tokens * C)
+    return out
+
+
 def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, q_per_kv: int = 1,
              softmax_scale: Optional[float] = None, diag_bias: float = 0.0, out: Optional[torch.Tensor] = None):
     """q [Bq, Lq, C], k/v [Bq/q_per_kv, Lk, C] fp16 token-major -> [Bq, Lq, C]."""
@@ -64,9 +124,12 @@ def temporal_attn_fwd(q_raw, k_raw, v_src, fwd_map, traj_mask, chunks: int, head
     B, tokens, C = q_raw.shape
     frames = B // chunks
     out = torch.empty_like(v_src)
+    ev = _prof_begin()
     L.check(L.lib().fresco_temporal_attn_fwd(L.ptr(q_raw), L.ptr(k_raw), L.ptr(v_src), L.ptr(out), L.ptr(fwd_map),
                                              L.ptr(traj_mask), chunks, frames, tokens, heads, C // heads,
                                              float(scale), L.stream()), "fresco_temporal_attn_fwd")
+    # algorithmic bytes: 3 reads + 1 write of [B, L, C] fp16 (+ indices and mask, < 1 %)
+    _prof_end(ev, "temporal_d%d_L%d_N%d" % (C // heads, tokens, frames), 8.0 * B * tokens * C)
     return out
 
 

@@ -47,6 +47,16 @@ int fresco_set_option(const char* name, int value);
  * k_out/v_out half [chunks, n_sel, channels]; shared by every query frame (no N x broadcast) */
 int fresco_kv_compact(const void* k, const void* v, const int32_t* idx, void* k_out, void* v_out, int chunks,
                       int rows_per_chunk, int n_sel, int channels, void* stream);
+/* same selection, K and V rows side by side: kv_out half [chunks, out_rows, 2*channels], rows [0, n_sel) written
+ * (the send buffer of the frame-sharded K/V exchange, SURVEY 8e exchange 1; out_rows >= n_sel is the padded count) */
+int fresco_kv_compact_packed(const void* k, const void* v, const int32_t* idx, void* kv_out, int chunks,
+                             int rows_per_chunk, int n_sel, int out_rows, int channels, void* stream);
+/* row gather / scatter by index (16-byte granularity), the data movement around the collectives of the frame-sharded
+ * path: gather  dst[r, dst_offset : dst_offset+row_bytes] = src[idx[r], :]  (dst rows dst_stride_bytes apart);
+ *       scatter dst[idx[r], :] = src[r, :]. */
+int fresco_rows_gather(const void* src, const int32_t* idx, void* dst, long long n_rows, int row_bytes,
+                       int dst_stride_bytes, int dst_offset_bytes, void* stream);
+int fresco_rows_scatter(const void* src, const int32_t* idx, void* dst, long long n_rows, int row_bytes, void* stream);
 
 /* ---- A3 / A4: dense attention forward (tcgen05 + TMEM + TMA) -------------------------------
  * replaces F.scaled_dot_product_attention at src/diffusion_hacked.py:281-285 (spatial-guided:
@@ -56,6 +66,12 @@ int fresco_kv_compact(const void* k, const void* v, const int32_t* idx, void* k_
  * out = softmax(q k^T * softmax_scale + diag_bias * I) v, per head. head_dim in {40,64,80,128}. */
 int fresco_attn_fwd(const void* q, const void* k, const void* v, void* out, int batch_q, int q_len, int kv_len,
                     int heads, int head_dim, int q_per_kv, float softmax_scale, float diag_bias, void* stream);
+/* same with explicit K/V strides in elements (rows kv_row_stride apart, batches kv_batch_stride apart): K and V may
+ * live side by side in one [batch, kv_len, 2*heads*head_dim] buffer (v = k + heads*head_dim), as the frame-sharded
+ * exchange delivers them. */
+int fresco_attn_fwd_kv_strided(const void* q, const void* k, const void* v, void* out, int batch_q, int q_len,
+                               int kv_len, int heads, int head_dim, int q_per_kv, long long kv_row_stride,
+                               long long kv_batch_stride, float softmax_scale, float diag_bias, void* stream);
 
 /* ---- A5: temporal-guided (FLATTEN) attention, fused gather -> N x N softmax -> scatter -----
  * replaces src/diffusion_hacked.py:320-367.
@@ -66,6 +82,11 @@ int fresco_attn_fwd(const void* q, const void* k, const void* v, void* out, int 
 int fresco_temporal_attn_fwd(const void* q_raw, const void* k_raw, const void* v_src, void* out,
                              const int64_t* fwd_map, const uint8_t* traj_mask, int chunks, int frames, int tokens,
                              int heads, int head_dim, float scale, void* stream);
+/* same with the q/k/v token rows in_row_stride elements apart (>= heads*head_dim; e.g. q | k | v interleaved in one
+ * 3C-wide row, as the trajectory-sharded exchange delivers them); out stays dense. */
+int fresco_temporal_attn_fwd_strided(const void* q_raw, const void* k_raw, const void* v_src, void* out,
+                                     const int64_t* fwd_map, const uint8_t* traj_mask, int chunks, int frames,
+                                     int tokens, int heads, int head_dim, int in_row_stride, float scale, void* stream);
 
 /* ---- W3: bilinear flow warp (zero padding per tap, pixel coordinates) ----------------------
  * replaces gmflow/geometry.py:65-72 (flow_warp) + :41-62 (grid_sample, align_corners=True).
@@ -125,7 +146,7 @@ size_t fresco_gram_grad_workspace_bytes(int batch, int tokens, int channels);
  * fresco_adain replaces src/utils.py:70-78 incl. the eps quirk (style eps = 1, content eps = 1e-5,
  * unbiased variance).  content float [planes, hw]; style/out half or float [planes, hw].          */
 int fresco_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, int step,
-                     float lr, float beta1, float beta2, float eps, void* stream);
+                     double lr, double beta1, double beta2, double eps, void* stream);
 int fresco_adain(const float* content, const void* style, void* out, int is_half, int planes, int hw, void* stream);
 
 /* ---- G1: GMFlow global correlation + softmax + expected coordinates -------------------------

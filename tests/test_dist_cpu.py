@@ -14,10 +14,25 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 class TorchBackend:
-    def kv_compact(self, k, v, idx, chunks):
+    """torch stand-ins with the semantics of the C entry points (fresco_kv_compact_packed, fresco_rows_gather /
+    _scatter, fresco_attn_fwd[_kv_strided], fresco_temporal_attn_fwd[_strided])"""
+
+    def kv_compact_packed(self, k, v, idx, kv_out, chunks):
         B, L, C = k.shape
         rows = (B // chunks) * L
-        return k.reshape(chunks, rows, C)[:, idx.long()], v.reshape(chunks, rows, C)[:, idx.long()]
+        n = idx.numel()
+        kv_out[:, :n, :C] = k.reshape(chunks, rows, C)[:, idx.long()]
+        kv_out[:, :n, C:] = v.reshape(chunks, rows, C)[:, idx.long()]
+        kv_out[:, n:] = float("nan")                       # padding rows must never be read
+        return kv_out
+
+    def rows_gather(self, src, idx, dst, dst_col=0):
+        dst[:, dst_col:dst_col + src.shape[-1]] = src[idx.long()]
+        return dst
+
+    def rows_scatter(self, src, idx, dst):
+        dst[idx.long()] = src
+        return dst
 
     def attn_fwd(self, q, k, v, heads, q_per_kv, softmax_scale, diag_bias=0.0):
         B, L, C = q.shape
@@ -29,6 +44,15 @@ class TorchBackend:
         if diag_bias:
             s = s + torch.eye(L, kh.shape[2]) * diag_bias
         return (torch.softmax(s, -1) @ vh).transpose(1, 2).reshape(B, L, C)
+
+    def attn_fwd_kv_packed(self, q, kv, heads, q_per_kv, softmax_scale):
+        C = q.shape[-1]
+        return self.attn_fwd(q, kv[..., :C].contiguous(), kv[..., C:].contiguous(), heads, q_per_kv, softmax_scale)
+
+    def temporal_attn_fwd_packed(self, qkv, fwd_map, traj_mask, chunks, heads, scale):
+        C = qkv.shape[-1] // 3
+        return self.temporal_attn_fwd(qkv[..., :C].contiguous(), qkv[..., C:2 * C].contiguous(), qkv[..., 2 * C:].contiguous(),
+                                      fwd_map, traj_mask, chunks, heads, scale)
 
     def temporal_attn_fwd(self, q, k, v, fwd_map, traj_mask, chunks, heads, scale):
         B, L, C = q.shape

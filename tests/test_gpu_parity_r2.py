@@ -72,9 +72,9 @@ def attn_opts(fb):
 
 
 VARIANTS = [
-    dict(FRESCO_ATTN_WIDE=1, FRESCO_ATTN_POLY=0),
-    dict(FRESCO_ATTN_WIDE=1, FRESCO_ATTN_POLY=4),
-    dict(FRESCO_ATTN_WIDE=1, FRESCO_ATTN_POLY=8),
+    dict(FRESCO_ATTN_WIDE=2, FRESCO_ATTN_POLY=0),
+    dict(FRESCO_ATTN_WIDE=2, FRESCO_ATTN_POLY=4),
+    dict(FRESCO_ATTN_WIDE=4, FRESCO_ATTN_POLY=0),                        # four threads per row: head_dim 64 / 80
     dict(FRESCO_ATTN_WIDE=0, FRESCO_ATTN_POLY=0, FRESCO_ATTN_ROWSUM=0),
     dict(FRESCO_ATTN_WIDE=0, FRESCO_ATTN_POLY=0, FRESCO_ATTN_ROWSUM=1),
     dict(FRESCO_ATTN_WIDE=0, FRESCO_ATTN_POLY=4, FRESCO_ATTN_ROWSUM=1),
@@ -89,6 +89,8 @@ def test_attention_variants_all_head_dims(fb, attn_opts, variant, d):
     half of the wide kernel fully masked (20, 33, 77), the diagonal bias + k-scale of spatial-guided attention."""
     if variant.get("FRESCO_ATTN_NARROW") and d != 40:
         pytest.skip("narrow kernel: head_dim 40 only")
+    if variant.get("FRESCO_ATTN_WIDE") == 4 and d not in (64, 80):
+        pytest.skip("four threads per row: head_dim 64 / 80 only")
     attn_opts(**variant)
     heads = 2
     g = torch.Generator(device="cuda").manual_seed(17 + d)
