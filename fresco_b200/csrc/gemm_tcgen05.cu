@@ -37,6 +37,8 @@ struct GemmParams {
   int w;
   int flow_batch_offset;      // forward flows at [0,B), backward at [B,2B)
   float scale_log2;
+  const float2* vals;         // optional V [batch, N] (2 channels per key); null: V = the key's (x, y) pixel coordinate and
+                              // the query's own coordinate is subtracted from the result (flow = correspondence - grid)
 };
 
 template <int EPI, bool B_MN>
@@ -294,13 +296,15 @@ tile_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           tmem_ld_wait();
           const int colbase = n0 + c * 32;
           int kx = colbase % p.w, ky = colbase / p.w;
+          const float2* vrow = p.vals ? p.vals + (size_t)batch * p.N + colbase : nullptr;
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             if (colbase + i < p.N) {
               const float pe = fast_exp2(fmaf(__uint_as_float(r[i]), p.scale_log2, -m_new));
+              const float2 vv = vrow ? __ldg(vrow + i) : make_float2((float)kx, (float)ky);
               s0 += pe;
-              sx = fmaf(pe, (float)kx, sx);
-              sy = fmaf(pe, (float)ky, sy);
+              sx = fmaf(pe, vv.x, sx);
+              sy = fmaf(pe, vv.y, sy);
             }
             if (++kx == p.w) {
               kx = 0;
@@ -324,8 +328,8 @@ tile_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       const float inv = 1.f / l_run;
       const int qx = gm % p.w, qy = gm / p.w;
       float* f = p.flow + (size_t)(p.flow_batch_offset + batch) * 2 * p.M;
-      f[gm] = ax * inv - (float)qx;
-      f[p.M + gm] = ay * inv - (float)qy;
+      f[gm] = ax * inv - (p.vals ? 0.f : (float)qx);
+      f[p.M + gm] = ay * inv - (p.vals ? 0.f : (float)qy);
     }
   }
   tc_fence_before();
@@ -464,18 +468,25 @@ extern "C" int fresco_gram_grad(const void* tsign, const void* xhat, const float
     return set_error(FRESCO_ERR_ARG, "fresco_gram_grad: tokens and channels must be multiples of 8");
   if (workspace_bytes < fresco_gram_grad_workspace_bytes(batch, tokens, channels))
     return set_error(FRESCO_ERR_ARG, "fresco_gram_grad: workspace too small");
-  CUtensorMap ta, tb;
-  if (make_kmajor_map(&ta, tsign, tokens, tokens, batch)) return FRESCO_ERR_TENSORMAP;
-  if (make_mnmajor_map(&tb, xhat, tokens, channels, batch)) return FRESCO_ERR_TENSORMAP;
-  GemmParams p = {};
-  p.M = tokens;
-  p.N = channels;
-  p.K = tokens;
-  p.n_iter = 1;
-  p.out = static_cast<float*>(workspace);
-  p.alpha = (float)((double)weight / ((double)batch * tokens * tokens));
   cudaStream_t s = (cudaStream_t)stream;
-  int rc = launch_gemm<EPI_STORE, true>(ta, tb, p, dim3((channels + 127) / 128, (tokens + 127) / 128, batch), s);
+  const float alpha = (float)((double)weight / ((double)batch * tokens * tokens));
+  int rc;
+  if (option(OPT_GRAM_V, 2) == 2) {
+    // persistent 128 x 256 tiles (gram_tcgen05.cu): tensor-pipe bound instead of MMA-issue bound
+    rc = fresco_gram_tx(tsign, xhat, static_cast<float*>(workspace), batch, tokens, channels, alpha, stream);
+  } else {
+    CUtensorMap ta, tb;
+    if (make_kmajor_map(&ta, tsign, tokens, tokens, batch)) return FRESCO_ERR_TENSORMAP;
+    if (make_mnmajor_map(&tb, xhat, tokens, channels, batch)) return FRESCO_ERR_TENSORMAP;
+    GemmParams p = {};
+    p.M = tokens;
+    p.N = channels;
+    p.K = tokens;
+    p.n_iter = 1;
+    p.out = static_cast<float*>(workspace);
+    p.alpha = alpha;
+    rc = launch_gemm<EPI_STORE, true>(ta, tb, p, dim3((channels + 127) / 128, (tokens + 127) / 128, batch), s);
+  }
   if (rc) return rc;
   const int tiles = (tokens + 31) / 32;
   gram_project_kernel<<<batch * tiles, 256, 0, s>>>(static_cast<const float*>(workspace), (const __half*)xhat, norms,
@@ -524,4 +535,28 @@ extern "C" int gmflow_global_corr_softmax(const float* feature0, const float* fe
   if (rc || !bidir) return rc;
   p.flow_batch_offset = batch;                                  // backward: softmax over the transposed volume
   return launch_gemm<EPI_GMFLOW, false>(m1, m0, p, grid, s);
+}
+
+// GMFlow's flow-propagation attention (gmflow/transformer.py:353-374): out = softmax(q k^T / sqrt(C)) flow, with the
+// 2-channel flow field as V.  Same kernel as the global correlation (online softmax over all key tiles, the
+// [B, L, L] probability volume never exists); q, k are token-major fp16 [batch, tokens, channels].
+extern "C" int gmflow_flow_attention(const void* q, const void* k, const float* values, float* out, int batch, int tokens,
+                                     int channels, float softmax_scale, void* stream) {
+  if (!q || !k || !values || !out) return set_error(FRESCO_ERR_ARG, "gmflow_flow_attention: null pointer");
+  if (batch <= 0 || tokens <= 0 || channels <= 0 || channels % 8 != 0 || softmax_scale <= 0.f)
+    return set_error(FRESCO_ERR_ARG, "gmflow_flow_attention: bad shape (channels must be a multiple of 8)");
+  CUtensorMap mq, mk;
+  if (make_kmajor_map(&mq, q, tokens, channels, batch)) return FRESCO_ERR_TENSORMAP;
+  if (make_kmajor_map(&mk, k, tokens, channels, batch)) return FRESCO_ERR_TENSORMAP;
+  GemmParams p = {};
+  p.M = tokens;
+  p.N = tokens;
+  p.K = channels;
+  p.n_iter = (tokens + 127) / 128;
+  p.flow = out;
+  p.w = tokens;                    // unused with vals
+  p.flow_batch_offset = 0;
+  p.scale_log2 = softmax_scale * 1.4426950408889634f;
+  p.vals = reinterpret_cast<const float2*>(values);
+  return launch_gemm<EPI_GMFLOW, false>(mq, mk, p, dim3(1, (tokens + 127) / 128, batch), (cudaStream_t)stream);
 }

@@ -334,12 +334,35 @@ class OptimizeTrace:
         self.losses: List[float] = []
 
 
+class GramTarget:
+    """Spatial-consistency target of one decoder level in the form the kernels want it: the row-normalised reference
+    features ``yhat`` [2N, L, C] fp16 -- exactly the operand the reference feeds its fp16 ``bmm``
+    (src/diffusion_hacked.py:889-893) -- instead of the fp32 [2N, L, L] product (1.07 GB at layer 3, read once per Adam
+    iteration by the reference).  The Gram tile is recomputed inside the loss kernel.  Quacks like the tensor the
+    reference stores where optimize_feature looks at it (``.shape[1] == h*w``); ``dense()`` materialises the
+    reference's tensor."""
+
+    def __init__(self, yhat: torch.Tensor):
+        self.yhat = yhat.contiguous()
+        b, l, _ = yhat.shape
+        self.shape = torch.Size((b, l, l))
+        self.dtype = torch.float32
+        self.device = yhat.device
+
+    def dense(self) -> torch.Tensor:
+        return torch.bmm(self.yhat, self.yhat.transpose(-1, -2)).to(torch.float32)
+
+
 def spatial_loss_grad(cs_bcl, target, intra_weight, grad_bcl, loss_acc=None):
     """One evaluation of the spatial-consistency term (src/diffusion_hacked.py:469-476) and its gradient:
     ``grad_bcl += d/dcs [ intra_weight * l1_loss(Xh Xh^T, target) ]`` for cs [2N, C, L] fp32 (channel-major, as the
-    UNet holds it); ``loss_acc`` (device float or None) gets the loss value added."""
+    UNet holds it); ``target`` is a GramTarget (fast path) or the reference's dense fp32 [2N, L, L] tensor;
+    ``loss_acc`` (device float or None) gets the loss value added."""
     xhat, norms = ops.gram_normalize(cs_bcl)
-    tsign = ops.gram_sign(xhat, target, intra_weight, loss_acc)
+    if isinstance(target, GramTarget):
+        tsign = ops.gram_sign_ref(xhat, target.yhat, intra_weight, loss_acc)
+    else:
+        tsign = ops.gram_sign(xhat, target, intra_weight, loss_acc)
     ops.gram_grad(tsign, xhat, norms, grad_bcl, intra_weight)
 
 
@@ -370,7 +393,7 @@ def optimize_feature(sample, flows, occs, correlation_matrix=[], intra_weight=1e
             target = tmp
             break
     spatial = target is not None and intra_weight > 0
-    if spatial:
+    if spatial and not isinstance(target, GramTarget):
         target = target.to(torch.float32).contiguous()
     loss_acc = torch.zeros(1, dtype=torch.float32, device=sample.device) if trace is not None else None
     for it in range(1, iters + 1):
@@ -481,14 +504,18 @@ def cross_frame_attn_masks(bwd_occs: torch.Tensor, scales: Sequence[float] = (8.
 
 
 @torch.no_grad()
-def gram_targets(features: Sequence[torch.Tensor]):
-    """Normalised-Gram targets of decoder features, fp32 [2N, L, L] each
-    (src/diffusion_hacked.py:889-895)."""
+def gram_targets(features: Sequence[torch.Tensor], dense: bool = False):
+    """Normalised-Gram targets of decoder features (src/diffusion_hacked.py:889-895).  ``dense=True`` gives what the
+    reference stores, fp32 [2N, L, L] each; the default keeps the normalised features (GramTarget) and lets the loss
+    kernel recompute the products."""
     out = []
     for t in features:
         v = t.reshape(t.shape[0], t.shape[1], -1).transpose(1, 2)
         v = v / ((v ** 2).sum(dim=2, keepdim=True) ** 0.5)
-        out.append(torch.bmm(v, v.transpose(-1, -2)).to(torch.float32))
+        if dense or not v.is_cuda:
+            out.append(torch.bmm(v, v.transpose(-1, -2)).to(torch.float32))
+        else:
+            out.append(GramTarget(v.to(torch.float16)))
     return out
 
 

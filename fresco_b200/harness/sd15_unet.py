@@ -282,7 +282,13 @@ class SD15UNet(nn.Module):
                 mid_block_additional_residual: Optional[torch.Tensor] = None, encoder_attention_mask=None,
                 return_dict: bool = True):
         if not torch.is_tensor(timestep):
-            timestep = torch.tensor([timestep], dtype=torch.int64, device=sample.device)
+            # one device tensor per distinct python timestep, made once: a host-to-device copy per forward would be a
+            # sync (and is not allowed while a CUDA graph is being captured)
+            key = (int(timestep), str(sample.device))
+            cache = self.__dict__.setdefault("_timestep_cache", {})
+            if key not in cache:
+                cache[key] = torch.tensor([int(timestep)], dtype=torch.int64, device=sample.device)
+            timestep = cache[key]
         elif timestep.ndim == 0:
             timestep = timestep[None].to(sample.device)
         timestep = timestep.expand(sample.shape[0])

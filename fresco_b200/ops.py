@@ -22,11 +22,13 @@ def _prof_begin():
     return ev
 
 
-def _prof_end(ev, tag, work):
+def _prof_end(ev, tag, work, bound="tensor"):
+    """``work`` = algorithmic flops (bound "tensor") or bytes (bound "hbm") of the launch(es) between the two events,
+    per SURVEY.md 8(d)."""
     if ev is not None:
         end = torch.cuda.Event(enable_timing=True)
         end.record(torch.cuda.current_stream())
-        PROFILE.append((tag, work, ev, end))
+        PROFILE.append((tag, work, ev, end, bound))
 
 
 def kv_compact(k: torch.Tensor, v: torch.Tensor, idx: torch.Tensor, chunks: int):
@@ -36,8 +38,10 @@ def kv_compact(k: torch.Tensor, v: torch.Tensor, idx: torch.Tensor, chunks: int)
     n_sel = idx.numel()
     k_out = torch.empty(chunks, n_sel, C, dtype=k.dtype, device=k.device)
     v_out = torch.empty_like(k_out)
+    ev = _prof_begin()
     L.check(L.lib().fresco_kv_compact(L.ptr(k), L.ptr(v), L.ptr(idx), L.ptr(k_out), L.ptr(v_out), chunks, rows,
                                       n_sel, C, L.stream()), "fresco_kv_compact")
+    _prof_end(ev, "kv_compact_C%d_n%d" % (C, n_sel), 8.0 * chunks * n_sel * C, "hbm")     # K and V rows: read + write
     return k_out, v_out
 
 
@@ -45,8 +49,10 @@ def kv_compact_packed(k: torch.Tensor, v: torch.Tensor, idx: torch.Tensor, kv_ou
     """Selected K and V rows side by side into rows [0, n_sel) of kv_out [chunks, out_rows, 2C] (exchange send buffer)."""
     B, tokens, C = k.shape
     rows = (B // chunks) * tokens
+    ev = _prof_begin()
     L.check(L.lib().fresco_kv_compact_packed(L.ptr(k), L.ptr(v), L.ptr(idx), L.ptr(kv_out), chunks, rows, idx.numel(),
                                              kv_out.shape[1], C, L.stream()), "fresco_kv_compact_packed")
+    _prof_end(ev, "kv_compact_C%d_n%d" % (C, idx.numel()), 8.0 * chunks * idx.numel() * C, "hbm")
     return kv_out
 
 
@@ -149,13 +155,28 @@ def warp_fuse_chain(sample, bwd_flow, fwd_flow_last, blend, chunks: int, out=Non
     is_half = 1 if sample.dtype == torch.float16 else 0
     if not is_half and sample.dtype != torch.float32:
         raise L.FrescoError("warp_fuse_chain: fp16 or fp32 only")
+    ev = _prof_begin()
     L.check(L.lib().fresco_warp_fuse_chain(L.ptr(sample), L.ptr(out), is_half, L.ptr(bwd_flow), L.ptr(fwd_flow_last),
                                            L.ptr(blend), chunks, B // chunks, C, h, w, L.stream()),
             "fresco_warp_fuse_chain")
+    # every frame read once and written once (SURVEY 8d counts 3 fp32 passes for the reference's unfused chain)
+    _prof_end(ev, "warp_chain_C%d_%dx%d" % (C, h, w), 2.0 * sample.numel() * sample.element_size(), "hbm")
     return out
 
 
 ELL_SLOTS = 8
+
+_WORKSPACES: dict = {}
+
+
+def _workspace(key, nbytes: int, device) -> torch.Tensor:
+    """Scratch buffers of the kernels that need one, kept per (use, device) and grown on demand (a fresh torch.empty per
+    call costs an allocator round trip 80 times per optimised step)."""
+    ws = _WORKSPACES.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _WORKSPACES[key] = ws
+    return ws
 
 
 def warp_adjoint_ell(flow: torch.Tensor):
@@ -207,11 +228,14 @@ def warp_loss_fwd_bwd(cs, fwd_flow, bwd_flow, fwd_keep, bwd_keep, grad, loss_acc
     if adjoint is None:
         adjoint = warp_adjoint_pair(bwd_flow, fwd_flow)
     bwd_ell, fwd_ell, ovf, n_ovf = adjoint
+    ev = _prof_begin()
     L.check(L.lib().fresco_warp_loss_fwd_bwd(L.ptr(cs), L.ptr(fwd_flow), L.ptr(bwd_flow), L.ptr(fwd_keep),
                                              L.ptr(bwd_keep), L.ptr(bwd_ell), L.ptr(fwd_ell), L.ptr(ovf), int(n_ovf),
                                              L.ptr(grad), L.ptr(loss_acc) if loss_acc is not None else None,
                                              1 if accumulate else 0, chunks, frames, C, h, w, L.stream()),
             "fresco_warp_loss_fwd_bwd")
+    # read c1, c2 + write g1, g2 = 4 fp32 passes (the fused kernel moves 2 + 1/N of them)
+    _prof_end(ev, "warp_loss_C%d_%dx%d" % (C, h, w), 16.0 * cs.numel(), "hbm")
     return grad
 
 
@@ -231,32 +255,53 @@ def gram_normalize(cs_bcl: torch.Tensor):
     B, C, Lt = cs_bcl.shape
     xhat = torch.empty(B, Lt, C, dtype=torch.float16, device=cs_bcl.device)
     norms = torch.empty(B, Lt, dtype=torch.float32, device=cs_bcl.device)
+    ev = _prof_begin()
     L.check(L.lib().fresco_gram_normalize(L.ptr(cs_bcl), L.ptr(xhat), L.ptr(norms), B, C, Lt, L.stream()),
             "fresco_gram_normalize")
+    _prof_end(ev, "gram_normalize_C%d_L%d" % (C, Lt), 6.0 * B * C * Lt, "hbm")          # fp32 in, fp16 out
     return xhat, norms
 
 
 def gram_sign(xhat, target, weight: float, loss_acc=None):
     B, Lt, C = xhat.shape
     tsign = torch.empty(B, Lt, Lt, dtype=torch.float16, device=xhat.device)
+    ev = _prof_begin()
     L.check(L.lib().fresco_gram_sign(L.ptr(xhat), L.ptr(target), L.ptr(tsign),
                                      L.ptr(loss_acc) if loss_acc is not None else None, B, Lt, C, float(weight),
                                      L.stream()), "fresco_gram_sign")
+    _prof_end(ev, "gram_sign_C%d_L%d" % (C, Lt), 2.0 * B * Lt * Lt * C, "tensor")       # forward Gram
+    return tsign
+
+
+def gram_sign_ref(xhat, yhat, weight: float, loss_acc=None):
+    """T = 2 sign(xhat xhat^T - yhat yhat^T) with the target recomputed in the kernel from the normalised reference
+    features yhat [B, L, C] fp16 (no [B, L, L] fp32 target)."""
+    B, Lt, C = xhat.shape
+    tsign = torch.empty(B, Lt, Lt, dtype=torch.float16, device=xhat.device)
+    ev = _prof_begin()
+    L.check(L.lib().fresco_gram_sign_ref(L.ptr(xhat), L.ptr(yhat), L.ptr(tsign),
+                                         L.ptr(loss_acc) if loss_acc is not None else None, B, Lt, C, float(weight),
+                                         L.stream()), "fresco_gram_sign_ref")
+    _prof_end(ev, "gram_sign_C%d_L%d" % (C, Lt), 2.0 * B * Lt * Lt * C, "tensor")       # SURVEY 8d: forward Gram
     return tsign
 
 
 def gram_grad(tsign, xhat, norms, grad_bcl, weight: float):
     B, Lt, C = xhat.shape
     nbytes = int(L.lib().fresco_gram_grad_workspace_bytes(B, Lt, C))
-    ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=xhat.device)
+    ws = _workspace(("gram_grad", xhat.device), max(nbytes, 16), xhat.device)
+    ev = _prof_begin()
     L.check(L.lib().fresco_gram_grad(L.ptr(tsign), L.ptr(xhat), L.ptr(norms), L.ptr(grad_bcl), B, Lt, C,
                                      float(weight), L.ptr(ws), nbytes, L.stream()), "fresco_gram_grad")
+    _prof_end(ev, "gram_grad_C%d_L%d" % (C, Lt), 4.0 * B * Lt * Lt * C, "tensor")       # SURVEY 8d: the two backward products
     return grad_bcl
 
 
 def adam_step(param, grad, exp_avg, exp_avg_sq, step: int, lr=0.2, beta1=0.9, beta2=0.999, eps=1e-8):
+    ev = _prof_begin()
     L.check(L.lib().fresco_adam_step(L.ptr(param), L.ptr(grad), L.ptr(exp_avg), L.ptr(exp_avg_sq), param.numel(),
                                      int(step), lr, beta1, beta2, eps, L.stream()), "fresco_adam_step")
+    _prof_end(ev, "adam_n%d" % param.numel(), 28.0 * param.numel(), "hbm")               # read p, g, m, v; write p, m, v
 
 
 def adain(content_f32: torch.Tensor, style: torch.Tensor) -> torch.Tensor:
@@ -265,8 +310,10 @@ def adain(content_f32: torch.Tensor, style: torch.Tensor) -> torch.Tensor:
     is_half = 1 if style.dtype == torch.float16 else 0
     if not is_half and style.dtype != torch.float32:
         raise L.FrescoError("adain: fp16 or fp32 style only")
+    ev = _prof_begin()
     L.check(L.lib().fresco_adain(L.ptr(content_f32), L.ptr(style), L.ptr(out), is_half, n * c, h * w, L.stream()),
             "fresco_adain")
+    _prof_end(ev, "adain_C%d_%dx%d" % (c, h, w), style.numel() * (4.0 + 2 * style.element_size()), "hbm")
     return out
 
 
@@ -274,10 +321,24 @@ def gmflow_global_corr_softmax(f0: torch.Tensor, f1: torch.Tensor, bidir: bool):
     b, c, h, w = f0.shape
     flow = torch.empty(b * (2 if bidir else 1), 2, h, w, dtype=torch.float32, device=f0.device)
     nbytes = int(L.lib().fresco_gmflow_corr_workspace_bytes(b, c, h, w))
-    ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=f0.device)
+    ws = _workspace(("gmflow", f0.device), max(nbytes, 16), f0.device)
+    ev = _prof_begin()
     L.check(L.lib().gmflow_global_corr_softmax(L.ptr(f0), L.ptr(f1), L.ptr(flow), b, c, h, w, 1 if bidir else 0,
                                                L.ptr(ws), nbytes, L.stream()), "gmflow_global_corr_softmax")
+    Lt = h * w
+    _prof_end(ev, "gmflow_corr_C%d_L%d" % (c, Lt), 2.0 * b * Lt * Lt * c + 2.0 * (2 * b) * Lt * Lt * 2, "tensor")
     return flow
+
+
+def gmflow_flow_attention(q: torch.Tensor, k: torch.Tensor, values: torch.Tensor, softmax_scale: float):
+    """q, k fp16 [B, L, C]; values fp32 [B, L, 2] -> fp32 [B, 2, L] = softmax(q k^T * scale) values."""
+    B, Lt, C = q.shape
+    out = torch.empty(B, 2, Lt, dtype=torch.float32, device=q.device)
+    ev = _prof_begin()
+    L.check(L.lib().gmflow_flow_attention(L.ptr(q), L.ptr(k), L.ptr(values), L.ptr(out), B, Lt, C, float(softmax_scale),
+                                          L.stream()), "gmflow_flow_attention")
+    _prof_end(ev, "gmflow_flow_attn_C%d_L%d" % (C, Lt), 2.0 * B * Lt * Lt * C + 2.0 * B * Lt * Lt * 2, "tensor")
+    return out
 
 
 def mapping_single(bwd_flow: torch.Tensor, bwd_occ: torch.Tensor, imgs: torch.Tensor, scale: int):

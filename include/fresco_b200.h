@@ -36,7 +36,7 @@ const char* fresco_last_error(void);
 /* number of kernels launched by this library in this process (for bench.py's gpu_launches) */
 long long fresco_launch_count(void);
 /* tuning option by the name of its environment variable (FRESCO_ATTN_WIDE, FRESCO_ATTN_NARROW, FRESCO_ATTN_POLY,
- * FRESCO_ATTN_ROWSUM, FRESCO_ATTN_ABLATE, FRESCO_TEMPORAL_V); the environment is read once, this overrides it;
+ * FRESCO_ATTN_ROWSUM, FRESCO_ATTN_ABLATE, FRESCO_TEMPORAL_V, FRESCO_GRAM_V); the environment is read once, this overrides it;
  * value < 0 restores the built-in default. */
 int fresco_set_option(const char* name, int value);
 
@@ -139,6 +139,15 @@ int fresco_gram_sign(const void* xhat, const float* target, void* tsign, float* 
 int fresco_gram_grad(const void* tsign, const void* xhat, const float* norms, float* grad, int batch, int tokens,
                      int channels, float weight, void* workspace, size_t workspace_bytes, void* stream);
 size_t fresco_gram_grad_workspace_bytes(int batch, int tokens, int channels);
+/* step 2 with the Gram target RECOMPUTED in the kernel from the row-normalised reference features
+ * yhat half [batch, tokens, channels] (what src/diffusion_hacked.py:889-893 feeds its bmm): D = xhat xhat^T - yhat yhat^T in
+ * one K = 2*channels contraction, tsign = 2 sign(D), loss += weight/(batch*tokens^2) * sum |D|.  The fp32
+ * [batch, tokens, tokens] target (1.07 GB per Adam iteration at layer 3) is never read or stored.
+ * fresco_gram_tx: the tensor-core product of step 3 alone, ghat float [batch, tokens, channels] = alpha * tsign xhat. */
+int fresco_gram_sign_ref(const void* xhat, const void* yhat, void* tsign, float* loss_acc, int batch, int tokens,
+                         int channels, float weight, void* stream);
+int fresco_gram_tx(const void* tsign, const void* xhat, float* ghat, int batch, int tokens, int channels, float alpha,
+                   void* stream);
 
 /* ---- O4 / O5: Adam update and AdaIN ---------------------------------------------------------
  * fresco_adam_step replaces torch.optim.Adam.step at src/diffusion_hacked.py:433,485
@@ -156,6 +165,12 @@ int fresco_adain(const float* content, const void* style, void* out, int is_half
 int gmflow_global_corr_softmax(const float* feature0, const float* feature1, float* flow, int batch, int channels,
                                int h, int w, int bidir, void* workspace, size_t workspace_bytes, void* stream);
 size_t fresco_gmflow_corr_workspace_bytes(int batch, int channels, int h, int w);
+/* GMFlow's flow-propagation attention, replaces FeatureFlowAttention.forward, gmflow/transformer.py:353-374 (the global
+ * path): out = softmax(q k^T * softmax_scale) values.  q, k half [batch, tokens, channels] (token-major projections);
+ * values float [batch, tokens, 2] (the flow field, channel-last); out float [batch, 2, tokens].  The [batch, tokens, tokens]
+ * probability volume (1 GB at 512 x 512) is never materialised. */
+int gmflow_flow_attention(const void* q, const void* k, const float* values, float* out, int batch, int tokens,
+                          int channels, float softmax_scale, void* stream);
 
 /* ---- M1: pixel correspondence between two frames (integer, bit-exact) -----------------------
  * replaces get_single_mapping_ind, src/flow_utils.py:57-102 (incl. the sequential loop :84-101).

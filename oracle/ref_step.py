@@ -68,32 +68,6 @@ class OracleProcessor:
         return out
 
 
-def pick_threads(max_threads: int) -> int:
-    """Oversubscribing a many-core host makes torch's CPU kernels slower, so time one representative
-    attention-sized matmul chain at a few thread counts and keep the fastest (the count is reported)."""
-    cands = sorted({max_threads, max(1, max_threads // 2), max(1, max_threads // 4), min(max_threads, 32),
-                    min(max_threads, 16)}, reverse=True)
-    q = torch.randn(2, 8, 4096, 40)
-    x = torch.randn(2, 640, 64, 64)
-    w = torch.randn(640, 640, 3, 3)
-
-    def work():
-        torch.softmax(q @ q.transpose(-1, -2), -1) @ q             # FRESCO-attention-sized
-        torch.nn.functional.conv2d(x, w, padding=1)               # UNet-body-sized
-
-    best, best_t = cands[0], float("inf")
-    for n in cands:
-        torch.set_num_threads(n)
-        work()                                                     # warm
-        t0 = time.perf_counter()
-        work()
-        dt = time.perf_counter() - t0
-        if dt < best_t:
-            best, best_t = n, dt
-    torch.set_num_threads(best)
-    return best
-
-
 def _attn_flops(B, L, Lk, C, intra):
     return 4.0 * B * L * Lk * C + (4.0 * B * L * L * C if intra else 0.0)
 
@@ -177,6 +151,7 @@ def run(n_full: int, n_sample: int, res: int, schedule: List[int], opt_steps: Li
             break
     mean_scaled = sum(scaled_times) / len(scaled_times)
     return {"steps_per_s": 1.0 / mean_scaled, "steps": done, "warmup": min(warmup, k),
+            "raw_ms_per_step": 1000.0 * sum(raw_times) / len(raw_times),
             "sample": ("%d of %d keyframes per step at 512x512 (CFG batch %d), 1 of %d FRESCO attention layers per "
                        "level evaluated (time x%d), oracle fp32 on %d threads, %d step(s); "
                        "component times scaled to N=%d by algorithmic work (UNet body, warp: x%.1f; attention: "

@@ -277,7 +277,37 @@ def main():
     flow_u, _ = matching.global_correlation_softmax(f0, f1, pred_bidir_flow=False)
     np.savez_compressed(os.path.join(HERE, "gmflow_corr.npz"), f0=f0.numpy(), f1=f1.numpy(),
                         flow_bidir=flow_b.numpy(), flow_uni=flow_u.numpy(), prob_bidir=prob_b.numpy())
+    scenario_gmflow_attention()
     print("golden fixtures written to", HERE)
+
+
+def scenario_gmflow_attention():
+    """GMFlow transformer attention (gmflow/transformer.py): plain, 2 x 2 windows, shifted 2 x 2 windows, and the
+    flow-propagation attention, at C = 128 on a 32 x 32 grid (inputs are fp16-representable so that the fp16 kernels
+    see exactly these operands)."""
+    from gmflow import transformer as T
+    g = torch.Generator().manual_seed(2024)
+    b, h, w, c = 1, 32, 32, 128
+    q = (torch.randn(b, h * w, c, generator=g) * 1.5).half().float()
+    k = torch.randn(b, h * w, c, generator=g).half().float()
+    v = torch.randn(b, h * w, c, generator=g).half().float()
+    res = {"q": q.half().numpy(), "k": k.half().numpy(), "v": v.half().numpy(), "h": h, "w": w}
+    res["out_full"] = T.single_head_full_attention(q, k, v).numpy()
+    res["out_split"] = T.single_head_split_window_attention(q, k, v, num_splits=2, with_shift=False, h=h, w=w).numpy()
+    mask = T.generate_shift_window_attn_mask((h, w), h // 2, w // 2, h // 4, w // 4, device=torch.device("cpu"))
+    res["out_shift"] = T.single_head_split_window_attention(q, k, v, num_splits=2, with_shift=True, h=h, w=w,
+                                                            attn_mask=mask).numpy()
+    torch.manual_seed(7)
+    ffa = T.FeatureFlowAttention(in_channels=c)
+    with torch.no_grad():
+        for prm in ffa.parameters():
+            prm.copy_(prm.half().float())
+        f0 = torch.randn(2, c, h, w, generator=g).half().float()
+        flow = torch.randn(2, 2, h, w, generator=g) * 4
+        res.update(ffa_f0=f0.half().numpy(), ffa_flow=flow.numpy(), ffa_out=ffa(f0, flow).numpy(),
+                   ffa_wq=ffa.q_proj.weight.numpy(), ffa_bq=ffa.q_proj.bias.numpy(), ffa_wk=ffa.k_proj.weight.numpy(),
+                   ffa_bk=ffa.k_proj.bias.numpy())
+    np.savez_compressed(os.path.join(HERE, "gmflow_attn.npz"), **res)
 
 
 if __name__ == "__main__":

@@ -338,3 +338,56 @@ def test_sharded_plan_follows_the_mask_tensor():
     ctrl.enable_cfattn([m2])
     p2 = sh._plan(64)
     assert p2 is not p1 and p2.total == 64 + 5 + 7
+
+
+class _TorchAttnOps:
+    """fp32 stand-ins for the kernels fresco_b200.gmflow_transformer calls (host-logic test only)"""
+
+    @staticmethod
+    def attn_fwd(q, k, v, heads, q_per_kv=1, softmax_scale=None, diag_bias=0.0, out=None):
+        q, k, v = q.float(), k.float(), v.float()
+        return (torch.softmax(q @ k.transpose(1, 2) * softmax_scale, -1) @ v).half()
+
+    @staticmethod
+    def rows_gather(src, idx, dst, dst_col=0):
+        dst[:, dst_col:dst_col + src.shape[-1]] = src[idx.long()]
+        return dst
+
+    @staticmethod
+    def rows_scatter(src, idx, dst):
+        dst[idx.long()] = src
+        return dst
+
+    @staticmethod
+    def gmflow_flow_attention(q, k, values, scale):
+        p = torch.softmax(q.float() @ k.float().transpose(1, 2) * scale, -1)
+        return (p @ values).transpose(1, 2).contiguous()
+
+
+def test_gmflow_transformer_attention_host_logic(golden, monkeypatch):
+    """the window / shifted-window decomposition and the flow-propagation attention of
+    fresco_b200.gmflow_transformer reproduce the REFERENCE's outputs (gmflow/transformer.py) with their kernel calls
+    served by torch stand-ins."""
+    from fresco_b200 import gmflow_transformer as gt
+    monkeypatch.setattr(gt, "ops", _TorchAttnOps)
+    g = golden("gmflow_attn")
+    T = torch.from_numpy
+    q, k, v = (T(g[n]).float() for n in "qkv")
+    h, w = int(g["h"]), int(g["w"])
+    tol = 2e-3 * float(abs(g["out_full"]).max())
+    assert (gt.single_head_full_attention(q, k, v) - T(g["out_full"])).abs().max().item() < tol
+    o = gt.single_head_split_window_attention(q, k, v, num_splits=2, with_shift=False, h=h, w=w)
+    assert (o - T(g["out_split"])).abs().max().item() < tol
+    o = gt.single_head_split_window_attention(q, k, v, num_splits=2, with_shift=True, h=h, w=w, attn_mask=None)
+    assert (o - T(g["out_shift"])).abs().max().item() < tol
+
+    class FFA(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            c = g["ffa_wq"].shape[0]
+            self.q_proj, self.k_proj = torch.nn.Linear(c, c), torch.nn.Linear(c, c)
+            with torch.no_grad():
+                self.q_proj.weight.copy_(T(g["ffa_wq"])), self.q_proj.bias.copy_(T(g["ffa_bq"]))
+                self.k_proj.weight.copy_(T(g["ffa_wk"])), self.k_proj.bias.copy_(T(g["ffa_bk"]))
+    out = gt.feature_flow_attention(FFA(), T(g["ffa_f0"]).float(), T(g["ffa_flow"]))
+    assert (out - T(g["ffa_out"])).abs().max().item() < 2e-2            # flow units (pixels), fp16 projections

@@ -323,9 +323,10 @@ def test_spatial_loss_teacher_forced_layer_shapes(fb, N, C, h):
     _, _, cs = _layer_case(N, C, h, seed=7 + h)
     cs = cs.cuda()
     ref_feat = (cs + 0.7 * torch.randn(cs.shape, device="cuda", generator=torch.Generator(device="cuda").manual_seed(h))).half()
-    target = fb.dh.gram_targets([ref_feat.reshape(B, C, h, h)])[0]                   # the reference's fp16-bmm -> fp32 store
-    assert target.shape == (B, L, L) and target.dtype == torch.float32
-    loss_ref, grad_ref = O.spatial_loss_and_grad(cs, target, 100.0)
+    target = fb.dh.gram_targets([ref_feat.reshape(B, C, h, h)])[0]                   # GramTarget: normalised features
+    dense = target.dense()                                                           # the reference's fp16-bmm -> fp32 store
+    assert tuple(target.shape) == (B, L, L) and dense.shape == (B, L, L) and dense.dtype == torch.float32
+    loss_ref, grad_ref = O.spatial_loss_and_grad(cs, dense, 100.0)
     # one evaluation of optimize_feature's spatial branch (the function optimize_feature itself calls)
     grad = torch.zeros(B, C, L, device="cuda")
     loss = torch.zeros(1, device="cuda")
@@ -335,6 +336,12 @@ def test_spatial_loss_teacher_forced_layer_shapes(fb, N, C, h):
     rel = ((grad - gr).abs().mean() / gr.abs().mean()).item()
     cos = torch.nn.functional.cosine_similarity(grad.flatten(), gr.flatten(), dim=0).item()
     assert rel < 3e-2 and cos > 0.999, (rel, cos)
+    # the dense-target entry point (what a caller holding the reference's own correlation_matrix uses) agrees
+    grad2 = torch.zeros(B, C, L, device="cuda")
+    loss2 = torch.zeros(1, device="cuda")
+    fb.dh.spatial_loss_grad(cs.view(B, C, L), dense, 100.0, grad2, loss2)
+    assert abs(loss2.item() - float(loss_ref)) < 2e-3 * float(loss_ref)
+    assert torch.nn.functional.cosine_similarity(grad2.flatten(), gr.flatten(), dim=0).item() > 0.999
 
 
 def test_optimize_feature_full_layer3_loss_curve(fb):
@@ -349,7 +356,7 @@ def test_optimize_feature_full_layer3_loss_curve(fb):
     fl, oc = [f.cuda() for f in flows], [o.cuda() for o in occs]
     tr = fb.dh.OptimizeTrace()
     out = fb.dh.optimize_feature(sample, fl, oc, correlation_matrix=[target], intra_weight=1e2, iters=20, trace=tr)
-    ref_out, ref_trace = O.optimize_feature(sample, fl, oc, correlation_matrix=[target], intra_weight=1e2, iters=20,
+    ref_out, ref_trace = O.optimize_feature(sample, fl, oc, correlation_matrix=[target.dense()], intra_weight=1e2, iters=20,
                                             return_trace=True)
     ref_losses = [t["loss"] for t in ref_trace]
     del ref_trace
@@ -362,6 +369,45 @@ def test_optimize_feature_full_layer3_loss_curve(fb):
     losses = np.array(tr.losses)
     assert losses[-1] < losses[0]
     assert np.allclose(losses, np.array(ref_losses), rtol=1e-2), (losses, ref_losses)
+
+
+@pytest.mark.parametrize("B,C,h,w", [(4, 64, 8, 8), (2, 320, 16, 24), (2, 16, 24, 24), (2, 640, 32, 32), (2, 1280, 16, 16)])
+def test_gram_sign_recomputed_target(fb, B, C, h, w):
+    """O3 with the target recomputed in the kernel (fresco_gram_sign_ref) + the 128 x 256 T Xh product: sign matrix exact
+    outside the fp16 error band, loss, gradient -- incl. plane sizes that are not multiples of the tile (576, 384)."""
+    L = h * w
+    g = torch.Generator().manual_seed(C + h)
+    cs = torch.randn(B, C, L, generator=g)
+    ref = (cs + 0.7 * torch.randn(B, C, L, generator=g)).half().cuda()
+    target = fb.dh.gram_targets([ref.reshape(B, C, h, w)])[0]
+    assert isinstance(target, fb.dh.GramTarget)
+    dense = target.dense().cpu()
+    loss_ref, grad_ref = O.spatial_loss_and_grad(cs.reshape(1, B, C, h, w), dense, 100.0)
+    X = cs.transpose(1, 2)
+    Xh = X / (X ** 2).sum(2, keepdim=True) ** 0.5
+    D = torch.bmm(Xh, Xh.transpose(1, 2)) - dense
+    T_ref = torch.sign(D) + torch.sign(D.transpose(1, 2))
+    xhat, norms = fb.ops.gram_normalize(cs.cuda())
+    loss = torch.zeros(1, device="cuda")
+    tsign = fb.ops.gram_sign_ref(xhat, target.yhat, 100.0, loss)
+    safe = (D.abs() > 2e-3) & (D.transpose(1, 2).abs() > 2e-3)
+    assert safe.float().mean() > 0.8
+    assert torch.equal(tsign.float().cpu()[safe], T_ref[safe])
+    assert abs(loss.item() - float(loss_ref)) < 2e-3 * float(loss_ref)
+    grad = torch.zeros(B, C, L, device="cuda")
+    fb.ops.gram_grad(tsign, xhat, norms, grad, 100.0)
+    gr = grad_ref.reshape(B, C, L)
+    rel = ((grad.cpu() - gr).abs().mean() / gr.abs().mean()).item()
+    cos = torch.nn.functional.cosine_similarity(grad.cpu().flatten(), gr.flatten(), dim=0).item()
+    assert rel < 3e-2 and cos > 0.999, (rel, cos)
+    # the round-1 128 x 128 product behind the same entry point gives the same gradient
+    fb.lib.set_option("FRESCO_GRAM_V", 1)
+    try:
+        grad1 = torch.zeros(B, C, L, device="cuda")
+        fb.ops.gram_grad(tsign, xhat, norms, grad1, 100.0)
+    finally:
+        fb.lib.set_option("FRESCO_GRAM_V", -1)
+    assert (grad1 - grad).abs().max().item() < 1e-5 * grad.abs().max().item() + 1e-12
 
 
 # ------------------------------------------------------------------------------------------------ caches, dtypes
@@ -392,3 +438,111 @@ def test_warp_tensor_fp16_image_resolution(fb):
     out = fb.fu.warp_tensor(img.cuda(), [f.cuda() for f in flows], [o.cuda() for o in occs], sal.cuda(), 1)
     assert out.dtype == torch.float16
     assert (out.float().cpu() - ref).abs().max().item() < 4e-3
+
+
+# ------------------------------------------------------------------------------------------------ GMFlow transformer rows
+def test_gmflow_transformer_attention_golden(fb, golden):
+    """SURVEY 8(f)-1 through the kernels: full / 2 x 2 windows / shifted windows (d = 128, one head) and the
+    flow-propagation attention (V = flow) against the reference's outputs."""
+    from fresco_b200 import gmflow_transformer as gt
+    g = golden("gmflow_attn")
+    q, k, v = (T(g[n]).float() for n in "qkv")
+    h, w = int(g["h"]), int(g["w"])
+    tol = 2e-3 * float(abs(g["out_full"]).max())
+    assert (gt.single_head_full_attention(q, k, v).cpu() - T(g["out_full"], "cpu")).abs().max().item() < tol
+    o = gt.single_head_split_window_attention(q, k, v, num_splits=2, with_shift=False, h=h, w=w)
+    assert (o.cpu() - T(g["out_split"], "cpu")).abs().max().item() < tol
+    o = gt.single_head_split_window_attention(q, k, v, num_splits=2, with_shift=True, h=h, w=w)
+    assert (o.cpu() - T(g["out_shift"], "cpu")).abs().max().item() < tol
+
+    class FFA(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            c = g["ffa_wq"].shape[0]
+            self.q_proj, self.k_proj = torch.nn.Linear(c, c), torch.nn.Linear(c, c)
+            with torch.no_grad():
+                self.q_proj.weight.copy_(T(g["ffa_wq"], "cpu")), self.q_proj.bias.copy_(T(g["ffa_bq"], "cpu"))
+                self.k_proj.weight.copy_(T(g["ffa_wk"], "cpu")), self.k_proj.bias.copy_(T(g["ffa_bk"], "cpu"))
+    out = gt.feature_flow_attention(FFA().cuda(), T(g["ffa_f0"]).float(), T(g["ffa_flow"]))
+    assert (out.cpu() - T(g["ffa_out"], "cpu")).abs().max().item() < 2e-2            # pixels
+    # GMFlow's real shape at 512 x 512: 64 x 64 tokens, 8 pairs bidirectional -> 16 x 4 windows of 1024 tokens
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    qq, kk, vv = (torch.randn(4, 4096, 128, device="cuda", generator=gen) for _ in range(3))
+    o = gt.single_head_split_window_attention(qq, kk, vv, num_splits=2, with_shift=True, h=64, w=64)
+    rows = [0, 31 * 64 + 31, 32 * 64 + 5, 47 * 64 + 50, 63 * 64 + 63]              # one token of each region type
+    sh = 16
+    yy, xx = torch.meshgrid(torch.arange(64), torch.arange(64), indexing="ij")
+    ry, rx = (yy - sh) % 64, (xx - sh) % 64                                           # rolled coordinates of every token
+    cls = lambda t: (t >= 32).long() * 2 + ((t >= 32) & (t >= 48)).long()             # window half + seam class
+    key_all = (cls(ry) * 4 + cls(rx)).reshape(-1).cuda()
+    for r in rows:
+        allowed = key_all == key_all[r]
+        s = (qq[:, r].half().float()[:, None] * kk.half().float()).sum(-1) / math.sqrt(128)
+        s = s.masked_fill(~allowed[None], float("-inf"))
+        ref = torch.einsum("bl,blc->bc", torch.softmax(s, -1), vv.half().float())
+        assert (o[:, r] - ref).abs().max().item() < 2e-3 * ref.abs().max().item()
+
+
+# ------------------------------------------------------------------------------------------------ NCCL, world size 2
+def _nccl_worker(rank, world, port, ret):
+    import os
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from fresco_b200 import diffusion_hacked as dh
+    from fresco_b200.dist import ShardedFRESCOAttention, frame_range
+    dev = torch.device("cuda", rank)
+    ok = True
+    for (N, L, heads, d) in [(4, 256, 2, 40), (8, 1024, 8, 80)]:
+        C, chunks = heads * d, 2
+        g = torch.Generator().manual_seed(N * 7 + L)
+        q, k, v, rq, rk = (torch.randn(chunks * N, L, C, generator=g).half().to(dev) for _ in range(5))
+        mask = torch.rand(N, L, generator=g) > 0.6
+        mask[0] = True
+        fwd, tmask = _trajectory_case(N, L, seed=3)
+        paras = {"fwd_mappings": [fwd[:, None].to(dev)], "bwd_mappings": [torch.argsort(fwd, 1)[:, None].to(dev)],
+                 "interattn_masks": [tmask[:, None].to(dev)]}
+        for flags in range(8):
+            ctrl = dh.AttentionControl()
+            if flags & 2:
+                ctrl.stored_attn["decoder_attn"] = [q]
+                ctrl.enable_intraattn()
+            if flags & 4:
+                ctrl.enable_interattn(paras)
+            if flags & 1:
+                ctrl.enable_cfattn([mask.to(dev)])
+            full = ShardedFRESCOAttention(ctrl, 1, 0, chunks)(q, k, v, heads, ref_q=rq, ref_k=rk)
+            lo, hi = frame_range(N, world, rank)
+            sel = torch.cat([torch.arange(c * N + lo, c * N + hi) for c in range(chunks)]).to(dev)
+            mine = ShardedFRESCOAttention(ctrl, world, rank, chunks)(q[sel].contiguous(), k[sel].contiguous(), v[sel].contiguous(),
+                                                                   heads, ref_q=rq[sel].contiguous(), ref_k=rk[sel].contiguous())
+            ok = ok and bool(torch.equal(mine, full[sel]))
+    t = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        ret.put(int(t.item()))
+    dist.destroy_process_group()
+
+
+def test_sharded_attention_nccl_world2_bit_identical(fb):
+    """frame-sharded FRESCO attention over NCCL on two GPUs (K/V all-gather, trajectory all-to-alls) == unsharded,
+    bit for bit, all 8 mode combinations.  Needs two devices (gpurun --gpus 2); skipped on a one-GPU box."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    assert ret.get(timeout=5) == 1
