@@ -45,6 +45,9 @@ _SIGNATURES = {
     "gmflow_global_corr_softmax": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
     "fresco_gmflow_corr_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "gmflow_flow_attention": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_float, _P]),
+    "fresco_dilate": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
+    "fresco_cfg_pred_x0": (c_int, [_P, _P, _P, _P, c_int, c_longlong, c_float, c_float, _P]),
+    "fresco_ddpm_prev": (c_int, [_P, _P, _P, _P, c_int, c_longlong, c_longlong, c_int, c_float, c_float, c_float, _P]),
     "fresco_mapping_single": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P, _P, c_size_t, _P]),
     "fresco_mapping_workspace_bytes": (c_size_t, [c_int]),
 }

@@ -984,6 +984,51 @@ __global__ void gram_normalize_kernel(const float* __restrict__ cs, __half* __re
   }
 }
 
+// =============================================================================================
+// S1  classifier-free guidance + DDPM step arithmetic  (src/pipe_FRESCO.py:212-215, :22-35, :49-73)
+// two elementwise passes because the background-smoothing VAE round trip sits between them (:44-47)
+// =============================================================================================
+// noise = uncond + g * (text - uncond);  x0 = (sample - sqrt(1 - a_t) * noise) / sqrt(a_t)
+template <typename T>
+__global__ void cfg_pred_x0_kernel(const T* __restrict__ uncond, const T* __restrict__ text, const T* __restrict__ sample,
+                                   T* __restrict__ x0, long long n, float guidance, float sqrt_beta, float inv_sqrt_alpha) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float u = ld_as_float(uncond + i);
+    const float e = text ? u + guidance * (ld_as_float(text + i) - u) : u;
+    st_from_float(x0 + i, (ld_as_float(sample + i) - sqrt_beta * e) * inv_sqrt_alpha);
+  }
+}
+// prev = c_x0 * x0 + c_xt * sample + sigma * noise   (noise of frame 0 for every frame when repeat_noise, :67-68)
+template <typename T>
+__global__ void ddpm_prev_kernel(const T* __restrict__ x0, const T* __restrict__ sample, const T* __restrict__ noise,
+                                 T* __restrict__ prev, long long n, long long per_frame, int repeat_noise, float c_x0,
+                                 float c_xt, float sigma) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float z = ld_as_float(noise + (repeat_noise ? i % per_frame : i));
+    st_from_float(prev + i, c_x0 * ld_as_float(x0 + i) + c_xt * ld_as_float(sample + i) + sigma * z);
+  }
+}
+
+// =============================================================================================
+// W2  binary dilation with replicate padding  (src/utils.py:81-93: replicate-pad + conv2d(ones k x k) + clamp[0,1])
+// for masks in [0, 1] the clamped box sum of a {0,1} mask is its k x k maximum; general inputs take the clamped sum
+// =============================================================================================
+__global__ void dilate_kernel(const float* __restrict__ in, float* __restrict__ out, int planes, int h, int w, int k) {
+  const int r = (k - 1) / 2;
+  const long long total = (long long)planes * h * w;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(t % w), y = (int)((t / w) % h);
+    const float* pl = in + (t / ((long long)h * w)) * (long long)h * w;
+    float acc = 0.f;
+    for (int dy = -r; dy <= r; ++dy) {
+      const int yy = min(max(y + dy, 0), h - 1);
+      for (int dx = -r; dx <= r; ++dx) acc += pl[(long long)yy * w + min(max(x + dx, 0), w - 1)];
+    }
+    out[t] = fminf(fmaxf(acc, 0.f), 1.f);
+  }
+}
+
 }  // namespace fresco
 
 using namespace fresco;
@@ -1315,4 +1360,41 @@ extern "C" int fresco_gram_normalize(const float* cs, void* xhat, float* norms, 
   const int tiles = (tokens + 31) / 32;
   gram_normalize_kernel<<<batch * tiles, 256, 0, (cudaStream_t)stream>>>(cs, (__half*)xhat, norms, channels, tokens);
   return check_launch("gram_normalize_kernel");
+}
+
+extern "C" int fresco_cfg_pred_x0(const void* noise_uncond, const void* noise_text, const void* sample, void* x0,
+                                  int is_half, long long n, float guidance_scale, float alpha_prod_t, void* stream) {
+  if (!noise_uncond || !sample || !x0) return set_error(FRESCO_ERR_ARG, "fresco_cfg_pred_x0: null pointer");
+  if (n <= 0 || !(alpha_prod_t > 0.f) || alpha_prod_t > 1.f) return set_error(FRESCO_ERR_ARG, "fresco_cfg_pred_x0: bad n / alpha");
+  const float sb = sqrtf(1.f - alpha_prod_t), isa = 1.f / sqrtf(alpha_prod_t);
+  const int grid = grid_for(n, 256);
+  if (is_half)
+    cfg_pred_x0_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)noise_uncond, (const __half*)noise_text,
+                                                                       (const __half*)sample, (__half*)x0, n, guidance_scale, sb, isa);
+  else
+    cfg_pred_x0_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)noise_uncond, (const float*)noise_text,
+                                                                      (const float*)sample, (float*)x0, n, guidance_scale, sb, isa);
+  return check_launch("cfg_pred_x0_kernel");
+}
+
+extern "C" int fresco_ddpm_prev(const void* x0, const void* sample, const void* noise, void* prev, int is_half, long long n,
+                                long long per_frame, int repeat_noise, float c_x0, float c_xt, float sigma, void* stream) {
+  if (!x0 || !sample || !noise || !prev) return set_error(FRESCO_ERR_ARG, "fresco_ddpm_prev: null pointer");
+  if (n <= 0 || per_frame <= 0 || n % per_frame != 0) return set_error(FRESCO_ERR_ARG, "fresco_ddpm_prev: bad n / per_frame");
+  const int grid = grid_for(n, 256);
+  if (is_half)
+    ddpm_prev_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)x0, (const __half*)sample, (const __half*)noise,
+                                                                     (__half*)prev, n, per_frame, repeat_noise, c_x0, c_xt, sigma);
+  else
+    ddpm_prev_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x0, (const float*)sample, (const float*)noise,
+                                                                    (float*)prev, n, per_frame, repeat_noise, c_x0, c_xt, sigma);
+  return check_launch("ddpm_prev_kernel");
+}
+
+extern "C" int fresco_dilate(const float* in, float* out, int planes, int h, int w, int kernel, void* stream) {
+  if (!in || !out || in == out) return set_error(FRESCO_ERR_ARG, "fresco_dilate: null pointer / in-place");
+  if (planes <= 0 || h <= 0 || w <= 0 || kernel <= 0 || kernel % 2 == 0)
+    return set_error(FRESCO_ERR_ARG, "fresco_dilate: bad shape (odd kernel)");
+  dilate_kernel<<<grid_for((long long)planes * h * w, 256), 256, 0, (cudaStream_t)stream>>>(in, out, planes, h, w, kernel);
+  return check_launch("dilate_kernel");
 }

@@ -38,9 +38,7 @@ def forward_backward_consistency_check(fwd_flow, bwd_flow, alpha=0.01, beta=0.5)
 
 def _dilate(x: torch.Tensor, k: int) -> torch.Tensor:
     """k x k binary dilation with replicate padding (src/utils.py:81-93)."""
-    p = (k - 1) // 2
-    x = F.pad(x, (p, p, p, p), mode="replicate")
-    return torch.clamp(F.conv2d(x, torch.ones(1, 1, k, k, dtype=x.dtype, device=x.device)), 0, 1)
+    return ops.dilate(x.float().contiguous(), k)
 
 
 _PREP_CACHE: "dict" = {}

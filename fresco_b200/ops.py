@@ -341,6 +341,37 @@ def gmflow_flow_attention(q: torch.Tensor, k: torch.Tensor, values: torch.Tensor
     return out
 
 
+def dilate(x: torch.Tensor, k: int) -> torch.Tensor:
+    """fp32 [..., h, w] masks -> k x k dilation with replicate padding (src/utils.py:81-93)."""
+    h, w = x.shape[-2], x.shape[-1]
+    out = torch.empty_like(x)
+    L.check(L.lib().fresco_dilate(L.ptr(x), L.ptr(out), x.numel() // (h * w), h, w, int(k), L.stream()), "fresco_dilate")
+    return out
+
+
+def cfg_pred_x0(noise_pred_2n: torch.Tensor, sample: torch.Tensor, guidance_scale: float, alpha_prod_t: float,
+                do_cfg: bool = True) -> torch.Tensor:
+    """noise_pred [2N, ...] (uncond | text chunks, or [N, ...] when do_cfg is False), sample [N, ...] -> predicted x0."""
+    n = sample.numel()
+    x0 = torch.empty_like(sample)
+    is_half = 1 if sample.dtype == torch.float16 else 0
+    base = L.ptr(noise_pred_2n)
+    text = base + n * sample.element_size() if do_cfg else None
+    L.check(L.lib().fresco_cfg_pred_x0(base, text, L.ptr(sample), L.ptr(x0), is_half, n, float(guidance_scale),
+                                       float(alpha_prod_t), L.stream()), "fresco_cfg_pred_x0")
+    return x0
+
+
+def ddpm_prev(x0, sample, noise, c_x0: float, c_xt: float, sigma: float, repeat_noise: bool = False):
+    prev = torch.empty_like(sample)
+    is_half = 1 if sample.dtype == torch.float16 else 0
+    per_frame = sample[0].numel()
+    L.check(L.lib().fresco_ddpm_prev(L.ptr(x0), L.ptr(sample), L.ptr(noise), L.ptr(prev), is_half, sample.numel(),
+                                     per_frame, 1 if repeat_noise else 0, float(c_x0), float(c_xt), float(sigma),
+                                     L.stream()), "fresco_ddpm_prev")
+    return prev
+
+
 def mapping_single(bwd_flow: torch.Tensor, bwd_occ: torch.Tensor, imgs: torch.Tensor, scale: int):
     """bwd_flow [1,2,H,W], bwd_occ [1,H,W], imgs [2,3,H,W] fp32 -> mapping int64 [L], unlinked bool [L]."""
     H, W = imgs.shape[2], imgs.shape[3]

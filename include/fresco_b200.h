@@ -158,6 +158,22 @@ int fresco_adam_step(float* param, const float* grad, float* exp_avg, float* exp
                      double lr, double beta1, double beta2, double eps, void* stream);
 int fresco_adain(const float* content, const void* style, void* out, int is_half, int planes, int hw, void* stream);
 
+/* ---- W2: binary dilation of occlusion masks (background smoothing at image resolution) -------
+ * replaces Dilate, src/utils.py:81-93 (replicate padding + conv2d with ones(k x k) + clamp to [0,1]).
+ * in, out float [planes, h, w]; kernel odd.                                                     */
+int fresco_dilate(const float* in, float* out, int planes, int h, int w, int kernel, void* stream);
+
+/* ---- S1: classifier-free guidance + DDPM step arithmetic -----------------------------------
+ * replaces the elementwise parts of src/pipe_FRESCO.py: guidance (:212-215) fused with the predicted x0 (:22-35), and
+ * the posterior mean + noise (:49-73); two entry points because the background-smoothing VAE round trip may replace
+ * x0 between them (:44-47).  Tensors half (is_half=1) or float, n elements; noise_text may be null (no guidance).
+ * x0 = (sample - sqrt(1-alpha_prod_t) * (u + g (t - u))) / sqrt(alpha_prod_t)
+ * prev = c_x0 * x0 + c_xt * sample + sigma * noise[repeat_noise ? i % per_frame : i]                 */
+int fresco_cfg_pred_x0(const void* noise_uncond, const void* noise_text, const void* sample, void* x0, int is_half,
+                       long long n, float guidance_scale, float alpha_prod_t, void* stream);
+int fresco_ddpm_prev(const void* x0, const void* sample, const void* noise, void* prev, int is_half, long long n,
+                     long long per_frame, int repeat_noise, float c_x0, float c_xt, float sigma, void* stream);
+
 /* ---- G1: GMFlow global correlation + softmax + expected coordinates -------------------------
  * replaces gmflow/matching.py:7-36.  feature0/1 float [batch, channels, h, w];
  * flow float [batch*(bidir?2:1), 2, h, w], order [fwd(batch), bwd(batch)].  The L x L volume is

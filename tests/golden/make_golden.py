@@ -278,7 +278,45 @@ def main():
     np.savez_compressed(os.path.join(HERE, "gmflow_corr.npz"), f0=f0.numpy(), f1=f1.numpy(),
                         flow_bidir=flow_b.numpy(), flow_uni=flow_u.numpy(), prob_bidir=prob_b.numpy())
     scenario_gmflow_attention()
+    scenario_ddpm_step()
     print("golden fixtures written to", HERE)
+
+
+def scenario_ddpm_step():
+    """src/pipe_FRESCO.py step() (no background smoothing) on a DDPM-1000 scaled-linear table, incl. repeat_noise, and
+    the classifier-free-guidance combine of inference() (:212-215); Dilate(5) and Dilate(13) of src/utils.py:81-93."""
+    import src.pipe_FRESCO as pf
+    import src.utils as ut
+
+    class Sched:
+        def __init__(self):
+            betas = torch.linspace(0.00085 ** 0.5, 0.012 ** 0.5, 1000, dtype=torch.float32) ** 2
+            self.alphas_cumprod = torch.cumprod(1.0 - betas, dim=0)
+            self.one = torch.tensor(1.0)
+
+        def previous_timestep(self, t):
+            return t - 50
+
+    class Pipe:
+        scheduler = Sched()
+
+    g = torch.Generator().manual_seed(77)
+    N = 3
+    raw = torch.randn(2 * N, 4, 16, 24, generator=g)
+    sample = torch.randn(N, 4, 16, 24, generator=g)
+    res = {"raw": raw.numpy(), "sample": sample.numpy(), "alphas_cumprod": Pipe.scheduler.alphas_cumprod.numpy()}
+    u, t = raw.chunk(2)
+    guided = u + 7.5 * (t - u)
+    for tag, ts, rep in (("a", 700, False), ("b", 0, False), ("c", 350, True)):
+        gen = torch.Generator().manual_seed(5)
+        prev, x0 = pf.step(Pipe, guided, ts, sample, gen, repeat_noise=rep)
+        noise = torch.randn(guided.shape, generator=torch.Generator().manual_seed(5))
+        res.update({f"{tag}_t": ts, f"{tag}_prev": prev.numpy(), f"{tag}_x0": x0.numpy(), f"{tag}_noise": noise.numpy(),
+                    f"{tag}_repeat": rep})
+    m = (torch.rand(3, 1, 40, 56, generator=g) > 0.9).float()
+    res.update(dil_in=m.numpy(), dil5=ut.Dilate(kernel_size=5, device="cpu")(m).numpy(),
+               dil13=ut.Dilate(kernel_size=13, device="cpu")(m).numpy())
+    np.savez_compressed(os.path.join(HERE, "ddpm_step.npz"), **res)
 
 
 def scenario_gmflow_attention():

@@ -261,6 +261,11 @@ class _TorchWarpOps:
         from oracle import fresco_oracle as O
         return O.single_mapping_ind(bwd_flow, bwd_occ, imgs, float(scale))
 
+    @staticmethod
+    def dilate(x, k):
+        from oracle import fresco_oracle as O
+        return O.dilate(x, k)
+
 
 @pytest.mark.parametrize("fixture", ["set_a", "set_b"])
 def test_warp_tensor_and_mapping_host_logic_against_reference_outputs(golden, monkeypatch, fixture):
@@ -391,3 +396,56 @@ def test_gmflow_transformer_attention_host_logic(golden, monkeypatch):
                 self.k_proj.weight.copy_(T(g["ffa_wk"])), self.k_proj.bias.copy_(T(g["ffa_bk"]))
     out = gt.feature_flow_attention(FFA(), T(g["ffa_f0"]).float(), T(g["ffa_flow"]))
     assert (out - T(g["ffa_out"])).abs().max().item() < 2e-2            # flow units (pixels), fp16 projections
+
+
+class _TorchStepOps:
+    """stand-ins for fresco_cfg_pred_x0 / fresco_ddpm_prev (host-logic tests of fresco_b200.pipe_FRESCO)"""
+
+    @staticmethod
+    def cfg_pred_x0(noise_pred, sample, guidance_scale, alpha_prod_t, do_cfg=True):
+        if do_cfg:
+            u, t = noise_pred.chunk(2)
+            eps = u + guidance_scale * (t - u)
+        else:
+            eps = noise_pred
+        return (sample - (1 - alpha_prod_t) ** 0.5 * eps) / alpha_prod_t ** 0.5
+
+    @staticmethod
+    def ddpm_prev(x0, sample, noise, c_x0, c_xt, sigma, repeat_noise=False):
+        z = noise[0:1].expand_as(noise) if repeat_noise else noise
+        return c_x0 * x0 + c_xt * sample + sigma * z
+
+
+class _Sched:
+    def __init__(self, ac):
+        self.alphas_cumprod = ac
+        self.one = torch.tensor(1.0)
+        self.order = 1
+
+    def previous_timestep(self, t):
+        return t - 50
+
+    def add_noise(self, x0, noise, t):
+        a = self.alphas_cumprod[t]
+        return a ** 0.5 * x0 + (1 - a) ** 0.5 * noise
+
+
+def test_pipe_step_host_logic_against_reference(golden, monkeypatch):
+    """fresco_b200.pipe_FRESCO.step: coefficient arithmetic + noise draw reproduce the reference's step() outputs, with
+    the guidance fused (raw [2N] UNet output) or applied by the caller as in the reference."""
+    from fresco_b200 import pipe_FRESCO as pf
+    monkeypatch.setattr(pf, "ops", _TorchStepOps)
+    g = golden("ddpm_step")
+    T = torch.from_numpy
+
+    class Pipe:
+        scheduler = _Sched(T(g["alphas_cumprod"]))
+    raw, sample = T(g["raw"]), T(g["sample"])
+    u, t = raw.chunk(2)
+    guided = u + 7.5 * (t - u)
+    for tag in "abc":
+        ts, rep = int(g[f"{tag}_t"]), bool(g[f"{tag}_repeat"])
+        prev, x0 = pf.step(Pipe, guided, ts, sample, torch.Generator().manual_seed(5), repeat_noise=rep)
+        assert (prev - T(g[f"{tag}_prev"])).abs().max() < 1e-5 and (x0 - T(g[f"{tag}_x0"])).abs().max() < 1e-5
+        prev, x0 = pf.step(Pipe, raw, ts, sample, torch.Generator().manual_seed(5), repeat_noise=rep, guidance_scale=7.5)
+        assert (prev - T(g[f"{tag}_prev"])).abs().max() < 1e-5 and (x0 - T(g[f"{tag}_x0"])).abs().max() < 1e-5

@@ -137,3 +137,114 @@ def test_frame_range():
     sys.path.insert(0, ROOT)
     from fresco_b200.dist import frame_range
     assert [frame_range(16, 4, r) for r in range(4)] == [(0, 4), (4, 8), (8, 12), (12, 16)]
+
+
+# ------------------------------------------------------------------------------------------------ sharded inference loop
+class _StubVAE:
+    class config:
+        scaling_factor = 0.5
+
+    def encode(self, x):
+        class D:
+            def __init__(self, v):
+                self.latent_dist = self
+                self.v = v
+
+            def sample(self):
+                return self.v
+        return D(torch.nn.functional.avg_pool2d(x, 8)[:, :1].repeat(1, 4, 1, 1))
+
+
+class _StubUNet(torch.nn.Module):
+    """per-frame 'UNet': every output frame depends on its own input frame only, like the real UNet body"""
+
+    class config:
+        in_channels = 4
+
+    def __init__(self):
+        super().__init__()
+        self.dtype = torch.float32
+
+    def forward(self, x, t, encoder_hidden_states=None, **kw):
+        return (torch.tanh(x * 0.7 + 0.001 * float(t)) + 0.1 * encoder_hidden_states.mean((1, 2))[:, None, None, None],)
+
+
+class _StubPipe:
+    def __init__(self, ac):
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from test_cpu_host import _Sched
+        self.scheduler = _Sched(ac)
+        self.vae = _StubVAE()
+        self.unet = _StubUNet()
+        self._execution_device = torch.device("cpu")
+
+    def prepare_latents(self, B, C, H, W, dtype, device, generator, latents=None):
+        return torch.randn(B, C, H // 8, W // 8, generator=generator, dtype=dtype)
+
+    def progress_bar(self, total=None):
+        import contextlib
+        return contextlib.nullcontext()
+
+
+class _Ctrl:
+    class controller:
+        @staticmethod
+        def disable_intraattn():
+            pass
+
+        @staticmethod
+        def disable_interattn():
+            pass
+
+
+def _inference_worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import numpy as np
+    from fresco_b200 import pipe_FRESCO as pf
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_cpu_host import _TorchStepOps
+    pf.ops = _TorchStepOps
+    ac = torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden", "ddpm_step.npz"))["alphas_cumprod"])
+    N = 4
+    g = torch.Generator().manual_seed(1)
+    imgs = torch.rand(N, 3, 64, 64, generator=g)
+    pe = torch.randn(2 * N, 5, 8, generator=g)
+    timesteps = [950 - 50 * i for i in range(20)]
+    ok = True
+    for repeat in (False, True):
+        rec_full, rec_sh = [], []
+        for propagation in (False, True):
+            kw = dict(num_warmup_steps=14, use_controlnet=False, seed=3, repeat_noise=repeat, bg_smoothing_steps=[],
+                      propagation_mode=propagation)
+            full = pf.inference(_StubPipe(ac), None, _Ctrl, imgs, pe, None, timesteps, record_latents=rec_full, **kw)
+            mine = pf.inference(_StubPipe(ac), None, _Ctrl, imgs, pe, None, timesteps, record_latents=rec_sh,
+                                shard=(world, rank, None), **kw)
+            lo, hi = rank * N // world, (rank + 1) * N // world
+            ok = ok and torch.equal(mine, full[lo:hi]) and len(rec_full) == len(rec_sh)
+            ok = ok and all(torch.equal(a, b) for a, b in zip(rec_full, rec_sh))
+    t = torch.tensor([1 if ok else 0])
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        ret.put(int(t.item()))
+    dist.destroy_process_group()
+
+
+def test_sharded_inference_loop_world2_gloo():
+    """fresco_b200.pipe_FRESCO.inference frame-sharded over 2 ranks == unsharded, bit for bit: shared noise streams,
+    repeat_noise, record_latents (first batch and propagation mode)."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    procs = [ctx.Process(target=_inference_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert ret.get(timeout=5) == 1

@@ -483,6 +483,39 @@ def test_gmflow_transformer_attention_golden(fb, golden):
         assert (o[:, r] - ref).abs().max().item() < 2e-3 * ref.abs().max().item()
 
 
+# ------------------------------------------------------------------------------------------------ step epilogue, dilation
+def test_ddpm_step_kernels_and_dilate_golden(fb, golden):
+    """fresco_cfg_pred_x0 / fresco_ddpm_prev through fresco_b200.pipe_FRESCO.step vs the reference's step()
+    (src/pipe_FRESCO.py:14-77, guidance :212-215), fp32 to 1e-5 and fp16 to 3 fp16 ulps of the largest value; Dilate exact."""
+    from fresco_b200 import pipe_FRESCO as pf
+    g = golden("ddpm_step")
+
+    class Sched:
+        alphas_cumprod = T(g["alphas_cumprod"], "cpu")
+        one = torch.tensor(1.0)
+
+        @staticmethod
+        def previous_timestep(t):
+            return t - 50
+
+    class Pipe:
+        scheduler = Sched()
+    raw, sample = T(g["raw"]), T(g["sample"])
+    for tag in "abc":
+        ts, rep = int(g[f"{tag}_t"]), bool(g[f"{tag}_repeat"])
+        prev, x0 = pf.step(Pipe, raw, ts, sample, None, repeat_noise=rep, guidance_scale=7.5, noise=T(g[f"{tag}_noise"]))
+        assert (prev.cpu() - T(g[f"{tag}_prev"], "cpu")).abs().max().item() < 1e-5
+        assert (x0.cpu() - T(g[f"{tag}_x0"], "cpu")).abs().max().item() < 1e-5
+        prev16, _ = pf.step(Pipe, raw.half(), ts, sample.half(), None, repeat_noise=rep, guidance_scale=7.5,
+                            noise=T(g[f"{tag}_noise"]).half())
+        ref = T(g[f"{tag}_prev"], "cpu")
+        assert prev16.dtype == torch.float16
+        assert (prev16.float().cpu() - ref).abs().max().item() < 4e-3 * ref.abs().max().item()
+    m = T(g["dil_in"])
+    assert torch.equal(fb.ops.dilate(m, 5).cpu(), T(g["dil5"], "cpu"))
+    assert torch.equal(fb.ops.dilate(m, 13).cpu(), T(g["dil13"], "cpu"))
+
+
 # ------------------------------------------------------------------------------------------------ NCCL, world size 2
 def _nccl_worker(rank, world, port, ret):
     import os

@@ -139,3 +139,19 @@ def test_set_b_odd_frames_nonsquare_head_dim_80(golden):
             assert (out - ref).abs().max() < 1e-4
         else:
             assert (out - ref).abs().mean() / ref.abs().mean() < 5e-2
+
+
+def test_ddpm_step_and_dilate_oracle_against_reference(golden):
+    """oracle cfg_ddpm_step / dilate vs the reference's step() (src/pipe_FRESCO.py:14-77) and Dilate (src/utils.py:81-93)"""
+    g = golden("ddpm_step")
+    ac = T(g["alphas_cumprod"])
+    raw, sample = T(g["raw"]), T(g["sample"])
+    for tag in "abc":
+        t = int(g[f"{tag}_t"])
+        a_t = ac[t]
+        a_prev = ac[t - 50] if t - 50 >= 0 else torch.tensor(1.0)
+        prev, x0 = O.cfg_ddpm_step(raw, sample, T(g[f"{tag}_noise"]), a_t, a_prev, 7.5, bool(g[f"{tag}_repeat"]))
+        assert (x0 - T(g[f"{tag}_x0"])).abs().max() < 1e-5
+        assert (prev - T(g[f"{tag}_prev"])).abs().max() < 1e-5
+    assert torch.equal(O.dilate(T(g["dil_in"]), 5), T(g["dil5"]))
+    assert torch.equal(O.dilate(T(g["dil_in"]), 13), T(g["dil13"]))
