@@ -208,8 +208,12 @@ class Workload:
                      [(1280, lat // 4)] * 2 + [(1280, lat // 8)] * 3
             mk = lambda c, s: (0.1 * torch.randn(CHUNKS * n_local, c, s, s, generator=gg)).half().to(device)
             self.residuals = (tuple(mk(c, s) for c, s in shapes), mk(1280, lat // 8))
-        if shard is not None and not warp:
-            return                # config 4: attention only (warp_tensor / optimise are frame chains)
+        if shard is not None:
+            # frame-sharded batch: FRESCO attention (K/V all-gather, trajectory all-to-alls) + the warp_tensor fusion of
+            # config 2 with the chain re-sharded by channel (two all-to-alls per decoder feature)
+            dh.apply_FRESCO_opt(self.pipe, steps=OPT_STEPS, flows=self.flows, occs=self.occs, correlation_matrix=[],
+                                optimize_temporal=False, saliency=self.saliency, shard=(shard[0], shard[1], None))
+            return
         if optimise:
             # BASELINE configs[2]: FRESCO feature optimisation (20 Adam iterations, temporal + Gram-L1 loss) on the 4
             # decoder features on the optimisation steps, Gram targets from the reference pass (get_intraframe_paras)
@@ -577,7 +581,7 @@ def main():
         wl = Workload(device, seed=0, n_frames=n_frames, res=res, shard=(world, rank) if world > 1 else None, controlnet=True)
         config.update({"workload": "N=8 keyframes 768x768 (CFG batch 16) + ControlNet-shaped down/mid residuals, SD1.5-shaped "
                        "random-init fp16 UNet, FRESCO attention on 6 decoder layers (L = 9216 / 2304)" +
-                       (", frame-sharded over the ranks" if world > 1 else " + warp_tensor fusion on 4 decoder features"),
+                       " + warp_tensor fusion on 4 decoder features" + (", frame-sharded over the ranks" if world > 1 else ""),
                        "resolution": res,
                        "parallelism": "one GPU" if world == 1 else "frame-sharded x%d (strong scaling of one batch)" % world})
     elif workload == "config4":
@@ -587,7 +591,8 @@ def main():
         config.update({"workload": "ONE batch of N=16 keyframes 512x512 (CFG batch 32) frame-sharded over the ranks, SD1.5-"
                        "shaped random-init fp16 UNet, FRESCO attention on 6 decoder layers: one NCCL all-gather of the "
                        "compacted K/V per layer + trajectory-sharded temporal attention (two all-to-alls per layer while "
-                       "it is on); value counts 8-keyframe batch-steps (one step of this batch = 2)",
+                       "it is on) + warp_tensor fusion on 4 decoder features re-sharded by channel (two all-to-alls each); "
+                       "value counts 8-keyframe batch-steps (one step of this batch = 2)",
                        "frames": n_frames, "parallelism": "frame-sharded x%d (strong scaling of one batch)" % world})
     else:
         wl = Workload(device, seed=rank, optimise=workload == "config3", with_gmflow=workload == "config3")

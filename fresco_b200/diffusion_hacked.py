@@ -414,7 +414,7 @@ def optimize_feature(sample, flows, occs, correlation_matrix=[], intra_weight=1e
 
 
 def my_forward(self, steps=[], layers=[0, 1, 2, 3], flows=None, occs=None, correlation_matrix=[],
-               intra_weight=1e2, iters=20, optimize_temporal=True, saliency=None):
+               intra_weight=1e2, iters=20, optimize_temporal=True, saliency=None, shard=None):
     """Replacement for ``pipe.unet.forward`` (src/diffusion_hacked.py:491-816).
 
     The reference carries a verbatim copy of diffusers-0.19.3's UNet forward with
@@ -448,10 +448,18 @@ def my_forward(self, steps=[], layers=[0, 1, 2, 3], flows=None, occs=None, corre
                 up_samples.append(feat)
                 if not optimise:
                     return None
-                new = optimize_feature(feat, flows, occs, correlation_matrix, intra_weight, iters,
-                                       optimize_temporal=optimize_temporal)
+                if shard is not None and shard[0] > 1:
+                    # frame-sharded batch: the warp chain re-shards by channel (flow_utils.warp_tensor); the feature
+                    # optimisation is not sharded (its temporal term couples neighbouring frames every Adam iteration)
+                    if (flows is not None and occs is not None and optimize_temporal) or \
+                            (intra_weight != 0 and len(correlation_matrix) > 0):
+                        raise FrescoError("optimize_feature on a frame-sharded batch is not supported")
+                    new = feat
+                else:
+                    new = optimize_feature(feat, flows, occs, correlation_matrix, intra_weight, iters,
+                                           optimize_temporal=optimize_temporal)
                 if saliency is not None:
-                    new = warp_tensor(new, flows, occs, saliency, 2)
+                    new = warp_tensor(new, flows, occs, saliency, 2, shard=shard)
                 if "hidden_states" in h_kwargs:
                     h_kwargs = dict(h_kwargs)
                     h_kwargs["hidden_states"] = new
@@ -475,12 +483,12 @@ def my_forward(self, steps=[], layers=[0, 1, 2, 3], flows=None, occs=None, corre
 
 
 def apply_FRESCO_opt(pipe, steps=[], layers=[0, 1, 2, 3], flows=None, occs=None, correlation_matrix=[],
-                     intra_weight=1e2, iters=20, optimize_temporal=True, saliency=None):
+                     intra_weight=1e2, iters=20, optimize_temporal=True, saliency=None, shard=None):
     """src/diffusion_hacked.py:819-825.  Called once per keyframe batch (run_fresco.py:232-234): per-batch
     preparation cached for the previous batch's flows is dropped here."""
     clear_prep_cache()
     pipe.unet.forward = my_forward(pipe.unet, steps, layers, flows, occs, correlation_matrix, intra_weight, iters,
-                                   optimize_temporal, saliency)
+                                   optimize_temporal, saliency, shard=shard)
 
 
 def disable_FRESCO_opt(pipe):

@@ -98,12 +98,19 @@ def adjoint_csr(flows, occs, size_h: int):
 
 # --------------------------------------------------------------------------- warp_tensor
 @torch.no_grad()
-def warp_tensor(sample, flows, occs, saliency, unet_chunk_size):
+def warp_tensor(sample, flows, occs, saliency, unet_chunk_size, shard=None):
     """Warp + fuse along the frame chain (src/flow_utils.py:18-53).
 
     Unlike the reference (which aliases and mutates fp32 inputs, :36) this never
-    modifies ``sample``; the result has the dtype of ``sample``."""
-    n = sample.shape[0] // unet_chunk_size
+    modifies ``sample``; the result has the dtype of ``sample``.
+
+    ``shard=(world, rank[, group])`` (not in the reference): ``sample`` holds this rank's frames of a frame-sharded
+    batch (flows / occs / saliency describe ALL N frames).  The chain is sequential over frames but independent per
+    (chunk, channel) plane, so the batch is re-sharded by CHANNEL for the chain: one all-to-all turns
+    [frames/G, all channels] into [all frames, channels/G], every rank runs the chain kernel on its channel slice, a
+    second all-to-all brings the frames back ("sequential pieces")."""
+    world = 1 if shard is None else shard[0]
+    n = sample.shape[0] // unet_chunk_size * world
     h, w = sample.shape[2], sample.shape[3]
 
     def prepare():
@@ -128,8 +135,24 @@ def warp_tensor(sample, flows, occs, saliency, unet_chunk_size):
     # reference's own `.to(torch.float32)` copy (flow_utils.py:36)
     if x.dtype not in (torch.float16, torch.float32) or 2 * h * w * 4 > 200 * 1024:
         x = x.float()
-    out = ops.warp_fuse_chain(x, bwd_flow, fwd_flow_last, blend, unet_chunk_size)
-    return out.to(sample.dtype)
+    if world == 1:
+        out = ops.warp_fuse_chain(x, bwd_flow, fwd_flow_last, blend, unet_chunk_size)
+        return out.to(sample.dtype)
+    import torch.distributed as dist
+    group = shard[2] if len(shard) > 2 else None
+    chunks, n_local, C = unet_chunk_size, n // world, x.shape[1]
+    if C % world != 0:
+        raise ValueError(f"{C} channels do not split evenly over {world} ranks")
+    cg = C // world
+    send = x.view(chunks, n_local, world, cg, h * w).permute(2, 1, 0, 3, 4).contiguous()      # [dest, frame, chunk, cg, hw]
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send, group=group)            # [source rank = frame block, frame, chunk, cg, hw]
+    planes = recv.view(n, chunks * cg, h, w)                    # all N frames x my channel slice of both chunks
+    fused = ops.warp_fuse_chain(planes, bwd_flow, fwd_flow_last, blend, 1)
+    back = torch.empty_like(fused)
+    dist.all_to_all_single(back, fused, group=group)           # [source rank = channel block, frame, chunk, cg, hw]
+    out = back.view(world, n_local, chunks, cg, h * w).permute(2, 1, 0, 3, 4).reshape(chunks * n_local, C, h, w)
+    return out.contiguous().to(sample.dtype)
 
 
 # --------------------------------------------------------------------------- pixel mapping

@@ -248,3 +248,48 @@ def test_sharded_inference_loop_world2_gloo():
         p.join(120)
         assert p.exitcode == 0
     assert ret.get(timeout=5) == 1
+
+
+# ------------------------------------------------------------------------------------------------ channel-resharded warp chain
+def _warp_worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from fresco_b200 import flow_utils as fu
+    from oracle import fresco_oracle as O
+    from test_cpu_host import _TorchWarpOps
+    fu.ops = _TorchWarpOps
+    N, chunks, C, h = 4, 2, 6, 8
+    flows, occs = O.synth_flows(N, 64, 64, seed=5, mag=5.0)
+    sal = torch.rand(N, 1, 32, 32, generator=torch.Generator().manual_seed(2))
+    feat = torch.randn(chunks * N, C, h, h, generator=torch.Generator().manual_seed(3))
+    want = O.warp_tensor(feat, flows, occs, sal, chunks)
+    lo, hi = rank * N // world, (rank + 1) * N // world
+    sel = torch.cat([torch.arange(c * N + lo, c * N + hi) for c in range(chunks)])
+    got = fu.warp_tensor(feat[sel].contiguous(), flows, occs, sal, chunks, shard=(world, rank, None))
+    ok = (got - want[sel]).abs().max().item() < 1e-5
+    t = torch.tensor([1 if ok else 0])
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        ret.put(int(t.item()))
+    dist.destroy_process_group()
+
+
+def test_sharded_warp_tensor_world2_gloo():
+    """warp_tensor on a frame-sharded batch: re-shard by channel (all-to-all), chain, all-to-all back == the oracle on the
+    full batch."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    procs = [ctx.Process(target=_warp_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert ret.get(timeout=5) == 1

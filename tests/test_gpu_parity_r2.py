@@ -552,6 +552,18 @@ def _nccl_worker(rank, world, port, ret):
             mine = ShardedFRESCOAttention(ctrl, world, rank, chunks)(q[sel].contiguous(), k[sel].contiguous(), v[sel].contiguous(),
                                                                    heads, ref_q=rq[sel].contiguous(), ref_k=rk[sel].contiguous())
             ok = ok and bool(torch.equal(mine, full[sel]))
+    # warp_tensor on the frame shard (chain re-sharded by channel: two all-to-alls) == unsharded, bit for bit
+    from fresco_b200 import flow_utils as fu
+    N, chunks = 8, 2
+    flows, occs = O.synth_flows(N, 256, 256, seed=5, mag=6.0)
+    flows, occs = [f.to(dev) for f in flows], [o.to(dev) for o in occs]
+    sal = torch.rand(N, 1, 128, 128, generator=torch.Generator().manual_seed(2)).to(dev)
+    feat = torch.randn(chunks * N, 64, 32, 32, generator=torch.Generator().manual_seed(3)).half().to(dev)
+    full = fu.warp_tensor(feat, flows, occs, sal, chunks)
+    lo, hi = frame_range(N, world, rank)
+    sel = torch.cat([torch.arange(c * N + lo, c * N + hi) for c in range(chunks)]).to(dev)
+    mine = fu.warp_tensor(feat[sel].contiguous(), flows, occs, sal, chunks, shard=(world, rank, None))
+    ok = ok and bool(torch.equal(mine, full[sel]))
     t = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
