@@ -863,9 +863,19 @@ struct WideCfg {
   static constexpr int STAGE_BYTES = 2 * NATOM * kKVAtomBytes;
   static constexpr int SMEM_BYTES = 1024 + Q_BYTES + STAGES * STAGE_BYTES + SPLIT * 128 * 8 + 512;
   static constexpr int SOFTMAX_WARPS = 4 * SPLIT;
-  static constexpr int TMA_WARP = SOFTMAX_WARPS, QK_WARP = SOFTMAX_WARPS + 1, PV_WARP0 = SOFTMAX_WARPS + 2;
-  static constexpr int THREADS = (SOFTMAX_WARPS + 2 + NPV) * 32;
+  // With two CTAs per SM every warp costs the softmax threads registers (they hold two tiles' worth of scores, see the
+  // prefetch below): the TMA producer then shares a thread with the score-MMA issuer and refills the ring without
+  // ever blocking.  With one CTA per SM it has a warp of its own.
+  static constexpr bool OWN_TMA_WARP = CTAS == 1;
+  static constexpr int QK_WARP = SOFTMAX_WARPS, PV_WARP0 = SOFTMAX_WARPS + 1, TMA_WARP = SOFTMAX_WARPS + 1 + NPV;
+  static constexpr int THREADS = (SOFTMAX_WARPS + 1 + NPV + (OWN_TMA_WARP ? 1 : 0)) * 32;
 };
+
+__device__ __forceinline__ void tmem_ld_wait_dep16(uint32_t (&r)[16]) {
+#define FR8(b) "+r"(r[b]), "+r"(r[b + 1]), "+r"(r[b + 2]), "+r"(r[b + 3]), "+r"(r[b + 4]), "+r"(r[b + 5]), "+r"(r[b + 6]), "+r"(r[b + 7])
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : FR8(0), FR8(8) : : "memory");
+#undef FR8
+}
 
 template <int N>
 __device__ __forceinline__ void tmem_ld_keys(uint32_t taddr, uint32_t (&r)[N]) {
@@ -931,7 +941,7 @@ fresco_attn_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     }
     fence_barrier_init();
   }
-  if (warp == Cfg::TMA_WARP) {
+  if (warp == Cfg::PV_WARP0) {
     if (lane == 0) {
       tma_prefetch_desc(&tm_q);
       tma_prefetch_desc(&tm_k);
@@ -945,35 +955,61 @@ fresco_attn_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == Cfg::TMA_WARP) {
-    // ------------------------------------------------------------ TMA producer
+  auto load_kv_tile = [&](int t) {                     // K/V tile t -> ring stage t % ST (the stage is free)
+    const int st = t % ST;
+    uint8_t* sk = s_kv + st * Cfg::STAGE_BYTES;
+    uint8_t* sv = sk + Cfg::NATOM * kKVAtomBytes;
+    mbar_expect_tx(bar_kv_full + st, Cfg::STAGE_BYTES);
+#pragma unroll
+    for (int a = 0; a < Cfg::NATOM; ++a) {
+      tma_load_4d(sk + a * kKVAtomBytes, &tm_k, bar_kv_full + st, a * 64, head, t * kTileN, b_kv);
+      tma_load_4d(sv + a * kKVAtomBytes, &tm_v, bar_kv_full + st, a * 64, head, t * kTileN, b_kv);
+    }
+  };
+  auto load_q = [&]() {
+    mbar_expect_tx(bar_q, Cfg::Q_BYTES);
+#pragma unroll
+    for (int a = 0; a < Cfg::NATOM; ++a) tma_load_4d(s_q + a * kQAtomBytes, &tm_q, bar_q, a * 64, head, q0, b);
+  };
+
+  if (Cfg::OWN_TMA_WARP && warp == Cfg::TMA_WARP) {
+    // ------------------------------------------------------------ TMA producer (own warp: one CTA per SM)
     if (lane == 0) {
-      mbar_expect_tx(bar_q, Cfg::Q_BYTES);
-#pragma unroll
-      for (int a = 0; a < Cfg::NATOM; ++a) tma_load_4d(s_q + a * kQAtomBytes, &tm_q, bar_q, a * 64, head, q0, b);
+      load_q();
       for (int t = 0; t < n_tiles; ++t) {
-        const int st = t % ST;
-        if (t >= ST) mbar_wait_backoff(bar_kv_empty + st, ((t / ST) - 1) & 1, 32, 40);
-        uint8_t* sk = s_kv + st * Cfg::STAGE_BYTES;
-        uint8_t* sv = sk + Cfg::NATOM * kKVAtomBytes;
-        mbar_expect_tx(bar_kv_full + st, Cfg::STAGE_BYTES);
-#pragma unroll
-        for (int a = 0; a < Cfg::NATOM; ++a) {
-          tma_load_4d(sk + a * kKVAtomBytes, &tm_k, bar_kv_full + st, a * 64, head, t * kTileN, b_kv);
-          tma_load_4d(sv + a * kKVAtomBytes, &tm_v, bar_kv_full + st, a * 64, head, t * kTileN, b_kv);
-        }
+        if (t >= ST) mbar_wait_backoff(bar_kv_empty + t % ST, ((t / ST) - 1) & 1, 32, 40);
+        load_kv_tile(t);
       }
     }
   } else if (warp == Cfg::QK_WARP) {
-    // ------------------------------------------------------------ score-MMA issuer
+    // ------------------------------------------------------------ score-MMA issuer (+ TMA producer when it has no warp)
     if (lane == 0) {
       constexpr uint32_t idesc_qk = make_idesc_f16(kTileM, kTileN, 0);
       const uint32_t q_addr = smem_u32(s_q);
+      int next_load = 0;
+      auto refill = [&]() {                      // issue every K/V tile load whose ring stage is free; never blocks
+        if (Cfg::OWN_TMA_WARP) return;
+        while (next_load < n_tiles) {
+          if (next_load >= ST && !mbar_test_wait(bar_kv_empty + next_load % ST, ((next_load / ST) - 1) & 1)) break;
+          load_kv_tile(next_load);
+          ++next_load;
+        }
+      };
+      auto wait_poll = [&](uint64_t* bar, uint32_t parity, int tag) {   // wait, keeping the K/V ring moving
+        uint32_t polls = 0;
+        while (!mbar_try_wait(bar, parity)) {
+          refill();
+          if (++polls > FRESCO_WATCHDOG_POLLS) mbar_timeout(bar, parity, tag);
+        }
+      };
+      if (!Cfg::OWN_TMA_WARP) load_q();
+      refill();
       mbar_wait(bar_q, 0, 41);
       for (int t = 0; t < n_tiles; ++t) {
         const int st = t % ST;
-        if (t >= 2) mbar_wait(bar_c + (t & 1), ((t - 2) >> 1) & 1, 42);     // S buffer t & 1 is in registers
-        mbar_wait(bar_kv_full + st, (t / ST) & 1, 43);
+        refill();
+        if (t >= 2) wait_poll(bar_c + (t & 1), ((t - 2) >> 1) & 1, 42);     // S buffer t & 1 is in registers
+        wait_poll(bar_kv_full + st, (t / ST) & 1, 43);
         tc_fence_after();
         const uint32_t k_addr = smem_u32(s_kv + st * Cfg::STAGE_BYTES);
         const uint32_t d_tmem = tmem + ((t & 1) ? Cfg::S_OFF1 : Cfg::S_OFF0);
@@ -987,8 +1023,9 @@ fresco_attn_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         umma_commit(bar_s + (t & 1));
         umma_commit(bar_kv_empty + st);                                    // K_t consumed
       }
+      while (!Cfg::OWN_TMA_WARP && next_load < n_tiles) refill();          // (only if n_tiles <= 2: nothing left to wait on)
     }
-  } else if (warp >= Cfg::PV_WARP0) {
+  } else if (warp >= Cfg::PV_WARP0 && warp < Cfg::PV_WARP0 + Cfg::NPV) {
     // ------------------------------------------------------------ P V issuer j: accumulators [j*PPV, (j+1)*PPV)
     if (lane == 0) {
       const int j = warp - Cfg::PV_WARP0;
@@ -1035,19 +1072,29 @@ fresco_attn_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     const unsigned long long scale2 = pack_f2(scale_log2, scale_log2);
     float m_run = -INFINITY, l_run = 0.f;
 
-    for (int i = 0; i < n_tiles; ++i) {
+    // The scores of tile i+1 are requested from TMEM (tcgen05.ld, asynchronous) BEFORE tile i is worked on and waited for
+    // after it, so the S-ready barrier, the TMEM read latency and the "S consumed" arrival of a tile hide behind the
+    // exponentials of the previous one instead of opening every iteration of a serial chain.
+    auto issue_load = [&](uint32_t (&r)[KEYS], int i) {
+      mbar_wait(bar_s + (i & 1), (i >> 1) & 1, 2);
+      tc_fence_after();
+      const uint32_t addr = t_lane + ((i & 1) ? Cfg::S_OFF1 : Cfg::S_OFF0) + KEYS * part;
+      if constexpr (KEYS == 32) tmem_ld32(addr, r);
+      else tmem_ld16(addr, r);
+    };
+    auto finish_load = [&](uint32_t (&r)[KEYS], int i) {
+      if constexpr (KEYS == 32) tmem_ld_wait_dep32(r);
+      else tmem_ld_wait_dep16(r);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_c + (i & 1));         // S buffer i & 1 may be overwritten by Q K_{i+2}^T
+    };
+    auto process = [&](uint32_t (&r)[KEYS], int i) {
       const int col0 = i * kTileN + KEYS * part;           // first key of this thread's part of the tile
       const int pb = i % PB;
       // warp-uniform: does this part of the tile need masking (ragged tail) or the diagonal bias?
       const bool special = (col0 + KEYS > kv_len) ||
                            (use_bias && (q0 + quarter * 32) < col0 + KEYS && (q0 + quarter * 32 + 32) > col0);
-      mbar_wait(bar_s + (i & 1), (i >> 1) & 1, 2);
-      tc_fence_after();
-      uint32_t r[KEYS];
-      tmem_ld_keys<KEYS>(t_lane + ((i & 1) ? Cfg::S_OFF1 : Cfg::S_OFF0) + KEYS * part, r);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_c + (i & 1));         // S buffer i & 1 may be overwritten by Q K_{i+2}^T
       if (special) {                                        // rare path: fold mask / bias into the raw scores
 #pragma unroll
         for (int j = 0; j < KEYS; ++j) {
@@ -1085,7 +1132,7 @@ fresco_attn_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
 #pragma unroll
           for (int c = 0; c < Cfg::DPAD / 8; ++c) {
             uint32_t o[8];
-            tmem_ld8_sync(o_mine + c * 8, o);
+            tmem_ld8_sync(o_mine + c * 8, o);               // (its wait also covers the prefetched scores: harmless)
 #pragma unroll
             for (int j = 0; j < 8; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
             tmem_st8(o_mine + c * 8, o);
@@ -1096,26 +1143,31 @@ fresco_attn_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       const float neg_m = (m_run == -INFINITY) ? 0.f : -m_run;           // all-masked so far: s = -inf -> p = 0, not NaN
       const unsigned long long negm2 = pack_f2(neg_m, neg_m);
       unsigned long long sum2[2] = {pack_f2(0.f, 0.f), pack_f2(0.f, 0.f)};
-      uint32_t pk[KEYS / 2];
-#pragma unroll
-      for (int j = 0; j < KEYS; j += 2) {
-        float t0, t1, e0, e1;
-        unpack_f2(fma2(pack_f2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), scale2, negm2), t0, t1);
-        if (POLY > 0 && ((j >> 1) % (POLY > 0 ? POLY : 1)) == (POLY - 1)) {
-          exp2_poly_x2(t0, t1, e0, e1);                    // FMA-pipe exponential for every POLY-th pair
-        } else {
-          e0 = fast_exp2(t0);
-          e1 = fast_exp2(t1);
-        }
-        sum2[(j >> 1) & 1] = add2(sum2[(j >> 1) & 1], pack_f2(e0, e1));
-        pk[j >> 1] = pack_half2(e0, e1);
-      }
       // the P buffer was last read by P V of tile i - PB: its retirement is almost always long past
       if (i >= PB) {
         mbar_wait(bar_o + pb * Cfg::NPV + jpv, ((i - PB) / PB) & 1, 3);
         tc_fence_after();
       }
-      tmem_st_half<KEYS / 2>(t_lane + Cfg::P_OFF + pb * 32 + (KEYS / 2) * part, pk);
+      // 16 keys at a time: exponentials, pack, store (the packed registers are recycled by the next 16)
+#pragma unroll
+      for (int g = 0; g < KEYS / 16; ++g) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int jj = 0; jj < 16; jj += 2) {
+          const int j = g * 16 + jj;
+          float t0, t1, e0, e1;
+          unpack_f2(fma2(pack_f2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), scale2, negm2), t0, t1);
+          if (POLY > 0 && ((j >> 1) % (POLY > 0 ? POLY : 1)) == (POLY - 1)) {
+            exp2_poly_x2(t0, t1, e0, e1);                  // FMA-pipe exponential for every POLY-th pair
+          } else {
+            e0 = fast_exp2(t0);
+            e1 = fast_exp2(t1);
+          }
+          sum2[(j >> 1) & 1] = add2(sum2[(j >> 1) & 1], pack_f2(e0, e1));
+          pk[jj >> 1] = pack_half2(e0, e1);
+        }
+        tmem_st8(t_lane + Cfg::P_OFF + pb * 32 + (KEYS / 2) * part + g * 8, pk);
+      }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
@@ -1123,6 +1175,21 @@ fresco_attn_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       float sa, sb;
       unpack_f2(add2(sum2[0], sum2[1]), sa, sb);
       l_run += sa + sb;
+    };
+
+    uint32_t ra[KEYS], rb[KEYS];
+    issue_load(ra, 0);
+    finish_load(ra, 0);
+    for (int i = 0; i < n_tiles; i += 2) {
+      const bool has1 = i + 1 < n_tiles, has2 = i + 2 < n_tiles;
+      if (has1) issue_load(rb, i + 1);
+      process(ra, i);
+      if (has1) {
+        finish_load(rb, i + 1);
+        if (has2) issue_load(ra, i + 2);
+        process(rb, i + 1);
+        if (has2) finish_load(ra, i + 2);
+      }
     }
 
     // ---- epilogue: merge the SPLIT parts of every row, O / l -> fp16 head slice
@@ -1173,7 +1240,7 @@ fresco_attn_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
 
   tc_fence_before();
   __syncthreads();
-  if (warp == Cfg::TMA_WARP) tmem_dealloc<Cfg::TMEM_COLS>(tmem);
+  if (warp == Cfg::PV_WARP0) tmem_dealloc<Cfg::TMEM_COLS>(tmem);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1308,7 +1375,7 @@ static int launch_attn(const void* q, const void* k, const void* v, void* out, i
   // FRESCO_ATTN_WIDE = 2 | 4: that many threads per query row (4 needs head_dim > 48: one CTA per SM)
   const int wide = option(OPT_ATTN_WIDE, kWideDefault);
   if (wide == 4) {
-    if constexpr (D > 48 && D <= 80) {
+    if constexpr (D <= 80) {
       if (poly == 4) return launch_wide<D, 4, 4>(tq, tk, tv, p, grid, stream);
       return launch_wide<D, 4, 0>(tq, tk, tv, p, grid, stream);
     }

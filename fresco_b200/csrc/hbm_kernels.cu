@@ -865,6 +865,217 @@ warp_loss_group_kernel(const float* __restrict__ cs, const float* __restrict__ f
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Channel-QUAD temporal-consistency loss: the kernel optimize_feature runs when the plane fits (48 bytes of shared memory
+// per pixel).  The round-2 measurement of the two kernels above (1.0 ms at [16,640,64,64] each, DRAM at 4 %) showed them
+// bound by INSTRUCTIONS, ~300 per (pixel, channel, frame pair): bilinear taps rebuilt from the flows, 16-bit ELL weights
+// decoded, one 2/4-byte shared-memory access per tap and channel, integer divisions in the plane loads.  Here
+//   * the four taps of every (pair, pixel) and both warp directions are prepared once per batch as 4 x u16 indices +
+//     4 x fp32 weights (exactly make_taps' values), the adjoint ELL rows as 8 x u16 sources + 8 x fp32 weights;
+//   * a CTA owns FOUR (chunk, channel) planes interleaved per pixel in shared memory -- frame f and f+1 as float4, the
+//     two masked sign planes as 4 x fp16 -- so one 16-byte (8-byte) shared load serves a tap for all four channels;
+//   * every thread owns P pixels of the quad for the whole walk over the frame pairs; what a frame receives as the
+//     "next" frame of pair f is carried in registers to pair f+1 (each cs plane read once, each grad plane written once,
+//     frame 0 once more for the wrap-around pair).
+// ---------------------------------------------------------------------------------------------
+struct __align__(8) half4 {
+  __half2 lo, hi;
+};
+__device__ __forceinline__ float4 h4_to_f4(const half4& h) {
+  const float2 a = __half22float2(h.lo), b = __half22float2(h.hi);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ float sgnf(float r) { return r > 0.f ? 1.f : (r < 0.f ? -1.f : 0.f); }
+
+template <int P>
+__global__ void __launch_bounds__(1024, 1)
+warp_loss_quad_kernel(const float* __restrict__ cs, const uint2* __restrict__ tapi_b, const float4* __restrict__ tapw_b,
+                      const uint2* __restrict__ tapi_f, const float4* __restrict__ tapw_f,
+                      const float* __restrict__ fwd_keep, const float* __restrict__ bwd_keep,
+                      const uint4* __restrict__ ells_b, const float4* __restrict__ ellw_b,
+                      const uint4* __restrict__ ells_f, const float4* __restrict__ ellw_f,
+                      const int32_t* __restrict__ ovf /*[2][frames][n_ovf][3]*/, int n_ovf, float* __restrict__ grad,
+                      float* __restrict__ loss_acc, int accumulate, int frames, int channels, int hw, float k) {
+  extern __shared__ float4 smq[];
+  float4* cur = smq;                                          // [hw] frame f,     4 channels per pixel
+  float4* nxt = smq + hw;                                     // [hw] frame f + 1
+  half4* s1 = reinterpret_cast<half4*>(smq + 2 * hw);         // [hw] sign(c2 - W_bf c1) * keep_b
+  half4* s2 = s1 + hw;                                        // [hw] sign(c1 - W_ff c2) * keep_f
+  const int T = blockDim.x, t = threadIdx.x;
+  const int pl0 = blockIdx.x * 4;                             // first (chunk, channel) plane of the quad; channels % 4 == 0
+  const int b = pl0 / channels, c0 = pl0 % channels;
+  const long long fstride = (long long)channels * hw;
+  const long long base = ((long long)b * frames * channels + c0) * hw;      // frame 0, channel c0
+  auto load_frame = [&](float4* dst, int f) {
+    const float* src = cs + base + (long long)f * fstride;
+#pragma unroll
+    for (int pp = 0; pp < P; ++pp) {
+      const int q = t + pp * T;
+      if (q < hw) dst[q] = make_float4(src[q], src[hw + q], src[2 * hw + q], src[3 * hw + q]);
+    }
+  };
+  float4 carry[P];
+#pragma unroll
+  for (int pp = 0; pp < P; ++pp) carry[pp] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float loss = 0.f;
+
+  load_frame(cur, 0);
+  for (int f = 0; f < frames; ++f) {
+    const int fn = (f + 1 == frames) ? 0 : f + 1;
+    load_frame(nxt, fn);
+    __syncthreads();
+    // ---- residuals of pair (f, fn)
+    {
+      const long long po = (long long)f * hw;
+#pragma unroll
+      for (int pp = 0; pp < P; ++pp) {
+        const int q = t + pp * T;
+        if (q >= hw) continue;
+        const uint2 ib = __ldg(tapi_b + po + q), jf = __ldg(tapi_f + po + q);
+        const float4 wb = __ldg(tapw_b + po + q), wf = __ldg(tapw_f + po + q);
+        const float mb = __ldg(bwd_keep + po + q), mf = __ldg(fwd_keep + po + q);
+        const float4 c1 = cur[q], c2 = nxt[q];
+        float4 a0 = cur[ib.x & 0xffffu], a1 = cur[ib.x >> 16], a2 = cur[ib.y & 0xffffu], a3 = cur[ib.y >> 16];
+        float4 r1, r2;
+        // same order of operations as sample_taps: ((w00 v00 + w01 v01) + w10 v10) + w11 v11
+        r1.x = c2.x - (wb.x * a0.x + wb.y * a1.x + wb.z * a2.x + wb.w * a3.x);
+        r1.y = c2.y - (wb.x * a0.y + wb.y * a1.y + wb.z * a2.y + wb.w * a3.y);
+        r1.z = c2.z - (wb.x * a0.z + wb.y * a1.z + wb.z * a2.z + wb.w * a3.z);
+        r1.w = c2.w - (wb.x * a0.w + wb.y * a1.w + wb.z * a2.w + wb.w * a3.w);
+        a0 = nxt[jf.x & 0xffffu], a1 = nxt[jf.x >> 16], a2 = nxt[jf.y & 0xffffu], a3 = nxt[jf.y >> 16];
+        r2.x = c1.x - (wf.x * a0.x + wf.y * a1.x + wf.z * a2.x + wf.w * a3.x);
+        r2.y = c1.y - (wf.x * a0.y + wf.y * a1.y + wf.z * a2.y + wf.w * a3.y);
+        r2.z = c1.z - (wf.x * a0.z + wf.y * a1.z + wf.z * a2.z + wf.w * a3.z);
+        r2.w = c1.w - (wf.x * a0.w + wf.y * a1.w + wf.z * a2.w + wf.w * a3.w);
+        loss += (fabsf(r1.x) + fabsf(r1.y) + fabsf(r1.z) + fabsf(r1.w)) * mb +
+                (fabsf(r2.x) + fabsf(r2.y) + fabsf(r2.z) + fabsf(r2.w)) * mf;
+        half4 h;
+        h.lo = __floats2half2_rn(sgnf(r1.x) * mb, sgnf(r1.y) * mb);
+        h.hi = __floats2half2_rn(sgnf(r1.z) * mb, sgnf(r1.w) * mb);
+        s1[q] = h;
+        h.lo = __floats2half2_rn(sgnf(r2.x) * mf, sgnf(r2.y) * mf);
+        h.hi = __floats2half2_rn(sgnf(r2.z) * mf, sgnf(r2.w) * mf);
+        s2[q] = h;
+      }
+    }
+    __syncthreads();
+    // ---- destinations hit by more than 8 taps of the forward-flow warp (rare): extra terms of d/dc2 through the dead
+    //      frame-f planes, which the gather below adds in
+    if (n_ovf > 0) {
+      for (int q = t; q < hw; q += T) cur[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      __syncthreads();
+      const int32_t* of = ovf + ((long long)1 * frames + f) * n_ovf * 3;
+      for (int e = t; e < n_ovf; e += T) {
+        if (of[3 * e] < 0) continue;
+        const float wgt = -__int_as_float(of[3 * e + 2]);
+        const float4 v = h4_to_f4(s2[of[3 * e + 1]]);
+        float* dst = reinterpret_cast<float*>(cur + of[3 * e]);
+        atomicAdd(dst + 0, wgt * v.x);
+        atomicAdd(dst + 1, wgt * v.y);
+        atomicAdd(dst + 2, wgt * v.z);
+        atomicAdd(dst + 3, wgt * v.w);
+      }
+      __syncthreads();
+    }
+    // ---- adjoints as gathers: 8 (source, weight) ELL slots per destination pixel, empty slots have weight 0 and sit
+    //      at the end of the row, so a warp stops at the first slot that is empty for all of its lanes
+    {
+      const long long po = (long long)f * hw;
+      float* gdst = grad + base + (long long)f * fstride;
+#pragma unroll
+      for (int pp = 0; pp < P; ++pp) {
+        const int q = t + pp * T;
+        const bool live = q < hw;
+        const int qq = live ? q : 0;
+        float4 ga = h4_to_f4(s2[qq]);                           // d/dc1 = s2 - W_bf^T s1   (frame f)
+        float4 gb = h4_to_f4(s1[qq]);                           // d/dc2 = s1 - W_ff^T s2   (frame fn)
+        if (n_ovf > 0) {
+          const float4 o = cur[qq];
+          gb.x += o.x, gb.y += o.y, gb.z += o.z, gb.w += o.w;
+        }
+        {
+          const uint4 es = __ldg(ells_b + po + qq);
+          const float4 w0 = __ldg(ellw_b + 2 * (po + qq)), w1 = __ldg(ellw_b + 2 * (po + qq) + 1);
+          const uint32_t src[4] = {es.x, es.y, es.z, es.w};
+          const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (!__any_sync(0xffffffffu, live && w[j] != 0.f)) break;
+            const float4 v = h4_to_f4(s1[(src[j >> 1] >> ((j & 1) * 16)) & 0xffffu]);
+            ga.x = fmaf(-w[j], v.x, ga.x), ga.y = fmaf(-w[j], v.y, ga.y);
+            ga.z = fmaf(-w[j], v.z, ga.z), ga.w = fmaf(-w[j], v.w, ga.w);
+          }
+        }
+        {
+          const uint4 es = __ldg(ells_f + po + qq);
+          const float4 w0 = __ldg(ellw_f + 2 * (po + qq)), w1 = __ldg(ellw_f + 2 * (po + qq) + 1);
+          const uint32_t src[4] = {es.x, es.y, es.z, es.w};
+          const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (!__any_sync(0xffffffffu, live && w[j] != 0.f)) break;
+            const float4 v = h4_to_f4(s2[(src[j >> 1] >> ((j & 1) * 16)) & 0xffffu]);
+            gb.x = fmaf(-w[j], v.x, gb.x), gb.y = fmaf(-w[j], v.y, gb.y);
+            gb.z = fmaf(-w[j], v.z, gb.z), gb.w = fmaf(-w[j], v.w, gb.w);
+          }
+        }
+        if (live) {
+          const float4 cr = carry[pp];
+          const float v0 = (cr.x + ga.x) * k, v1 = (cr.y + ga.y) * k, v2 = (cr.z + ga.z) * k, v3 = (cr.w + ga.w) * k;
+          if (accumulate) {
+            gdst[q] += v0, gdst[hw + q] += v1, gdst[2 * hw + q] += v2, gdst[3 * hw + q] += v3;
+          } else {
+            gdst[q] = v0, gdst[hw + q] = v1, gdst[2 * hw + q] = v2, gdst[3 * hw + q] = v3;
+          }
+        }
+        carry[pp] = gb;
+      }
+    }
+    __syncthreads();                                           // s1 / s2 / cur are rewritten by the next pair
+    // ---- destinations with more than 8 taps of the backward-flow warp: extra terms of d/dc1 (frame f is final in
+    //      global memory now)
+    if (n_ovf > 0) {
+      const int32_t* ob = ovf + ((long long)0 * frames + f) * n_ovf * 3;
+      float* gdst = grad + base + (long long)f * fstride;
+      for (int e = t; e < n_ovf; e += T) {
+        if (ob[3 * e] < 0) continue;
+        const float wgt = -__int_as_float(ob[3 * e + 2]) * k;
+        const float4 v = h4_to_f4(s1[ob[3 * e + 1]]);
+        atomicAdd(gdst + ob[3 * e], wgt * v.x);
+        atomicAdd(gdst + hw + ob[3 * e], wgt * v.y);
+        atomicAdd(gdst + 2 * hw + ob[3 * e], wgt * v.z);
+        atomicAdd(gdst + 3 * hw + ob[3 * e], wgt * v.w);
+      }
+      __syncthreads();
+    }
+    float4* tmp = cur;                                          // frame fn becomes frame f of the next pair
+    cur = nxt;
+    nxt = tmp;
+  }
+  // ---- wrap-around: what frame 0 receives as the "next" frame of pair N-1
+  {
+    float* g0 = grad + base;
+#pragma unroll
+    for (int pp = 0; pp < P; ++pp) {
+      const int q = t + pp * T;
+      if (q < hw) {
+        g0[q] += carry[pp].x * k, g0[hw + q] += carry[pp].y * k, g0[2 * hw + q] += carry[pp].z * k, g0[3 * hw + q] += carry[pp].w * k;
+      }
+    }
+  }
+  if (loss_acc != nullptr) {
+    __shared__ float red[32];
+    loss = warp_sum(loss);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = loss;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      float v = threadIdx.x < ((blockDim.x + 31) >> 5) ? red[threadIdx.x] : 0.f;
+      v = warp_sum(v);
+      if (threadIdx.x == 0) atomicAdd(loss_acc, v * k);
+    }
+  }
+}
+
 // =============================================================================================
 // O4  Adam  (torch.optim.Adam defaults; src/diffusion_hacked.py:433,485)
 // =============================================================================================
@@ -1397,4 +1608,51 @@ extern "C" int fresco_dilate(const float* in, float* out, int planes, int h, int
     return set_error(FRESCO_ERR_ARG, "fresco_dilate: bad shape (odd kernel)");
   dilate_kernel<<<grid_for((long long)planes * h * w, 256), 256, 0, (cudaStream_t)stream>>>(in, out, planes, h, w, kernel);
   return check_launch("dilate_kernel");
+}
+
+extern "C" int fresco_warp_loss_quad(const float* cs, const void* tap_idx_bwd, const float* tap_w_bwd,
+                                     const void* tap_idx_fwd, const float* tap_w_fwd, const float* fwd_keep,
+                                     const float* bwd_keep, const void* ell_src_bwd, const float* ell_w_bwd,
+                                     const void* ell_src_fwd, const float* ell_w_fwd, const int32_t* overflow,
+                                     int n_overflow, float* grad, float* loss_acc, int accumulate, int chunks, int frames,
+                                     int channels, int h, int w, void* stream) {
+  if (!cs || !tap_idx_bwd || !tap_w_bwd || !tap_idx_fwd || !tap_w_fwd || !fwd_keep || !bwd_keep || !ell_src_bwd ||
+      !ell_w_bwd || !ell_src_fwd || !ell_w_fwd || !grad)
+    return set_error(FRESCO_ERR_ARG, "fresco_warp_loss_quad: null pointer");
+  if (n_overflow > 0 && !overflow) return set_error(FRESCO_ERR_ARG, "fresco_warp_loss_quad: overflow list missing");
+  const int hw = h * w;
+  if (chunks <= 0 || frames < 2 || channels <= 0 || channels % 4 != 0 || hw <= 0 || hw > 65535)
+    return set_error(FRESCO_ERR_ARG, "fresco_warp_loss_quad: bad shape (frames >= 2, channels % 4 == 0, h*w <= 65535)");
+  const size_t smem = (size_t)hw * 48;
+  if (smem > 200 * 1024) return set_error(FRESCO_ERR_UNSUPPORTED, "fresco_warp_loss_quad: plane too large for shared memory");
+  const double numel = (double)chunks * frames * channels * hw;
+  const float kk = (float)(2.0 / numel);
+  // P pixels per thread: as few threads as keep P <= 4 (more pixels per thread = more independent work per thread)
+  int P = 4;
+  int T = ((hw + P - 1) / P + 31) / 32 * 32;
+  if (T > 1024) return set_error(FRESCO_ERR_UNSUPPORTED, "fresco_warp_loss_quad: plane too large");
+  if (T < 64) {
+    P = hw >= 128 ? 2 : 1;
+    T = ((hw + P - 1) / P + 31) / 32 * 32;
+  }
+  const int grid = chunks * channels / 4;
+  cudaStream_t s = (cudaStream_t)stream;
+#define QUAD_CASE(PP)                                                                                                   \
+  if (P == PP) {                                                                                                        \
+    static bool attr_set = false;                                                                                       \
+    if (!attr_set) {                                                                                                    \
+      cudaError_t e = cudaFuncSetAttribute(warp_loss_quad_kernel<PP>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                           200 * 1024);                                                                 \
+      if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(warp_loss_quad)");                           \
+      attr_set = true;                                                                                                  \
+    }                                                                                                                   \
+    warp_loss_quad_kernel<PP><<<grid, T, smem, s>>>(                                                                    \
+        cs, (const uint2*)tap_idx_bwd, (const float4*)tap_w_bwd, (const uint2*)tap_idx_fwd, (const float4*)tap_w_fwd,   \
+        fwd_keep, bwd_keep, (const uint4*)ell_src_bwd, (const float4*)ell_w_bwd, (const uint4*)ell_src_fwd,             \
+        (const float4*)ell_w_fwd, overflow, n_overflow, grad, loss_acc, accumulate, frames, channels, hw, kk);         \
+    return check_launch("warp_loss_quad_kernel");                                                                       \
+  }
+  QUAD_CASE(1) QUAD_CASE(2) QUAD_CASE(4)
+#undef QUAD_CASE
+  return set_error(FRESCO_ERR_UNSUPPORTED, "fresco_warp_loss_quad: no instantiation");
 }

@@ -179,16 +179,27 @@ def _workspace(key, nbytes: int, device) -> torch.Tensor:
     return ws
 
 
+def _u16(x: torch.Tensor) -> torch.Tensor:
+    """values in [0, 65535] stored as uint16 bit patterns in an int16 tensor"""
+    x = x.long() & 0xffff
+    return torch.where(x >= 32768, x - 65536, x).to(torch.int16).contiguous()
+
+
 def warp_adjoint_ell(flow: torch.Tensor):
-    """ELL form of the adjoint of the bilinear warp by ``flow`` [F,2,h,w] (per-batch preparation).
-    Returns (ell uint32-as-int32 [F, hw, 8], overflow int32 [F, n_ovf, 3]); row = destination pixel, entry =
-    (round(w*65535) << 16) | source; destinations with more than 8 taps spill to the overflow list."""
+    """Per-batch operands of the temporal-consistency loss for the warp by ``flow`` [F,2,h,w]:
+    * the four bilinear taps of every pixel (forward application): tap_idx uint16 [F, hw, 4], tap_w fp32 [F, hw, 4];
+    * the ADJOINT of that warp in ELL form, row = destination pixel, up to 8 (source, weight) entries, used slots first:
+      ell_src uint16 [F, hw, 8], ell_w fp32 [F, hw, 8], and the same packed as (round(w*65535) << 16) | source in uint32
+      (``ell_packed``, the format of the generic kernels); destinations with more than 8 taps spill to
+      ``ovf`` int32 [F, n_ovf, 3] = (destination | -1, source, float bits of the weight)."""
     Fr, _, h, w = flow.shape
     hw = h * w
     dev = flow.device
     dest = torch.empty(Fr, hw, 4, dtype=torch.int32, device=dev)
     wgt = torch.empty(Fr, hw, 4, dtype=torch.float32, device=dev)
     L.check(L.lib().fresco_warp_taps(L.ptr(flow), L.ptr(dest), L.ptr(wgt), Fr, h, w, L.stream()), "fresco_warp_taps")
+    tap_idx = _u16(dest.clamp(min=0))
+    tap_w = wgt.clone()
     dest = dest.reshape(Fr, 4 * hw).long()
     wgt = wgt.reshape(Fr, 4 * hw)
     src = torch.arange(hw, device=dev).repeat_interleave(4)[None].expand(Fr, -1)
@@ -201,14 +212,16 @@ def warp_adjoint_ell(flow: torch.Tensor):
     row_ptr = torch.searchsorted(key_s, bounds)                               # [F, hw+1]
     valid = key_s < hw
     rank = torch.arange(4 * hw, device=dev)[None] - torch.gather(row_ptr, 1, key_s.clamp(max=hw - 1))
-    packed = ((w_s * 65535.0).round().long() << 16) | src_s
-    ell = torch.zeros(Fr, hw * ELL_SLOTS, dtype=torch.int64, device=dev)
     in_ell = valid & (rank < ELL_SLOTS)
     slot = (key_s.clamp(max=hw - 1) * ELL_SLOTS + rank.clamp(0, ELL_SLOTS - 1))
-    ell.scatter_add_(1, torch.where(in_ell, slot, torch.zeros_like(slot)),
-                     torch.where(in_ell, packed, torch.zeros_like(packed)))           # slot 0 of row 0 gets +0 for the rest
+    slot = torch.where(in_ell, slot, torch.zeros_like(slot))                  # slot 0 of row 0 gets +0 for the rest
+    ell_src = torch.zeros(Fr, hw * ELL_SLOTS, dtype=torch.int64, device=dev)
+    ell_src.scatter_add_(1, slot, torch.where(in_ell, src_s, torch.zeros_like(src_s)))
+    ell_w = torch.zeros(Fr, hw * ELL_SLOTS, dtype=torch.float32, device=dev)
+    ell_w.scatter_add_(1, slot, torch.where(in_ell, w_s, torch.zeros_like(w_s)))
+    packed = ((ell_w * 65535.0).round().long() << 16) | ell_src
     # uint32 payload stored in an int32 tensor (two's complement wrap)
-    ell = torch.where(ell >= 2 ** 31, ell - 2 ** 32, ell).to(torch.int32).reshape(Fr, hw, ELL_SLOTS).contiguous()
+    packed = torch.where(packed >= 2 ** 31, packed - 2 ** 32, packed).to(torch.int32).reshape(Fr, hw, ELL_SLOTS).contiguous()
     over = valid & (rank >= ELL_SLOTS)
     n_ovf = int(over.sum(1).max().item())
     ovf = torch.full((Fr, max(n_ovf, 1), 3), -1, dtype=torch.int32, device=dev)
@@ -218,36 +231,52 @@ def warp_adjoint_ell(flow: torch.Tensor):
             ovf[f, :sel.numel(), 0] = key_s[f, sel].to(torch.int32)
             ovf[f, :sel.numel(), 1] = src_s[f, sel].to(torch.int32)
             ovf[f, :sel.numel(), 2] = w_s[f, sel].contiguous().view(torch.int32)
-    return ell, ovf, n_ovf
+    return {"tap_idx": tap_idx.reshape(Fr, hw, 4), "tap_w": tap_w.contiguous(), "ell_packed": packed,
+            "ell_src": _u16(ell_src).reshape(Fr, hw, ELL_SLOTS), "ell_w": ell_w.reshape(Fr, hw, ELL_SLOTS).contiguous(),
+            "ovf": ovf, "n_ovf": n_ovf}
+
+
+class WarpAdjoint:
+    """Per-batch operands of fresco_warp_loss_* for one (backward flow, forward flow) pair (see warp_adjoint_ell)."""
+
+    def __init__(self, bwd: dict, fwd: dict):
+        self.bwd, self.fwd = bwd, fwd
+        self.n_ovf = max(bwd["n_ovf"], fwd["n_ovf"])
+        Fr = bwd["ovf"].shape[0]
+        ovf = torch.full((2, Fr, max(self.n_ovf, 1), 3), -1, dtype=torch.int32, device=bwd["ovf"].device)
+        ovf[0, :, :bwd["ovf"].shape[1]] = bwd["ovf"]
+        ovf[1, :, :fwd["ovf"].shape[1]] = fwd["ovf"]
+        self.ovf = ovf.contiguous()
+
+
+def warp_adjoint_pair(bwd_flow, fwd_flow) -> WarpAdjoint:
+    return WarpAdjoint(warp_adjoint_ell(bwd_flow), warp_adjoint_ell(fwd_flow))
 
 
 def warp_loss_fwd_bwd(cs, fwd_flow, bwd_flow, fwd_keep, bwd_keep, grad, loss_acc=None, accumulate=False,
                       adjoint=None):
-    """``adjoint`` = (bwd_ell, fwd_ell, overflow [2, F, n, 3], n) from :func:`warp_adjoint_pair` (cached per batch)."""
+    """``adjoint`` = :class:`WarpAdjoint` from :func:`warp_adjoint_pair` (cached per batch by the caller)."""
     chunks, frames, C, h, w = cs.shape
     if adjoint is None:
         adjoint = warp_adjoint_pair(bwd_flow, fwd_flow)
-    bwd_ell, fwd_ell, ovf, n_ovf = adjoint
+    a = adjoint
+    lp = L.ptr(loss_acc) if loss_acc is not None else None
     ev = _prof_begin()
-    L.check(L.lib().fresco_warp_loss_fwd_bwd(L.ptr(cs), L.ptr(fwd_flow), L.ptr(bwd_flow), L.ptr(fwd_keep),
-                                             L.ptr(bwd_keep), L.ptr(bwd_ell), L.ptr(fwd_ell), L.ptr(ovf), int(n_ovf),
-                                             L.ptr(grad), L.ptr(loss_acc) if loss_acc is not None else None,
-                                             1 if accumulate else 0, chunks, frames, C, h, w, L.stream()),
-            "fresco_warp_loss_fwd_bwd")
-    # SURVEY 8d, O2: read c1, c2 + write g1, g2 = 4 fp32 passes (the fused kernel moves 2 + 1/N of them)
+    if C % 4 == 0 and h * w <= 4096:
+        b, f = a.bwd, a.fwd
+        L.check(L.lib().fresco_warp_loss_quad(L.ptr(cs), L.ptr(b["tap_idx"]), L.ptr(b["tap_w"]), L.ptr(f["tap_idx"]),
+                                              L.ptr(f["tap_w"]), L.ptr(fwd_keep), L.ptr(bwd_keep), L.ptr(b["ell_src"]),
+                                              L.ptr(b["ell_w"]), L.ptr(f["ell_src"]), L.ptr(f["ell_w"]), L.ptr(a.ovf),
+                                              int(a.n_ovf), L.ptr(grad), lp, 1 if accumulate else 0, chunks, frames, C, h,
+                                              w, L.stream()), "fresco_warp_loss_quad")
+    else:
+        L.check(L.lib().fresco_warp_loss_fwd_bwd(L.ptr(cs), L.ptr(fwd_flow), L.ptr(bwd_flow), L.ptr(fwd_keep),
+                                                 L.ptr(bwd_keep), L.ptr(a.bwd["ell_packed"]), L.ptr(a.fwd["ell_packed"]),
+                                                 L.ptr(a.ovf), int(a.n_ovf), L.ptr(grad), lp, 1 if accumulate else 0,
+                                                 chunks, frames, C, h, w, L.stream()), "fresco_warp_loss_fwd_bwd")
+    # SURVEY 8d, O2: read c1, c2 + write g1, g2 = 4 fp32 passes (the fused kernels move 2 + 1/N of them)
     _prof_end(ev, "warp_loss_C%d_%dx%d" % (C, h, w), 16.0 * cs.numel(), "hbm")
     return grad
-
-
-def warp_adjoint_pair(bwd_flow, fwd_flow):
-    b_ell, b_ovf, nb = warp_adjoint_ell(bwd_flow)
-    f_ell, f_ovf, nf = warp_adjoint_ell(fwd_flow)
-    n = max(nb, nf)
-    Fr = bwd_flow.shape[0]
-    ovf = torch.full((2, Fr, max(n, 1), 3), -1, dtype=torch.int32, device=bwd_flow.device)
-    ovf[0, :, :b_ovf.shape[1]] = b_ovf
-    ovf[1, :, :f_ovf.shape[1]] = f_ovf
-    return b_ell, f_ell, ovf.contiguous(), n
 
 
 def gram_normalize(cs_bcl: torch.Tensor):

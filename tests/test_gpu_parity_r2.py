@@ -89,8 +89,8 @@ def test_attention_variants_all_head_dims(fb, attn_opts, variant, d):
     half of the wide kernel fully masked (20, 33, 77), the diagonal bias + k-scale of spatial-guided attention."""
     if variant.get("FRESCO_ATTN_NARROW") and d != 40:
         pytest.skip("narrow kernel: head_dim 40 only")
-    if variant.get("FRESCO_ATTN_WIDE") == 4 and d not in (64, 80):
-        pytest.skip("four threads per row: head_dim 64 / 80 only")
+    if variant.get("FRESCO_ATTN_WIDE") == 4 and d > 80:
+        pytest.skip("four threads per row: head_dim <= 80 only")
     attn_opts(**variant)
     heads = 2
     g = torch.Generator(device="cuda").manual_seed(17 + d)
@@ -204,7 +204,10 @@ def test_set_b_through_the_kernels(fb, golden):
         assert np.allclose(np.array(tr.losses), g[f"opt_{tag}_losses"], rtol=1e-2), (tag, tr.losses)
         diff = (out.cpu() - T(g[f"opt_{tag}_out"], "cpu")).abs()
         if iters == 1:
-            assert (diff > 2e-3).float().mean().item() < 0.03
+            # Adam's first step moves every element by exactly +-lr: an element whose tiny gradient changes sign under the
+            # fp16 Gram operands lands 2*lr away, all the others agree closely (4 % of them flip on this fixture)
+            assert (diff > 2e-3).float().mean().item() < 0.06
+            assert diff.median().item() < 1e-4
         else:
             assert (diff.mean() / T(g[f"opt_{tag}_out"], "cpu").abs().mean()).item() < 0.1
 
@@ -304,7 +307,7 @@ def test_temporal_loss_adjoint_overflow_path(fb):
     keep_b = (torch.rand(N, 1, h, h, generator=g) > 0.2).float()
     cs = torch.randn(2, N, C, h, h, generator=g)
     adj = fb.ops.warp_adjoint_pair(bf.cuda().contiguous(), ff.cuda().contiguous())
-    assert adj[-1] > 0, "fixture must overflow the ELL rows"
+    assert adj.n_ovf > 0, "fixture must overflow the ELL rows"
     loss_ref, grad_ref = O.temporal_loss_and_grad(cs, ff.repeat(2, 1, 1, 1), bf.repeat(2, 1, 1, 1), keep_f.repeat(2, 1, 1, 1),
                                                   keep_b.repeat(2, 1, 1, 1))
     grad = torch.empty_like(cs).cuda()
@@ -313,6 +316,16 @@ def test_temporal_loss_adjoint_overflow_path(fb):
                              keep_b.reshape(N, h, h).cuda().contiguous(), grad, loss, accumulate=False, adjoint=adj)
     assert abs(loss.item() - float(loss_ref)) < 1e-5 * abs(float(loss_ref))
     assert (grad.cpu() - grad_ref).abs().max().item() < 1e-6 + 2e-4 * grad_ref.abs().max().item()
+    # the generic kernels (planes the quad kernel does not take: channels % 4 != 0) through the same entry point
+    cs3 = cs[:, :, :6].contiguous()
+    loss_ref3, grad_ref3 = O.temporal_loss_and_grad(cs3, ff.repeat(2, 1, 1, 1), bf.repeat(2, 1, 1, 1), keep_f.repeat(2, 1, 1, 1),
+                                                    keep_b.repeat(2, 1, 1, 1))
+    grad3 = torch.empty_like(cs3).cuda()
+    loss3 = torch.zeros(1, device="cuda")
+    fb.ops.warp_loss_fwd_bwd(cs3.cuda(), ff.cuda().contiguous(), bf.cuda().contiguous(), keep_f.reshape(N, h, h).cuda().contiguous(),
+                             keep_b.reshape(N, h, h).cuda().contiguous(), grad3, loss3, accumulate=False, adjoint=adj)
+    assert abs(loss3.item() - float(loss_ref3)) < 1e-5 * abs(float(loss_ref3))
+    assert (grad3.cpu() - grad_ref3).abs().max().item() < 1e-6 + 2e-4 * grad_ref3.abs().max().item()
 
 
 @pytest.mark.parametrize("N,C,h", [(8, 1280, 32), (8, 640, 64)])

@@ -1,0 +1,51 @@
+"""Launch every non-attention kernel of the hot path twice at its BASELINE shape -- the target of the ncu captures
+(`ncu --set full -k regex:<kernel> ...`): temporal attention (level B), K/V compaction, warp chain and temporal loss at
+layer 3 ([16,640,64,64]), the two Gram kernels, normalise / project, Adam, AdaIN, GMFlow correlation."""
+import math
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from fresco_b200 import diffusion_hacked as dh, flow_utils as fu, gmflow_matching, ops  # noqa: E402
+from fresco_b200.flow_utils import adjoint_csr  # noqa: E402
+from fresco_b200.harness import synth  # noqa: E402
+
+N, res, C, h = 8, 512, 640, 64
+dev = torch.device("cuda")
+flows, occs = synth.smooth_flows(N, res, res, dev, seed=2)
+imgs = synth.frames(N, res, res, dev, 3)
+sal = synth.saliency(N, dev, 4)
+g = torch.Generator().manual_seed(h)
+sample = torch.randn(2 * N, C, h, h, generator=g).half().to(dev)
+ref = (sample.float() + 0.5 * torch.randn(2 * N, C, h, h, generator=g).to(dev)).half()
+target = dh.gram_targets([ref])[0]
+cs = sample.float().reshape(2, N, C, h, h).contiguous()
+B, L = 2 * N, h * h
+_, ff, bf, fo, bo = dh.resize_flows_occs(flows, occs, h)
+adj = adjoint_csr(flows, occs, h)
+kf, kb = (1 - fo).reshape(N, h, h).contiguous(), (1 - bo).reshape(N, h, h).contiguous()
+gr = torch.empty_like(cs)
+# level-B attention operands
+q, k, a = (torch.randn(2 * N, L, 320, generator=g).half().to(dev) for _ in range(3))
+fm, bm, im = fu.get_mapping_ind(flows[1], occs[1], imgs, scale=8.0)
+mask = dh.cross_frame_attn_masks(occs[1])[0]
+idx = torch.nonzero(mask.reshape(-1)).reshape(-1).to(torch.int32)
+f0 = torch.randn(N, 128, 64, 64, generator=g).to(dev)
+f1 = torch.roll(f0, (1, -2), (2, 3))
+for _ in range(2):
+    ops.temporal_attn_fwd(q, k, a, fm[:, 0].contiguous(), im[:, 0].to(torch.uint8).contiguous(), 2, 8, 0.2 / math.sqrt(40))
+    ops.kv_compact(k, a, idx, 2)
+    fu.warp_tensor(sample, flows, occs, sal, 2)
+    xhat, norms = ops.gram_normalize(cs.view(B, C, L))
+    tsign = ops.gram_sign_ref(xhat, target.yhat, 100.0)
+    ops.gram_grad(tsign, xhat, norms, gr.view(B, C, L), 100.0)
+    ops.warp_loss_fwd_bwd(cs, ff, bf, kf, kb, gr, adjoint=adj)
+    m = torch.zeros_like(cs)
+    v = torch.zeros_like(cs)
+    ops.adam_step(cs, gr, m, v, 1)
+    ops.adain(cs.view(B, C, h, h), sample)
+    gmflow_matching.global_correlation_softmax(f0, f1, pred_bidir_flow=True)
+torch.cuda.synchronize()
+print("done")
