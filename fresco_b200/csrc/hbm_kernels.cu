@@ -504,6 +504,87 @@ warp_chain_group_kernel(const T* __restrict__ sample, T* __restrict__ out, const
   }
 }
 
+// Channel-QUAD variant (same idea as warp_loss_quad_kernel below): four (chunk, channel) planes interleaved per pixel as
+// float4 in shared memory, so one 16-byte shared load serves a bilinear tap for all four; the taps of every chain step
+// come prepared (4 x u16 index + 4 x fp32 weight per pixel: make_taps' values), no flow decoding in the loop.
+template <typename T, int P>
+__global__ void __launch_bounds__(1024, 1)
+warp_chain_quad_kernel(const T* __restrict__ sample, T* __restrict__ out, const uint2* __restrict__ tap_idx,
+                       const float4* __restrict__ tap_w /*[frames][hw]: steps 0..N-2 backward flow, N-1 closing flow*/,
+                       const float* __restrict__ blend, int frames, int channels, int hw) {
+  extern __shared__ float4 chq[];
+  float4* cur = chq;
+  float4* nxt = chq + hw;
+  const int T_ = blockDim.x, t = threadIdx.x;
+  const int pl0 = blockIdx.x * 4;
+  const int j = pl0 / channels, c0 = pl0 % channels;
+  const long long fstride = (long long)channels * hw;
+  const long long base = ((long long)j * frames * channels + c0) * hw;
+  auto ld4 = [&](const T* src, int q) {
+    return make_float4(ld_as_float(src + q), ld_as_float(src + hw + q), ld_as_float(src + 2 * hw + q),
+                       ld_as_float(src + 3 * hw + q));
+  };
+  auto st4 = [&](T* dst, int q, const float4& v) {
+    st_from_float(dst + q, v.x), st_from_float(dst + hw + q, v.y), st_from_float(dst + 2 * hw + q, v.z),
+        st_from_float(dst + 3 * hw + q, v.w);
+  };
+  auto sample4 = [&](const float4* plane, const uint2 id, const float4 w) {
+    const float4 a0 = plane[id.x & 0xffffu], a1 = plane[id.x >> 16], a2 = plane[id.y & 0xffffu], a3 = plane[id.y >> 16];
+    return make_float4(w.x * a0.x + w.y * a1.x + w.z * a2.x + w.w * a3.x, w.x * a0.y + w.y * a1.y + w.z * a2.y + w.w * a3.y,
+                       w.x * a0.z + w.y * a1.z + w.z * a2.z + w.w * a3.z, w.x * a0.w + w.y * a1.w + w.z * a2.w + w.w * a3.w);
+  };
+#pragma unroll
+  for (int pp = 0; pp < P; ++pp) {
+    const int q = t + pp * T_;
+    if (q < hw) {
+      const float4 v = ld4(sample + base, q);
+      cur[q] = v;
+      st4(out + base, q, v);
+    }
+  }
+  __syncthreads();
+  for (int ii = 0; ii + 1 < frames; ++ii) {
+    const bool last = (ii + 2 == frames);
+    const long long foff = (long long)(ii + 1) * fstride, po = (long long)ii * hw;
+#pragma unroll
+    for (int pp = 0; pp < P; ++pp) {
+      const int q = t + pp * T_;
+      if (q >= hw) continue;
+      const float m = __ldg(blend + po + q);
+      const float4 z = ld4(sample + base + foff, q);
+      const float4 wv = sample4(cur, __ldg(tap_idx + po + q), __ldg(tap_w + po + q));
+      const float4 v = make_float4(z.x * (1.f - m) + wv.x * m, z.y * (1.f - m) + wv.y * m, z.z * (1.f - m) + wv.z * m,
+                                   z.w * (1.f - m) + wv.w * m);
+      nxt[q] = v;
+      if (!last) st4(out + base + foff, q, v);
+    }
+    __syncthreads();
+    float4* tmp = cur;
+    cur = nxt;
+    nxt = tmp;
+  }
+  // closing blend: frame N-1 <- warp(frame 0, fwd_flow[N-1])  (flow_utils.py:47-51)
+#pragma unroll
+  for (int pp = 0; pp < P; ++pp) {
+    const int q = t + pp * T_;
+    if (q < hw) nxt[q] = ld4(sample + base, q);
+  }
+  __syncthreads();
+  {
+    const long long loff = (long long)(frames - 1) * fstride, po = (long long)(frames - 1) * hw;
+#pragma unroll
+    for (int pp = 0; pp < P; ++pp) {
+      const int q = t + pp * T_;
+      if (q >= hw) continue;
+      const float m = __ldg(blend + po + q);
+      const float4 c = cur[q];
+      const float4 wv = sample4(nxt, __ldg(tap_idx + po + q), __ldg(tap_w + po + q));
+      st4(out + base + loff, q, make_float4(c.x * (1.f - m) + wv.x * m, c.y * (1.f - m) + wv.y * m,
+                                            c.z * (1.f - m) + wv.z * m, c.w * (1.f - m) + wv.w * m));
+    }
+  }
+}
+
 // planes too large for shared memory (image resolution): one launch per chain step, fp32 scratch
 __global__ void warp_blend_step_kernel(const float* __restrict__ src_frames, float* __restrict__ dst_frames,
                                        const float* __restrict__ flow, const float* __restrict__ mask, int chunks,
@@ -1655,4 +1736,49 @@ extern "C" int fresco_warp_loss_quad(const float* cs, const void* tap_idx_bwd, c
   QUAD_CASE(1) QUAD_CASE(2) QUAD_CASE(4)
 #undef QUAD_CASE
   return set_error(FRESCO_ERR_UNSUPPORTED, "fresco_warp_loss_quad: no instantiation");
+}
+
+template <typename T>
+static int launch_chain_quad(const void* sample, void* out, const void* tap_idx, const float* tap_w, const float* blend,
+                             int chunks, int frames, int channels, int hw, cudaStream_t s) {
+  int P = 4;
+  int Tn = ((hw + P - 1) / P + 31) / 32 * 32;
+  if (Tn > 1024) return FRESCO_ERR_UNSUPPORTED;
+  if (Tn < 64) {
+    P = hw >= 128 ? 2 : 1;
+    Tn = ((hw + P - 1) / P + 31) / 32 * 32;
+  }
+  const size_t smem = (size_t)hw * 32;
+  const int grid = chunks * channels / 4;
+#define CHAIN_CASE(PP)                                                                                                \
+  if (P == PP) {                                                                                                      \
+    static bool attr_set = false;                                                                                     \
+    if (!attr_set) {                                                                                                  \
+      cudaError_t e = cudaFuncSetAttribute(warp_chain_quad_kernel<T, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                           200 * 1024);                                                               \
+      if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(warp_chain_quad)");                        \
+      attr_set = true;                                                                                                \
+    }                                                                                                                 \
+    warp_chain_quad_kernel<T, PP><<<grid, Tn, smem, s>>>((const T*)sample, (T*)out, (const uint2*)tap_idx,            \
+                                                         (const float4*)tap_w, blend, frames, channels, hw);          \
+    return check_launch("warp_chain_quad_kernel");                                                                    \
+  }
+  CHAIN_CASE(1) CHAIN_CASE(2) CHAIN_CASE(4)
+#undef CHAIN_CASE
+  return FRESCO_ERR_UNSUPPORTED;
+}
+
+extern "C" int fresco_warp_fuse_chain_taps(const void* sample, void* out, int is_half, const void* tap_idx,
+                                           const float* tap_w, const float* blend, int chunks, int frames, int channels,
+                                           int h, int w, void* stream) {
+  if (!sample || !out || !tap_idx || !tap_w || !blend)
+    return set_error(FRESCO_ERR_ARG, "fresco_warp_fuse_chain_taps: null pointer");
+  const int hw = h * w;
+  if (chunks <= 0 || frames < 2 || channels <= 0 || channels % 4 != 0 || hw <= 0 || hw > 4096)
+    return set_error(FRESCO_ERR_UNSUPPORTED, "fresco_warp_fuse_chain_taps: channels % 4 == 0 and h*w <= 4096 only");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int rc = is_half ? launch_chain_quad<__half>(sample, out, tap_idx, tap_w, blend, chunks, frames, channels, hw, s)
+                         : launch_chain_quad<float>(sample, out, tap_idx, tap_w, blend, chunks, frames, channels, hw, s);
+  if (rc == FRESCO_ERR_UNSUPPORTED) return set_error(rc, "fresco_warp_fuse_chain_taps: no instantiation for this plane size");
+  return rc;
 }

@@ -125,10 +125,21 @@ def warp_tensor(sample, flows, occs, saliency, unet_chunk_size, shard=None):
         blend = torch.empty(n, 1, h, w, dtype=torch.float32, device=sample.device)
         blend[:n - 1] = (1 - bwd_occ[:n - 1]) * sal[1:n] * warp_sal[:n - 1]       # :45
         blend[n - 1:] = (1 - fwd_occ[n - 1:n]) * sal[n - 1:n] * warp_sal_last      # :50
-        return bwd_flow, fwd_flow[n - 1].contiguous(), blend.contiguous()
+        taps = None
+        if h * w <= 4096:
+            # taps of the chain steps for the quad kernel: backward flow of pairs 0..N-2, then the closing forward flow
+            step_flows = torch.cat([bwd_flow[:n - 1], fwd_flow[n - 1:n]], dim=0).contiguous()
+            taps = ops.warp_taps(step_flows)
+        return bwd_flow, fwd_flow[n - 1].contiguous(), blend.contiguous(), taps
 
-    bwd_flow, fwd_flow_last, blend = _cache_get(("warp_tensor", n, h, w),
-                                                 (flows[0], flows[1], occs[0], occs[1], saliency), prepare)
+    bwd_flow, fwd_flow_last, blend, taps = _cache_get(("warp_tensor", n, h, w),
+                                                       (flows[0], flows[1], occs[0], occs[1], saliency), prepare)
+
+    def chain(planes, chunks):
+        if taps is not None and planes.shape[1] % 4 == 0 and hasattr(ops, "warp_fuse_chain_taps"):
+            return ops.warp_fuse_chain_taps(planes, taps[0], taps[1], blend, chunks)
+        return ops.warp_fuse_chain(planes, bwd_flow, fwd_flow_last, blend, chunks)
+
     x = sample.contiguous()
     # the shared-memory chain kernel takes fp16 or fp32 planes up to 100 KB; image-resolution planes (background
     # smoothing, src/pipe_FRESCO.py:46, fp16 VAE output) run the per-step kernel, which works on fp32 like the
@@ -136,8 +147,7 @@ def warp_tensor(sample, flows, occs, saliency, unet_chunk_size, shard=None):
     if x.dtype not in (torch.float16, torch.float32) or 2 * h * w * 4 > 200 * 1024:
         x = x.float()
     if world == 1:
-        out = ops.warp_fuse_chain(x, bwd_flow, fwd_flow_last, blend, unet_chunk_size)
-        return out.to(sample.dtype)
+        return chain(x, unet_chunk_size).to(sample.dtype)
     import torch.distributed as dist
     group = shard[2] if len(shard) > 2 else None
     chunks, n_local, C = unet_chunk_size, n // world, x.shape[1]
@@ -148,7 +158,7 @@ def warp_tensor(sample, flows, occs, saliency, unet_chunk_size, shard=None):
     recv = torch.empty_like(send)
     dist.all_to_all_single(recv, send, group=group)            # [source rank = frame block, frame, chunk, cg, hw]
     planes = recv.view(n, chunks * cg, h, w)                    # all N frames x my channel slice of both chunks
-    fused = ops.warp_fuse_chain(planes, bwd_flow, fwd_flow_last, blend, 1)
+    fused = chain(planes, 1)
     back = torch.empty_like(fused)
     dist.all_to_all_single(back, fused, group=group)           # [source rank = channel block, frame, chunk, cg, hw]
     out = back.view(world, n_local, chunks, cg, h * w).permute(2, 1, 0, 3, 4).reshape(chunks * n_local, C, h, w)

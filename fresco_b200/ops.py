@@ -103,7 +103,7 @@ def temporal_attn_fwd_packed(qkv: torch.Tensor, fwd_map, traj_mask, chunks: int,
     L.check(L.lib().fresco_temporal_attn_fwd_strided(base, base + 2 * C, base + 4 * C, L.ptr(out), L.ptr(fwd_map),
                                                      L.ptr(traj_mask), chunks, frames, tokens, heads, C // heads, C3,
                                                      float(scale), L.stream()), "fresco_temporal_attn_fwd_strided")
-    _prof_end(ev, "temporal_d%d_L%d_N%d" % (C // heads, tokens, frames), 8.0 * B * tokens * C)
+    _prof_end(ev, "temporal_d%d_L%d_N%d" % (C // heads, tokens, frames), 8.0 * B * tokens * C, "hbm")
     return out
 
 
@@ -135,7 +135,7 @@ def temporal_attn_fwd(q_raw, k_raw, v_src, fwd_map, traj_mask, chunks: int, head
                                              L.ptr(traj_mask), chunks, frames, tokens, heads, C // heads,
                                              float(scale), L.stream()), "fresco_temporal_attn_fwd")
     # algorithmic bytes: 3 reads + 1 write of [B, L, C] fp16 (+ indices and mask, < 1 %)
-    _prof_end(ev, "temporal_d%d_L%d_N%d" % (C // heads, tokens, frames), 8.0 * B * tokens * C)
+    _prof_end(ev, "temporal_d%d_L%d_N%d" % (C // heads, tokens, frames), 8.0 * B * tokens * C, "hbm")
     return out
 
 
@@ -160,6 +160,29 @@ def warp_fuse_chain(sample, bwd_flow, fwd_flow_last, blend, chunks: int, out=Non
                                            L.ptr(blend), chunks, B // chunks, C, h, w, L.stream()),
             "fresco_warp_fuse_chain")
     # every frame read once and written once (SURVEY 8d counts 3 fp32 passes for the reference's unfused chain)
+    _prof_end(ev, "warp_chain_C%d_%dx%d" % (C, h, w), 2.0 * sample.numel() * sample.element_size(), "hbm")
+    return out
+
+
+def warp_taps(flow: torch.Tensor):
+    """The four bilinear taps of every pixel for the warp by ``flow`` [F,2,h,w], as the quad kernels consume them:
+    tap_idx uint16 (stored in int16) [F, hw, 4], tap_w fp32 [F, hw, 4]; a tap outside the plane has index 0, weight 0."""
+    Fr, _, h, w = flow.shape
+    dest = torch.empty(Fr, h * w, 4, dtype=torch.int32, device=flow.device)
+    wgt = torch.empty(Fr, h * w, 4, dtype=torch.float32, device=flow.device)
+    L.check(L.lib().fresco_warp_taps(L.ptr(flow), L.ptr(dest), L.ptr(wgt), Fr, h, w, L.stream()), "fresco_warp_taps")
+    return _u16(dest.clamp(min=0)), wgt
+
+
+def warp_fuse_chain_taps(sample, tap_idx, tap_w, blend, chunks: int, out=None):
+    B, C, h, w = sample.shape
+    if out is None:
+        out = torch.empty_like(sample)
+    is_half = 1 if sample.dtype == torch.float16 else 0
+    ev = _prof_begin()
+    L.check(L.lib().fresco_warp_fuse_chain_taps(L.ptr(sample), L.ptr(out), is_half, L.ptr(tap_idx), L.ptr(tap_w),
+                                                L.ptr(blend), chunks, B // chunks, C, h, w, L.stream()),
+            "fresco_warp_fuse_chain_taps")
     _prof_end(ev, "warp_chain_C%d_%dx%d" % (C, h, w), 2.0 * sample.numel() * sample.element_size(), "hbm")
     return out
 

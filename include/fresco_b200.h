@@ -106,6 +106,13 @@ int fresco_warp_fuse_chain(const void* sample, void* out, int is_half, const flo
                            const float* fwd_flow_last, const float* blend, int chunks, int frames, int channels,
                            int h, int w, void* stream);
 
+/* the same chain with the bilinear taps of every step prepared once per batch (fresco_warp_taps; index 0 + weight 0 for a
+ * tap outside the plane): tap_idx uint16 [frames, h*w, 4], tap_w float [frames, h*w, 4], entries 0..N-2 = backward flow
+ * of pair i, entry N-1 = forward flow of pair N-1 (closing blend).  channels % 4 == 0, h*w <= 4096: four planes per CTA
+ * interleaved in shared memory (what warp_tensor runs on decoder features).                                       */
+int fresco_warp_fuse_chain_taps(const void* sample, void* out, int is_half, const void* tap_idx, const float* tap_w,
+                                const float* blend, int chunks, int frames, int channels, int h, int w, void* stream);
+
 /* ---- O2: temporal-consistency loss, forward + backward -------------------------------------
  * replaces src/diffusion_hacked.py:461-466 and its autograd backward.
  * cs, grad float [chunks, frames, channels, h, w]; fwd_flow/bwd_flow float [frames,2,h,w];

@@ -517,8 +517,8 @@ def test_ddpm_step_kernels_and_dilate_golden(fb, golden):
     for tag in "abc":
         ts, rep = int(g[f"{tag}_t"]), bool(g[f"{tag}_repeat"])
         prev, x0 = pf.step(Pipe, raw, ts, sample, None, repeat_noise=rep, guidance_scale=7.5, noise=T(g[f"{tag}_noise"]))
-        assert (prev.cpu() - T(g[f"{tag}_prev"], "cpu")).abs().max().item() < 1e-5
-        assert (x0.cpu() - T(g[f"{tag}_x0"], "cpu")).abs().max().item() < 1e-5
+        for got, want in ((prev, T(g[f"{tag}_prev"], "cpu")), (x0, T(g[f"{tag}_x0"], "cpu"))):
+            assert (got.cpu() - want).abs().max().item() < 2e-6 * want.abs().max().item() + 1e-6     # fp32, values up to ~40
         prev16, _ = pf.step(Pipe, raw.half(), ts, sample.half(), None, repeat_noise=rep, guidance_scale=7.5,
                             noise=T(g[f"{tag}_noise"]).half())
         ref = T(g[f"{tag}_prev"], "cpu")
