@@ -893,7 +893,9 @@ __device__ __forceinline__ void tmem_st_half(uint32_t taddr, const uint32_t (&r)
   else tmem_st8(taddr, r);
 }
 
-template <int D, int SPLIT, int POLY>
+// PIPE 3: scores of tile i+1 prefetched while tile i is processed.  PIPE 4: additionally the row max of tile i+1 is taken
+// between the exponentials of tile i and the publication of P_i, so the TMEM store latency of P_i hides behind it.
+template <int D, int SPLIT, int POLY, int PIPE>
 __global__ void __launch_bounds__(WideCfg<D, SPLIT>::THREADS, WideCfg<D, SPLIT>::CTAS)
 fresco_attn_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                         const __grid_constant__ CUtensorMap tm_v, const AttnParams p) {
@@ -1089,9 +1091,8 @@ fresco_attn_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_c + (i & 1));         // S buffer i & 1 may be overwritten by Q K_{i+2}^T
     };
-    auto process = [&](uint32_t (&r)[KEYS], int i) {
+    auto tile_max = [&](uint32_t (&r)[KEYS], int i) -> float {     // (mask / bias folded in) row max * scale
       const int col0 = i * kTileN + KEYS * part;           // first key of this thread's part of the tile
-      const int pb = i % PB;
       // warp-uniform: does this part of the tile need masking (ragged tail) or the diagonal bias?
       const bool special = (col0 + KEYS > kv_len) ||
                            (use_bias && (q0 + quarter * 32) < col0 + KEYS && (q0 + quarter * 32 + 32) > col0);
@@ -1113,7 +1114,10 @@ fresco_attn_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         mx2 = max3(mx2, __uint_as_float(r[j + 4]), __uint_as_float(r[j + 5]));
         mx3 = max3(mx3, __uint_as_float(r[j + 6]), __uint_as_float(r[j + 7]));
       }
-      const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
+      return fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
+    };
+    auto tile_exp = [&](uint32_t (&r)[KEYS], int i, float m_tile) {   // lazy max, exponentials, P stores (not waited for)
+      const int pb = i % PB;
       // ---- lazy running max of THIS part: raise it (and rescale O_part in TMEM) only when it grows by more than 2^8.
       //      (m_run stays -inf while every key of this part has been masked; exp2(-inf) = 0 keeps P, l and O at zero.)
       if (i == 0) {
@@ -1168,27 +1172,54 @@ fresco_attn_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         }
         tmem_st8(t_lane + Cfg::P_OFF + pb * 32 + (KEYS / 2) * part + g * 8, pk);
       }
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_p + pb * Cfg::NPV + jpv);
       float sa, sb;
       unpack_f2(add2(sum2[0], sum2[1]), sa, sb);
       l_run += sa + sb;
+    };
+    auto publish = [&](int i) {                                       // P_i is in TMEM: tell its P V issuer
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p + (i % PB) * Cfg::NPV + jpv);
     };
 
     uint32_t ra[KEYS], rb[KEYS];
     issue_load(ra, 0);
     finish_load(ra, 0);
-    for (int i = 0; i < n_tiles; i += 2) {
-      const bool has1 = i + 1 < n_tiles, has2 = i + 2 < n_tiles;
-      if (has1) issue_load(rb, i + 1);
-      process(ra, i);
-      if (has1) {
-        finish_load(rb, i + 1);
-        if (has2) issue_load(ra, i + 2);
-        process(rb, i + 1);
-        if (has2) finish_load(ra, i + 2);
+    if constexpr (PIPE == 4) {
+      float ma = tile_max(ra, 0), mb = 0.f;
+      for (int i = 0; i < n_tiles; i += 2) {
+        const bool has1 = i + 1 < n_tiles, has2 = i + 2 < n_tiles;
+        if (has1) issue_load(rb, i + 1);
+        tile_exp(ra, i, ma);
+        if (has1) {
+          finish_load(rb, i + 1);
+          mb = tile_max(rb, i + 1);
+        }
+        publish(i);
+        if (has1) {
+          if (has2) issue_load(ra, i + 2);
+          tile_exp(rb, i + 1, mb);
+          if (has2) {
+            finish_load(ra, i + 2);
+            ma = tile_max(ra, i + 2);
+          }
+          publish(i + 1);
+        }
+      }
+    } else {
+      for (int i = 0; i < n_tiles; i += 2) {
+        const bool has1 = i + 1 < n_tiles, has2 = i + 2 < n_tiles;
+        if (has1) issue_load(rb, i + 1);
+        tile_exp(ra, i, tile_max(ra, i));
+        publish(i);
+        if (has1) {
+          finish_load(rb, i + 1);
+          if (has2) issue_load(ra, i + 2);
+          tile_exp(rb, i + 1, tile_max(rb, i + 1));
+          publish(i + 1);
+          if (has2) finish_load(ra, i + 2);
+        }
       }
     }
 
@@ -1291,9 +1322,11 @@ static int make_head_tile_map(CUtensorMap* map, const void* base, int head_dim, 
 // overrides): which kernel, and how many of the exponentials go to the FMA pipe.  Defaults = measured best on B200.
 //   FRESCO_ATTN_WIDE    1 = wide kernel (two threads per row), 0 = pipelined kernel
 //   FRESCO_ATTN_NARROW  3 | 4 = narrow kernel with that many CTAs per SM (head_dim 40 only; 0 = off)
-//   FRESCO_ATTN_POLY    0 | 4 | 8: every n-th pair of exponentials on the FMA pipe
+//   FRESCO_ATTN_PIPE    3 | 4: software-pipelining depth of the wide kernel's softmax loop
+//   FRESCO_ATTN_POLY    0 | 4 | 8: every n-th pair of exponentials on the FMA pipe (8: pipelined kernel only)
 //   FRESCO_ATTN_ROWSUM  pipelined kernel, head_dim 40: row sums from the tensor core
-constexpr int kWideDefault = 2;
+constexpr int kWideDefault = 0;
+constexpr int kPipeDefault = 4;
 constexpr int kNarrowDefault = 0;
 constexpr int kPolyDefault = 0;
 constexpr int kRowsumDefault = 1;
@@ -1331,18 +1364,18 @@ static int launch_narrow(const CUtensorMap& tq, const CUtensorMap& tk, const CUt
   return check_launch("fresco_attn_narrow_kernel");
 }
 
-template <int D, int SPLIT, int POLY>
+template <int D, int SPLIT, int POLY, int PIPE>
 static int launch_wide(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, dim3 grid,
                        cudaStream_t stream) {
   using Cfg = WideCfg<D, SPLIT>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(fresco_attn_wide_kernel<D, SPLIT, POLY>,
+    cudaError_t e = cudaFuncSetAttribute(fresco_attn_wide_kernel<D, SPLIT, POLY, PIPE>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(attn wide)");
     attr_set = true;
   }
-  fresco_attn_wide_kernel<D, SPLIT, POLY><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tq, tk, tv, p);
+  fresco_attn_wide_kernel<D, SPLIT, POLY, PIPE><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tq, tk, tv, p);
   return check_launch("fresco_attn_wide_kernel");
 }
 
@@ -1372,18 +1405,21 @@ static int launch_attn(const void* q, const void* k, const void* v, void* out, i
     if (narrow == 3) return launch_narrow<D, 3>(tq, tk, tv, p, grid, stream);
     if (narrow == 4) return launch_narrow<D, 4>(tq, tk, tv, p, grid, stream);
   }
-  // FRESCO_ATTN_WIDE = 2 | 4: that many threads per query row (4 needs head_dim > 48: one CTA per SM)
+  // FRESCO_ATTN_WIDE = 2 | 4: that many threads per query row (4: head_dim <= 80, one CTA per SM)
+  // FRESCO_ATTN_PIPE = 3 | 4: software-pipelining depth of the softmax loop (see the kernel)
   const int wide = option(OPT_ATTN_WIDE, kWideDefault);
+  const int pipe = option(OPT_ATTN_PIPE, kPipeDefault);
   if (wide == 4) {
     if constexpr (D <= 80) {
-      if (poly == 4) return launch_wide<D, 4, 4>(tq, tk, tv, p, grid, stream);
-      return launch_wide<D, 4, 0>(tq, tk, tv, p, grid, stream);
+      if (poly == 4) return launch_wide<D, 4, 4, 4>(tq, tk, tv, p, grid, stream);
+      if (pipe == 3) return launch_wide<D, 4, 0, 3>(tq, tk, tv, p, grid, stream);
+      return launch_wide<D, 4, 0, 4>(tq, tk, tv, p, grid, stream);
     }
   }
   if (wide >= 1) {
-    if (poly == 4) return launch_wide<D, 2, 4>(tq, tk, tv, p, grid, stream);
-    if (poly == 8) return launch_wide<D, 2, 8>(tq, tk, tv, p, grid, stream);
-    return launch_wide<D, 2, 0>(tq, tk, tv, p, grid, stream);
+    if (poly == 4) return launch_wide<D, 2, 4, 4>(tq, tk, tv, p, grid, stream);
+    if (pipe == 3) return launch_wide<D, 2, 0, 3>(tq, tk, tv, p, grid, stream);
+    return launch_wide<D, 2, 0, 4>(tq, tk, tv, p, grid, stream);
   }
   if constexpr (AttnCfg<D, true>::MMA_ROWSUM) {
     if (option(OPT_ATTN_ROWSUM, kRowsumDefault)) {

@@ -1,6 +1,16 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_parity_r2.py -q -k "attention_variants or level_a" 2>&1 | tail -40 > gpurun_out/r02_c4_attn_parity.txt
-timeout 300 python tools/bench_attn.py FRESCO_ATTN_WIDE=0 FRESCO_ATTN_WIDE=2 FRESCO_ATTN_WIDE=4 FRESCO_ATTN_WIDE=2,FRESCO_ATTN_POLY=4 FRESCO_ATTN_WIDE=4,FRESCO_ATTN_POLY=4 > gpurun_out/r02_c4_bench_attn.jsonl 2>&1
-timeout 900 python -m pytest tests -q -m gpu --deselect tests/test_gpu_parity_r2.py::test_attention_variants_all_head_dims 2>&1 | tail -60 > gpurun_out/r02_c4_pytest_all.txt
-timeout 300 python tools/bench_opt.py > gpurun_out/r02_c4_bench_opt.txt 2>&1
-tail -5 gpurun_out/r02_c4_attn_parity.txt; cat gpurun_out/r02_c4_bench_attn.jsonl; grep -E "^(FAILED|ERROR)|passed|failed" gpurun_out/r02_c4_pytest_all.txt; tail -6 gpurun_out/r02_c4_bench_opt.txt | cut -c1-900
+nvidia-smi --query-gpu=index,name --format=csv > gpurun_out/r02_c5_smi.txt
+timeout 600 python -m pytest tests/test_gpu_parity_r2.py -q -k "nccl" 2>&1 | tail -30 > gpurun_out/r02_c5_nccl_test.txt
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 15 --warmup 3 > gpurun_out/r02_c5_bench_g2.json 2> gpurun_out/r02_c5_bench_g2.err
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 15 --warmup 3 --graphs off > gpurun_out/r02_c5_bench_g2_eager.json 2> gpurun_out/r02_c5_bench_g2_eager.err
+tail -4 gpurun_out/r02_c5_nccl_test.txt; tail -5 gpurun_out/r02_c5_bench_g2.err; python - <<'PY'
+import json
+for f in ("gpurun_out/r02_c5_bench_g2.json", "gpurun_out/r02_c5_bench_g2_eager.json"):
+    try:
+        d = json.loads(open(f).read().strip().splitlines()[-1])
+    except Exception as e:
+        print(f, "unreadable", e); continue
+    print(f, "value", d["value"], "ms/step", d["ms_per_step"], "e2e", d["e2e"]["value"], d["config"]["execution"], d.get("sharded_check"), "launches", d["gpu_launches"])
+    for k, v in d.get("kernels", {}).items():
+        print("  %-34s %-6s ms %-8s ach %-8s frac %-6s n %s" % (k, v["bound"], v["ms"], v["achieved"], v["frac"], v["launches"]))
+PY
