@@ -504,19 +504,37 @@ warp_chain_group_kernel(const T* __restrict__ sample, T* __restrict__ out, const
   }
 }
 
-// Channel-QUAD variant (same idea as warp_loss_quad_kernel below): four (chunk, channel) planes interleaved per pixel as
-// float4 in shared memory, so one 16-byte shared load serves a bilinear tap for all four; the taps of every chain step
-// come prepared (4 x u16 index + 4 x fp32 weight per pixel: make_taps' values), no flow decoding in the loop.
-template <typename T, int P>
+struct __align__(8) half4 {
+  __half2 lo, hi;
+};
+__device__ __forceinline__ float4 h4_to_f4(const half4& h) {
+  const float2 a = __half22float2(h.lo), b = __half22float2(h.hi);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ float sgnf(float r) { return r > 0.f ? 1.f : (r < 0.f ? -1.f : 0.f); }
+__device__ __forceinline__ float4 sample_taps4(const float4* plane, const Taps& t) {
+  const float4 a0 = plane[t.i00], a1 = plane[t.i01], a2 = plane[t.i10], a3 = plane[t.i11];
+  return make_float4(t.w00 * a0.x + t.w01 * a1.x + t.w10 * a2.x + t.w11 * a3.x,
+                     t.w00 * a0.y + t.w01 * a1.y + t.w10 * a2.y + t.w11 * a3.y,
+                     t.w00 * a0.z + t.w01 * a1.z + t.w10 * a2.z + t.w11 * a3.z,
+                     t.w00 * a0.w + t.w01 * a1.w + t.w10 * a2.w + t.w11 * a3.w);
+}
+
+// Channel-QUAD variant (the one warp_tensor runs on decoder features; see warp_loss_quad_kernel below for the
+// measurement behind it): NQ quads of four (chunk, channel) planes per CTA, interleaved per pixel as float4 in shared
+// memory, so the flows / blend weight of a pixel are fetched and its taps built once for 4 NQ channels and one 16-byte
+// shared load serves a tap for four of them.  Same arithmetic per element as the kernels above.
+template <typename T, int P, int NQ>
 __global__ void __launch_bounds__(1024, 1)
-warp_chain_quad_kernel(const T* __restrict__ sample, T* __restrict__ out, const uint2* __restrict__ tap_idx,
-                       const float4* __restrict__ tap_w /*[frames][hw]: steps 0..N-2 backward flow, N-1 closing flow*/,
-                       const float* __restrict__ blend, int frames, int channels, int hw) {
+warp_chain_quad_kernel(const T* __restrict__ sample, T* __restrict__ out, const float* __restrict__ bwd_flow,
+                       const float* __restrict__ fwd_flow_last, const float* __restrict__ blend, int frames,
+                       int channels, int h, int w) {
   extern __shared__ float4 chq[];
-  float4* cur = chq;
-  float4* nxt = chq + hw;
+  const int hw = h * w;
+  float4* cur = chq;                       // [NQ][hw]
+  float4* nxt = chq + NQ * hw;             // [NQ][hw]
   const int T_ = blockDim.x, t = threadIdx.x;
-  const int pl0 = blockIdx.x * 4;
+  const int pl0 = blockIdx.x * 4 * NQ;
   const int j = pl0 / channels, c0 = pl0 % channels;
   const long long fstride = (long long)channels * hw;
   const long long base = ((long long)j * frames * channels + c0) * hw;
@@ -528,35 +546,39 @@ warp_chain_quad_kernel(const T* __restrict__ sample, T* __restrict__ out, const 
     st_from_float(dst + q, v.x), st_from_float(dst + hw + q, v.y), st_from_float(dst + 2 * hw + q, v.z),
         st_from_float(dst + 3 * hw + q, v.w);
   };
-  auto sample4 = [&](const float4* plane, const uint2 id, const float4 w) {
-    const float4 a0 = plane[id.x & 0xffffu], a1 = plane[id.x >> 16], a2 = plane[id.y & 0xffffu], a3 = plane[id.y >> 16];
-    return make_float4(w.x * a0.x + w.y * a1.x + w.z * a2.x + w.w * a3.x, w.x * a0.y + w.y * a1.y + w.z * a2.y + w.w * a3.y,
-                       w.x * a0.z + w.y * a1.z + w.z * a2.z + w.w * a3.z, w.x * a0.w + w.y * a1.w + w.z * a2.w + w.w * a3.w);
-  };
 #pragma unroll
   for (int pp = 0; pp < P; ++pp) {
     const int q = t + pp * T_;
     if (q < hw) {
-      const float4 v = ld4(sample + base, q);
-      cur[q] = v;
-      st4(out + base, q, v);
+#pragma unroll
+      for (int nq = 0; nq < NQ; ++nq) {
+        const float4 v = ld4(sample + base + (long long)nq * 4 * hw, q);
+        cur[nq * hw + q] = v;
+        st4(out + base + (long long)nq * 4 * hw, q, v);
+      }
     }
   }
   __syncthreads();
   for (int ii = 0; ii + 1 < frames; ++ii) {
+    const float* fl = bwd_flow + (long long)ii * 2 * hw;
+    const float* mk = blend + (long long)ii * hw;
     const bool last = (ii + 2 == frames);
-    const long long foff = (long long)(ii + 1) * fstride, po = (long long)ii * hw;
+    const long long foff = (long long)(ii + 1) * fstride;
 #pragma unroll
     for (int pp = 0; pp < P; ++pp) {
       const int q = t + pp * T_;
       if (q >= hw) continue;
-      const float m = __ldg(blend + po + q);
-      const float4 z = ld4(sample + base + foff, q);
-      const float4 wv = sample4(cur, __ldg(tap_idx + po + q), __ldg(tap_w + po + q));
-      const float4 v = make_float4(z.x * (1.f - m) + wv.x * m, z.y * (1.f - m) + wv.y * m, z.z * (1.f - m) + wv.z * m,
-                                   z.w * (1.f - m) + wv.w * m);
-      nxt[q] = v;
-      if (!last) st4(out + base + foff, q, v);
+      const Taps tp = make_taps((q % w) + __ldg(fl + q), (q / w) + __ldg(fl + hw + q), h, w);
+      const float m = __ldg(mk + q);
+#pragma unroll
+      for (int nq = 0; nq < NQ; ++nq) {
+        const float4 z = ld4(sample + base + foff + (long long)nq * 4 * hw, q);
+        const float4 wv = sample_taps4(cur + nq * hw, tp);
+        const float4 v = make_float4(z.x * (1.f - m) + wv.x * m, z.y * (1.f - m) + wv.y * m, z.z * (1.f - m) + wv.z * m,
+                                     z.w * (1.f - m) + wv.w * m);
+        nxt[nq * hw + q] = v;
+        if (!last) st4(out + base + foff + (long long)nq * 4 * hw, q, v);
+      }
     }
     __syncthreads();
     float4* tmp = cur;
@@ -567,20 +589,29 @@ warp_chain_quad_kernel(const T* __restrict__ sample, T* __restrict__ out, const 
 #pragma unroll
   for (int pp = 0; pp < P; ++pp) {
     const int q = t + pp * T_;
-    if (q < hw) nxt[q] = ld4(sample + base, q);
+    if (q < hw) {
+#pragma unroll
+      for (int nq = 0; nq < NQ; ++nq) nxt[nq * hw + q] = ld4(sample + base + (long long)nq * 4 * hw, q);
+    }
   }
   __syncthreads();
   {
-    const long long loff = (long long)(frames - 1) * fstride, po = (long long)(frames - 1) * hw;
+    const float* mk = blend + (long long)(frames - 1) * hw;
+    const long long loff = (long long)(frames - 1) * fstride;
 #pragma unroll
     for (int pp = 0; pp < P; ++pp) {
       const int q = t + pp * T_;
       if (q >= hw) continue;
-      const float m = __ldg(blend + po + q);
-      const float4 c = cur[q];
-      const float4 wv = sample4(nxt, __ldg(tap_idx + po + q), __ldg(tap_w + po + q));
-      st4(out + base + loff, q, make_float4(c.x * (1.f - m) + wv.x * m, c.y * (1.f - m) + wv.y * m,
-                                            c.z * (1.f - m) + wv.z * m, c.w * (1.f - m) + wv.w * m));
+      const Taps tp = make_taps((q % w) + __ldg(fwd_flow_last + q), (q / w) + __ldg(fwd_flow_last + hw + q), h, w);
+      const float m = __ldg(mk + q);
+#pragma unroll
+      for (int nq = 0; nq < NQ; ++nq) {
+        const float4 c = cur[nq * hw + q];
+        const float4 wv = sample_taps4(nxt + nq * hw, tp);
+        st4(out + base + loff + (long long)nq * 4 * hw, q,
+            make_float4(c.x * (1.f - m) + wv.x * m, c.y * (1.f - m) + wv.y * m, c.z * (1.f - m) + wv.z * m,
+                        c.w * (1.f - m) + wv.w * m));
+      }
     }
   }
 }
@@ -947,43 +978,33 @@ warp_loss_group_kernel(const float* __restrict__ cs, const float* __restrict__ f
 }
 
 // ---------------------------------------------------------------------------------------------
-// Channel-QUAD temporal-consistency loss: the kernel optimize_feature runs when the plane fits (48 bytes of shared memory
-// per pixel).  The round-2 measurement of the two kernels above (1.0 ms at [16,640,64,64] each, DRAM at 4 %) showed them
-// bound by INSTRUCTIONS, ~300 per (pixel, channel, frame pair): bilinear taps rebuilt from the flows, 16-bit ELL weights
-// decoded, one 2/4-byte shared-memory access per tap and channel, integer divisions in the plane loads.  Here
-//   * the four taps of every (pair, pixel) and both warp directions are prepared once per batch as 4 x u16 indices +
-//     4 x fp32 weights (exactly make_taps' values), the adjoint ELL rows as 8 x u16 sources + 8 x fp32 weights;
-//   * a CTA owns FOUR (chunk, channel) planes interleaved per pixel in shared memory -- frame f and f+1 as float4, the
-//     two masked sign planes as 4 x fp16 -- so one 16-byte (8-byte) shared load serves a tap for all four channels;
-//   * every thread owns P pixels of the quad for the whole walk over the frame pairs; what a frame receives as the
-//     "next" frame of pair f is carried in registers to pair f+1 (each cs plane read once, each grad plane written once,
-//     frame 0 once more for the wrap-around pair).
+// Channel-QUAD temporal-consistency loss: the kernel optimize_feature runs when the planes fit shared memory.
+// Round-2 measurements: the two kernels above and a first quad kernel all moved ~3.4 TB/s from L2 whatever their
+// structure -- the per-(pair, pixel) operands (two flows, two keep masks, two 32-byte ELL rows: 88 bytes) are re-read by
+// every CTA for every frame pair and dwarf the 8 bytes per (pixel, channel) of payload.  So a CTA takes as many channels
+// as shared memory allows -- NQ quads of four (chunk, channel) planes, interleaved per pixel: frame f and f+1 as float4,
+// the two masked sign planes as 4 x fp16, 48 bytes per pixel and quad -- and everything that depends on the pixel only
+// (taps from the flows, keep masks, ELL rows) is fetched and decoded once per pixel for all 4 NQ channels; a 16-byte
+// (8-byte) shared load serves a tap for four channels.  Every thread owns P pixels for the whole walk over the frame
+// pairs; what a frame receives as the "next" frame of pair f is carried in registers to pair f+1 (each cs plane read
+// once, each grad plane written once, frame 0 once more for the wrap-around pair).
 // ---------------------------------------------------------------------------------------------
-struct __align__(8) half4 {
-  __half2 lo, hi;
-};
-__device__ __forceinline__ float4 h4_to_f4(const half4& h) {
-  const float2 a = __half22float2(h.lo), b = __half22float2(h.hi);
-  return make_float4(a.x, a.y, b.x, b.y);
-}
-__device__ __forceinline__ float sgnf(float r) { return r > 0.f ? 1.f : (r < 0.f ? -1.f : 0.f); }
-
-template <int P>
+template <int P, int NQ>
 __global__ void __launch_bounds__(1024, 1)
-warp_loss_quad_kernel(const float* __restrict__ cs, const uint2* __restrict__ tapi_b, const float4* __restrict__ tapw_b,
-                      const uint2* __restrict__ tapi_f, const float4* __restrict__ tapw_f,
-                      const float* __restrict__ fwd_keep, const float* __restrict__ bwd_keep,
-                      const uint4* __restrict__ ells_b, const float4* __restrict__ ellw_b,
-                      const uint4* __restrict__ ells_f, const float4* __restrict__ ellw_f,
-                      const int32_t* __restrict__ ovf /*[2][frames][n_ovf][3]*/, int n_ovf, float* __restrict__ grad,
-                      float* __restrict__ loss_acc, int accumulate, int frames, int channels, int hw, float k) {
+warp_loss_quad_kernel(const float* __restrict__ cs, const float* __restrict__ fwd_flow,
+                      const float* __restrict__ bwd_flow, const float* __restrict__ fwd_keep,
+                      const float* __restrict__ bwd_keep, const uint4* __restrict__ bwd_ell,
+                      const uint4* __restrict__ fwd_ell, const int32_t* __restrict__ ovf /*[2][frames][n_ovf][3]*/,
+                      int n_ovf, float* __restrict__ grad, float* __restrict__ loss_acc, int accumulate, int frames,
+                      int channels, int h, int w, float k) {
   extern __shared__ float4 smq[];
-  float4* cur = smq;                                          // [hw] frame f,     4 channels per pixel
-  float4* nxt = smq + hw;                                     // [hw] frame f + 1
-  half4* s1 = reinterpret_cast<half4*>(smq + 2 * hw);         // [hw] sign(c2 - W_bf c1) * keep_b
-  half4* s2 = s1 + hw;                                        // [hw] sign(c1 - W_ff c2) * keep_f
+  const int hw = h * w;
+  float4* cur = smq;                                          // [NQ][hw] frame f,     4 channels per pixel
+  float4* nxt = smq + NQ * hw;                                // [NQ][hw] frame f + 1
+  half4* s1 = reinterpret_cast<half4*>(smq + 2 * NQ * hw);    // [NQ][hw] sign(c2 - W_bf c1) * keep_b
+  half4* s2 = s1 + NQ * hw;                                   // [NQ][hw] sign(c1 - W_ff c2) * keep_f
   const int T = blockDim.x, t = threadIdx.x;
-  const int pl0 = blockIdx.x * 4;                             // first (chunk, channel) plane of the quad; channels % 4 == 0
+  const int pl0 = blockIdx.x * 4 * NQ;                        // first (chunk, channel) plane; channels % (4 NQ) == 0
   const int b = pl0 / channels, c0 = pl0 % channels;
   const long long fstride = (long long)channels * hw;
   const long long base = ((long long)b * frames * channels + c0) * hw;      // frame 0, channel c0
@@ -992,12 +1013,20 @@ warp_loss_quad_kernel(const float* __restrict__ cs, const uint2* __restrict__ ta
 #pragma unroll
     for (int pp = 0; pp < P; ++pp) {
       const int q = t + pp * T;
-      if (q < hw) dst[q] = make_float4(src[q], src[hw + q], src[2 * hw + q], src[3 * hw + q]);
+      if (q < hw) {
+#pragma unroll
+        for (int nq = 0; nq < NQ; ++nq) {
+          const float* s4 = src + (long long)nq * 4 * hw;
+          dst[nq * hw + q] = make_float4(s4[q], s4[hw + q], s4[2 * hw + q], s4[3 * hw + q]);
+        }
+      }
     }
   };
-  float4 carry[P];
+  float4 carry[P][NQ];
 #pragma unroll
-  for (int pp = 0; pp < P; ++pp) carry[pp] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int pp = 0; pp < P; ++pp)
+#pragma unroll
+    for (int nq = 0; nq < NQ; ++nq) carry[pp][nq] = make_float4(0.f, 0.f, 0.f, 0.f);
   float loss = 0.f;
 
   load_frame(cur, 0);
@@ -1005,111 +1034,129 @@ warp_loss_quad_kernel(const float* __restrict__ cs, const uint2* __restrict__ ta
     const int fn = (f + 1 == frames) ? 0 : f + 1;
     load_frame(nxt, fn);
     __syncthreads();
-    // ---- residuals of pair (f, fn)
+    // ---- residuals of pair (f, fn): taps and keep masks once per pixel, applied to the 4 NQ channels
     {
-      const long long po = (long long)f * hw;
+      const float* bf = bwd_flow + (long long)f * 2 * hw;
+      const float* ff = fwd_flow + (long long)f * 2 * hw;
+      const float* mbp = bwd_keep + (long long)f * hw;
+      const float* mfp = fwd_keep + (long long)f * hw;
 #pragma unroll
       for (int pp = 0; pp < P; ++pp) {
         const int q = t + pp * T;
         if (q >= hw) continue;
-        const uint2 ib = __ldg(tapi_b + po + q), jf = __ldg(tapi_f + po + q);
-        const float4 wb = __ldg(tapw_b + po + q), wf = __ldg(tapw_f + po + q);
-        const float mb = __ldg(bwd_keep + po + q), mf = __ldg(fwd_keep + po + q);
-        const float4 c1 = cur[q], c2 = nxt[q];
-        float4 a0 = cur[ib.x & 0xffffu], a1 = cur[ib.x >> 16], a2 = cur[ib.y & 0xffffu], a3 = cur[ib.y >> 16];
-        float4 r1, r2;
-        // same order of operations as sample_taps: ((w00 v00 + w01 v01) + w10 v10) + w11 v11
-        r1.x = c2.x - (wb.x * a0.x + wb.y * a1.x + wb.z * a2.x + wb.w * a3.x);
-        r1.y = c2.y - (wb.x * a0.y + wb.y * a1.y + wb.z * a2.y + wb.w * a3.y);
-        r1.z = c2.z - (wb.x * a0.z + wb.y * a1.z + wb.z * a2.z + wb.w * a3.z);
-        r1.w = c2.w - (wb.x * a0.w + wb.y * a1.w + wb.z * a2.w + wb.w * a3.w);
-        a0 = nxt[jf.x & 0xffffu], a1 = nxt[jf.x >> 16], a2 = nxt[jf.y & 0xffffu], a3 = nxt[jf.y >> 16];
-        r2.x = c1.x - (wf.x * a0.x + wf.y * a1.x + wf.z * a2.x + wf.w * a3.x);
-        r2.y = c1.y - (wf.x * a0.y + wf.y * a1.y + wf.z * a2.y + wf.w * a3.y);
-        r2.z = c1.z - (wf.x * a0.z + wf.y * a1.z + wf.z * a2.z + wf.w * a3.z);
-        r2.w = c1.w - (wf.x * a0.w + wf.y * a1.w + wf.z * a2.w + wf.w * a3.w);
-        loss += (fabsf(r1.x) + fabsf(r1.y) + fabsf(r1.z) + fabsf(r1.w)) * mb +
-                (fabsf(r2.x) + fabsf(r2.y) + fabsf(r2.z) + fabsf(r2.w)) * mf;
-        half4 h;
-        h.lo = __floats2half2_rn(sgnf(r1.x) * mb, sgnf(r1.y) * mb);
-        h.hi = __floats2half2_rn(sgnf(r1.z) * mb, sgnf(r1.w) * mb);
-        s1[q] = h;
-        h.lo = __floats2half2_rn(sgnf(r2.x) * mf, sgnf(r2.y) * mf);
-        h.hi = __floats2half2_rn(sgnf(r2.z) * mf, sgnf(r2.w) * mf);
-        s2[q] = h;
+        const int x = q % w, y = q / w;
+        const Taps tb = make_taps(x + __ldg(bf + q), y + __ldg(bf + hw + q), h, w);
+        const Taps tf = make_taps(x + __ldg(ff + q), y + __ldg(ff + hw + q), h, w);
+        const float mb = __ldg(mbp + q), mf = __ldg(mfp + q);
+#pragma unroll
+        for (int nq = 0; nq < NQ; ++nq) {
+          const float4* c1p = cur + nq * hw;
+          const float4* c2p = nxt + nq * hw;
+          const float4 c1 = c1p[q], c2 = c2p[q];
+          const float4 wb = sample_taps4(c1p, tb), wf = sample_taps4(c2p, tf);
+          const float4 r1 = make_float4(c2.x - wb.x, c2.y - wb.y, c2.z - wb.z, c2.w - wb.w);     // c2 - W_bf(c1)
+          const float4 r2 = make_float4(c1.x - wf.x, c1.y - wf.y, c1.z - wf.z, c1.w - wf.w);     // c1 - W_ff(c2)
+          loss += (fabsf(r1.x) + fabsf(r1.y) + fabsf(r1.z) + fabsf(r1.w)) * mb +
+                  (fabsf(r2.x) + fabsf(r2.y) + fabsf(r2.z) + fabsf(r2.w)) * mf;
+          half4 hv;
+          hv.lo = __floats2half2_rn(sgnf(r1.x) * mb, sgnf(r1.y) * mb);
+          hv.hi = __floats2half2_rn(sgnf(r1.z) * mb, sgnf(r1.w) * mb);
+          s1[nq * hw + q] = hv;
+          hv.lo = __floats2half2_rn(sgnf(r2.x) * mf, sgnf(r2.y) * mf);
+          hv.hi = __floats2half2_rn(sgnf(r2.z) * mf, sgnf(r2.w) * mf);
+          s2[nq * hw + q] = hv;
+        }
       }
     }
     __syncthreads();
     // ---- destinations hit by more than 8 taps of the forward-flow warp (rare): extra terms of d/dc2 through the dead
     //      frame-f planes, which the gather below adds in
     if (n_ovf > 0) {
-      for (int q = t; q < hw; q += T) cur[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int q = t; q < NQ * hw; q += T) cur[q] = make_float4(0.f, 0.f, 0.f, 0.f);
       __syncthreads();
       const int32_t* of = ovf + ((long long)1 * frames + f) * n_ovf * 3;
       for (int e = t; e < n_ovf; e += T) {
         if (of[3 * e] < 0) continue;
         const float wgt = -__int_as_float(of[3 * e + 2]);
-        const float4 v = h4_to_f4(s2[of[3 * e + 1]]);
-        float* dst = reinterpret_cast<float*>(cur + of[3 * e]);
-        atomicAdd(dst + 0, wgt * v.x);
-        atomicAdd(dst + 1, wgt * v.y);
-        atomicAdd(dst + 2, wgt * v.z);
-        atomicAdd(dst + 3, wgt * v.w);
+        for (int nq = 0; nq < NQ; ++nq) {
+          const float4 v = h4_to_f4(s2[nq * hw + of[3 * e + 1]]);
+          float* dst = reinterpret_cast<float*>(cur + nq * hw + of[3 * e]);
+          atomicAdd(dst + 0, wgt * v.x);
+          atomicAdd(dst + 1, wgt * v.y);
+          atomicAdd(dst + 2, wgt * v.z);
+          atomicAdd(dst + 3, wgt * v.w);
+        }
       }
       __syncthreads();
     }
-    // ---- adjoints as gathers: 8 (source, weight) ELL slots per destination pixel, empty slots have weight 0 and sit
-    //      at the end of the row, so a warp stops at the first slot that is empty for all of its lanes
+    // ---- adjoints as gathers: 8 packed (source:u16, weight:unorm16) ELL slots per destination pixel, used slots first,
+    //      so a warp stops at the first slot that is empty for all of its lanes
     {
-      const long long po = (long long)f * hw;
+      const uint4* ebp = bwd_ell + (long long)f * hw * 2;
+      const uint4* efp = fwd_ell + (long long)f * hw * 2;
       float* gdst = grad + base + (long long)f * fstride;
 #pragma unroll
       for (int pp = 0; pp < P; ++pp) {
         const int q = t + pp * T;
         const bool live = q < hw;
         const int qq = live ? q : 0;
-        float4 ga = h4_to_f4(s2[qq]);                           // d/dc1 = s2 - W_bf^T s1   (frame f)
-        float4 gb = h4_to_f4(s1[qq]);                           // d/dc2 = s1 - W_ff^T s2   (frame fn)
-        if (n_ovf > 0) {
-          const float4 o = cur[qq];
-          gb.x += o.x, gb.y += o.y, gb.z += o.z, gb.w += o.w;
-        }
-        {
-          const uint4 es = __ldg(ells_b + po + qq);
-          const float4 w0 = __ldg(ellw_b + 2 * (po + qq)), w1 = __ldg(ellw_b + 2 * (po + qq) + 1);
-          const uint32_t src[4] = {es.x, es.y, es.z, es.w};
-          const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        float4 ga[NQ], gb[NQ];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            if (!__any_sync(0xffffffffu, live && w[j] != 0.f)) break;
-            const float4 v = h4_to_f4(s1[(src[j >> 1] >> ((j & 1) * 16)) & 0xffffu]);
-            ga.x = fmaf(-w[j], v.x, ga.x), ga.y = fmaf(-w[j], v.y, ga.y);
-            ga.z = fmaf(-w[j], v.z, ga.z), ga.w = fmaf(-w[j], v.w, ga.w);
+        for (int nq = 0; nq < NQ; ++nq) {
+          ga[nq] = h4_to_f4(s2[nq * hw + qq]);                  // d/dc1 = s2 - W_bf^T s1   (frame f)
+          gb[nq] = h4_to_f4(s1[nq * hw + qq]);                  // d/dc2 = s1 - W_ff^T s2   (frame fn)
+          if (n_ovf > 0) {
+            const float4 o = cur[nq * hw + qq];
+            gb[nq].x += o.x, gb[nq].y += o.y, gb[nq].z += o.z, gb[nq].w += o.w;
           }
         }
         {
-          const uint4 es = __ldg(ells_f + po + qq);
-          const float4 w0 = __ldg(ellw_f + 2 * (po + qq)), w1 = __ldg(ellw_f + 2 * (po + qq) + 1);
-          const uint32_t src[4] = {es.x, es.y, es.z, es.w};
-          const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+          const uint4 e0 = __ldg(ebp + 2 * qq), e1 = __ldg(ebp + 2 * qq + 1);
+          const uint32_t e[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            if (!__any_sync(0xffffffffu, live && w[j] != 0.f)) break;
-            const float4 v = h4_to_f4(s2[(src[j >> 1] >> ((j & 1) * 16)) & 0xffffu]);
-            gb.x = fmaf(-w[j], v.x, gb.x), gb.y = fmaf(-w[j], v.y, gb.y);
-            gb.z = fmaf(-w[j], v.z, gb.z), gb.w = fmaf(-w[j], v.w, gb.w);
+            if (!__any_sync(0xffffffffu, live && (e[j] >> 16) != 0)) break;
+            const float wj = -(float)(e[j] >> 16) * (1.0f / 65535.0f);
+            const int src = e[j] & 0xffffu;
+#pragma unroll
+            for (int nq = 0; nq < NQ; ++nq) {
+              const float4 v = h4_to_f4(s1[nq * hw + src]);
+              ga[nq].x = fmaf(wj, v.x, ga[nq].x), ga[nq].y = fmaf(wj, v.y, ga[nq].y);
+              ga[nq].z = fmaf(wj, v.z, ga[nq].z), ga[nq].w = fmaf(wj, v.w, ga[nq].w);
+            }
           }
         }
-        if (live) {
-          const float4 cr = carry[pp];
-          const float v0 = (cr.x + ga.x) * k, v1 = (cr.y + ga.y) * k, v2 = (cr.z + ga.z) * k, v3 = (cr.w + ga.w) * k;
-          if (accumulate) {
-            gdst[q] += v0, gdst[hw + q] += v1, gdst[2 * hw + q] += v2, gdst[3 * hw + q] += v3;
-          } else {
-            gdst[q] = v0, gdst[hw + q] = v1, gdst[2 * hw + q] = v2, gdst[3 * hw + q] = v3;
+        {
+          const uint4 e0 = __ldg(efp + 2 * qq), e1 = __ldg(efp + 2 * qq + 1);
+          const uint32_t e[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (!__any_sync(0xffffffffu, live && (e[j] >> 16) != 0)) break;
+            const float wj = -(float)(e[j] >> 16) * (1.0f / 65535.0f);
+            const int src = e[j] & 0xffffu;
+#pragma unroll
+            for (int nq = 0; nq < NQ; ++nq) {
+              const float4 v = h4_to_f4(s2[nq * hw + src]);
+              gb[nq].x = fmaf(wj, v.x, gb[nq].x), gb[nq].y = fmaf(wj, v.y, gb[nq].y);
+              gb[nq].z = fmaf(wj, v.z, gb[nq].z), gb[nq].w = fmaf(wj, v.w, gb[nq].w);
+            }
           }
         }
-        carry[pp] = gb;
+#pragma unroll
+        for (int nq = 0; nq < NQ; ++nq) {
+          if (live) {
+            const float4 cr = carry[pp][nq];
+            float* g4 = gdst + (long long)nq * 4 * hw;
+            const float v0 = (cr.x + ga[nq].x) * k, v1 = (cr.y + ga[nq].y) * k, v2 = (cr.z + ga[nq].z) * k,
+                        v3 = (cr.w + ga[nq].w) * k;
+            if (accumulate) {
+              g4[q] += v0, g4[hw + q] += v1, g4[2 * hw + q] += v2, g4[3 * hw + q] += v3;
+            } else {
+              g4[q] = v0, g4[hw + q] = v1, g4[2 * hw + q] = v2, g4[3 * hw + q] = v3;
+            }
+          }
+          carry[pp][nq] = gb[nq];
+        }
       }
     }
     __syncthreads();                                           // s1 / s2 / cur are rewritten by the next pair
@@ -1121,11 +1168,14 @@ warp_loss_quad_kernel(const float* __restrict__ cs, const uint2* __restrict__ ta
       for (int e = t; e < n_ovf; e += T) {
         if (ob[3 * e] < 0) continue;
         const float wgt = -__int_as_float(ob[3 * e + 2]) * k;
-        const float4 v = h4_to_f4(s1[ob[3 * e + 1]]);
-        atomicAdd(gdst + ob[3 * e], wgt * v.x);
-        atomicAdd(gdst + hw + ob[3 * e], wgt * v.y);
-        atomicAdd(gdst + 2 * hw + ob[3 * e], wgt * v.z);
-        atomicAdd(gdst + 3 * hw + ob[3 * e], wgt * v.w);
+        for (int nq = 0; nq < NQ; ++nq) {
+          const float4 v = h4_to_f4(s1[nq * hw + ob[3 * e + 1]]);
+          float* g4 = gdst + (long long)nq * 4 * hw + ob[3 * e];
+          atomicAdd(g4, wgt * v.x);
+          atomicAdd(g4 + hw, wgt * v.y);
+          atomicAdd(g4 + 2 * hw, wgt * v.z);
+          atomicAdd(g4 + 3 * hw, wgt * v.w);
+        }
       }
       __syncthreads();
     }
@@ -1134,13 +1184,15 @@ warp_loss_quad_kernel(const float* __restrict__ cs, const uint2* __restrict__ ta
     nxt = tmp;
   }
   // ---- wrap-around: what frame 0 receives as the "next" frame of pair N-1
-  {
-    float* g0 = grad + base;
 #pragma unroll
-    for (int pp = 0; pp < P; ++pp) {
-      const int q = t + pp * T;
-      if (q < hw) {
-        g0[q] += carry[pp].x * k, g0[hw + q] += carry[pp].y * k, g0[2 * hw + q] += carry[pp].z * k, g0[3 * hw + q] += carry[pp].w * k;
+  for (int pp = 0; pp < P; ++pp) {
+    const int q = t + pp * T;
+    if (q < hw) {
+#pragma unroll
+      for (int nq = 0; nq < NQ; ++nq) {
+        float* g0 = grad + base + (long long)nq * 4 * hw;
+        const float4 cr = carry[pp][nq];
+        g0[q] += cr.x * k, g0[hw + q] += cr.y * k, g0[2 * hw + q] += cr.z * k, g0[3 * hw + q] += cr.w * k;
       }
     }
   }
@@ -1483,12 +1535,59 @@ static int launch_chain_group(const void* sample, void* out, const float* bwd_fl
   return check_launch("warp_chain_group_kernel");
 }
 
+// (P pixels per thread, NQ channel quads per CTA) for a plane of hw pixels: as many quads as shared memory (bytes_per_px
+// per quad, 200 KB) and the divisibility of the channel count allow, at most 4 values per thread to carry, threads <= 1024
+static bool quad_config(int hw, int channels, int planes, int bytes_per_px, int& P, int& NQ, int& T) {
+  if (channels % 4 != 0) return false;
+  for (NQ = 4; NQ >= 1; NQ >>= 1) {
+    if (channels % (4 * NQ) != 0) continue;
+    if ((size_t)NQ * hw * bytes_per_px > 200 * 1024) continue;
+    if (NQ > 1 && planes / (4 * NQ) < 148) continue;                 // keep every SM busy
+    P = 4 / NQ;                                                       // P * NQ == 4 carried float4 per thread
+    T = ((hw + P - 1) / P + 31) / 32 * 32;
+    while (T > 1024 && P * NQ < 4 * 4) {                              // large planes: more pixels per thread
+      P *= 2;
+      T = ((hw + P - 1) / P + 31) / 32 * 32;
+    }
+    if (T > 1024 || P > 4) continue;
+    if (T < 32) T = 32;
+    return true;
+  }
+  return false;
+}
+
+template <typename T, int P, int NQ>
+static int launch_chain_quad(const void* sample, void* out, const float* bwd_flow, const float* fwd_flow_last,
+                             const float* blend, int chunks, int frames, int channels, int h, int w, int threads,
+                             cudaStream_t s) {
+  const size_t smem = (size_t)NQ * h * w * 32;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(warp_chain_quad_kernel<T, P, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         200 * 1024);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(warp_chain_quad)");
+    attr_set = true;
+  }
+  warp_chain_quad_kernel<T, P, NQ><<<chunks * channels / (4 * NQ), threads, smem, s>>>(
+      (const T*)sample, (T*)out, bwd_flow, fwd_flow_last, blend, frames, channels, h, w);
+  return check_launch("warp_chain_quad_kernel");
+}
+
 template <typename T>
 static int launch_chain(const void* sample, void* out, const float* bwd_flow, const float* fwd_flow_last,
                         const float* blend, int chunks, int frames, int channels, int h, int w, cudaStream_t s) {
+  const int planes = chunks * channels;
+  int P, NQ, threads;
+  if (quad_config(h * w, channels, planes, 32, P, NQ, threads)) {
+#define CQ(PP, QQ)                                                                                                     \
+  if (P == PP && NQ == QQ)                                                                                             \
+    return launch_chain_quad<T, PP, QQ>(sample, out, bwd_flow, fwd_flow_last, blend, chunks, frames, channels, h, w,   \
+                                        threads, s);
+    CQ(1, 4) CQ(2, 2) CQ(4, 1) CQ(1, 2) CQ(2, 1) CQ(1, 1)
+#undef CQ
+  }
   // planes per CTA: as many as keep two CTAs on an SM (<= ~100 KB of shared memory each) and the grid above two waves
   const size_t plane2 = (size_t)2 * h * w * sizeof(float);
-  const int planes = chunks * channels;
   if (8 * plane2 <= 100 * 1024 && planes / 8 >= 296)
     return launch_chain_group<T, 8>(sample, out, bwd_flow, fwd_flow_last, blend, chunks, frames, channels, h, w, s);
   if (3 * plane2 <= 100 * 1024 && planes / 3 >= 296)
@@ -1552,6 +1651,30 @@ extern "C" int fresco_warp_loss_fwd_bwd(const float* cs, const float* fwd_flow, 
   const double numel = (double)chunks * frames * channels * h * w;
   const float kk = (float)(2.0 / numel);
   cudaStream_t s = (cudaStream_t)stream;
+  // ---- channel-quad kernel: 4 NQ planes per CTA interleaved in shared memory (48 bytes per pixel and quad)
+  {
+    int P, NQ, threads;
+    if (quad_config(h * w, channels, chunks * channels, 48, P, NQ, threads)) {
+      const size_t smem_q = (size_t)NQ * h * w * 48;
+      const int grid_q = chunks * channels / (4 * NQ);
+#define LQ(PP, QQ)                                                                                                      \
+  if (P == PP && NQ == QQ) {                                                                                            \
+    static bool attr_set = false;                                                                                       \
+    if (!attr_set) {                                                                                                    \
+      cudaError_t e = cudaFuncSetAttribute(warp_loss_quad_kernel<PP, QQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                           200 * 1024);                                                                 \
+      if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(warp_loss_quad)");                           \
+      attr_set = true;                                                                                                  \
+    }                                                                                                                   \
+    warp_loss_quad_kernel<PP, QQ><<<grid_q, threads, smem_q, s>>>(                                                      \
+        cs, fwd_flow, bwd_flow, fwd_keep, bwd_keep, (const uint4*)bwd_ell, (const uint4*)fwd_ell, overflow, n_overflow, \
+        grad, loss_acc, accumulate, frames, channels, h, w, kk);                                                        \
+    return check_launch("warp_loss_quad_kernel");                                                                       \
+  }
+      LQ(1, 4) LQ(2, 2) LQ(4, 1) LQ(1, 2) LQ(2, 1) LQ(1, 1)
+#undef LQ
+    }
+  }
   // ---- channel-grouped kernel: 512 threads; P pixel slots x KT planes per thread (carried in registers)
   {
     const int T = 512, hw = h * w, planes = chunks * channels;
@@ -1691,94 +1814,3 @@ extern "C" int fresco_dilate(const float* in, float* out, int planes, int h, int
   return check_launch("dilate_kernel");
 }
 
-extern "C" int fresco_warp_loss_quad(const float* cs, const void* tap_idx_bwd, const float* tap_w_bwd,
-                                     const void* tap_idx_fwd, const float* tap_w_fwd, const float* fwd_keep,
-                                     const float* bwd_keep, const void* ell_src_bwd, const float* ell_w_bwd,
-                                     const void* ell_src_fwd, const float* ell_w_fwd, const int32_t* overflow,
-                                     int n_overflow, float* grad, float* loss_acc, int accumulate, int chunks, int frames,
-                                     int channels, int h, int w, void* stream) {
-  if (!cs || !tap_idx_bwd || !tap_w_bwd || !tap_idx_fwd || !tap_w_fwd || !fwd_keep || !bwd_keep || !ell_src_bwd ||
-      !ell_w_bwd || !ell_src_fwd || !ell_w_fwd || !grad)
-    return set_error(FRESCO_ERR_ARG, "fresco_warp_loss_quad: null pointer");
-  if (n_overflow > 0 && !overflow) return set_error(FRESCO_ERR_ARG, "fresco_warp_loss_quad: overflow list missing");
-  const int hw = h * w;
-  if (chunks <= 0 || frames < 2 || channels <= 0 || channels % 4 != 0 || hw <= 0 || hw > 65535)
-    return set_error(FRESCO_ERR_ARG, "fresco_warp_loss_quad: bad shape (frames >= 2, channels % 4 == 0, h*w <= 65535)");
-  const size_t smem = (size_t)hw * 48;
-  if (smem > 200 * 1024) return set_error(FRESCO_ERR_UNSUPPORTED, "fresco_warp_loss_quad: plane too large for shared memory");
-  const double numel = (double)chunks * frames * channels * hw;
-  const float kk = (float)(2.0 / numel);
-  // P pixels per thread: as few threads as keep P <= 4 (more pixels per thread = more independent work per thread)
-  int P = 4;
-  int T = ((hw + P - 1) / P + 31) / 32 * 32;
-  if (T > 1024) return set_error(FRESCO_ERR_UNSUPPORTED, "fresco_warp_loss_quad: plane too large");
-  if (T < 64) {
-    P = hw >= 128 ? 2 : 1;
-    T = ((hw + P - 1) / P + 31) / 32 * 32;
-  }
-  const int grid = chunks * channels / 4;
-  cudaStream_t s = (cudaStream_t)stream;
-#define QUAD_CASE(PP)                                                                                                   \
-  if (P == PP) {                                                                                                        \
-    static bool attr_set = false;                                                                                       \
-    if (!attr_set) {                                                                                                    \
-      cudaError_t e = cudaFuncSetAttribute(warp_loss_quad_kernel<PP>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
-                                           200 * 1024);                                                                 \
-      if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(warp_loss_quad)");                           \
-      attr_set = true;                                                                                                  \
-    }                                                                                                                   \
-    warp_loss_quad_kernel<PP><<<grid, T, smem, s>>>(                                                                    \
-        cs, (const uint2*)tap_idx_bwd, (const float4*)tap_w_bwd, (const uint2*)tap_idx_fwd, (const float4*)tap_w_fwd,   \
-        fwd_keep, bwd_keep, (const uint4*)ell_src_bwd, (const float4*)ell_w_bwd, (const uint4*)ell_src_fwd,             \
-        (const float4*)ell_w_fwd, overflow, n_overflow, grad, loss_acc, accumulate, frames, channels, hw, kk);         \
-    return check_launch("warp_loss_quad_kernel");                                                                       \
-  }
-  QUAD_CASE(1) QUAD_CASE(2) QUAD_CASE(4)
-#undef QUAD_CASE
-  return set_error(FRESCO_ERR_UNSUPPORTED, "fresco_warp_loss_quad: no instantiation");
-}
-
-template <typename T>
-static int launch_chain_quad(const void* sample, void* out, const void* tap_idx, const float* tap_w, const float* blend,
-                             int chunks, int frames, int channels, int hw, cudaStream_t s) {
-  int P = 4;
-  int Tn = ((hw + P - 1) / P + 31) / 32 * 32;
-  if (Tn > 1024) return FRESCO_ERR_UNSUPPORTED;
-  if (Tn < 64) {
-    P = hw >= 128 ? 2 : 1;
-    Tn = ((hw + P - 1) / P + 31) / 32 * 32;
-  }
-  const size_t smem = (size_t)hw * 32;
-  const int grid = chunks * channels / 4;
-#define CHAIN_CASE(PP)                                                                                                \
-  if (P == PP) {                                                                                                      \
-    static bool attr_set = false;                                                                                     \
-    if (!attr_set) {                                                                                                  \
-      cudaError_t e = cudaFuncSetAttribute(warp_chain_quad_kernel<T, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                           200 * 1024);                                                               \
-      if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(warp_chain_quad)");                        \
-      attr_set = true;                                                                                                \
-    }                                                                                                                 \
-    warp_chain_quad_kernel<T, PP><<<grid, Tn, smem, s>>>((const T*)sample, (T*)out, (const uint2*)tap_idx,            \
-                                                         (const float4*)tap_w, blend, frames, channels, hw);          \
-    return check_launch("warp_chain_quad_kernel");                                                                    \
-  }
-  CHAIN_CASE(1) CHAIN_CASE(2) CHAIN_CASE(4)
-#undef CHAIN_CASE
-  return FRESCO_ERR_UNSUPPORTED;
-}
-
-extern "C" int fresco_warp_fuse_chain_taps(const void* sample, void* out, int is_half, const void* tap_idx,
-                                           const float* tap_w, const float* blend, int chunks, int frames, int channels,
-                                           int h, int w, void* stream) {
-  if (!sample || !out || !tap_idx || !tap_w || !blend)
-    return set_error(FRESCO_ERR_ARG, "fresco_warp_fuse_chain_taps: null pointer");
-  const int hw = h * w;
-  if (chunks <= 0 || frames < 2 || channels <= 0 || channels % 4 != 0 || hw <= 0 || hw > 4096)
-    return set_error(FRESCO_ERR_UNSUPPORTED, "fresco_warp_fuse_chain_taps: channels % 4 == 0 and h*w <= 4096 only");
-  cudaStream_t s = (cudaStream_t)stream;
-  const int rc = is_half ? launch_chain_quad<__half>(sample, out, tap_idx, tap_w, blend, chunks, frames, channels, hw, s)
-                         : launch_chain_quad<float>(sample, out, tap_idx, tap_w, blend, chunks, frames, channels, hw, s);
-  if (rc == FRESCO_ERR_UNSUPPORTED) return set_error(rc, "fresco_warp_fuse_chain_taps: no instantiation for this plane size");
-  return rc;
-}

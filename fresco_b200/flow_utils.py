@@ -125,19 +125,12 @@ def warp_tensor(sample, flows, occs, saliency, unet_chunk_size, shard=None):
         blend = torch.empty(n, 1, h, w, dtype=torch.float32, device=sample.device)
         blend[:n - 1] = (1 - bwd_occ[:n - 1]) * sal[1:n] * warp_sal[:n - 1]       # :45
         blend[n - 1:] = (1 - fwd_occ[n - 1:n]) * sal[n - 1:n] * warp_sal_last      # :50
-        taps = None
-        if h * w <= 4096:
-            # taps of the chain steps for the quad kernel: backward flow of pairs 0..N-2, then the closing forward flow
-            step_flows = torch.cat([bwd_flow[:n - 1], fwd_flow[n - 1:n]], dim=0).contiguous()
-            taps = ops.warp_taps(step_flows)
-        return bwd_flow, fwd_flow[n - 1].contiguous(), blend.contiguous(), taps
+        return bwd_flow, fwd_flow[n - 1].contiguous(), blend.contiguous()
 
-    bwd_flow, fwd_flow_last, blend, taps = _cache_get(("warp_tensor", n, h, w),
-                                                       (flows[0], flows[1], occs[0], occs[1], saliency), prepare)
+    bwd_flow, fwd_flow_last, blend = _cache_get(("warp_tensor", n, h, w),
+                                                 (flows[0], flows[1], occs[0], occs[1], saliency), prepare)
 
     def chain(planes, chunks):
-        if taps is not None and planes.shape[1] % 4 == 0 and hasattr(ops, "warp_fuse_chain_taps"):
-            return ops.warp_fuse_chain_taps(planes, taps[0], taps[1], blend, chunks)
         return ops.warp_fuse_chain(planes, bwd_flow, fwd_flow_last, blend, chunks)
 
     x = sample.contiguous()

@@ -164,29 +164,6 @@ def warp_fuse_chain(sample, bwd_flow, fwd_flow_last, blend, chunks: int, out=Non
     return out
 
 
-def warp_taps(flow: torch.Tensor):
-    """The four bilinear taps of every pixel for the warp by ``flow`` [F,2,h,w], as the quad kernels consume them:
-    tap_idx uint16 (stored in int16) [F, hw, 4], tap_w fp32 [F, hw, 4]; a tap outside the plane has index 0, weight 0."""
-    Fr, _, h, w = flow.shape
-    dest = torch.empty(Fr, h * w, 4, dtype=torch.int32, device=flow.device)
-    wgt = torch.empty(Fr, h * w, 4, dtype=torch.float32, device=flow.device)
-    L.check(L.lib().fresco_warp_taps(L.ptr(flow), L.ptr(dest), L.ptr(wgt), Fr, h, w, L.stream()), "fresco_warp_taps")
-    return _u16(dest.clamp(min=0)), wgt
-
-
-def warp_fuse_chain_taps(sample, tap_idx, tap_w, blend, chunks: int, out=None):
-    B, C, h, w = sample.shape
-    if out is None:
-        out = torch.empty_like(sample)
-    is_half = 1 if sample.dtype == torch.float16 else 0
-    ev = _prof_begin()
-    L.check(L.lib().fresco_warp_fuse_chain_taps(L.ptr(sample), L.ptr(out), is_half, L.ptr(tap_idx), L.ptr(tap_w),
-                                                L.ptr(blend), chunks, B // chunks, C, h, w, L.stream()),
-            "fresco_warp_fuse_chain_taps")
-    _prof_end(ev, "warp_chain_C%d_%dx%d" % (C, h, w), 2.0 * sample.numel() * sample.element_size(), "hbm")
-    return out
-
-
 ELL_SLOTS = 8
 
 _WORKSPACES: dict = {}
@@ -202,27 +179,17 @@ def _workspace(key, nbytes: int, device) -> torch.Tensor:
     return ws
 
 
-def _u16(x: torch.Tensor) -> torch.Tensor:
-    """values in [0, 65535] stored as uint16 bit patterns in an int16 tensor"""
-    x = x.long() & 0xffff
-    return torch.where(x >= 32768, x - 65536, x).to(torch.int16).contiguous()
-
-
 def warp_adjoint_ell(flow: torch.Tensor):
     """Per-batch operands of the temporal-consistency loss for the warp by ``flow`` [F,2,h,w]:
-    * the four bilinear taps of every pixel (forward application): tap_idx uint16 [F, hw, 4], tap_w fp32 [F, hw, 4];
-    * the ADJOINT of that warp in ELL form, row = destination pixel, up to 8 (source, weight) entries, used slots first:
-      ell_src uint16 [F, hw, 8], ell_w fp32 [F, hw, 8], and the same packed as (round(w*65535) << 16) | source in uint32
-      (``ell_packed``, the format of the generic kernels); destinations with more than 8 taps spill to
-      ``ovf`` int32 [F, n_ovf, 3] = (destination | -1, source, float bits of the weight)."""
+    the ADJOINT of that warp in ELL form, row = destination pixel, up to 8 entries (round(w*65535) << 16) | source in
+    uint32, used slots first (``ell_packed`` [F, hw, 8]); destinations with more than 8 taps spill to ``ovf`` int32
+    [F, n_ovf, 3] = (destination | -1, source, float bits of the weight)."""
     Fr, _, h, w = flow.shape
     hw = h * w
     dev = flow.device
     dest = torch.empty(Fr, hw, 4, dtype=torch.int32, device=dev)
     wgt = torch.empty(Fr, hw, 4, dtype=torch.float32, device=dev)
     L.check(L.lib().fresco_warp_taps(L.ptr(flow), L.ptr(dest), L.ptr(wgt), Fr, h, w, L.stream()), "fresco_warp_taps")
-    tap_idx = _u16(dest.clamp(min=0))
-    tap_w = wgt.clone()
     dest = dest.reshape(Fr, 4 * hw).long()
     wgt = wgt.reshape(Fr, 4 * hw)
     src = torch.arange(hw, device=dev).repeat_interleave(4)[None].expand(Fr, -1)
@@ -254,9 +221,7 @@ def warp_adjoint_ell(flow: torch.Tensor):
             ovf[f, :sel.numel(), 0] = key_s[f, sel].to(torch.int32)
             ovf[f, :sel.numel(), 1] = src_s[f, sel].to(torch.int32)
             ovf[f, :sel.numel(), 2] = w_s[f, sel].contiguous().view(torch.int32)
-    return {"tap_idx": tap_idx.reshape(Fr, hw, 4), "tap_w": tap_w.contiguous(), "ell_packed": packed,
-            "ell_src": _u16(ell_src).reshape(Fr, hw, ELL_SLOTS), "ell_w": ell_w.reshape(Fr, hw, ELL_SLOTS).contiguous(),
-            "ovf": ovf, "n_ovf": n_ovf}
+    return {"ell_packed": packed, "ovf": ovf, "n_ovf": n_ovf}
 
 
 class WarpAdjoint:
@@ -285,18 +250,10 @@ def warp_loss_fwd_bwd(cs, fwd_flow, bwd_flow, fwd_keep, bwd_keep, grad, loss_acc
     a = adjoint
     lp = L.ptr(loss_acc) if loss_acc is not None else None
     ev = _prof_begin()
-    if C % 4 == 0 and h * w <= 4096:
-        b, f = a.bwd, a.fwd
-        L.check(L.lib().fresco_warp_loss_quad(L.ptr(cs), L.ptr(b["tap_idx"]), L.ptr(b["tap_w"]), L.ptr(f["tap_idx"]),
-                                              L.ptr(f["tap_w"]), L.ptr(fwd_keep), L.ptr(bwd_keep), L.ptr(b["ell_src"]),
-                                              L.ptr(b["ell_w"]), L.ptr(f["ell_src"]), L.ptr(f["ell_w"]), L.ptr(a.ovf),
-                                              int(a.n_ovf), L.ptr(grad), lp, 1 if accumulate else 0, chunks, frames, C, h,
-                                              w, L.stream()), "fresco_warp_loss_quad")
-    else:
-        L.check(L.lib().fresco_warp_loss_fwd_bwd(L.ptr(cs), L.ptr(fwd_flow), L.ptr(bwd_flow), L.ptr(fwd_keep),
-                                                 L.ptr(bwd_keep), L.ptr(a.bwd["ell_packed"]), L.ptr(a.fwd["ell_packed"]),
-                                                 L.ptr(a.ovf), int(a.n_ovf), L.ptr(grad), lp, 1 if accumulate else 0,
-                                                 chunks, frames, C, h, w, L.stream()), "fresco_warp_loss_fwd_bwd")
+    L.check(L.lib().fresco_warp_loss_fwd_bwd(L.ptr(cs), L.ptr(fwd_flow), L.ptr(bwd_flow), L.ptr(fwd_keep),
+                                             L.ptr(bwd_keep), L.ptr(a.bwd["ell_packed"]), L.ptr(a.fwd["ell_packed"]),
+                                             L.ptr(a.ovf), int(a.n_ovf), L.ptr(grad), lp, 1 if accumulate else 0,
+                                             chunks, frames, C, h, w, L.stream()), "fresco_warp_loss_fwd_bwd")
     # read c1, c2 + write g1, g2 = 4 fp32 passes (the fused kernels move 2 + 1/N of them)
     _prof_end(ev, "warp_loss_C%d_%dx%d" % (C, h, w), 16.0 * cs.numel(), "hbm")
     return grad

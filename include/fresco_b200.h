@@ -106,13 +106,6 @@ int fresco_warp_fuse_chain(const void* sample, void* out, int is_half, const flo
                            const float* fwd_flow_last, const float* blend, int chunks, int frames, int channels,
                            int h, int w, void* stream);
 
-/* the same chain with the bilinear taps of every step prepared once per batch (fresco_warp_taps; index 0 + weight 0 for a
- * tap outside the plane): tap_idx uint16 [frames, h*w, 4], tap_w float [frames, h*w, 4], entries 0..N-2 = backward flow
- * of pair i, entry N-1 = forward flow of pair N-1 (closing blend).  channels % 4 == 0, h*w <= 4096: four planes per CTA
- * interleaved in shared memory (what warp_tensor runs on decoder features).                                       */
-int fresco_warp_fuse_chain_taps(const void* sample, void* out, int is_half, const void* tap_idx, const float* tap_w,
-                                const float* blend, int chunks, int frames, int channels, int h, int w, void* stream);
-
 /* ---- O2: temporal-consistency loss, forward + backward -------------------------------------
  * replaces src/diffusion_hacked.py:461-466 and its autograd backward.
  * cs, grad float [chunks, frames, channels, h, w]; fwd_flow/bwd_flow float [frames,2,h,w];
@@ -129,19 +122,6 @@ int fresco_warp_loss_fwd_bwd(const float* cs, const float* fwd_flow, const float
                              const float* bwd_keep, const void* bwd_ell, const void* fwd_ell, const int32_t* overflow,
                              int n_overflow, float* grad, float* loss_acc, int accumulate, int chunks, int frames,
                              int channels, int h, int w, void* stream);
-
-/* The same loss with four (chunk, channel) planes per CTA and the per-(pair, pixel) operands prepared once per batch
- * in the form the inner loops consume (what optimize_feature runs when a plane needs <= 48 bytes/pixel of shared memory
- * x h*w <= 200 KB and channels % 4 == 0):
- *   tap_idx_* uint16 [frames, h*w, 4], tap_w_* float [frames, h*w, 4]: the bilinear taps of fresco_warp_taps for the
- *   backward / forward flow of every pair (index 0 + weight 0 for a tap outside the plane);
- *   ell_src_* uint16 [frames, h*w, 8], ell_w_* float [frames, h*w, 8]: the warp adjoints, row = destination pixel, used
- *   slots first; overflow as above.                                                                            */
-int fresco_warp_loss_quad(const float* cs, const void* tap_idx_bwd, const float* tap_w_bwd, const void* tap_idx_fwd,
-                          const float* tap_w_fwd, const float* fwd_keep, const float* bwd_keep, const void* ell_src_bwd,
-                          const float* ell_w_bwd, const void* ell_src_fwd, const float* ell_w_fwd, const int32_t* overflow,
-                          int n_overflow, float* grad, float* loss_acc, int accumulate, int chunks, int frames,
-                          int channels, int h, int w, void* stream);
 
 /* ---- O3: spatial-consistency (normalised Gram, L1) loss, forward + backward -----------------
  * replaces src/diffusion_hacked.py:469-476 and its backward.

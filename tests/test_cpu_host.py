@@ -266,42 +266,6 @@ class _TorchWarpOps:
         from oracle import fresco_oracle as O
         return O.dilate(x, k)
 
-    @staticmethod
-    def warp_taps(flow):
-        """fresco_warp_taps in torch: clamped tap index + weight (0 outside the plane) for x+fx, y+fy"""
-        Fr, _, h, w = flow.shape
-        ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float32), torch.arange(w, dtype=torch.float32), indexing="ij")
-        x, y = xs[None] + flow[:, 0], ys[None] + flow[:, 1]
-        x0, y0 = torch.floor(x), torch.floor(y)
-        ax, ay = x - x0, y - y0
-        idx, wgt = [], []
-        for dy, wy in ((0, 1 - ay), (1, ay)):
-            for dx, wx in ((0, 1 - ax), (1, ax)):
-                xi, yi = x0 + dx, y0 + dy
-                ok = (xi >= 0) & (xi <= w - 1) & (yi >= 0) & (yi <= h - 1)
-                idx.append((yi.clamp(0, h - 1) * w + xi.clamp(0, w - 1)).long())
-                wgt.append(torch.where(ok, wx * wy, torch.zeros_like(wx)))
-        idx, wgt = torch.stack(idx, -1).reshape(Fr, h * w, 4), torch.stack(wgt, -1).reshape(Fr, h * w, 4)
-        return torch.where(wgt != 0, idx, torch.zeros_like(idx)), wgt
-
-    @staticmethod
-    def warp_fuse_chain_taps(sample, tap_idx, tap_w, blend, chunks, out=None):
-        z = sample.float().clone()
-        n = sample.shape[0] // chunks
-        hw = sample.shape[2] * sample.shape[3]
-
-        def warp(plane, step):                                   # [C, h, w] through the taps of chain step `step`
-            flat = plane.reshape(plane.shape[0], hw)
-            return (flat[:, tap_idx[step].long()] * tap_w[step][None]).sum(-1).reshape(plane.shape)
-        for j in range(chunks):
-            base = n * j
-            for ii in range(n - 1):
-                m = blend[ii]
-                z[base + ii + 1] = z[base + ii + 1] * (1 - m) + warp(z[base + ii], ii) * m
-            m = blend[n - 1]
-            z[base + n - 1] = z[base + n - 1] * (1 - m) + warp(z[base], n - 1) * m
-        return z.to(sample.dtype)
-
 
 @pytest.mark.parametrize("fixture", ["set_a", "set_b"])
 def test_warp_tensor_and_mapping_host_logic_against_reference_outputs(golden, monkeypatch, fixture):
