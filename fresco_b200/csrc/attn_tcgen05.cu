@@ -866,7 +866,7 @@ struct WideCfg {
   // With two CTAs per SM every warp costs the softmax threads registers (they hold two tiles' worth of scores, see the
   // prefetch below): the TMA producer then shares a thread with the score-MMA issuer and refills the ring without
   // ever blocking.  With one CTA per SM it has a warp of its own.
-  static constexpr bool OWN_TMA_WARP = CTAS == 1;
+  static constexpr bool OWN_TMA_WARP = true;      // (measured: sharing the thread costs the 2-CTA variant 9 %)
   static constexpr int QK_WARP = SOFTMAX_WARPS, PV_WARP0 = SOFTMAX_WARPS + 1, TMA_WARP = SOFTMAX_WARPS + 1 + NPV;
   static constexpr int THREADS = (SOFTMAX_WARPS + 1 + NPV + (OWN_TMA_WARP ? 1 : 0)) * 32;
 };
@@ -893,7 +893,7 @@ __device__ __forceinline__ void tmem_st_half(uint32_t taddr, const uint32_t (&r)
   else tmem_st8(taddr, r);
 }
 
-// PIPE 3: scores of tile i+1 prefetched while tile i is processed.  PIPE 4: additionally the row max of tile i+1 is taken
+// PIPE 2: plain loop.  PIPE 3: scores of tile i+1 prefetched while tile i is processed.  PIPE 4: additionally the row max of tile i+1 is taken
 // between the exponentials of tile i and the publication of P_i, so the TMEM store latency of P_i hides behind it.
 template <int D, int SPLIT, int POLY, int PIPE>
 __global__ void __launch_bounds__(WideCfg<D, SPLIT>::THREADS, WideCfg<D, SPLIT>::CTAS)
@@ -1186,7 +1186,16 @@ fresco_attn_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     uint32_t ra[KEYS], rb[KEYS];
     issue_load(ra, 0);
     finish_load(ra, 0);
-    if constexpr (PIPE == 4) {
+    if constexpr (PIPE == 2) {                       // no prefetch: every tile is loaded when its turn comes
+      for (int i = 0; i < n_tiles; ++i) {
+        if (i > 0) {
+          issue_load(ra, i);
+          finish_load(ra, i);
+        }
+        tile_exp(ra, i, tile_max(ra, i));
+        publish(i);
+      }
+    } else if constexpr (PIPE == 4) {
       float ma = tile_max(ra, 0), mb = 0.f;
       for (int i = 0; i < n_tiles; i += 2) {
         const bool has1 = i + 1 < n_tiles, has2 = i + 2 < n_tiles;
@@ -1275,6 +1284,321 @@ fresco_attn_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
 }
 
 // ---------------------------------------------------------------------------------------------
+// head_dim <= 64: the "ping-pong" kernel -- two query tiles per CTA, the exponential pipe handed back and forth
+// ---------------------------------------------------------------------------------------------
+// What the traces of the pipelined kernel say: a softmax warp spends ~620 clocks of a tile in its
+// exponential phase when it has the MUFU pipe to itself (512 of them are the 64 ex2) and ~500 in everything else; with
+// two independent CTAs per SM the exponential phases of the two warps that share a sub-partition collide at random,
+// each stretches to ~900 and the tile costs ~800 clocks per SM, although the pipe is busy only 64 % of the time.
+// Here the two warps of a sub-partition belong to the SAME CTA -- one CTA per SM owns TWO 128-row query tiles, warps
+// 0-3 tile 0, warps 4-7 tile 1 -- and a pair of named barriers makes the exponential phases strictly alternate: while
+// warpgroup 0 runs its 64 ex2, warpgroup 1 waits for scores, reads TMEM, takes row maxima, stores P and arrives; then
+// they swap.  The pipe never sees two exponential phases at once and is never left idle while one is pending.  Side
+// effects of the pairing: every K/V tile is loaded once for 256 query rows (half the TMA / L2 traffic), and the TMEM of
+// the SM is one 512-column allocation (tile t at columns 256 t: S0, S1, P0, P1, O as in the pipelined kernel).
+//   warps 0-3 / 4-7  softmax of query tile 0 / 1 (one row per thread)
+//   warp 8           TMA producer: both Q tiles once, K/V tiles through the ring
+//   warp 9           score-MMA issuer for both query tiles
+//   warps 10, 11     P V (+ row-sum) issuer of tile 0 / 1
+template <int D>
+struct PPCfg {
+  static_assert(D <= 64, "ping-pong kernel: one 64-wide atom per head");
+  static constexpr int KSTEPS = (D + 15) / 16;
+  static constexpr int DPAD = KSTEPS * 16;
+  static constexpr int S_OFF0 = 0, S_OFF1 = 64, P_OFF0 = 128, P_OFF1 = 160, O_OFF = 192, TILE_COLS = 256, TMEM_COLS = 512;
+  static constexpr bool MMA_ROWSUM = DPAD + 16 <= 64;       // 16 spare O columns (head_dim <= 48): row sums from the tensor core
+  static constexpr int L_COL = 48;
+  static constexpr int ONES_BYTES = MMA_ROWSUM ? 2048 : 0;
+  static constexpr int STAGES = 8;
+  static constexpr int Q_BYTES = 2 * kQAtomBytes;
+  static constexpr int STAGE_BYTES = 2 * kKVAtomBytes;
+  static constexpr int SMEM_BYTES = 1024 + Q_BYTES + STAGES * STAGE_BYTES + ONES_BYTES + 512;
+  static constexpr int THREADS = 384;
+};
+
+template <int D>
+__global__ void __launch_bounds__(PPCfg<D>::THREADS, 1)
+fresco_attn_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                      const __grid_constant__ CUtensorMap tm_v, const AttnParams p) {
+  using Cfg = PPCfg<D>;
+  constexpr int ST = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_q = smem;                                                   // [2][128 rows x 128 B]
+  uint8_t* s_kv = smem + Cfg::Q_BYTES;
+  uint8_t* s_ones = s_kv + ST * Cfg::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ones + Cfg::ONES_BYTES);
+  uint64_t* bar_q = bars + 0;
+  uint64_t* bar_kv_full = bars + 1;            // [ST]
+  uint64_t* bar_kv_empty = bars + 1 + ST;      // [ST]  1 (score issuer) + 2 (P V issuers)
+  uint64_t* bar_s = bars + 1 + 2 * ST;         // [2 tiles][2 buffers]
+  uint64_t* bar_p = bar_s + 4;                 // [2][2] P_i written (one elected arrival per softmax warp)
+  uint64_t* bar_o = bar_s + 8;                 // [2][2] P_i V_i retired
+  uint64_t* bar_c = bar_s + 12;                // [2][2] S_i copied to registers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s + 16);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 2 * kTileM;      // first query row of the PAIR of tiles
+  const int head = blockIdx.y;
+  const int b = blockIdx.z;
+  const int b_kv = b / p.q_per_kv;
+  const int n_tiles = (p.kv_len + kTileN - 1) / kTileN;
+
+  if (warp == 9 && lane == 0) {
+    mbar_init(bar_q, 1);
+    for (int s = 0; s < ST; ++s) {
+      mbar_init(bar_kv_full + s, 1);
+      mbar_init(bar_kv_empty + s, 3);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(bar_s + i, 1);
+      mbar_init(bar_p + i, 4);
+      mbar_init(bar_o + i, 1);
+      mbar_init(bar_c + i, 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 8) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tm_q);
+      tma_prefetch_desc(&tm_k);
+      tma_prefetch_desc(&tm_v);
+    }
+    __syncwarp();
+    tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  }
+  if (Cfg::MMA_ROWSUM) {
+    for (int i = threadIdx.x; i < Cfg::ONES_BYTES / 4; i += Cfg::THREADS) reinterpret_cast<uint32_t*>(s_ones)[i] = 0x3C003C00u;
+    fence_proxy_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 8) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(bar_q, Cfg::Q_BYTES);
+      tma_load_4d(s_q, &tm_q, bar_q, 0, head, q0, b);
+      tma_load_4d(s_q + kQAtomBytes, &tm_q, bar_q, 0, head, q0 + kTileM, b);      // (rows past q_len: zero fill)
+      for (int t = 0; t < n_tiles; ++t) {
+        const int st = t % ST;
+        if (t >= ST) mbar_wait_backoff(bar_kv_empty + st, ((t / ST) - 1) & 1, 32, 70);
+        uint8_t* sk = s_kv + st * Cfg::STAGE_BYTES;
+        mbar_expect_tx(bar_kv_full + st, Cfg::STAGE_BYTES);
+        tma_load_4d(sk, &tm_k, bar_kv_full + st, 0, head, t * kTileN, b_kv);
+        tma_load_4d(sk + kKVAtomBytes, &tm_v, bar_kv_full + st, 0, head, t * kTileN, b_kv);
+      }
+    }
+  } else if (warp == 9) {
+    // ------------------------------------------------------------ score-MMA issuer: S_t of tile 0, then of tile 1
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = make_idesc_f16(kTileM, kTileN, 0);
+      const uint32_t q_addr = smem_u32(s_q);
+      mbar_wait(bar_q, 0, 71);
+      for (int t = 0; t < n_tiles; ++t) {
+        const int st = t % ST;
+        mbar_wait(bar_kv_full + st, (t / ST) & 1, 72);
+        const uint32_t k_addr = smem_u32(s_kv + st * Cfg::STAGE_BYTES);
+#pragma unroll
+        for (int qt = 0; qt < 2; ++qt) {
+          if (t >= 2) mbar_wait(bar_c + qt * 2 + (t & 1), ((t - 2) >> 1) & 1, 73);   // S buffer is in registers
+          tc_fence_after();
+          const uint32_t d_tmem = tmem + qt * Cfg::TILE_COLS + ((t & 1) ? Cfg::S_OFF1 : Cfg::S_OFF0);
+#pragma unroll
+          for (int ks = 0; ks < Cfg::KSTEPS; ++ks)
+            umma_ss(d_tmem, make_smem_desc_sw128(q_addr + qt * kQAtomBytes + ks * 32, 16, 1024),
+                    make_smem_desc_sw128(k_addr + ks * 32, 16, 1024), idesc_qk, ks > 0);
+          umma_commit(bar_s + qt * 2 + (t & 1));
+        }
+        umma_commit(bar_kv_empty + st);                                    // K_t consumed by both tiles
+      }
+    }
+  } else if (warp >= 10) {
+    // ------------------------------------------------------------ P V issuer of query tile qt
+    if (lane == 0) {
+      const int qt = warp - 10;
+      constexpr uint32_t idesc_pv = make_idesc_f16(kTileM, Cfg::DPAD, 1);
+      constexpr uint32_t idesc_ones = make_idesc_f16(kTileM, 16, 1);
+      const uint32_t t_base = tmem + qt * Cfg::TILE_COLS;
+      for (int t = 0; t < n_tiles; ++t) {
+        const int st = t % ST;
+        mbar_wait_backoff(bar_p + qt * 2 + (t & 1), (t >> 1) & 1, 20, 74);   // P_t in TMEM
+        mbar_wait(bar_kv_full + st, (t / ST) & 1, 75);                      // V_t landed long ago; observe it
+        tc_fence_after();
+        const uint32_t v_addr = smem_u32(s_kv + st * Cfg::STAGE_BYTES + kKVAtomBytes);
+#pragma unroll
+        for (int k2 = 0; k2 < kTileN / 16; ++k2) {
+          const uint32_t acc = (k2 > 0 || t > 0) ? 1u : 0u;
+          const uint32_t p_tmem = t_base + ((t & 1) ? Cfg::P_OFF1 : Cfg::P_OFF0) + k2 * 8;
+          umma_ts(t_base + Cfg::O_OFF, p_tmem, make_smem_desc_sw128(v_addr + k2 * 2048, kKVAtomBytes, 1024), idesc_pv, acc);
+          if (Cfg::MMA_ROWSUM)
+            umma_ts(t_base + Cfg::O_OFF + Cfg::L_COL, p_tmem, make_smem_desc_sw128(smem_u32(s_ones), 2048, 1024),
+                    idesc_ones, acc);
+        }
+        umma_commit(bar_kv_empty + st);
+        umma_commit(bar_o + qt * 2 + (t & 1));
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ softmax warps: query tile qt, one row per thread
+    const int qt = warp >> 2, quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t t_lane = tmem + qt * Cfg::TILE_COLS + (static_cast<uint32_t>(quarter * 32) << 16);
+    const int q_tile0 = q0 + qt * kTileM;
+    const int q_row = q_tile0 + row;
+    const int kv_len = p.kv_len;
+    const float scale_log2 = p.scale_log2, bias_log2 = p.diag_bias_log2;
+    const bool use_bias = bias_log2 != 0.f;
+    const unsigned long long scale2 = pack_f2(scale_log2, scale_log2);
+    uint64_t* my_s = bar_s + qt * 2;
+    uint64_t* my_p = bar_p + qt * 2;
+    uint64_t* my_o = bar_o + qt * 2;
+    uint64_t* my_c = bar_c + qt * 2;
+    float m_run = -INFINITY, l_run = 0.f;
+    // the exponential pipe token: named barrier 2 admits warpgroup 0, barrier 3 warpgroup 1; each hands over after its
+    // exponentials (bar.arrive on the other's barrier).  Warpgroup 1 gives the first token away.
+    if (qt == 1) asm volatile("bar.arrive 2, 256;" ::: "memory");
+
+    for (int i = 0; i < n_tiles; ++i) {
+      const int col0 = i * kTileN;
+      const bool special = (col0 + kTileN > kv_len) ||
+                           (use_bias && (q_tile0 + quarter * 32) < col0 + kTileN && (q_tile0 + quarter * 32 + 32) > col0);
+      mbar_wait(my_s + (i & 1), (i >> 1) & 1, 2);
+      tc_fence_after();
+      const uint32_t s_addr = t_lane + ((i & 1) ? Cfg::S_OFF1 : Cfg::S_OFF0);
+      uint32_t r[64];
+      tmem_ld16(s_addr + 0, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+      tmem_ld16(s_addr + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+      tmem_ld16(s_addr + 32, *reinterpret_cast<uint32_t(*)[16]>(&r[32]));
+      tmem_ld16(s_addr + 48, *reinterpret_cast<uint32_t(*)[16]>(&r[48]));
+      tmem_ld_wait_dep64(r);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(my_c + (i & 1));          // S buffer (i & 1) may be overwritten by Q K_{i+2}^T
+      if (special) {
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+          const int col = col0 + j;
+          float v = __uint_as_float(r[j]);
+          if (use_bias && col == q_row) v += bias_log2 / scale_log2;
+          if (col >= kv_len) v = -INFINITY;
+          r[j] = __float_as_uint(v);
+        }
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 64; j += 8) {
+        mx0 = max3(mx0, __uint_as_float(r[j]), __uint_as_float(r[j + 1]));
+        mx1 = max3(mx1, __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+        mx2 = max3(mx2, __uint_as_float(r[j + 4]), __uint_as_float(r[j + 5]));
+        mx3 = max3(mx3, __uint_as_float(r[j + 6]), __uint_as_float(r[j + 7]));
+      }
+      const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
+      // P buffer (i & 1) was last read by P_{i-2} V_{i-2}
+      if (i >= 2) {
+        mbar_wait(my_o + (i & 1), ((i - 2) >> 1) & 1, 3);
+        tc_fence_after();
+      }
+      // ---- lazy running max: raise it (and rescale O in TMEM) only when it grows by more than 2^8
+      if (i == 0) {
+        m_run = m_tile;
+      } else {
+        const bool need = m_tile > m_run + 8.0f;
+        if (__any_sync(0xffffffffu, need)) {
+          mbar_wait(my_o + ((i - 1) & 1), ((i - 1) >> 1) & 1, 5);
+          tc_fence_after();
+          const float alpha = need ? fast_exp2(m_run - m_tile) : 1.0f;
+          if (need) {
+            l_run *= alpha;
+            m_run = m_tile;
+          }
+#pragma unroll
+          for (int c = 0; c < Cfg::DPAD / 8 + (Cfg::MMA_ROWSUM ? 1 : 0); ++c) {
+            uint32_t o[8];
+            const uint32_t addr = t_lane + Cfg::O_OFF + c * 8;              // (L_COL == DPAD when MMA_ROWSUM: next chunk)
+            tmem_ld8_sync(addr, o);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
+            tmem_st8(addr, o);
+          }
+        }
+      }
+      // ---- exponential phase, under the token
+      const float neg_m = (m_run == -INFINITY) ? 0.f : -m_run;
+      unsigned long long negm2 = pack_f2(neg_m, neg_m);
+      // (negm2 is an operand of every fma2 below: listing it as in/out keeps the whole phase behind the barrier)
+      if (qt == 0) asm volatile("bar.sync 2, 256;" : "+l"(negm2) : : "memory");
+      else asm volatile("bar.sync 3, 256;" : "+l"(negm2) : : "memory");
+#pragma unroll
+      for (int j = 0; j < 64; j += 2) {
+        float t0, t1;
+        unpack_f2(fma2(pack_f2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), scale2, negm2), t0, t1);
+        r[j] = __float_as_uint(fast_exp2(t0));
+        r[j + 1] = __float_as_uint(fast_exp2(t1));
+      }
+      // (results listed as in/out: the hand-over cannot be scheduled above the exponentials that produce them)
+#define PP_DEPS "+r"(r[7]), "+r"(r[15]), "+r"(r[23]), "+r"(r[31]), "+r"(r[39]), "+r"(r[47]), "+r"(r[55]), "+r"(r[62]), "+r"(r[63])
+      if (qt == 0) asm volatile("bar.arrive 3, 256;" : PP_DEPS : : "memory");
+      else asm volatile("bar.arrive 2, 256;" : PP_DEPS : : "memory");
+#undef PP_DEPS
+      unsigned long long sum2[4] = {pack_f2(0.f, 0.f), pack_f2(0.f, 0.f), pack_f2(0.f, 0.f), pack_f2(0.f, 0.f)};
+      if (!Cfg::MMA_ROWSUM) {
+#pragma unroll
+        for (int j = 0; j < 64; j += 2)
+          sum2[(j >> 1) & 3] = add2(sum2[(j >> 1) & 3], pack_f2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])));
+      }
+      uint32_t pk[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) pk[j] = pack_half2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+      const uint32_t p_addr = t_lane + ((i & 1) ? Cfg::P_OFF1 : Cfg::P_OFF0);
+      tmem_st16(p_addr, *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
+      tmem_st16(p_addr + 16, *reinterpret_cast<uint32_t(*)[16]>(&pk[16]));
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(my_p + (i & 1));
+      float sa, sb;
+      unpack_f2(add2(add2(sum2[0], sum2[1]), add2(sum2[2], sum2[3])), sa, sb);
+      l_run += sa + sb;
+    }
+    // drain: the other warpgroup's last hand-over has no taker; absorb it so that no barrier is left half full
+    if (qt == 0) asm volatile("bar.sync 2, 256;" ::: "memory");
+
+    // ---- epilogue: O / l -> fp16 head slice of this row
+    mbar_wait(my_o + ((n_tiles - 1) & 1), ((n_tiles - 1) >> 1) & 1, 4);
+    tc_fence_after();
+    if (Cfg::MMA_ROWSUM) {
+      uint32_t lcol[8];
+      tmem_ld8_sync(t_lane + Cfg::O_OFF + Cfg::L_COL, lcol);
+      l_run = __uint_as_float(lcol[0]);
+    }
+    const float inv = 1.f / l_run;
+    __half* dst = p.out + (static_cast<size_t>(b) * p.q_len + q_row) * (static_cast<size_t>(p.heads) * D) +
+                  static_cast<size_t>(head) * D;
+#pragma unroll
+    for (int c = 0; c < D / 8; ++c) {
+      uint32_t o[8];
+      tmem_ld8_sync(t_lane + Cfg::O_OFF + c * 8, o);
+      if (q_row < p.q_len) {
+        uint4 pkt;
+        pkt.x = pack_half2(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
+        pkt.y = pack_half2(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
+        pkt.z = pack_half2(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
+        pkt.w = pack_half2(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
+        reinterpret_cast<uint4*>(dst)[c] = pkt;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc<Cfg::TMEM_COLS>(tmem);
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 
@@ -1320,13 +1644,15 @@ static int make_head_tile_map(CUtensorMap* map, const void* base, int head_dim, 
 
 // Tuning knobs (fresco_internal.h: option(); environment variable of the same name read once, fresco_set_option()
 // overrides): which kernel, and how many of the exponentials go to the FMA pipe.  Defaults = measured best on B200.
-//   FRESCO_ATTN_WIDE    1 = wide kernel (two threads per row), 0 = pipelined kernel
+//   FRESCO_ATTN_PP      1 = ping-pong kernel (head_dim <= 64)
+//   FRESCO_ATTN_WIDE    2 | 4 = wide kernel with that many threads per row, 0 = pipelined kernel
 //   FRESCO_ATTN_NARROW  3 | 4 = narrow kernel with that many CTAs per SM (head_dim 40 only; 0 = off)
-//   FRESCO_ATTN_PIPE    3 | 4: software-pipelining depth of the wide kernel's softmax loop
+//   FRESCO_ATTN_PIPE    2 | 3 | 4: software-pipelining depth of the wide kernel's softmax loop
 //   FRESCO_ATTN_POLY    0 | 4 | 8: every n-th pair of exponentials on the FMA pipe (8: pipelined kernel only)
 //   FRESCO_ATTN_ROWSUM  pipelined kernel, head_dim 40: row sums from the tensor core
 constexpr int kWideDefault = 0;
-constexpr int kPipeDefault = 4;
+constexpr int kPipeDefault = 2;
+constexpr int kPPDefault = 0;
 constexpr int kNarrowDefault = 0;
 constexpr int kPolyDefault = 0;
 constexpr int kRowsumDefault = 1;
@@ -1380,6 +1706,22 @@ static int launch_wide(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
 }
 
 template <int D>
+static int launch_pp(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, dim3 grid,
+                     cudaStream_t stream) {
+  using Cfg = PPCfg<D>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(fresco_attn_pp_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(attn pp)");
+    attr_set = true;
+  }
+  grid.x = (grid.x + 1) / 2;                           // two query tiles per CTA
+  fresco_attn_pp_kernel<D><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tq, tk, tv, p);
+  return check_launch("fresco_attn_pp_kernel");
+}
+
+template <int D>
 static int launch_attn(const void* q, const void* k, const void* v, void* out, int batch_q, int q_len, int kv_len,
                        int heads, int q_per_kv, long long kv_row_stride, long long kv_batch_stride, float softmax_scale,
                        float diag_bias, cudaStream_t stream) {
@@ -1405,21 +1747,27 @@ static int launch_attn(const void* q, const void* k, const void* v, void* out, i
     if (narrow == 3) return launch_narrow<D, 3>(tq, tk, tv, p, grid, stream);
     if (narrow == 4) return launch_narrow<D, 4>(tq, tk, tv, p, grid, stream);
   }
+  // FRESCO_ATTN_PP = 1: ping-pong kernel (two query tiles per CTA, alternating exponential phases; head_dim <= 64)
+  if constexpr (D <= 64) {
+    if (option(OPT_ATTN_PP, kPPDefault) == 1) return launch_pp<D>(tq, tk, tv, p, grid, stream);
+  }
   // FRESCO_ATTN_WIDE = 2 | 4: that many threads per query row (4: head_dim <= 80, one CTA per SM)
   // FRESCO_ATTN_PIPE = 3 | 4: software-pipelining depth of the softmax loop (see the kernel)
   const int wide = option(OPT_ATTN_WIDE, kWideDefault);
   const int pipe = option(OPT_ATTN_PIPE, kPipeDefault);
   if (wide == 4) {
     if constexpr (D <= 80) {
-      if (poly == 4) return launch_wide<D, 4, 4, 4>(tq, tk, tv, p, grid, stream);
+      if (poly == 4) return launch_wide<D, 4, 4, 2>(tq, tk, tv, p, grid, stream);
       if (pipe == 3) return launch_wide<D, 4, 0, 3>(tq, tk, tv, p, grid, stream);
-      return launch_wide<D, 4, 0, 4>(tq, tk, tv, p, grid, stream);
+      if (pipe == 4) return launch_wide<D, 4, 0, 4>(tq, tk, tv, p, grid, stream);
+      return launch_wide<D, 4, 0, 2>(tq, tk, tv, p, grid, stream);
     }
   }
   if (wide >= 1) {
-    if (poly == 4) return launch_wide<D, 2, 4, 4>(tq, tk, tv, p, grid, stream);
+    if (poly == 4) return launch_wide<D, 2, 4, 2>(tq, tk, tv, p, grid, stream);
     if (pipe == 3) return launch_wide<D, 2, 0, 3>(tq, tk, tv, p, grid, stream);
-    return launch_wide<D, 2, 0, 4>(tq, tk, tv, p, grid, stream);
+    if (pipe == 4) return launch_wide<D, 2, 0, 4>(tq, tk, tv, p, grid, stream);
+    return launch_wide<D, 2, 0, 2>(tq, tk, tv, p, grid, stream);
   }
   if constexpr (AttnCfg<D, true>::MMA_ROWSUM) {
     if (option(OPT_ATTN_ROWSUM, kRowsumDefault)) {

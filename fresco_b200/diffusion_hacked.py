@@ -82,8 +82,9 @@ class AttentionControl:
 
     def enable_cfattn(self, attn_mask=None):
         if attn_mask:
-            self.attn_mask = attn_mask
-            self._kv_index_cache = {}
+            if attn_mask is not self.attn_mask:          # same object again (next denoise step): keep the derived indices
+                self.attn_mask = attn_mask
+                self._kv_index_cache = {}
             self.use_cfattn = True
         elif self.attn_mask:
             self.use_cfattn = True
@@ -97,8 +98,9 @@ class AttentionControl:
 
     def enable_interattn(self, interattn_paras=None):
         if interattn_paras:
-            self.interattn_paras = interattn_paras
-            self._traj_cache = {}
+            if interattn_paras is not self.interattn_paras:
+                self.interattn_paras = interattn_paras
+                self._traj_cache = {}
             self.use_interattn = True
         elif self.interattn_paras:
             self.use_interattn = True

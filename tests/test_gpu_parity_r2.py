@@ -58,7 +58,8 @@ def sdpa_ref(q, k, v, heads, q_per_kv=1, scale=None, diag_bias=0.0):
     return (torch.softmax(s, -1) @ vh).transpose(1, 2).reshape(B, Lq, C)
 
 
-ATTN_OPTS = ("FRESCO_ATTN_WIDE", "FRESCO_ATTN_NARROW", "FRESCO_ATTN_POLY", "FRESCO_ATTN_ROWSUM")
+ATTN_OPTS = ("FRESCO_ATTN_WIDE", "FRESCO_ATTN_NARROW", "FRESCO_ATTN_POLY", "FRESCO_ATTN_ROWSUM", "FRESCO_ATTN_PIPE",
+             "FRESCO_ATTN_PP")
 
 
 @pytest.fixture
@@ -72,6 +73,9 @@ def attn_opts(fb):
 
 
 VARIANTS = [
+    dict(FRESCO_ATTN_PP=1),                                              # ping-pong kernel: head_dim 40 / 64
+    dict(FRESCO_ATTN_WIDE=2, FRESCO_ATTN_PIPE=3),
+    dict(FRESCO_ATTN_WIDE=4, FRESCO_ATTN_PIPE=4),
     dict(FRESCO_ATTN_WIDE=2, FRESCO_ATTN_POLY=0),
     dict(FRESCO_ATTN_WIDE=2, FRESCO_ATTN_POLY=4),
     dict(FRESCO_ATTN_WIDE=4, FRESCO_ATTN_POLY=0),                        # four threads per row: head_dim 64 / 80
@@ -89,6 +93,8 @@ def test_attention_variants_all_head_dims(fb, attn_opts, variant, d):
     half of the wide kernel fully masked (20, 33, 77), the diagonal bias + k-scale of spatial-guided attention."""
     if variant.get("FRESCO_ATTN_NARROW") and d != 40:
         pytest.skip("narrow kernel: head_dim 40 only")
+    if variant.get("FRESCO_ATTN_PP") and d > 64:
+        pytest.skip("ping-pong kernel: head_dim <= 64 only")
     if variant.get("FRESCO_ATTN_WIDE") == 4 and d > 80:
         pytest.skip("four threads per row: head_dim <= 80 only")
     attn_opts(**variant)

@@ -1,11 +1,9 @@
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=index,name --format=csv > gpurun_out/r02_c5_smi.txt
-timeout 600 python -m pytest tests/test_gpu_parity_r2.py -q -k "nccl" 2>&1 | tail -30 > gpurun_out/r02_c5_nccl_test.txt
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 15 --warmup 3 > gpurun_out/r02_c5_bench_g2.json 2> gpurun_out/r02_c5_bench_g2.err
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 15 --warmup 3 --graphs off > gpurun_out/r02_c5_bench_g2_eager.json 2> gpurun_out/r02_c5_bench_g2_eager.err
-tail -4 gpurun_out/r02_c5_nccl_test.txt; tail -5 gpurun_out/r02_c5_bench_g2.err; python - <<'PY'
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 15 --warmup 3 > gpurun_out/r02_c6_bench_g2.json 2> gpurun_out/r02_c6_bench_g2.err
+grep -n "Error\|error" gpurun_out/r02_c6_bench_g2.err | grep -v "torch/distributed" | head -5
+python - <<'PY'
 import json
-for f in ("gpurun_out/r02_c5_bench_g2.json", "gpurun_out/r02_c5_bench_g2_eager.json"):
+for f in ("gpurun_out/r02_c6_bench_g2.json",):
     try:
         d = json.loads(open(f).read().strip().splitlines()[-1])
     except Exception as e:
