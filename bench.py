@@ -667,7 +667,8 @@ def main():
         kd = kernels[dom_tag]
         attn_ms = sum(v["total_ms"] for t, v in kernels.items() if t.startswith("attn_"))
         ours_ms = sum(v["total_ms"] for v in kernels.values())
-        roof = {"kernel": "fresco_attn_wide_kernel<40> (cross-frame, L=%d, Lk=%d, B=%d, 8 heads)" % (L_b, wl.kv_len[L_b], n_q),
+        roof = {"kernel": "%s (cross-frame, L=%d, Lk=%d, B=%d, 8 heads)" % (_lib.lib().fresco_attn_variant(40).decode(), L_b,
+                                                                                wl.kv_len[L_b], n_q),
                 "bound": "tensor", "achieved": kd["achieved"], "peak": peaks["tflops"], "unit": "TFLOP/s",
                 "frac": kd["frac"], "traffic": load_traffic(), "peak_source": peaks["source"],
                 "algorithmic_flops_per_launch": kd["work"], "avg_launch_ms": kd["ms"], "launches_timed": kd["launches"],
@@ -704,11 +705,16 @@ def main():
             except Exception as e:  # the baseline is a reported extra; never hide the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                         "sample": "failed: %r" % (e,)}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
+        # Leave without tearing NCCL down: destroying a process group whose collectives live in captured CUDA graphs
+        # hung for the full timeout on the 2-GPU box (profiles/README.md); everything is printed and flushed by now.
         import torch.distributed as dist
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

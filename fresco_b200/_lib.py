@@ -21,6 +21,7 @@ _SIGNATURES = {
     "fresco_last_error": (c_char_p, []),
     "fresco_launch_count": (c_longlong, []),
     "fresco_set_option": (c_int, [c_char_p, c_int]),
+    "fresco_attn_variant": (c_char_p, [c_int]),
     "fresco_kv_compact": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "fresco_attn_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, _P]),
     "fresco_attn_fwd_kv_strided": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_longlong, c_longlong,

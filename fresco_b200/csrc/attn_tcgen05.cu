@@ -1284,7 +1284,7 @@ fresco_attn_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
 }
 
 // ---------------------------------------------------------------------------------------------
-// head_dim <= 64: the "ping-pong" kernel -- two query tiles per CTA, the exponential pipe handed back and forth
+// head_dim <= 80: the "ping-pong" kernel -- two query tiles per CTA, the exponential pipe handed back and forth
 // ---------------------------------------------------------------------------------------------
 // What the traces of the pipelined kernel say: a softmax warp spends ~620 clocks of a tile in its
 // exponential phase when it has the MUFU pipe to itself (512 of them are the 64 ex2) and ~500 in everything else; with
@@ -1302,16 +1302,21 @@ fresco_attn_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
 //   warps 10, 11     P V (+ row-sum) issuer of tile 0 / 1
 template <int D>
 struct PPCfg {
-  static_assert(D <= 64, "ping-pong kernel: one 64-wide atom per head");
+  static_assert(D <= 80, "ping-pong kernel: a query tile's S, P and O must fit 256 TMEM columns");
+  static constexpr int NATOM = (D + 63) / 64;
   static constexpr int KSTEPS = (D + 15) / 16;
   static constexpr int DPAD = KSTEPS * 16;
-  static constexpr int S_OFF0 = 0, S_OFF1 = 64, P_OFF0 = 128, P_OFF1 = 160, O_OFF = 192, TILE_COLS = 256, TMEM_COLS = 512;
-  static constexpr bool MMA_ROWSUM = DPAD + 16 <= 64;       // 16 spare O columns (head_dim <= 48): row sums from the tensor core
-  static constexpr int L_COL = 48;
+  static constexpr int N0 = DPAD < 64 ? DPAD : 64, N1 = DPAD - N0;
+  // head_dim <= 64: P double-buffered (S0 S1 P0 P1 O = 64 64 32 32 64); head_dim 80: one P buffer (64 64 32 | O 80 | 16)
+  static constexpr int PBUF = DPAD <= 64 ? 2 : 1;
+  static constexpr int S_OFF0 = 0, S_OFF1 = 64, P_OFF0 = 128, P_OFF1 = 160, O_OFF = 128 + 32 * PBUF, TILE_COLS = 256,
+                       TMEM_COLS = 512;
+  static constexpr bool MMA_ROWSUM = O_OFF + DPAD + 16 <= TILE_COLS;   // 16 spare columns behind O: row sums from the tensor core
+  static constexpr int L_COL = DPAD;                                    // relative to O_OFF
   static constexpr int ONES_BYTES = MMA_ROWSUM ? 2048 : 0;
-  static constexpr int STAGES = 8;
-  static constexpr int Q_BYTES = 2 * kQAtomBytes;
-  static constexpr int STAGE_BYTES = 2 * kKVAtomBytes;
+  static constexpr int STAGES = NATOM == 1 ? 8 : 4;
+  static constexpr int Q_BYTES = 2 * NATOM * kQAtomBytes;
+  static constexpr int STAGE_BYTES = 2 * NATOM * kKVAtomBytes;
   static constexpr int SMEM_BYTES = 1024 + Q_BYTES + STAGES * STAGE_BYTES + ONES_BYTES + 512;
   static constexpr int THREADS = 384;
 };
@@ -1381,15 +1386,22 @@ fresco_attn_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       mbar_expect_tx(bar_q, Cfg::Q_BYTES);
-      tma_load_4d(s_q, &tm_q, bar_q, 0, head, q0, b);
-      tma_load_4d(s_q + kQAtomBytes, &tm_q, bar_q, 0, head, q0 + kTileM, b);      // (rows past q_len: zero fill)
+#pragma unroll
+      for (int qt = 0; qt < 2; ++qt)                                       // (rows past q_len: zero fill)
+#pragma unroll
+        for (int a = 0; a < Cfg::NATOM; ++a)
+          tma_load_4d(s_q + (qt * Cfg::NATOM + a) * kQAtomBytes, &tm_q, bar_q, a * 64, head, q0 + qt * kTileM, b);
       for (int t = 0; t < n_tiles; ++t) {
         const int st = t % ST;
         if (t >= ST) mbar_wait_backoff(bar_kv_empty + st, ((t / ST) - 1) & 1, 32, 70);
         uint8_t* sk = s_kv + st * Cfg::STAGE_BYTES;
+        uint8_t* sv = sk + Cfg::NATOM * kKVAtomBytes;
         mbar_expect_tx(bar_kv_full + st, Cfg::STAGE_BYTES);
-        tma_load_4d(sk, &tm_k, bar_kv_full + st, 0, head, t * kTileN, b_kv);
-        tma_load_4d(sk + kKVAtomBytes, &tm_v, bar_kv_full + st, 0, head, t * kTileN, b_kv);
+#pragma unroll
+        for (int a = 0; a < Cfg::NATOM; ++a) {
+          tma_load_4d(sk + a * kKVAtomBytes, &tm_k, bar_kv_full + st, a * 64, head, t * kTileN, b_kv);
+          tma_load_4d(sv + a * kKVAtomBytes, &tm_v, bar_kv_full + st, a * 64, head, t * kTileN, b_kv);
+        }
       }
     }
   } else if (warp == 9) {
@@ -1408,9 +1420,12 @@ fresco_attn_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           tc_fence_after();
           const uint32_t d_tmem = tmem + qt * Cfg::TILE_COLS + ((t & 1) ? Cfg::S_OFF1 : Cfg::S_OFF0);
 #pragma unroll
-          for (int ks = 0; ks < Cfg::KSTEPS; ++ks)
-            umma_ss(d_tmem, make_smem_desc_sw128(q_addr + qt * kQAtomBytes + ks * 32, 16, 1024),
-                    make_smem_desc_sw128(k_addr + ks * 32, 16, 1024), idesc_qk, ks > 0);
+          for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
+            const uint32_t qoff = (qt * Cfg::NATOM + (ks >> 2)) * kQAtomBytes + (ks & 3) * 32;
+            const uint32_t koff = (ks >> 2) * kKVAtomBytes + (ks & 3) * 32;
+            umma_ss(d_tmem, make_smem_desc_sw128(q_addr + qoff, 16, 1024), make_smem_desc_sw128(k_addr + koff, 16, 1024),
+                    idesc_qk, ks > 0);
+          }
           umma_commit(bar_s + qt * 2 + (t & 1));
         }
         umma_commit(bar_kv_empty + st);                                    // K_t consumed by both tiles
@@ -1420,26 +1435,31 @@ fresco_attn_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     // ------------------------------------------------------------ P V issuer of query tile qt
     if (lane == 0) {
       const int qt = warp - 10;
-      constexpr uint32_t idesc_pv = make_idesc_f16(kTileM, Cfg::DPAD, 1);
+      constexpr uint32_t idesc_pv0 = make_idesc_f16(kTileM, Cfg::N0, 1);
+      constexpr uint32_t idesc_pv1 = make_idesc_f16(kTileM, Cfg::N1 > 0 ? Cfg::N1 : 16, 1);
       constexpr uint32_t idesc_ones = make_idesc_f16(kTileM, 16, 1);
       const uint32_t t_base = tmem + qt * Cfg::TILE_COLS;
       for (int t = 0; t < n_tiles; ++t) {
         const int st = t % ST;
-        mbar_wait_backoff(bar_p + qt * 2 + (t & 1), (t >> 1) & 1, 20, 74);   // P_t in TMEM
+        const int pb = t % Cfg::PBUF;
+        mbar_wait_backoff(bar_p + qt * 2 + pb, (t / Cfg::PBUF) & 1, 20, 74);   // P_t in TMEM
         mbar_wait(bar_kv_full + st, (t / ST) & 1, 75);                      // V_t landed long ago; observe it
         tc_fence_after();
-        const uint32_t v_addr = smem_u32(s_kv + st * Cfg::STAGE_BYTES + kKVAtomBytes);
+        const uint32_t v_addr = smem_u32(s_kv + st * Cfg::STAGE_BYTES + Cfg::NATOM * kKVAtomBytes);
 #pragma unroll
         for (int k2 = 0; k2 < kTileN / 16; ++k2) {
           const uint32_t acc = (k2 > 0 || t > 0) ? 1u : 0u;
-          const uint32_t p_tmem = t_base + ((t & 1) ? Cfg::P_OFF1 : Cfg::P_OFF0) + k2 * 8;
-          umma_ts(t_base + Cfg::O_OFF, p_tmem, make_smem_desc_sw128(v_addr + k2 * 2048, kKVAtomBytes, 1024), idesc_pv, acc);
+          const uint32_t p_tmem = t_base + (pb ? Cfg::P_OFF1 : Cfg::P_OFF0) + k2 * 8;
+          umma_ts(t_base + Cfg::O_OFF, p_tmem, make_smem_desc_sw128(v_addr + k2 * 2048, kKVAtomBytes, 1024), idesc_pv0, acc);
+          if (Cfg::N1 > 0)
+            umma_ts(t_base + Cfg::O_OFF + 64, p_tmem,
+                    make_smem_desc_sw128(v_addr + kKVAtomBytes + k2 * 2048, kKVAtomBytes, 1024), idesc_pv1, acc);
           if (Cfg::MMA_ROWSUM)
             umma_ts(t_base + Cfg::O_OFF + Cfg::L_COL, p_tmem, make_smem_desc_sw128(smem_u32(s_ones), 2048, 1024),
                     idesc_ones, acc);
         }
         umma_commit(bar_kv_empty + st);
-        umma_commit(bar_o + qt * 2 + (t & 1));
+        umma_commit(bar_o + qt * 2 + pb);
       }
     }
   } else {
@@ -1497,9 +1517,10 @@ fresco_attn_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         mx3 = max3(mx3, __uint_as_float(r[j + 6]), __uint_as_float(r[j + 7]));
       }
       const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
-      // P buffer (i & 1) was last read by P_{i-2} V_{i-2}
-      if (i >= 2) {
-        mbar_wait(my_o + (i & 1), ((i - 2) >> 1) & 1, 3);
+      // the P buffer was last read by P V of tile i - PBUF
+      const int pb = i % Cfg::PBUF;
+      if (i >= Cfg::PBUF) {
+        mbar_wait(my_o + pb, ((i - Cfg::PBUF) / Cfg::PBUF) & 1, 3);
         tc_fence_after();
       }
       // ---- lazy running max: raise it (and rescale O in TMEM) only when it grows by more than 2^8
@@ -1508,7 +1529,7 @@ fresco_attn_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       } else {
         const bool need = m_tile > m_run + 8.0f;
         if (__any_sync(0xffffffffu, need)) {
-          mbar_wait(my_o + ((i - 1) & 1), ((i - 1) >> 1) & 1, 5);
+          mbar_wait(my_o + ((i - 1) % Cfg::PBUF), ((i - 1) / Cfg::PBUF) & 1, 5);
           tc_fence_after();
           const float alpha = need ? fast_exp2(m_run - m_tile) : 1.0f;
           if (need) {
@@ -1553,13 +1574,13 @@ fresco_attn_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       uint32_t pk[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) pk[j] = pack_half2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
-      const uint32_t p_addr = t_lane + ((i & 1) ? Cfg::P_OFF1 : Cfg::P_OFF0);
+      const uint32_t p_addr = t_lane + (pb ? Cfg::P_OFF1 : Cfg::P_OFF0);
       tmem_st16(p_addr, *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
       tmem_st16(p_addr + 16, *reinterpret_cast<uint32_t(*)[16]>(&pk[16]));
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(my_p + (i & 1));
+      if (lane == 0) mbar_arrive(my_p + pb);
       float sa, sb;
       unpack_f2(add2(add2(sum2[0], sum2[1]), add2(sum2[2], sum2[3])), sa, sb);
       l_run += sa + sb;
@@ -1568,7 +1589,7 @@ fresco_attn_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     if (qt == 0) asm volatile("bar.sync 2, 256;" ::: "memory");
 
     // ---- epilogue: O / l -> fp16 head slice of this row
-    mbar_wait(my_o + ((n_tiles - 1) & 1), ((n_tiles - 1) >> 1) & 1, 4);
+    mbar_wait(my_o + ((n_tiles - 1) % Cfg::PBUF), ((n_tiles - 1) / Cfg::PBUF) & 1, 4);
     tc_fence_after();
     if (Cfg::MMA_ROWSUM) {
       uint32_t lcol[8];
@@ -1644,7 +1665,7 @@ static int make_head_tile_map(CUtensorMap* map, const void* base, int head_dim, 
 
 // Tuning knobs (fresco_internal.h: option(); environment variable of the same name read once, fresco_set_option()
 // overrides): which kernel, and how many of the exponentials go to the FMA pipe.  Defaults = measured best on B200.
-//   FRESCO_ATTN_PP      1 = ping-pong kernel (head_dim <= 64)
+//   FRESCO_ATTN_PP      1 = ping-pong kernel (head_dim <= 80)
 //   FRESCO_ATTN_WIDE    2 | 4 = wide kernel with that many threads per row, 0 = pipelined kernel
 //   FRESCO_ATTN_NARROW  3 | 4 = narrow kernel with that many CTAs per SM (head_dim 40 only; 0 = off)
 //   FRESCO_ATTN_PIPE    2 | 3 | 4: software-pipelining depth of the wide kernel's softmax loop
@@ -1747,8 +1768,8 @@ static int launch_attn(const void* q, const void* k, const void* v, void* out, i
     if (narrow == 3) return launch_narrow<D, 3>(tq, tk, tv, p, grid, stream);
     if (narrow == 4) return launch_narrow<D, 4>(tq, tk, tv, p, grid, stream);
   }
-  // FRESCO_ATTN_PP = 1: ping-pong kernel (two query tiles per CTA, alternating exponential phases; head_dim <= 64)
-  if constexpr (D <= 64) {
+  // FRESCO_ATTN_PP = 1: ping-pong kernel (two query tiles per CTA, alternating exponential phases; head_dim <= 80)
+  if constexpr (D <= 80) {
     if (option(OPT_ATTN_PP, kPPDefault) == 1) return launch_pp<D>(tq, tk, tv, p, grid, stream);
   }
   // FRESCO_ATTN_WIDE = 2 | 4: that many threads per query row (4: head_dim <= 80, one CTA per SM)
@@ -1790,6 +1811,28 @@ extern "C" int fresco_debug_attn_trace(long long* host_out) {
   return cudaMemcpyFromSymbol(host_out, g_attn_trace, sizeof(long long) * 32 * 16) == cudaSuccess ? 0 : 1;
 }
 #endif
+
+// which kernel fresco_attn_fwd launches for a head dim under the current options (bench.py names it in its JSON line)
+extern "C" const char* fresco_attn_variant(int head_dim) {
+  static thread_local char buf[96];
+  const int poly = option(OPT_ATTN_POLY, kPolyDefault), wide = option(OPT_ATTN_WIDE, kWideDefault);
+  if (head_dim == 40) {
+    const int narrow = option(OPT_ATTN_NARROW, kNarrowDefault);
+    if (narrow == 3 || narrow == 4) {
+      snprintf(buf, sizeof(buf), "fresco_attn_narrow_kernel<40,%d>", narrow);
+      return buf;
+    }
+  }
+  if (head_dim <= 80 && option(OPT_ATTN_PP, kPPDefault) == 1) {
+    snprintf(buf, sizeof(buf), "fresco_attn_pp_kernel<%d> (two query tiles per CTA, ping-pong)", head_dim);
+  } else if (wide >= 1) {
+    snprintf(buf, sizeof(buf), "fresco_attn_wide_kernel<%d,%d,poly%d,pipe%d>", head_dim, (wide == 4 && head_dim <= 80) ? 4 : 2,
+             poly == 4 ? 4 : 0, option(OPT_ATTN_PIPE, kPipeDefault));
+  } else {
+    snprintf(buf, sizeof(buf), "fresco_attn_kernel<%d,poly%d> (pipelined)", head_dim, poly);
+  }
+  return buf;
+}
 
 extern "C" int fresco_attn_fwd(const void* q, const void* k, const void* v, void* out, int batch_q, int q_len,
                                int kv_len, int heads, int head_dim, int q_per_kv, float softmax_scale,

@@ -81,6 +81,8 @@ __global__ void rows_scatter_kernel(const uint4* __restrict__ src, const int32_t
 // computes ONE output row -- (trajectory, frame f, head h): N dot products of length d, a softmax over N held in
 // registers, N x d accumulation -- and the rows go back through shared memory with coalesced 16-byte stores to the
 // token the trajectory visits in frame f (fwd_map is a permutation, so every output row is written exactly once).
+// The q row of a thread goes straight to registers (k and v rows are shared by the N x heads threads of a trajectory,
+// q rows are not), which keeps shared memory at 2 N 2C bytes per trajectory and more CTAs on an SM.
 // Algorithmic traffic: 3 reads + 1 write of [2N, L, C] fp16 + 8 B of index and N B of mask per (trajectory, frame).
 template <int D, int NMAX>
 __global__ void __launch_bounds__(256)
@@ -99,8 +101,7 @@ temporal_attn_rows_kernel(const __half* __restrict__ q_raw, const __half* __rest
   const int b = blockIdx.x / blocks_per_chunk;
   const int p0 = (blockIdx.x % blocks_per_chunk) * tpb;
   const int n_traj = min(tpb, tokens - p0);
-  uint4* sq = smem_rows;                                       // [tpb][N][row_vecs]   (reused for the output rows)
-  uint4* sk = sq + tpb * traj_vecs;
+  uint4* sk = smem_rows;                                       // [tpb][N][row_vecs]   (reused for the output rows)
   uint4* sv = sk + tpb * traj_vecs;
   int* spos = reinterpret_cast<int*>(sv + tpb * traj_vecs);    // [tpb][N] token visited in frame f
 
@@ -109,28 +110,36 @@ temporal_attn_rows_kernel(const __half* __restrict__ q_raw, const __half* __rest
     spos[tr * N + f] = (int)fwd_map[(long long)f * tokens + p0 + tr];
   }
   __syncthreads();
-  // ---- gather: consecutive threads read consecutive 16-byte pieces of a 2C-byte token row
+  // ---- this thread's output row (trajectory tr, frame f, head h): its q row goes straight to registers ...
+  const int rows = n_traj * N * heads;                         // == blockDim.x rounded down (one row per thread)
+  const int r = threadIdx.x;
+  const bool active = r < rows;
+  const int tr = active ? r / (N * heads) : 0, fh = active ? r % (N * heads) : 0;
+  const int f = fh / heads, h = fh % heads;
+  uint4 qraw[VPR];
+  if (active) {
+    const uint4* qrow = reinterpret_cast<const uint4*>(q_raw) +
+                        (((long long)b * N + f) * tokens + spos[tr * N + f]) * in_row_vecs + h * VPR;
+#pragma unroll
+    for (int c = 0; c < VPR; ++c) qraw[c] = __ldg(qrow + c);
+  }
+  // ---- ... while the k and v rows of the CTA's trajectories are gathered cooperatively: consecutive threads read
+  //      consecutive 16-byte pieces of a token row, all loads in flight before anything is used
   const int total_vecs = n_traj * traj_vecs;
   for (int i = threadIdx.x; i < total_vecs; i += blockDim.x) {
-    const int tr = i / traj_vecs, rem = i % traj_vecs;
-    const int f = rem / row_vecs, part = rem % row_vecs;
-    const long long src = (((long long)b * N + f) * tokens + spos[tr * N + f]) * in_row_vecs + part;
-    sq[i] = __ldg(reinterpret_cast<const uint4*>(q_raw) + src);
+    const int t2 = i / traj_vecs, rem = i % traj_vecs;
+    const int f2 = rem / row_vecs, part = rem % row_vecs;
+    const long long src = (((long long)b * N + f2) * tokens + spos[t2 * N + f2]) * in_row_vecs + part;
     sk[i] = __ldg(reinterpret_cast<const uint4*>(k_raw) + src);
     sv[i] = __ldg(reinterpret_cast<const uint4*>(v_src) + src);
   }
   __syncthreads();
-  // ---- one output row per thread: (trajectory tr, frame f, head h)
-  const int rows = n_traj * N * heads;
-  for (int r = threadIdx.x; r < rows; r += blockDim.x) {       // (one trip when blockDim == tpb * N * heads)
-    const int tr = r / (N * heads), fh = r % (N * heads);
-    const int f = fh / heads, h = fh % heads;
-    const uint4* qrow = sq + tr * traj_vecs + f * row_vecs + h * VPR;
+  uint4 orow[VPR];
+  if (active) {
     float2 qv[D / 2];
 #pragma unroll
     for (int c = 0; c < VPR; ++c) {
-      const uint4 x = qrow[c];
-      const __half2* xh = reinterpret_cast<const __half2*>(&x);
+      const __half2* xh = reinterpret_cast<const __half2*>(&qraw[c]);
 #pragma unroll
       for (int u = 0; u < 4; ++u) qv[c * 4 + u] = __half22float2(xh[u]);
     }
@@ -186,25 +195,27 @@ temporal_attn_rows_kernel(const __half* __restrict__ q_raw, const __half* __rest
         }
       }
     }
-    // q row (tr, f, h) is read by this thread only: reuse it as the output staging
-    uint4* orow = sq + tr * traj_vecs + f * row_vecs + h * VPR;
 #pragma unroll
     for (int c = 0; c < VPR; ++c) {
-      uint4 o;
-      o.x = pack_half2(acc[c * 4 + 0].x, acc[c * 4 + 0].y);
-      o.y = pack_half2(acc[c * 4 + 1].x, acc[c * 4 + 1].y);
-      o.z = pack_half2(acc[c * 4 + 2].x, acc[c * 4 + 2].y);
-      o.w = pack_half2(acc[c * 4 + 3].x, acc[c * 4 + 3].y);
-      orow[c] = o;
+      orow[c].x = pack_half2(acc[c * 4 + 0].x, acc[c * 4 + 0].y);
+      orow[c].y = pack_half2(acc[c * 4 + 1].x, acc[c * 4 + 1].y);
+      orow[c].z = pack_half2(acc[c * 4 + 2].x, acc[c * 4 + 2].y);
+      orow[c].w = pack_half2(acc[c * 4 + 3].x, acc[c * 4 + 3].y);
     }
   }
+  __syncthreads();                                             // every k row has been read: stage the output rows there
+  if (active) {
+    uint4* dst = sk + tr * traj_vecs + f * row_vecs + h * VPR;
+#pragma unroll
+    for (int c = 0; c < VPR; ++c) dst[c] = orow[c];
+  }
   __syncthreads();
-  // ---- scatter back to the tokens the trajectories visit
+  // ---- scatter back to the tokens the trajectories visit (coalesced 16-byte stores)
   for (int i = threadIdx.x; i < total_vecs; i += blockDim.x) {
-    const int tr = i / traj_vecs, rem = i % traj_vecs;
-    const int f = rem / row_vecs, part = rem % row_vecs;
-    const long long dst = (((long long)b * N + f) * tokens + spos[tr * N + f]) * (C / 8) + part;
-    reinterpret_cast<uint4*>(out)[dst] = sq[i];
+    const int t2 = i / traj_vecs, rem = i % traj_vecs;
+    const int f2 = rem / row_vecs, part = rem % row_vecs;
+    const long long dst = (((long long)b * N + f2) * tokens + spos[t2 * N + f2]) * (C / 8) + part;
+    reinterpret_cast<uint4*>(out)[dst] = sk[i];
   }
 }
 
@@ -1434,17 +1445,16 @@ template <int D, int NMAX>
 static int launch_temporal_rows(const void* q_raw, const void* k_raw, const void* v_src, void* out, const int64_t* fwd_map,
                                 const uint8_t* traj_mask, int chunks, int frames, int tokens, int heads, float scale,
                                 int in_row_stride, cudaStream_t s) {
-  // trajectories per CTA: one thread per output row, up to 256 threads; shared memory 3 * N * 2C bytes per trajectory
+  // trajectories per CTA: exactly one thread per output row (trajectory, frame, head), up to 256 threads; shared memory
+  // 2 * N * 2C bytes per trajectory (k and v rows; q rows go straight to registers)
   const int rows_per_traj = frames * heads;
+  if (rows_per_traj > 256) return FRESCO_ERR_UNSUPPORTED;
   int tpb = 256 / rows_per_traj;
-  if (tpb < 1) tpb = 1;
-  const size_t per_traj = (size_t)3 * frames * heads * D * sizeof(__half) + (size_t)frames * sizeof(int);
-  while (tpb > 1 && tpb * per_traj > 64 * 1024) --tpb;
+  const size_t per_traj = (size_t)2 * frames * heads * D * sizeof(__half) + (size_t)frames * sizeof(int);
+  while (tpb > 1 && tpb * per_traj > 48 * 1024) --tpb;
   const size_t smem = tpb * per_traj;
   if (smem > 200 * 1024) return FRESCO_ERR_UNSUPPORTED;
-  int threads = tpb * rows_per_traj;
-  threads = (threads + 31) / 32 * 32;
-  if (threads > 256) threads = 256;
+  int threads = (tpb * rows_per_traj + 31) / 32 * 32;
   static size_t attr_smem = 0;
   if (smem > 48 * 1024 && smem > attr_smem) {
     cudaError_t e = cudaFuncSetAttribute(temporal_attn_rows_kernel<D, NMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -39,6 +39,8 @@ long long fresco_launch_count(void);
  * FRESCO_ATTN_ROWSUM, FRESCO_ATTN_ABLATE, FRESCO_TEMPORAL_V, FRESCO_GRAM_V, FRESCO_ATTN_PIPE, FRESCO_ATTN_PP); the environment is read once, this overrides it;
  * value < 0 restores the built-in default. */
 int fresco_set_option(const char* name, int value);
+/* name of the kernel fresco_attn_fwd launches for a head dim under the current options (thread-local string) */
+const char* fresco_attn_variant(int head_dim);
 
 /* ---- A2: cross-frame K/V selection --------------------------------------------------------
  * replaces src/diffusion_hacked.py:234-247 (`key[:, attn_mask]` + `repeat(...)`).

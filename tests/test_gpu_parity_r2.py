@@ -93,8 +93,8 @@ def test_attention_variants_all_head_dims(fb, attn_opts, variant, d):
     half of the wide kernel fully masked (20, 33, 77), the diagonal bias + k-scale of spatial-guided attention."""
     if variant.get("FRESCO_ATTN_NARROW") and d != 40:
         pytest.skip("narrow kernel: head_dim 40 only")
-    if variant.get("FRESCO_ATTN_PP") and d > 64:
-        pytest.skip("ping-pong kernel: head_dim <= 64 only")
+    if variant.get("FRESCO_ATTN_PP") and d > 80:
+        pytest.skip("ping-pong kernel: head_dim <= 80 only")
     if variant.get("FRESCO_ATTN_WIDE") == 4 and d > 80:
         pytest.skip("four threads per row: head_dim <= 80 only")
     attn_opts(**variant)

@@ -55,7 +55,7 @@ def main():
             B, L, Lk, H, d, qpk = shp
             if int(kv.get("FRESCO_ATTN_NARROW", 0)) and d != 40:
                 continue
-            if int(kv.get("FRESCO_ATTN_PP", 0)) and d > 64:
+            if int(kv.get("FRESCO_ATTN_PP", 0)) and d > 80:
                 continue
             ms = timeit(lambda: ops.attn_fwd(q, k, v, H, qpk, out=out))
             row["d%d_L%d_Lk%d" % (d, L, Lk)] = [round(ms, 4), round(4.0 * B * L * Lk * H * d / ms / 1e9, 1)]
