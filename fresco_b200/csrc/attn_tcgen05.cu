@@ -32,8 +32,9 @@
 // tile is 192 tensor-core clocks but 512 MUFU clocks, and a warp cannot overlap its own MUFU.EX2 (8 clk) with its
 // half-rate max / fma2 / add2 / pack instructions (2 clk each): the bare arithmetic of a tile costs 854 clk with one
 // softmax warp per sub-partition, 671 with two (this kernel; 820 measured with TMEM traffic and barriers) and 562
-// with four.  The "narrow" kernel further down trades the pipelining for four CTAs per SM; it lands at the same
-// speed and is kept as a selectable variant.
+// with four.  Variants that were built, measured slower and removed again (numbers in DESIGN.md section 3.1): four
+// CTAs per SM without pipelining, prefetching the next tile's scores, and two query tiles per CTA taking turns on the
+// MUFU pipe.  The "wide" kernel further down (several threads per query row) wins at head_dim 64 / 80.
 #include "common.cuh"
 #include "fresco_internal.h"
 
@@ -548,277 +549,6 @@ fresco_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 }
 
 // ---------------------------------------------------------------------------------------------
-// head_dim <= 64: the "narrow" kernel
-// ---------------------------------------------------------------------------------------------
-// At head_dim 40 a 128x64 tile is 192 tensor-core clocks but 512 MUFU clocks (8192 ex2 at 16/clk/SM): the kernel is
-// bound by the ex2 pipe, and a softmax warp runs a serial chain per tile (wait S, TMEM load, row max, 64 ex2, pack,
-// TMEM store, arrive) in which it keeps that pipe busy only about a third of the time.  The pipelined kernel above has
-// two softmax warps per SM sub-partition and measured 64 % ex2-pipe utilisation.  This kernel goes for occupancy
-// instead of per-CTA pipelining: every CTA is as small as possible so that FOUR fit on an SM (four softmax warps per
-// sub-partition keep the ex2 pipe fed while the others sit in their non-ex2 phases or wait for an MMA round trip).
-//
-//   TMEM  128 columns per CTA: S [0,64) fp32, O [64,128) fp32.  P (fp16, 32 columns) overwrites the upper half of S
-//         once those scores are in registers: keys 32..63 -> columns [32,48), keys 0..31 -> columns [48,64).
-//   regs  a thread never holds more than 32 scores: the row is read twice from TMEM (max pass, exp pass; the second
-//         half stays in registers across the two), which keeps the kernel under 100 registers.
-//   smem  Q 16 KB + a 2-stage K/V ring of 16 KB stages.
-//   warps 0-3 softmax, warp 4 (one thread) TMA producer + both MMAs, strictly serial per tile:
-//         S_t = Q K_t^T -> softmax -> O += P_t V_t ; S_{t+1} ...   (tcgen05.mma executes in issue order, so S_{t+1}
-//         may be issued right behind P_t V_t although it overwrites the columns P_t is read from; the commit that
-//         publishes S_{t+1} also covers P_t V_t, hence O is stable whenever a softmax thread holds S_{t+1}.)
-template <int D, int CTAS>
-struct NarrowCfg {
-  static_assert(D <= 64, "narrow kernel: one 64-wide atom per head");
-  static constexpr int KSTEPS = (D + 15) / 16;
-  static constexpr int DPAD = KSTEPS * 16;
-  static constexpr int O_OFF = 64, P_HI = 32, P_LO = 48, TMEM_COLS = 128;
-  static constexpr int STAGES = CTAS >= 4 ? 2 : 3;
-  static constexpr int Q_BYTES = kQAtomBytes;
-  static constexpr int STAGE_BYTES = 2 * kKVAtomBytes;
-  static constexpr int SMEM_BYTES = 1024 + Q_BYTES + STAGES * STAGE_BYTES + 128;
-  static constexpr int THREADS = 160;
-};
-
-__device__ __forceinline__ void tmem_ld_wait_dep32(uint32_t (&r)[32]) {
-#define FR8(b) "+r"(r[b]), "+r"(r[b + 1]), "+r"(r[b + 2]), "+r"(r[b + 3]), "+r"(r[b + 4]), "+r"(r[b + 5]), "+r"(r[b + 6]), "+r"(r[b + 7])
-  asm volatile("tcgen05.wait::ld.sync.aligned;" : FR8(0), FR8(8), FR8(16), FR8(24) : : "memory");
-#undef FR8
-}
-
-template <int D, int CTAS>
-__global__ void __launch_bounds__(NarrowCfg<D, CTAS>::THREADS, CTAS)
-fresco_attn_narrow_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
-                          const __grid_constant__ CUtensorMap tm_v, const AttnParams p) {
-  using Cfg = NarrowCfg<D, CTAS>;
-  constexpr int ST = Cfg::STAGES;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* s_q = smem;
-  uint8_t* s_kv = smem + Cfg::Q_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_kv + ST * Cfg::STAGE_BYTES);
-  uint64_t* bar_q = bars + 0;
-  uint64_t* bar_kv_full = bars + 1;            // [ST]
-  uint64_t* bar_kv_empty = bars + 1 + ST;      // [ST]
-  uint64_t* bar_s = bars + 1 + 2 * ST;         // S_t ready (and every MMA issued before it retired); phase t & 1
-  uint64_t* bar_p = bar_s + 1;                 // P_t written, one elected arrival per softmax warp; phase t & 1
-  uint64_t* bar_o = bar_s + 2;                 // last P V retired
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s + 3);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * kTileM;
-  const int head = blockIdx.y;
-  const int b = blockIdx.z;
-  const int b_kv = b / p.q_per_kv;
-  const int n_tiles = (p.kv_len + kTileN - 1) / kTileN;
-
-  if (warp == 4) {
-    if (lane == 0) {
-      mbar_init(bar_q, 1);
-      for (int s = 0; s < ST; ++s) {
-        mbar_init(bar_kv_full + s, 1);
-        mbar_init(bar_kv_empty + s, 1);
-      }
-      mbar_init(bar_s, 1);
-      mbar_init(bar_p, 4);
-      mbar_init(bar_o, 1);
-      fence_barrier_init();
-      tma_prefetch_desc(&tm_q);
-      tma_prefetch_desc(&tm_k);
-      tma_prefetch_desc(&tm_v);
-    }
-    __syncwarp();
-    tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-
-  if (warp == 4) {
-    // ------------------------------------------------------------ TMA producer + MMA issuer (one thread)
-    if (lane == 0) {
-      constexpr uint32_t idesc_qk = make_idesc_f16(kTileM, kTileN, 0);
-      constexpr uint32_t idesc_pv = make_idesc_f16(kTileM, Cfg::DPAD, 1);
-      const uint32_t q_addr = smem_u32(s_q);
-      int next_load = 0;
-      auto refill = [&]() {                     // issue every K/V tile load whose ring stage is free; never blocks
-        while (next_load < n_tiles) {
-          const int st = next_load % ST;
-          if (next_load >= ST && !mbar_test_wait(bar_kv_empty + st, ((next_load / ST) - 1) & 1)) break;
-          uint8_t* sk = s_kv + st * Cfg::STAGE_BYTES;
-          mbar_expect_tx(bar_kv_full + st, Cfg::STAGE_BYTES);
-          tma_load_4d(sk, &tm_k, bar_kv_full + st, 0, head, next_load * kTileN, b_kv);
-          tma_load_4d(sk + kKVAtomBytes, &tm_v, bar_kv_full + st, 0, head, next_load * kTileN, b_kv);
-          ++next_load;
-        }
-      };
-      auto wait_poll = [&](uint64_t* bar, uint32_t parity, int tag) {   // wait, keeping the K/V ring moving
-        uint32_t polls = 0;
-        while (!mbar_try_wait(bar, parity)) {
-          refill();
-          if (++polls > FRESCO_WATCHDOG_POLLS) mbar_timeout(bar, parity, tag);
-        }
-      };
-      auto issue_qk = [&](int t) {
-        const int st = t % ST;
-        wait_poll(bar_kv_full + st, (t / ST) & 1, 20);
-        tc_fence_after();
-        const uint32_t k_addr = smem_u32(s_kv + st * Cfg::STAGE_BYTES);
-#pragma unroll
-        for (int ks = 0; ks < Cfg::KSTEPS; ++ks)
-          umma_ss(tmem, make_smem_desc_sw128(q_addr + ks * 32, 16, 1024), make_smem_desc_sw128(k_addr + ks * 32, 16, 1024),
-                  idesc_qk, ks > 0);
-        umma_commit(bar_s);
-      };
-      mbar_expect_tx(bar_q, Cfg::Q_BYTES);
-      tma_load_4d(s_q, &tm_q, bar_q, 0, head, q0, b);
-      refill();
-      mbar_wait(bar_q, 0, 21);
-      issue_qk(0);
-      for (int t = 0; t < n_tiles; ++t) {
-        const int st = t % ST;
-        wait_poll(bar_p, t & 1, 22);                                   // P_t in TMEM
-        tc_fence_after();
-        const uint32_t v_addr = smem_u32(s_kv + st * Cfg::STAGE_BYTES + kKVAtomBytes);
-#pragma unroll
-        for (int k2 = 0; k2 < kTileN / 16; ++k2) {
-          const uint32_t p_col = k2 < 2 ? Cfg::P_LO + k2 * 8 : Cfg::P_HI + (k2 - 2) * 8;
-          umma_ts(tmem + Cfg::O_OFF, tmem + p_col, make_smem_desc_sw128(v_addr + k2 * 2048, kKVAtomBytes, 1024), idesc_pv,
-                  (k2 > 0 || t > 0) ? 1u : 0u);
-        }
-        umma_commit(bar_kv_empty + st);                                // K_t and V_t consumed
-        if (t + 1 < n_tiles) issue_qk(t + 1);
-        else umma_commit(bar_o);
-      }
-    }
-  } else {
-    // ------------------------------------------------------------ softmax warps
-    const int row = warp * 32 + lane;                      // query row inside the tile == TMEM lane
-    const uint32_t t_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
-    const int q_row = q0 + row;
-    const int kv_len = p.kv_len;
-    const float scale_log2 = p.scale_log2, bias_log2 = p.diag_bias_log2;
-    const bool use_bias = bias_log2 != 0.f;
-    const unsigned long long scale2 = pack_f2(scale_log2, scale_log2);
-    float m_run = -INFINITY, l_run = 0.f;
-
-    for (int i = 0; i < n_tiles; ++i) {
-      const int col0 = i * kTileN;
-      // warp-uniform: does this tile need masking (ragged tail) or the diagonal bias?
-      const bool special = (col0 + kTileN > kv_len) ||
-                           (use_bias && (q0 + warp * 32) < col0 + kTileN && (q0 + warp * 32 + 32) > col0);
-      auto fixup = [&](uint32_t (&r)[32], int cbase) {     // rare path: fold mask / bias into the raw scores
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int col = cbase + j;
-          float v = __uint_as_float(r[j]);
-          if (use_bias && col == q_row) v += bias_log2 / scale_log2;
-          if (col >= kv_len) v = -INFINITY;
-          r[j] = __float_as_uint(v);
-        }
-      };
-      auto row_max = [&](const uint32_t (&r)[32]) {
-        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          mx0 = max3(mx0, __uint_as_float(r[j]), __uint_as_float(r[j + 1]));
-          mx1 = max3(mx1, __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-          mx2 = max3(mx2, __uint_as_float(r[j + 4]), __uint_as_float(r[j + 5]));
-          mx3 = max3(mx3, __uint_as_float(r[j + 6]), __uint_as_float(r[j + 7]));
-        }
-        return fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-      };
-      mbar_wait(bar_s, i & 1, 2);
-      tc_fence_after();
-      uint32_t r[32];
-      // ---- pass 1: row max over keys 0..31, then 32..63 (the second half stays in registers)
-      tmem_ld32(t_lane, r);
-      tmem_ld_wait_dep32(r);
-      if (special) fixup(r, col0);
-      const float mx_lo = row_max(r);
-      tmem_ld32(t_lane + 32, r);
-      tmem_ld_wait_dep32(r);
-      if (special) fixup(r, col0 + 32);
-      const float m_tile = fmaxf(mx_lo, row_max(r)) * scale_log2;
-      // ---- lazy running max: raise it (and rescale O in TMEM) only when it grows by more than 2^8.  O is stable here:
-      //      the commit that published S_i was issued after P_{i-1} V_{i-1}.
-      if (i == 0) {
-        m_run = m_tile;
-      } else {
-        const bool need = m_tile > m_run + 8.0f;
-        if (__any_sync(0xffffffffu, need)) {
-          const float alpha = need ? fast_exp2(m_run - m_tile) : 1.0f;
-          if (need) {
-            l_run *= alpha;
-            m_run = m_tile;
-          }
-#pragma unroll
-          for (int c = 0; c < D / 8; ++c) {
-            uint32_t o[8];
-            tmem_ld8_sync(t_lane + Cfg::O_OFF + c * 8, o);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
-            tmem_st8(t_lane + Cfg::O_OFF + c * 8, o);
-          }
-        }
-      }
-      // ---- pass 2: p = exp2(s*scale - m), packed to fp16 over the upper half of S
-      const unsigned long long negm2 = pack_f2(-m_run, -m_run);
-      unsigned long long sum2[4] = {pack_f2(0.f, 0.f), pack_f2(0.f, 0.f), pack_f2(0.f, 0.f), pack_f2(0.f, 0.f)};
-      auto exp_half = [&](uint32_t (&r)[32], uint32_t p_col) {
-        uint32_t pk[16];
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          float t0, t1;
-          unpack_f2(fma2(pack_f2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), scale2, negm2), t0, t1);
-          const float e0 = fast_exp2(t0), e1 = fast_exp2(t1);
-          sum2[(j >> 1) & 3] = add2(sum2[(j >> 1) & 3], pack_f2(e0, e1));
-          pk[j >> 1] = pack_half2(e0, e1);
-        }
-        tmem_st16(t_lane + p_col, pk);
-      };
-      exp_half(r, Cfg::P_HI);                   // keys 32..63 -> columns [32,48) (their scores are in registers)
-      tmem_ld32(t_lane, r);                     // keys 0..31 again (columns [0,32) are untouched so far)
-      tmem_ld_wait_dep32(r);
-      if (special) fixup(r, col0);
-      exp_half(r, Cfg::P_LO);                   // -> columns [48,64)
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_p);
-      float sa, sb;
-      unpack_f2(add2(add2(sum2[0], sum2[1]), add2(sum2[2], sum2[3])), sa, sb);
-      l_run += sa + sb;
-    }
-
-    // ---- epilogue: O / l -> fp16 head slice of this row
-    mbar_wait(bar_o, 0, 4);
-    tc_fence_after();
-    const float inv = 1.f / l_run;
-    __half* dst = p.out + (static_cast<size_t>(b) * p.q_len + q_row) * (static_cast<size_t>(p.heads) * D) +
-                  static_cast<size_t>(head) * D;
-#pragma unroll
-    for (int c = 0; c < D / 8; ++c) {
-      uint32_t o[8];
-      tmem_ld8_sync(t_lane + Cfg::O_OFF + c * 8, o);
-      if (q_row < p.q_len) {
-        uint4 pkt;
-        pkt.x = pack_half2(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
-        pkt.y = pack_half2(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
-        pkt.z = pack_half2(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
-        pkt.w = pack_half2(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
-        reinterpret_cast<uint4*>(dst)[c] = pkt;
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 4) tmem_dealloc<Cfg::TMEM_COLS>(tmem);
-}
-
-// ---------------------------------------------------------------------------------------------
 // the "wide" kernel: SPLIT threads per query row (split-KV inside the CTA), every head_dim
 // ---------------------------------------------------------------------------------------------
 // Written from two measurements (attention).  (1) A softmax warp runs a serial chain per tile (wait S, TMEM
@@ -863,39 +593,24 @@ struct WideCfg {
   static constexpr int STAGE_BYTES = 2 * NATOM * kKVAtomBytes;
   static constexpr int SMEM_BYTES = 1024 + Q_BYTES + STAGES * STAGE_BYTES + SPLIT * 128 * 8 + 512;
   static constexpr int SOFTMAX_WARPS = 4 * SPLIT;
-  // With two CTAs per SM every warp costs the softmax threads registers (they hold two tiles' worth of scores, see the
-  // prefetch below): the TMA producer then shares a thread with the score-MMA issuer and refills the ring without
-  // ever blocking.  With one CTA per SM it has a warp of its own.
-  static constexpr bool OWN_TMA_WARP = true;      // (measured: sharing the thread costs the 2-CTA variant 9 %)
+  // (the TMA producer has a warp of its own: sharing a thread with the score-MMA issuer was measured 9 % slower)
   static constexpr int QK_WARP = SOFTMAX_WARPS, PV_WARP0 = SOFTMAX_WARPS + 1, TMA_WARP = SOFTMAX_WARPS + 1 + NPV;
-  static constexpr int THREADS = (SOFTMAX_WARPS + 1 + NPV + (OWN_TMA_WARP ? 1 : 0)) * 32;
+  static constexpr int THREADS = (SOFTMAX_WARPS + 2 + NPV) * 32;
 };
 
+// tcgen05.wait::ld that names the loaded registers as in/outputs, so the compiler cannot move their uses above it
+__device__ __forceinline__ void tmem_ld_wait_dep32(uint32_t (&r)[32]) {
+#define FR8(b) "+r"(r[b]), "+r"(r[b + 1]), "+r"(r[b + 2]), "+r"(r[b + 3]), "+r"(r[b + 4]), "+r"(r[b + 5]), "+r"(r[b + 6]), "+r"(r[b + 7])
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : FR8(0), FR8(8), FR8(16), FR8(24) : : "memory");
+#undef FR8
+}
 __device__ __forceinline__ void tmem_ld_wait_dep16(uint32_t (&r)[16]) {
 #define FR8(b) "+r"(r[b]), "+r"(r[b + 1]), "+r"(r[b + 2]), "+r"(r[b + 3]), "+r"(r[b + 4]), "+r"(r[b + 5]), "+r"(r[b + 6]), "+r"(r[b + 7])
   asm volatile("tcgen05.wait::ld.sync.aligned;" : FR8(0), FR8(8) : : "memory");
 #undef FR8
 }
 
-template <int N>
-__device__ __forceinline__ void tmem_ld_keys(uint32_t taddr, uint32_t (&r)[N]) {
-  if constexpr (N == 32) {
-    tmem_ld32(taddr, r);
-    tmem_ld_wait_dep32(r);
-  } else {
-    static_assert(N == 16, "16 or 32 keys per thread");
-    tmem_ld16_sync(taddr, r);
-  }
-}
-template <int N>
-__device__ __forceinline__ void tmem_st_half(uint32_t taddr, const uint32_t (&r)[N]) {
-  if constexpr (N == 16) tmem_st16(taddr, r);
-  else tmem_st8(taddr, r);
-}
-
-// PIPE 2: plain loop.  PIPE 3: scores of tile i+1 prefetched while tile i is processed.  PIPE 4: additionally the row max of tile i+1 is taken
-// between the exponentials of tile i and the publication of P_i, so the TMEM store latency of P_i hides behind it.
-template <int D, int SPLIT, int POLY, int PIPE>
+template <int D, int SPLIT>
 __global__ void __launch_bounds__(WideCfg<D, SPLIT>::THREADS, WideCfg<D, SPLIT>::CTAS)
 fresco_attn_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                         const __grid_constant__ CUtensorMap tm_v, const AttnParams p) {
@@ -974,8 +689,8 @@ fresco_attn_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     for (int a = 0; a < Cfg::NATOM; ++a) tma_load_4d(s_q + a * kQAtomBytes, &tm_q, bar_q, a * 64, head, q0, b);
   };
 
-  if (Cfg::OWN_TMA_WARP && warp == Cfg::TMA_WARP) {
-    // ------------------------------------------------------------ TMA producer (own warp: one CTA per SM)
+  if (warp == Cfg::TMA_WARP) {
+    // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       load_q();
       for (int t = 0; t < n_tiles; ++t) {
@@ -984,34 +699,15 @@ fresco_attn_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       }
     }
   } else if (warp == Cfg::QK_WARP) {
-    // ------------------------------------------------------------ score-MMA issuer (+ TMA producer when it has no warp)
+    // ------------------------------------------------------------ score-MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc_qk = make_idesc_f16(kTileM, kTileN, 0);
       const uint32_t q_addr = smem_u32(s_q);
-      int next_load = 0;
-      auto refill = [&]() {                      // issue every K/V tile load whose ring stage is free; never blocks
-        if (Cfg::OWN_TMA_WARP) return;
-        while (next_load < n_tiles) {
-          if (next_load >= ST && !mbar_test_wait(bar_kv_empty + next_load % ST, ((next_load / ST) - 1) & 1)) break;
-          load_kv_tile(next_load);
-          ++next_load;
-        }
-      };
-      auto wait_poll = [&](uint64_t* bar, uint32_t parity, int tag) {   // wait, keeping the K/V ring moving
-        uint32_t polls = 0;
-        while (!mbar_try_wait(bar, parity)) {
-          refill();
-          if (++polls > FRESCO_WATCHDOG_POLLS) mbar_timeout(bar, parity, tag);
-        }
-      };
-      if (!Cfg::OWN_TMA_WARP) load_q();
-      refill();
       mbar_wait(bar_q, 0, 41);
       for (int t = 0; t < n_tiles; ++t) {
         const int st = t % ST;
-        refill();
-        if (t >= 2) wait_poll(bar_c + (t & 1), ((t - 2) >> 1) & 1, 42);     // S buffer t & 1 is in registers
-        wait_poll(bar_kv_full + st, (t / ST) & 1, 43);
+        if (t >= 2) mbar_wait(bar_c + (t & 1), ((t - 2) >> 1) & 1, 42);       // S buffer t & 1 is in registers
+        mbar_wait(bar_kv_full + st, (t / ST) & 1, 43);
         tc_fence_after();
         const uint32_t k_addr = smem_u32(s_kv + st * Cfg::STAGE_BYTES);
         const uint32_t d_tmem = tmem + ((t & 1) ? Cfg::S_OFF1 : Cfg::S_OFF0);
@@ -1025,7 +721,6 @@ fresco_attn_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         umma_commit(bar_s + (t & 1));
         umma_commit(bar_kv_empty + st);                                    // K_t consumed
       }
-      while (!Cfg::OWN_TMA_WARP && next_load < n_tiles) refill();          // (only if n_tiles <= 2: nothing left to wait on)
     }
   } else if (warp >= Cfg::PV_WARP0 && warp < Cfg::PV_WARP0 + Cfg::NPV) {
     // ------------------------------------------------------------ P V issuer j: accumulators [j*PPV, (j+1)*PPV)
@@ -1074,19 +769,17 @@ fresco_attn_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     const unsigned long long scale2 = pack_f2(scale_log2, scale_log2);
     float m_run = -INFINITY, l_run = 0.f;
 
-    // The scores of tile i+1 are requested from TMEM (tcgen05.ld, asynchronous) BEFORE tile i is worked on and waited for
-    // after it, so the S-ready barrier, the TMEM read latency and the "S consumed" arrival of a tile hide behind the
-    // exponentials of the previous one instead of opening every iteration of a serial chain.
-    auto issue_load = [&](uint32_t (&r)[KEYS], int i) {
+    auto load_scores = [&](uint32_t (&r)[KEYS], int i) {   // this part's scores of tile i: TMEM -> registers
       mbar_wait(bar_s + (i & 1), (i >> 1) & 1, 2);
       tc_fence_after();
       const uint32_t addr = t_lane + ((i & 1) ? Cfg::S_OFF1 : Cfg::S_OFF0) + KEYS * part;
-      if constexpr (KEYS == 32) tmem_ld32(addr, r);
-      else tmem_ld16(addr, r);
-    };
-    auto finish_load = [&](uint32_t (&r)[KEYS], int i) {
-      if constexpr (KEYS == 32) tmem_ld_wait_dep32(r);
-      else tmem_ld_wait_dep16(r);
+      if constexpr (KEYS == 32) {
+        tmem_ld32(addr, r);
+        tmem_ld_wait_dep32(r);
+      } else {
+        tmem_ld16(addr, r);
+        tmem_ld_wait_dep16(r);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_c + (i & 1));         // S buffer i & 1 may be overwritten by Q K_{i+2}^T
@@ -1161,12 +854,8 @@ fresco_attn_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
           const int j = g * 16 + jj;
           float t0, t1, e0, e1;
           unpack_f2(fma2(pack_f2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), scale2, negm2), t0, t1);
-          if (POLY > 0 && ((j >> 1) % (POLY > 0 ? POLY : 1)) == (POLY - 1)) {
-            exp2_poly_x2(t0, t1, e0, e1);                  // FMA-pipe exponential for every POLY-th pair
-          } else {
-            e0 = fast_exp2(t0);
-            e1 = fast_exp2(t1);
-          }
+          e0 = fast_exp2(t0);
+          e1 = fast_exp2(t1);
           sum2[(j >> 1) & 1] = add2(sum2[(j >> 1) & 1], pack_f2(e0, e1));
           pk[jj >> 1] = pack_half2(e0, e1);
         }
@@ -1183,53 +872,13 @@ fresco_attn_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       if (lane == 0) mbar_arrive(bar_p + (i % PB) * Cfg::NPV + jpv);
     };
 
-    uint32_t ra[KEYS], rb[KEYS];
-    issue_load(ra, 0);
-    finish_load(ra, 0);
-    if constexpr (PIPE == 2) {                       // no prefetch: every tile is loaded when its turn comes
-      for (int i = 0; i < n_tiles; ++i) {
-        if (i > 0) {
-          issue_load(ra, i);
-          finish_load(ra, i);
-        }
-        tile_exp(ra, i, tile_max(ra, i));
-        publish(i);
-      }
-    } else if constexpr (PIPE == 4) {
-      float ma = tile_max(ra, 0), mb = 0.f;
-      for (int i = 0; i < n_tiles; i += 2) {
-        const bool has1 = i + 1 < n_tiles, has2 = i + 2 < n_tiles;
-        if (has1) issue_load(rb, i + 1);
-        tile_exp(ra, i, ma);
-        if (has1) {
-          finish_load(rb, i + 1);
-          mb = tile_max(rb, i + 1);
-        }
-        publish(i);
-        if (has1) {
-          if (has2) issue_load(ra, i + 2);
-          tile_exp(rb, i + 1, mb);
-          if (has2) {
-            finish_load(ra, i + 2);
-            ma = tile_max(ra, i + 2);
-          }
-          publish(i + 1);
-        }
-      }
-    } else {
-      for (int i = 0; i < n_tiles; i += 2) {
-        const bool has1 = i + 1 < n_tiles, has2 = i + 2 < n_tiles;
-        if (has1) issue_load(rb, i + 1);
-        tile_exp(ra, i, tile_max(ra, i));
-        publish(i);
-        if (has1) {
-          finish_load(rb, i + 1);
-          if (has2) issue_load(ra, i + 2);
-          tile_exp(rb, i + 1, tile_max(rb, i + 1));
-          publish(i + 1);
-          if (has2) finish_load(ra, i + 2);
-        }
-      }
+    // (prefetching tile i+1's scores into a second register set before working on tile i was measured 5-20 % slower:
+    //  the extra registers cost more than the hidden TMEM latency buys)
+    uint32_t r[KEYS];
+    for (int i = 0; i < n_tiles; ++i) {
+      load_scores(r, i);
+      tile_exp(r, i, tile_max(r, i));
+      publish(i);
     }
 
     // ---- epilogue: merge the SPLIT parts of every row, O / l -> fp16 head slice
@@ -1284,342 +933,6 @@ fresco_attn_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
 }
 
 // ---------------------------------------------------------------------------------------------
-// head_dim <= 80: the "ping-pong" kernel -- two query tiles per CTA, the exponential pipe handed back and forth
-// ---------------------------------------------------------------------------------------------
-// What the traces of the pipelined kernel say: a softmax warp spends ~620 clocks of a tile in its
-// exponential phase when it has the MUFU pipe to itself (512 of them are the 64 ex2) and ~500 in everything else; with
-// two independent CTAs per SM the exponential phases of the two warps that share a sub-partition collide at random,
-// each stretches to ~900 and the tile costs ~800 clocks per SM, although the pipe is busy only 64 % of the time.
-// Here the two warps of a sub-partition belong to the SAME CTA -- one CTA per SM owns TWO 128-row query tiles, warps
-// 0-3 tile 0, warps 4-7 tile 1 -- and a pair of named barriers makes the exponential phases strictly alternate: while
-// warpgroup 0 runs its 64 ex2, warpgroup 1 waits for scores, reads TMEM, takes row maxima, stores P and arrives; then
-// they swap.  The pipe never sees two exponential phases at once and is never left idle while one is pending.  Side
-// effects of the pairing: every K/V tile is loaded once for 256 query rows (half the TMA / L2 traffic), and the TMEM of
-// the SM is one 512-column allocation (tile t at columns 256 t: S0, S1, P0, P1, O as in the pipelined kernel).
-//   warps 0-3 / 4-7  softmax of query tile 0 / 1 (one row per thread)
-//   warp 8           TMA producer: both Q tiles once, K/V tiles through the ring
-//   warp 9           score-MMA issuer for both query tiles
-//   warps 10, 11     P V (+ row-sum) issuer of tile 0 / 1
-template <int D>
-struct PPCfg {
-  static_assert(D <= 80, "ping-pong kernel: a query tile's S, P and O must fit 256 TMEM columns");
-  static constexpr int NATOM = (D + 63) / 64;
-  static constexpr int KSTEPS = (D + 15) / 16;
-  static constexpr int DPAD = KSTEPS * 16;
-  static constexpr int N0 = DPAD < 64 ? DPAD : 64, N1 = DPAD - N0;
-  // head_dim <= 64: P double-buffered (S0 S1 P0 P1 O = 64 64 32 32 64); head_dim 80: one P buffer (64 64 32 | O 80 | 16)
-  static constexpr int PBUF = DPAD <= 64 ? 2 : 1;
-  static constexpr int S_OFF0 = 0, S_OFF1 = 64, P_OFF0 = 128, P_OFF1 = 160, O_OFF = 128 + 32 * PBUF, TILE_COLS = 256,
-                       TMEM_COLS = 512;
-  static constexpr bool MMA_ROWSUM = O_OFF + DPAD + 16 <= TILE_COLS;   // 16 spare columns behind O: row sums from the tensor core
-  static constexpr int L_COL = DPAD;                                    // relative to O_OFF
-  static constexpr int ONES_BYTES = MMA_ROWSUM ? 2048 : 0;
-  static constexpr int STAGES = NATOM == 1 ? 8 : 4;
-  static constexpr int Q_BYTES = 2 * NATOM * kQAtomBytes;
-  static constexpr int STAGE_BYTES = 2 * NATOM * kKVAtomBytes;
-  static constexpr int SMEM_BYTES = 1024 + Q_BYTES + STAGES * STAGE_BYTES + ONES_BYTES + 512;
-  static constexpr int THREADS = 384;
-};
-
-template <int D>
-__global__ void __launch_bounds__(PPCfg<D>::THREADS, 1)
-fresco_attn_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
-                      const __grid_constant__ CUtensorMap tm_v, const AttnParams p) {
-  using Cfg = PPCfg<D>;
-  constexpr int ST = Cfg::STAGES;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* s_q = smem;                                                   // [2][128 rows x 128 B]
-  uint8_t* s_kv = smem + Cfg::Q_BYTES;
-  uint8_t* s_ones = s_kv + ST * Cfg::STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ones + Cfg::ONES_BYTES);
-  uint64_t* bar_q = bars + 0;
-  uint64_t* bar_kv_full = bars + 1;            // [ST]
-  uint64_t* bar_kv_empty = bars + 1 + ST;      // [ST]  1 (score issuer) + 2 (P V issuers)
-  uint64_t* bar_s = bars + 1 + 2 * ST;         // [2 tiles][2 buffers]
-  uint64_t* bar_p = bar_s + 4;                 // [2][2] P_i written (one elected arrival per softmax warp)
-  uint64_t* bar_o = bar_s + 8;                 // [2][2] P_i V_i retired
-  uint64_t* bar_c = bar_s + 12;                // [2][2] S_i copied to registers
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s + 16);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 2 * kTileM;      // first query row of the PAIR of tiles
-  const int head = blockIdx.y;
-  const int b = blockIdx.z;
-  const int b_kv = b / p.q_per_kv;
-  const int n_tiles = (p.kv_len + kTileN - 1) / kTileN;
-
-  if (warp == 9 && lane == 0) {
-    mbar_init(bar_q, 1);
-    for (int s = 0; s < ST; ++s) {
-      mbar_init(bar_kv_full + s, 1);
-      mbar_init(bar_kv_empty + s, 3);
-    }
-    for (int i = 0; i < 4; ++i) {
-      mbar_init(bar_s + i, 1);
-      mbar_init(bar_p + i, 4);
-      mbar_init(bar_o + i, 1);
-      mbar_init(bar_c + i, 4);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 8) {
-    if (lane == 0) {
-      tma_prefetch_desc(&tm_q);
-      tma_prefetch_desc(&tm_k);
-      tma_prefetch_desc(&tm_v);
-    }
-    __syncwarp();
-    tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
-  }
-  if (Cfg::MMA_ROWSUM) {
-    for (int i = threadIdx.x; i < Cfg::ONES_BYTES / 4; i += Cfg::THREADS) reinterpret_cast<uint32_t*>(s_ones)[i] = 0x3C003C00u;
-    fence_proxy_async_smem();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-
-  if (warp == 8) {
-    // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      mbar_expect_tx(bar_q, Cfg::Q_BYTES);
-#pragma unroll
-      for (int qt = 0; qt < 2; ++qt)                                       // (rows past q_len: zero fill)
-#pragma unroll
-        for (int a = 0; a < Cfg::NATOM; ++a)
-          tma_load_4d(s_q + (qt * Cfg::NATOM + a) * kQAtomBytes, &tm_q, bar_q, a * 64, head, q0 + qt * kTileM, b);
-      for (int t = 0; t < n_tiles; ++t) {
-        const int st = t % ST;
-        if (t >= ST) mbar_wait_backoff(bar_kv_empty + st, ((t / ST) - 1) & 1, 32, 70);
-        uint8_t* sk = s_kv + st * Cfg::STAGE_BYTES;
-        uint8_t* sv = sk + Cfg::NATOM * kKVAtomBytes;
-        mbar_expect_tx(bar_kv_full + st, Cfg::STAGE_BYTES);
-#pragma unroll
-        for (int a = 0; a < Cfg::NATOM; ++a) {
-          tma_load_4d(sk + a * kKVAtomBytes, &tm_k, bar_kv_full + st, a * 64, head, t * kTileN, b_kv);
-          tma_load_4d(sv + a * kKVAtomBytes, &tm_v, bar_kv_full + st, a * 64, head, t * kTileN, b_kv);
-        }
-      }
-    }
-  } else if (warp == 9) {
-    // ------------------------------------------------------------ score-MMA issuer: S_t of tile 0, then of tile 1
-    if (lane == 0) {
-      constexpr uint32_t idesc_qk = make_idesc_f16(kTileM, kTileN, 0);
-      const uint32_t q_addr = smem_u32(s_q);
-      mbar_wait(bar_q, 0, 71);
-      for (int t = 0; t < n_tiles; ++t) {
-        const int st = t % ST;
-        mbar_wait(bar_kv_full + st, (t / ST) & 1, 72);
-        const uint32_t k_addr = smem_u32(s_kv + st * Cfg::STAGE_BYTES);
-#pragma unroll
-        for (int qt = 0; qt < 2; ++qt) {
-          if (t >= 2) mbar_wait(bar_c + qt * 2 + (t & 1), ((t - 2) >> 1) & 1, 73);   // S buffer is in registers
-          tc_fence_after();
-          const uint32_t d_tmem = tmem + qt * Cfg::TILE_COLS + ((t & 1) ? Cfg::S_OFF1 : Cfg::S_OFF0);
-#pragma unroll
-          for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
-            const uint32_t qoff = (qt * Cfg::NATOM + (ks >> 2)) * kQAtomBytes + (ks & 3) * 32;
-            const uint32_t koff = (ks >> 2) * kKVAtomBytes + (ks & 3) * 32;
-            umma_ss(d_tmem, make_smem_desc_sw128(q_addr + qoff, 16, 1024), make_smem_desc_sw128(k_addr + koff, 16, 1024),
-                    idesc_qk, ks > 0);
-          }
-          umma_commit(bar_s + qt * 2 + (t & 1));
-        }
-        umma_commit(bar_kv_empty + st);                                    // K_t consumed by both tiles
-      }
-    }
-  } else if (warp >= 10) {
-    // ------------------------------------------------------------ P V issuer of query tile qt
-    if (lane == 0) {
-      const int qt = warp - 10;
-      constexpr uint32_t idesc_pv0 = make_idesc_f16(kTileM, Cfg::N0, 1);
-      constexpr uint32_t idesc_pv1 = make_idesc_f16(kTileM, Cfg::N1 > 0 ? Cfg::N1 : 16, 1);
-      constexpr uint32_t idesc_ones = make_idesc_f16(kTileM, 16, 1);
-      const uint32_t t_base = tmem + qt * Cfg::TILE_COLS;
-      for (int t = 0; t < n_tiles; ++t) {
-        const int st = t % ST;
-        const int pb = t % Cfg::PBUF;
-        mbar_wait_backoff(bar_p + qt * 2 + pb, (t / Cfg::PBUF) & 1, 20, 74);   // P_t in TMEM
-        mbar_wait(bar_kv_full + st, (t / ST) & 1, 75);                      // V_t landed long ago; observe it
-        tc_fence_after();
-        const uint32_t v_addr = smem_u32(s_kv + st * Cfg::STAGE_BYTES + Cfg::NATOM * kKVAtomBytes);
-#pragma unroll
-        for (int k2 = 0; k2 < kTileN / 16; ++k2) {
-          const uint32_t acc = (k2 > 0 || t > 0) ? 1u : 0u;
-          const uint32_t p_tmem = t_base + (pb ? Cfg::P_OFF1 : Cfg::P_OFF0) + k2 * 8;
-          umma_ts(t_base + Cfg::O_OFF, p_tmem, make_smem_desc_sw128(v_addr + k2 * 2048, kKVAtomBytes, 1024), idesc_pv0, acc);
-          if (Cfg::N1 > 0)
-            umma_ts(t_base + Cfg::O_OFF + 64, p_tmem,
-                    make_smem_desc_sw128(v_addr + kKVAtomBytes + k2 * 2048, kKVAtomBytes, 1024), idesc_pv1, acc);
-          if (Cfg::MMA_ROWSUM)
-            umma_ts(t_base + Cfg::O_OFF + Cfg::L_COL, p_tmem, make_smem_desc_sw128(smem_u32(s_ones), 2048, 1024),
-                    idesc_ones, acc);
-        }
-        umma_commit(bar_kv_empty + st);
-        umma_commit(bar_o + qt * 2 + pb);
-      }
-    }
-  } else {
-    // ------------------------------------------------------------ softmax warps: query tile qt, one row per thread
-    const int qt = warp >> 2, quarter = warp & 3;
-    const int row = quarter * 32 + lane;
-    const uint32_t t_lane = tmem + qt * Cfg::TILE_COLS + (static_cast<uint32_t>(quarter * 32) << 16);
-    const int q_tile0 = q0 + qt * kTileM;
-    const int q_row = q_tile0 + row;
-    const int kv_len = p.kv_len;
-    const float scale_log2 = p.scale_log2, bias_log2 = p.diag_bias_log2;
-    const bool use_bias = bias_log2 != 0.f;
-    const unsigned long long scale2 = pack_f2(scale_log2, scale_log2);
-    uint64_t* my_s = bar_s + qt * 2;
-    uint64_t* my_p = bar_p + qt * 2;
-    uint64_t* my_o = bar_o + qt * 2;
-    uint64_t* my_c = bar_c + qt * 2;
-    float m_run = -INFINITY, l_run = 0.f;
-    // the exponential pipe token: named barrier 2 admits warpgroup 0, barrier 3 warpgroup 1; each hands over after its
-    // exponentials (bar.arrive on the other's barrier).  Warpgroup 1 gives the first token away.
-    if (qt == 1) asm volatile("bar.arrive 2, 256;" ::: "memory");
-
-    for (int i = 0; i < n_tiles; ++i) {
-      const int col0 = i * kTileN;
-      const bool special = (col0 + kTileN > kv_len) ||
-                           (use_bias && (q_tile0 + quarter * 32) < col0 + kTileN && (q_tile0 + quarter * 32 + 32) > col0);
-      mbar_wait(my_s + (i & 1), (i >> 1) & 1, 2);
-      tc_fence_after();
-      const uint32_t s_addr = t_lane + ((i & 1) ? Cfg::S_OFF1 : Cfg::S_OFF0);
-      uint32_t r[64];
-      tmem_ld16(s_addr + 0, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
-      tmem_ld16(s_addr + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
-      tmem_ld16(s_addr + 32, *reinterpret_cast<uint32_t(*)[16]>(&r[32]));
-      tmem_ld16(s_addr + 48, *reinterpret_cast<uint32_t(*)[16]>(&r[48]));
-      tmem_ld_wait_dep64(r);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(my_c + (i & 1));          // S buffer (i & 1) may be overwritten by Q K_{i+2}^T
-      if (special) {
-#pragma unroll
-        for (int j = 0; j < 64; ++j) {
-          const int col = col0 + j;
-          float v = __uint_as_float(r[j]);
-          if (use_bias && col == q_row) v += bias_log2 / scale_log2;
-          if (col >= kv_len) v = -INFINITY;
-          r[j] = __float_as_uint(v);
-        }
-      }
-      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-      for (int j = 0; j < 64; j += 8) {
-        mx0 = max3(mx0, __uint_as_float(r[j]), __uint_as_float(r[j + 1]));
-        mx1 = max3(mx1, __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-        mx2 = max3(mx2, __uint_as_float(r[j + 4]), __uint_as_float(r[j + 5]));
-        mx3 = max3(mx3, __uint_as_float(r[j + 6]), __uint_as_float(r[j + 7]));
-      }
-      const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
-      // the P buffer was last read by P V of tile i - PBUF
-      const int pb = i % Cfg::PBUF;
-      if (i >= Cfg::PBUF) {
-        mbar_wait(my_o + pb, ((i - Cfg::PBUF) / Cfg::PBUF) & 1, 3);
-        tc_fence_after();
-      }
-      // ---- lazy running max: raise it (and rescale O in TMEM) only when it grows by more than 2^8
-      if (i == 0) {
-        m_run = m_tile;
-      } else {
-        const bool need = m_tile > m_run + 8.0f;
-        if (__any_sync(0xffffffffu, need)) {
-          mbar_wait(my_o + ((i - 1) % Cfg::PBUF), ((i - 1) / Cfg::PBUF) & 1, 5);
-          tc_fence_after();
-          const float alpha = need ? fast_exp2(m_run - m_tile) : 1.0f;
-          if (need) {
-            l_run *= alpha;
-            m_run = m_tile;
-          }
-#pragma unroll
-          for (int c = 0; c < Cfg::DPAD / 8 + (Cfg::MMA_ROWSUM ? 1 : 0); ++c) {
-            uint32_t o[8];
-            const uint32_t addr = t_lane + Cfg::O_OFF + c * 8;              // (L_COL == DPAD when MMA_ROWSUM: next chunk)
-            tmem_ld8_sync(addr, o);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
-            tmem_st8(addr, o);
-          }
-        }
-      }
-      // ---- exponential phase, under the token
-      const float neg_m = (m_run == -INFINITY) ? 0.f : -m_run;
-      unsigned long long negm2 = pack_f2(neg_m, neg_m);
-      // (negm2 is an operand of every fma2 below: listing it as in/out keeps the whole phase behind the barrier)
-      if (qt == 0) asm volatile("bar.sync 2, 256;" : "+l"(negm2) : : "memory");
-      else asm volatile("bar.sync 3, 256;" : "+l"(negm2) : : "memory");
-#pragma unroll
-      for (int j = 0; j < 64; j += 2) {
-        float t0, t1;
-        unpack_f2(fma2(pack_f2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), scale2, negm2), t0, t1);
-        r[j] = __float_as_uint(fast_exp2(t0));
-        r[j + 1] = __float_as_uint(fast_exp2(t1));
-      }
-      // (results listed as in/out: the hand-over cannot be scheduled above the exponentials that produce them)
-#define PP_DEPS "+r"(r[7]), "+r"(r[15]), "+r"(r[23]), "+r"(r[31]), "+r"(r[39]), "+r"(r[47]), "+r"(r[55]), "+r"(r[62]), "+r"(r[63])
-      if (qt == 0) asm volatile("bar.arrive 3, 256;" : PP_DEPS : : "memory");
-      else asm volatile("bar.arrive 2, 256;" : PP_DEPS : : "memory");
-#undef PP_DEPS
-      unsigned long long sum2[4] = {pack_f2(0.f, 0.f), pack_f2(0.f, 0.f), pack_f2(0.f, 0.f), pack_f2(0.f, 0.f)};
-      if (!Cfg::MMA_ROWSUM) {
-#pragma unroll
-        for (int j = 0; j < 64; j += 2)
-          sum2[(j >> 1) & 3] = add2(sum2[(j >> 1) & 3], pack_f2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])));
-      }
-      uint32_t pk[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) pk[j] = pack_half2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
-      const uint32_t p_addr = t_lane + (pb ? Cfg::P_OFF1 : Cfg::P_OFF0);
-      tmem_st16(p_addr, *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
-      tmem_st16(p_addr + 16, *reinterpret_cast<uint32_t(*)[16]>(&pk[16]));
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(my_p + pb);
-      float sa, sb;
-      unpack_f2(add2(add2(sum2[0], sum2[1]), add2(sum2[2], sum2[3])), sa, sb);
-      l_run += sa + sb;
-    }
-    // drain: the other warpgroup's last hand-over has no taker; absorb it so that no barrier is left half full
-    if (qt == 0) asm volatile("bar.sync 2, 256;" ::: "memory");
-
-    // ---- epilogue: O / l -> fp16 head slice of this row
-    mbar_wait(my_o + ((n_tiles - 1) % Cfg::PBUF), ((n_tiles - 1) / Cfg::PBUF) & 1, 4);
-    tc_fence_after();
-    if (Cfg::MMA_ROWSUM) {
-      uint32_t lcol[8];
-      tmem_ld8_sync(t_lane + Cfg::O_OFF + Cfg::L_COL, lcol);
-      l_run = __uint_as_float(lcol[0]);
-    }
-    const float inv = 1.f / l_run;
-    __half* dst = p.out + (static_cast<size_t>(b) * p.q_len + q_row) * (static_cast<size_t>(p.heads) * D) +
-                  static_cast<size_t>(head) * D;
-#pragma unroll
-    for (int c = 0; c < D / 8; ++c) {
-      uint32_t o[8];
-      tmem_ld8_sync(t_lane + Cfg::O_OFF + c * 8, o);
-      if (q_row < p.q_len) {
-        uint4 pkt;
-        pkt.x = pack_half2(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
-        pkt.y = pack_half2(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
-        pkt.z = pack_half2(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
-        pkt.w = pack_half2(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
-        reinterpret_cast<uint4*>(dst)[c] = pkt;
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 8) tmem_dealloc<Cfg::TMEM_COLS>(tmem);
-}
-
-// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 
@@ -1664,19 +977,15 @@ static int make_head_tile_map(CUtensorMap* map, const void* base, int head_dim, 
 }
 
 // Tuning knobs (fresco_internal.h: option(); environment variable of the same name read once, fresco_set_option()
-// overrides): which kernel, and how many of the exponentials go to the FMA pipe.  Defaults = measured best on B200.
-//   FRESCO_ATTN_PP      1 = ping-pong kernel (head_dim <= 80)
-//   FRESCO_ATTN_WIDE    2 | 4 = wide kernel with that many threads per row, 0 = pipelined kernel
-//   FRESCO_ATTN_NARROW  3 | 4 = narrow kernel with that many CTAs per SM (head_dim 40 only; 0 = off)
-//   FRESCO_ATTN_PIPE    2 | 3 | 4: software-pipelining depth of the wide kernel's softmax loop
-//   FRESCO_ATTN_POLY    0 | 4 | 8: every n-th pair of exponentials on the FMA pipe (8: pipelined kernel only)
+// overrides).  The defaults are the measured best on B200 per head_dim (profiles/README.md, attention sweep):
+//   FRESCO_ATTN_WIDE    -1 = per head_dim (below), 0 = pipelined kernel, 2 | 4 = wide kernel, that many threads per row
+//   FRESCO_ATTN_POLY    pipelined kernel: 0 | 4 | 8, every n-th pair of exponentials on the FMA pipe
 //   FRESCO_ATTN_ROWSUM  pipelined kernel, head_dim 40: row sums from the tensor core
-constexpr int kWideDefault = 0;
-constexpr int kPipeDefault = 2;
-constexpr int kPPDefault = 0;
-constexpr int kNarrowDefault = 0;
 constexpr int kPolyDefault = 0;
 constexpr int kRowsumDefault = 1;
+// threads per query row of the default kernel (0 = pipelined kernel): TF/s measured at L = 4096, 8 frames:
+//   d = 40: pipelined 446, wide2 436, wide4 353;  d = 80: pipelined 510, wide2 529, wide4 585;  d = 128: 510 / 508 / -
+constexpr int default_split(int head_dim) { return (head_dim == 64 || head_dim == 80) ? 4 : 0; }
 
 template <int D, int POLY, bool ROWSUM>
 static int launch_pipelined(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
@@ -1693,53 +1002,26 @@ static int launch_pipelined(const CUtensorMap& tq, const CUtensorMap& tk, const 
   return check_launch("fresco_attn_kernel");
 }
 
-template <int D, int CTAS>
-static int launch_narrow(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, dim3 grid,
-                         cudaStream_t stream) {
-  using Cfg = NarrowCfg<D, CTAS>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(fresco_attn_narrow_kernel<D, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::SMEM_BYTES);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(fresco_attn_narrow_kernel<D, CTAS>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                               cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(attn narrow)");
-    attr_set = true;
-  }
-  fresco_attn_narrow_kernel<D, CTAS><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tq, tk, tv, p);
-  return check_launch("fresco_attn_narrow_kernel");
-}
-
-template <int D, int SPLIT, int POLY, int PIPE>
+template <int D, int SPLIT>
 static int launch_wide(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, dim3 grid,
                        cudaStream_t stream) {
   using Cfg = WideCfg<D, SPLIT>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(fresco_attn_wide_kernel<D, SPLIT, POLY, PIPE>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(fresco_attn_wide_kernel<D, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(attn wide)");
     attr_set = true;
   }
-  fresco_attn_wide_kernel<D, SPLIT, POLY, PIPE><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tq, tk, tv, p);
+  fresco_attn_wide_kernel<D, SPLIT><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tq, tk, tv, p);
   return check_launch("fresco_attn_wide_kernel");
 }
 
-template <int D>
-static int launch_pp(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, dim3 grid,
-                     cudaStream_t stream) {
-  using Cfg = PPCfg<D>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(fresco_attn_pp_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(attn pp)");
-    attr_set = true;
-  }
-  grid.x = (grid.x + 1) / 2;                           // two query tiles per CTA
-  fresco_attn_pp_kernel<D><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tq, tk, tv, p);
-  return check_launch("fresco_attn_pp_kernel");
+static int wide_split(int head_dim) {       // threads per query row under the current options; 0 = pipelined kernel
+  int wide = option(OPT_ATTN_WIDE, -1);
+  if (wide < 0) wide = default_split(head_dim);
+  if (wide >= 4) return head_dim <= 80 ? 4 : 2;       // four accumulators of head_dim 128 do not fit TMEM
+  return wide >= 1 ? 2 : 0;
 }
 
 template <int D>
@@ -1763,33 +1045,11 @@ static int launch_attn(const void* q, const void* k, const void* v, void* out, i
   p.ablate = option(OPT_ATTN_ABLATE, 0);
   dim3 grid((q_len + kTileM - 1) / kTileM, heads, batch_q);
   const int poly = option(OPT_ATTN_POLY, kPolyDefault);
-  if constexpr (D == 40) {   // (the narrow kernel is written for any head_dim <= 64 but has only been validated at 40)
-    const int narrow = option(OPT_ATTN_NARROW, kNarrowDefault);
-    if (narrow == 3) return launch_narrow<D, 3>(tq, tk, tv, p, grid, stream);
-    if (narrow == 4) return launch_narrow<D, 4>(tq, tk, tv, p, grid, stream);
-  }
-  // FRESCO_ATTN_PP = 1: ping-pong kernel (two query tiles per CTA, alternating exponential phases; head_dim <= 80)
+  const int split = wide_split(D);
   if constexpr (D <= 80) {
-    if (option(OPT_ATTN_PP, kPPDefault) == 1) return launch_pp<D>(tq, tk, tv, p, grid, stream);
+    if (split == 4) return launch_wide<D, 4>(tq, tk, tv, p, grid, stream);
   }
-  // FRESCO_ATTN_WIDE = 2 | 4: that many threads per query row (4: head_dim <= 80, one CTA per SM)
-  // FRESCO_ATTN_PIPE = 3 | 4: software-pipelining depth of the softmax loop (see the kernel)
-  const int wide = option(OPT_ATTN_WIDE, kWideDefault);
-  const int pipe = option(OPT_ATTN_PIPE, kPipeDefault);
-  if (wide == 4) {
-    if constexpr (D <= 80) {
-      if (poly == 4) return launch_wide<D, 4, 4, 2>(tq, tk, tv, p, grid, stream);
-      if (pipe == 3) return launch_wide<D, 4, 0, 3>(tq, tk, tv, p, grid, stream);
-      if (pipe == 4) return launch_wide<D, 4, 0, 4>(tq, tk, tv, p, grid, stream);
-      return launch_wide<D, 4, 0, 2>(tq, tk, tv, p, grid, stream);
-    }
-  }
-  if (wide >= 1) {
-    if (poly == 4) return launch_wide<D, 2, 4, 2>(tq, tk, tv, p, grid, stream);
-    if (pipe == 3) return launch_wide<D, 2, 0, 3>(tq, tk, tv, p, grid, stream);
-    if (pipe == 4) return launch_wide<D, 2, 0, 4>(tq, tk, tv, p, grid, stream);
-    return launch_wide<D, 2, 0, 2>(tq, tk, tv, p, grid, stream);
-  }
+  if (split >= 2) return launch_wide<D, 2>(tq, tk, tv, p, grid, stream);
   if constexpr (AttnCfg<D, true>::MMA_ROWSUM) {
     if (option(OPT_ATTN_ROWSUM, kRowsumDefault)) {
       if (poly == 4) return launch_pipelined<D, 4, true>(tq, tk, tv, p, grid, stream);
@@ -1815,22 +1075,9 @@ extern "C" int fresco_debug_attn_trace(long long* host_out) {
 // which kernel fresco_attn_fwd launches for a head dim under the current options (bench.py names it in its JSON line)
 extern "C" const char* fresco_attn_variant(int head_dim) {
   static thread_local char buf[96];
-  const int poly = option(OPT_ATTN_POLY, kPolyDefault), wide = option(OPT_ATTN_WIDE, kWideDefault);
-  if (head_dim == 40) {
-    const int narrow = option(OPT_ATTN_NARROW, kNarrowDefault);
-    if (narrow == 3 || narrow == 4) {
-      snprintf(buf, sizeof(buf), "fresco_attn_narrow_kernel<40,%d>", narrow);
-      return buf;
-    }
-  }
-  if (head_dim <= 80 && option(OPT_ATTN_PP, kPPDefault) == 1) {
-    snprintf(buf, sizeof(buf), "fresco_attn_pp_kernel<%d> (two query tiles per CTA, ping-pong)", head_dim);
-  } else if (wide >= 1) {
-    snprintf(buf, sizeof(buf), "fresco_attn_wide_kernel<%d,%d,poly%d,pipe%d>", head_dim, (wide == 4 && head_dim <= 80) ? 4 : 2,
-             poly == 4 ? 4 : 0, option(OPT_ATTN_PIPE, kPipeDefault));
-  } else {
-    snprintf(buf, sizeof(buf), "fresco_attn_kernel<%d,poly%d> (pipelined)", head_dim, poly);
-  }
+  const int split = wide_split(head_dim);
+  if (split > 0) snprintf(buf, sizeof(buf), "fresco_attn_wide_kernel<%d,%d>", head_dim, split);
+  else snprintf(buf, sizeof(buf), "fresco_attn_kernel<%d,poly%d> (pipelined)", head_dim, option(OPT_ATTN_POLY, kPolyDefault));
   return buf;
 }
 

@@ -35,8 +35,8 @@ int fresco_abi_version(void);
 const char* fresco_last_error(void);
 /* number of kernels launched by this library in this process (for bench.py's gpu_launches) */
 long long fresco_launch_count(void);
-/* tuning option by the name of its environment variable (FRESCO_ATTN_WIDE, FRESCO_ATTN_NARROW, FRESCO_ATTN_POLY,
- * FRESCO_ATTN_ROWSUM, FRESCO_ATTN_ABLATE, FRESCO_TEMPORAL_V, FRESCO_GRAM_V, FRESCO_ATTN_PIPE, FRESCO_ATTN_PP); the environment is read once, this overrides it;
+/* tuning option by the name of its environment variable (FRESCO_ATTN_WIDE, FRESCO_ATTN_POLY, FRESCO_ATTN_ROWSUM,
+ * FRESCO_ATTN_ABLATE, FRESCO_TEMPORAL_V, FRESCO_GRAM_V); the environment is read once, this overrides it;
  * value < 0 restores the built-in default. */
 int fresco_set_option(const char* name, int value);
 /* name of the kernel fresco_attn_fwd launches for a head dim under the current options (thread-local string) */

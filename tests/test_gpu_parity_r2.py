@@ -58,8 +58,7 @@ def sdpa_ref(q, k, v, heads, q_per_kv=1, scale=None, diag_bias=0.0):
     return (torch.softmax(s, -1) @ vh).transpose(1, 2).reshape(B, Lq, C)
 
 
-ATTN_OPTS = ("FRESCO_ATTN_WIDE", "FRESCO_ATTN_NARROW", "FRESCO_ATTN_POLY", "FRESCO_ATTN_ROWSUM", "FRESCO_ATTN_PIPE",
-             "FRESCO_ATTN_PP")
+ATTN_OPTS = ("FRESCO_ATTN_WIDE", "FRESCO_ATTN_POLY", "FRESCO_ATTN_ROWSUM")
 
 
 @pytest.fixture
@@ -73,16 +72,13 @@ def attn_opts(fb):
 
 
 VARIANTS = [
-    dict(FRESCO_ATTN_PP=1),                                              # ping-pong kernel: head_dim 40 / 64
-    dict(FRESCO_ATTN_WIDE=2, FRESCO_ATTN_PIPE=3),
-    dict(FRESCO_ATTN_WIDE=4, FRESCO_ATTN_PIPE=4),
-    dict(FRESCO_ATTN_WIDE=2, FRESCO_ATTN_POLY=0),
-    dict(FRESCO_ATTN_WIDE=2, FRESCO_ATTN_POLY=4),
-    dict(FRESCO_ATTN_WIDE=4, FRESCO_ATTN_POLY=0),                        # four threads per row: head_dim 64 / 80
+    dict(),                                                              # the defaults (per head_dim)
+    dict(FRESCO_ATTN_WIDE=2),                                            # two threads per query row
+    dict(FRESCO_ATTN_WIDE=4),                                            # four: head_dim <= 80
     dict(FRESCO_ATTN_WIDE=0, FRESCO_ATTN_POLY=0, FRESCO_ATTN_ROWSUM=0),
     dict(FRESCO_ATTN_WIDE=0, FRESCO_ATTN_POLY=0, FRESCO_ATTN_ROWSUM=1),
     dict(FRESCO_ATTN_WIDE=0, FRESCO_ATTN_POLY=4, FRESCO_ATTN_ROWSUM=1),
-    dict(FRESCO_ATTN_WIDE=0, FRESCO_ATTN_NARROW=4),
+    dict(FRESCO_ATTN_WIDE=0, FRESCO_ATTN_POLY=8, FRESCO_ATTN_ROWSUM=0),
 ]
 
 
@@ -91,10 +87,6 @@ VARIANTS = [
 def test_attention_variants_all_head_dims(fb, attn_opts, variant, d):
     """ragged q / kv tails, shared K/V, a peaky softmax (gain 4: lazy rescale path), kv lengths that leave one key
     half of the wide kernel fully masked (20, 33, 77), the diagonal bias + k-scale of spatial-guided attention."""
-    if variant.get("FRESCO_ATTN_NARROW") and d != 40:
-        pytest.skip("narrow kernel: head_dim 40 only")
-    if variant.get("FRESCO_ATTN_PP") and d > 80:
-        pytest.skip("ping-pong kernel: head_dim <= 80 only")
     if variant.get("FRESCO_ATTN_WIDE") == 4 and d > 80:
         pytest.skip("four threads per row: head_dim <= 80 only")
     attn_opts(**variant)

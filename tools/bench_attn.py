@@ -20,7 +20,7 @@ SHAPES = [  # B, L, Lk, heads, d, q_per_kv
     (16, 1024, 1024, 8, 80, 1),       # level A, spatial-guided
     (32, 1024, 1024, 1, 128, 1),      # GMFlow-like single head, d = 128
 ]
-OPTS = ("FRESCO_ATTN_WIDE", "FRESCO_ATTN_NARROW", "FRESCO_ATTN_POLY", "FRESCO_ATTN_ROWSUM", "FRESCO_ATTN_PIPE", "FRESCO_ATTN_PP")
+OPTS = ("FRESCO_ATTN_WIDE", "FRESCO_ATTN_POLY", "FRESCO_ATTN_ROWSUM")
 
 
 def timeit(fn, iters=10):
@@ -53,10 +53,6 @@ def main():
         row = {"variant": variant}
         for shp, (q, k, v, out) in data.items():
             B, L, Lk, H, d, qpk = shp
-            if int(kv.get("FRESCO_ATTN_NARROW", 0)) and d != 40:
-                continue
-            if int(kv.get("FRESCO_ATTN_PP", 0)) and d > 80:
-                continue
             ms = timeit(lambda: ops.attn_fwd(q, k, v, H, qpk, out=out))
             row["d%d_L%d_Lk%d" % (d, L, Lk)] = [round(ms, 4), round(4.0 * B * L * Lk * H * d / ms / 1e9, 1)]
         print(json.dumps(row), flush=True)

@@ -1,4 +1,4 @@
-"""Launch every non-attention kernel of the hot path twice at its BASELINE shape -- the target of the ncu captures
+"""Launch every kernel of the hot path (PROF_ITERS times, default 2) at its BASELINE shape -- the target of the ncu captures
 (`ncu --set full -k regex:<kernel> ...`): temporal attention (level B), K/V compaction, warp chain and temporal loss at
 layer 3 ([16,640,64,64]), the two Gram kernels, normalise / project, Adam, AdaIN, GMFlow correlation."""
 import math
@@ -34,7 +34,14 @@ mask = dh.cross_frame_attn_masks(occs[1])[0]
 idx = torch.nonzero(mask.reshape(-1)).reshape(-1).to(torch.int32)
 f0 = torch.randn(N, 128, 64, 64, generator=g).to(dev)
 f1 = torch.roll(f0, (1, -2), (2, 3))
-for _ in range(2):
+# attention: level B (d = 40) cross-frame + spatial-guided, level A (d = 80) cross-frame
+kc, vc = ops.kv_compact(k, a, idx, 2)
+qa = torch.randn(2 * N, 1024, 640, generator=g).half().to(dev)
+ka, va = (torch.randn(2, 3897, 640, generator=g).half().to(dev) for _ in range(2))
+for _ in range(int(os.environ.get("PROF_ITERS", "2"))):
+    ops.attn_fwd(q, kc, vc, 8, N)
+    ops.attn_fwd(q, k, a, 8, 1, diag_bias=2.0)
+    ops.attn_fwd(qa, ka, va, 8, N)
     ops.temporal_attn_fwd(q, k, a, fm[:, 0].contiguous(), im[:, 0].to(torch.uint8).contiguous(), 2, 8, 0.2 / math.sqrt(40))
     ops.kv_compact(k, a, idx, 2)
     fu.warp_tensor(sample, flows, occs, sal, 2)
