@@ -13,7 +13,8 @@ from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_longlong, c_si
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfresco_b200.so")
+# FRESCO_B200_LIB: measurement tools only (A/B builds made with FRESCO_BUILD_TAG); the product is libfresco_b200.so
+LIB_PATH = os.environ.get("FRESCO_B200_LIB") or os.path.join(_HERE, "libfresco_b200.so")
 
 _P = c_void_p
 _SIGNATURES = {

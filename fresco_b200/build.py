@@ -14,8 +14,9 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "csrc", "_obj")
-LIB = os.path.join(HERE, "libfresco_b200.so")
+TAG = os.environ.get("FRESCO_BUILD_TAG", "")                 # A/B builds only: libfresco_b200<TAG>.so next to the product
+OBJ = os.path.join(HERE, "csrc", "_obj" + TAG)
+LIB = os.path.join(HERE, "libfresco_b200%s.so" % TAG)
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--use_fast_math=false",

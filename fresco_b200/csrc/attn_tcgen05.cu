@@ -277,7 +277,7 @@ fresco_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 
   if (Cfg::SPLIT && warp == 4) {
     // ------------------------------------------------------------ TMA producer (own warp)
-    if (lane == 0) {
+    if (FRESCO_ISSUER_THREAD(lane)) {
       load_q();
       for (int t = 0; t < n_tiles; ++t) {
         if (t >= ST) mbar_wait(bar_kv_empty + t % ST, ((t / ST) - 1) & 1, 1);
@@ -289,7 +289,7 @@ fresco_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     // tcgen05.mma issue is a serial affair for the issuing thread; with 7 small MMAs and 3 commits per 128x64 tile a
     // single issuer thread sat on the critical path.  The score MMAs are therefore issued here and the P V MMAs by
     // another warp.  Without a producer warp of its own this thread also refills the K/V ring, never blocking on it.
-    if (lane == 0) {
+    if (FRESCO_ISSUER_THREAD(lane)) {
       constexpr uint32_t idesc_qk = make_idesc_f16(kTileM, kTileN, 0);
       const uint32_t q_addr = smem_u32(s_q);
       int next_load = 0;
@@ -342,7 +342,7 @@ fresco_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     }
   } else if (warp == Cfg::PV_WARP) {
     // ------------------------------------------------------------ P V MMA issuer
-    if (lane == 0) {
+    if (FRESCO_ISSUER_THREAD(lane)) {
       constexpr uint32_t idesc_pv0 = make_idesc_f16(kTileM, Cfg::N0, 1);
       constexpr uint32_t idesc_pv1 = make_idesc_f16(kTileM, Cfg::N1 > 0 ? Cfg::N1 : 16, 1);
       constexpr uint32_t idesc_ones = make_idesc_f16(kTileM, 16, 1);
@@ -691,7 +691,7 @@ fresco_attn_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
 
   if (warp == Cfg::TMA_WARP) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (FRESCO_ISSUER_THREAD(lane)) {
       load_q();
       for (int t = 0; t < n_tiles; ++t) {
         if (t >= ST) mbar_wait_backoff(bar_kv_empty + t % ST, ((t / ST) - 1) & 1, 32, 40);
@@ -700,7 +700,7 @@ fresco_attn_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     }
   } else if (warp == Cfg::QK_WARP) {
     // ------------------------------------------------------------ score-MMA issuer
-    if (lane == 0) {
+    if (FRESCO_ISSUER_THREAD(lane)) {
       constexpr uint32_t idesc_qk = make_idesc_f16(kTileM, kTileN, 0);
       const uint32_t q_addr = smem_u32(s_q);
       mbar_wait(bar_q, 0, 41);
@@ -724,7 +724,7 @@ fresco_attn_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     }
   } else if (warp >= Cfg::PV_WARP0 && warp < Cfg::PV_WARP0 + Cfg::NPV) {
     // ------------------------------------------------------------ P V issuer j: accumulators [j*PPV, (j+1)*PPV)
-    if (lane == 0) {
+    if (FRESCO_ISSUER_THREAD(lane)) {
       const int j = warp - Cfg::PV_WARP0;
       constexpr uint32_t idesc_pv0 = make_idesc_f16(kTileM, Cfg::N0, 1);
       constexpr uint32_t idesc_pv1 = make_idesc_f16(kTileM, Cfg::N1 > 0 ? Cfg::N1 : 16, 1);
@@ -933,6 +933,353 @@ fresco_attn_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
 }
 
 // ---------------------------------------------------------------------------------------------
+// the "duo" kernel: TWO threads per query row that share ONE running max and ONE accumulator (head_dim <= 64)
+// ---------------------------------------------------------------------------------------------
+// Why: the pipelined kernel's softmax warp runs a serial chain per tile (wait S, TMEM load, row max, 64 exponentials,
+// pack, TMEM store, arrive) with ~350 clocks of pure latency in it, and two such warps per sub-partition (two CTAs
+// per SM, 168 registers per thread) cannot cover each other's bubbles: 800 clocks per 128 x 64 tile against a MUFU
+// floor of 512.  The wide kernel has four warps per sub-partition but splits the KEYS with private running max / O per
+// part, which at head_dim 40 leaves TMEM for a single P buffer -- and every tile then waits for the previous tile's P V
+// to retire (820 clocks per tile).  Here the row is split between two threads (32 keys each, < 100 registers) but
+// nothing else is: one running max, agreed through a named-barrier OR-reduction that costs one instruction on the
+// common tile, one O accumulator, row sums from the tensor core -- so S and P stay double-buffered in 256 TMEM columns,
+// two CTAs of eight softmax warps per SM = four softmax warps per sub-partition.
+template <int D>
+struct DuoCfg {
+  static_assert(D <= 64, "one K/V atom");
+  static constexpr int KSTEPS = (D + 15) / 16;
+  static constexpr int DPAD = KSTEPS * 16;
+  static constexpr int S_OFF0 = 0, S_OFF1 = 64, P_OFF0 = 128, P_OFF1 = 160, O_OFF = 192;
+  static constexpr int TMEM_COLS = 256;
+  static constexpr int STAGES = 5;
+  static constexpr bool MMA_ROWSUM = DPAD + 16 <= 64;      // row sums from the tensor core (16 spare O columns)
+  static constexpr int L_COL = 48;
+  static constexpr int ONES_BYTES = MMA_ROWSUM ? 2048 : 0;
+  static constexpr int Q_BYTES = kQAtomBytes;
+  static constexpr int STAGE_BYTES = 2 * kKVAtomBytes;
+  static constexpr int SMEM_BYTES = 1024 + Q_BYTES + STAGES * STAGE_BYTES + ONES_BYTES + 2 * 128 * 4 + 256;
+  static constexpr int SOFTMAX_WARPS = 8;
+  static constexpr int QK_WARP = 8, PV_WARP = 9;           // the score issuer also feeds the K/V ring (never blocking)
+  static constexpr int THREADS = 320;
+};
+
+// OR of `pred` over the `threads` threads that use named barrier `id` (also a barrier for them)
+template <int ID>
+__device__ __forceinline__ bool bar_red_or_id(bool pred) {          // 64 threads: the two warps of a row quarter
+  uint32_t out;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 q, %2, 0;\n\t"
+      "barrier.cta.red.or.pred p, %1, 64, q;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(out)
+      : "n"(ID), "r"((uint32_t)pred)
+      : "memory");
+  return out != 0;
+}
+__device__ __forceinline__ bool bar_red_or(int id, bool pred) {     // id in [1, 4]: immediates keep "used barriers" at 5
+  switch (id) {
+    case 1: return bar_red_or_id<1>(pred);
+    case 2: return bar_red_or_id<2>(pred);
+    case 3: return bar_red_or_id<3>(pred);
+    default: return bar_red_or_id<4>(pred);
+  }
+}
+__device__ __forceinline__ void bar_sync_named(int id) {
+  switch (id) {
+    case 1: asm volatile("barrier.cta.sync 1, 64;" ::: "memory"); break;
+    case 2: asm volatile("barrier.cta.sync 2, 64;" ::: "memory"); break;
+    case 3: asm volatile("barrier.cta.sync 3, 64;" ::: "memory"); break;
+    default: asm volatile("barrier.cta.sync 4, 64;" ::: "memory"); break;
+  }
+}
+
+template <int D, int POLY>
+__global__ void __launch_bounds__(DuoCfg<D>::THREADS, 2)
+fresco_attn_duo_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                       const __grid_constant__ CUtensorMap tm_v, const AttnParams p) {
+  using Cfg = DuoCfg<D>;
+  constexpr int ST = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_q = smem;
+  uint8_t* s_kv = smem + Cfg::Q_BYTES;
+  uint8_t* s_ones = s_kv + ST * Cfg::STAGE_BYTES;
+  float* s_x = reinterpret_cast<float*>(s_ones + Cfg::ONES_BYTES);   // [2][128] tile max (slow path) / row sum (epilogue)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_x + 2 * 128);
+  uint64_t* bar_q = bars + 0;
+  uint64_t* bar_kv_full = bars + 1;            // [ST]
+  uint64_t* bar_kv_empty = bars + 1 + ST;      // [ST]
+  uint64_t* bar_s = bars + 1 + 2 * ST;         // [2]  S buffer b holds tile i (i & 1 == b)
+  uint64_t* bar_p = bar_s + 2;                 // [2]  P_i written (one arrival per softmax warp)
+  uint64_t* bar_o = bar_s + 4;                 // [2]  P_i V_i retired (P buffer free, O stable)
+  uint64_t* bar_c = bar_s + 6;                 // [2]  S_i is in registers everywhere (S buffer free)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s + 8);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kTileM;
+  const int head = blockIdx.y;
+  const int b = blockIdx.z;
+  const int b_kv = b / p.q_per_kv;
+  const int n_tiles = (p.kv_len + kTileN - 1) / kTileN;
+
+  if (warp == Cfg::PV_WARP && lane == 0) {
+    mbar_init(bar_q, 1);
+    for (int s = 0; s < ST; ++s) {
+      mbar_init(bar_kv_full + s, 1);
+      mbar_init(bar_kv_empty + s, 2);          // released by the score issuer (K read) and by the P V issuer (V read)
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_s + i, 1);
+      mbar_init(bar_p + i, Cfg::SOFTMAX_WARPS);
+      mbar_init(bar_o + i, 1);
+      mbar_init(bar_c + i, Cfg::SOFTMAX_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == Cfg::QK_WARP) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tm_q);
+      tma_prefetch_desc(&tm_k);
+      tma_prefetch_desc(&tm_v);
+    }
+    __syncwarp();
+    tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  }
+  if (Cfg::MMA_ROWSUM) {
+    for (int i = threadIdx.x; i < Cfg::ONES_BYTES / 4; i += Cfg::THREADS) reinterpret_cast<uint32_t*>(s_ones)[i] = 0x3C003C00u;
+    fence_proxy_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  auto load_kv_tile = [&](int t) {
+    const int st = t % ST;
+    uint8_t* sk = s_kv + st * Cfg::STAGE_BYTES;
+    mbar_expect_tx(bar_kv_full + st, Cfg::STAGE_BYTES);
+    tma_load_4d(sk, &tm_k, bar_kv_full + st, 0, head, t * kTileN, b_kv);
+    tma_load_4d(sk + kKVAtomBytes, &tm_v, bar_kv_full + st, 0, head, t * kTileN, b_kv);
+  };
+
+  if (warp == Cfg::QK_WARP) {
+    // ------------------------------------------------------------ score-MMA issuer + TMA producer
+    if (FRESCO_ISSUER_THREAD(lane)) {
+      constexpr uint32_t idesc_qk = make_idesc_f16(kTileM, kTileN, 0);
+      const uint32_t q_addr = smem_u32(s_q);
+      int next_load = 0;
+      auto refill = [&]() {                     // issue every K/V tile load whose ring stage is free; never blocks
+        while (next_load < n_tiles) {
+          if (next_load >= ST && !mbar_test_wait(bar_kv_empty + next_load % ST, ((next_load / ST) - 1) & 1)) break;
+          load_kv_tile(next_load);
+          ++next_load;
+        }
+      };
+      auto issue_qk = [&](int t) {
+        const int st = t % ST;
+        uint32_t polls = 0;
+        while (!mbar_try_wait(bar_kv_full + st, (t / ST) & 1)) {
+          refill();
+          if (++polls > FRESCO_WATCHDOG_POLLS) mbar_timeout(bar_kv_full + st, (t / ST) & 1, 60);
+        }
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(s_kv + st * Cfg::STAGE_BYTES);
+        const uint32_t d_tmem = tmem + ((t & 1) ? Cfg::S_OFF1 : Cfg::S_OFF0);
+#pragma unroll
+        for (int ks = 0; ks < Cfg::KSTEPS; ++ks)
+          umma_ss(d_tmem, make_smem_desc_sw128(q_addr + ks * 32, 16, 1024), make_smem_desc_sw128(k_addr + ks * 32, 16, 1024),
+                  idesc_qk, ks > 0);
+        umma_commit(bar_s + (t & 1));
+        umma_commit(bar_kv_empty + st);
+      };
+      mbar_expect_tx(bar_q, Cfg::Q_BYTES);
+      tma_load_4d(s_q, &tm_q, bar_q, 0, head, q0, b);
+      refill();
+      mbar_wait(bar_q, 0, 61);
+      issue_qk(0);
+      if (n_tiles > 1) issue_qk(1);
+      for (int t = 0; t + 2 < n_tiles; ++t) {
+        refill();
+        uint32_t polls = 0;
+        while (!mbar_try_wait(bar_c + (t & 1), (t >> 1) & 1)) {      // S buffer t & 1 is in registers
+          refill();
+          if (++polls > FRESCO_WATCHDOG_POLLS) mbar_timeout(bar_c + (t & 1), (t >> 1) & 1, 62);
+        }
+        issue_qk(t + 2);
+      }
+      while (next_load < n_tiles) refill();
+    }
+  } else if (warp == Cfg::PV_WARP) {
+    // ------------------------------------------------------------ P V MMA issuer
+    if (FRESCO_ISSUER_THREAD(lane)) {
+      constexpr uint32_t idesc_pv = make_idesc_f16(kTileM, Cfg::DPAD, 1);
+      constexpr uint32_t idesc_ones = make_idesc_f16(kTileM, 16, 1);
+      for (int t = 0; t < n_tiles; ++t) {
+        const int st = t % ST;
+        mbar_wait_backoff(bar_p + (t & 1), (t >> 1) & 1, 20, 63);
+        mbar_wait(bar_kv_full + st, (t / ST) & 1, 64);
+        tc_fence_after();
+        const uint32_t v_addr = smem_u32(s_kv + st * Cfg::STAGE_BYTES + kKVAtomBytes);
+#pragma unroll
+        for (int k2 = 0; k2 < kTileN / 16; ++k2) {
+          const uint32_t acc = (k2 > 0 || t > 0) ? 1u : 0u;
+          const uint32_t p_tmem = tmem + ((t & 1) ? Cfg::P_OFF1 : Cfg::P_OFF0) + k2 * 8;
+          umma_ts(tmem + Cfg::O_OFF, p_tmem, make_smem_desc_sw128(v_addr + k2 * 2048, kKVAtomBytes, 1024), idesc_pv, acc);
+          if (Cfg::MMA_ROWSUM)
+            umma_ts(tmem + Cfg::O_OFF + Cfg::L_COL, p_tmem, make_smem_desc_sw128(smem_u32(s_ones), 2048, 1024),
+                    idesc_ones, acc);
+        }
+        umma_commit(bar_kv_empty + st);
+        umma_commit(bar_o + (t & 1));
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ softmax warps: (row quarter, key half)
+    const int quarter = warp & 3, part = warp >> 2;
+    const int row = quarter * 32 + lane;
+    const uint32_t t_lane = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
+    const int q_row = q0 + row;
+    const int kv_len = p.kv_len;
+    const float scale_log2 = p.scale_log2, bias_log2 = p.diag_bias_log2;
+    const bool use_bias = bias_log2 != 0.f;
+    const unsigned long long scale2 = pack_f2(scale_log2, scale_log2);
+    const int pair_bar = 1 + quarter;          // named barrier of the two warps that share these 32 rows
+    float m_run = -INFINITY, l_run = 0.f;
+
+    for (int i = 0; i < n_tiles; ++i) {
+      const int col0 = i * kTileN + 32 * part;
+      const bool special = (col0 + 32 > kv_len) ||
+                           (use_bias && (q0 + quarter * 32) < col0 + 32 && (q0 + quarter * 32 + 32) > col0);
+      mbar_wait(bar_s + (i & 1), (i >> 1) & 1, 2);
+      tc_fence_after();
+      uint32_t r[32];
+      tmem_ld32(t_lane + ((i & 1) ? Cfg::S_OFF1 : Cfg::S_OFF0) + 32 * part, r);
+      tmem_ld_wait_dep32(r);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_c + (i & 1));
+      if (special) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int col = col0 + j;
+          float v = __uint_as_float(r[j]);
+          if (use_bias && col == q_row) v += bias_log2 / scale_log2;
+          if (col >= kv_len) v = -INFINITY;
+          r[j] = __float_as_uint(v);
+        }
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        mx0 = max3(mx0, __uint_as_float(r[j]), __uint_as_float(r[j + 1]));
+        mx1 = max3(mx1, __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+        mx2 = max3(mx2, __uint_as_float(r[j + 4]), __uint_as_float(r[j + 5]));
+        mx3 = max3(mx3, __uint_as_float(r[j + 6]), __uint_as_float(r[j + 7]));
+      }
+      const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
+      // ---- lazy running max shared by the two threads of a row: one OR-reducing barrier on the common tile
+      if (bar_red_or(pair_bar, i == 0 || m_tile > m_run + 8.0f)) {
+        s_x[part * 128 + row] = m_tile;
+        bar_sync_named(pair_bar);
+        const float m_new = fmaxf(m_tile, s_x[(part ^ 1) * 128 + row]);
+        const bool need = (i == 0) || (m_new > m_run + 8.0f);
+        if (i > 0) {
+          // O may only be touched once P_{i-1} V_{i-1} has retired
+          mbar_wait(bar_o + ((i - 1) & 1), ((i - 1) >> 1) & 1, 5);
+          tc_fence_after();
+          const float alpha = need ? fast_exp2(m_run - m_new) : 1.0f;     // m_run = -inf cannot happen for i > 0 unless
+          l_run *= alpha;                                                 // every key so far was masked (O = l = 0 then)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {                                   // this thread's half of the 64 O columns
+            uint32_t o[8];
+            const uint32_t addr = t_lane + Cfg::O_OFF + part * 32 + c * 8;
+            tmem_ld8_sync(addr, o);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
+            tmem_st8(addr, o);
+          }
+        }
+        if (need) m_run = m_new;
+      }
+      // ---- P buffer (i & 1) was last read by P_{i-2} V_{i-2}: retired long ago in the common case
+      if (i >= 2) {
+        mbar_wait(bar_o + (i & 1), ((i - 2) >> 1) & 1, 3);
+        tc_fence_after();
+      }
+      const float neg_m = (m_run == -INFINITY) ? 0.f : -m_run;
+      const unsigned long long negm2 = pack_f2(neg_m, neg_m);
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        float t0, t1;
+        unpack_f2(fma2(pack_f2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), scale2, negm2), t0, t1);
+        if (POLY > 0 && ((j >> 1) % (POLY > 0 ? POLY : 1)) == (POLY - 1)) {
+          float p0, p1;
+          exp2_poly_x2(t0, t1, p0, p1);
+          r[j] = __float_as_uint(p0);
+          r[j + 1] = __float_as_uint(p1);
+        } else {
+          r[j] = __float_as_uint(fast_exp2(t0));
+          r[j + 1] = __float_as_uint(fast_exp2(t1));
+        }
+      }
+      if (!Cfg::MMA_ROWSUM) {
+        unsigned long long sum2[2] = {pack_f2(0.f, 0.f), pack_f2(0.f, 0.f)};
+#pragma unroll
+        for (int j = 0; j < 32; j += 2)
+          sum2[(j >> 1) & 1] = add2(sum2[(j >> 1) & 1], pack_f2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])));
+        float sa, sb;
+        unpack_f2(add2(sum2[0], sum2[1]), sa, sb);
+        l_run += sa + sb;
+      }
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) pk[j] = pack_half2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+      tmem_st16(t_lane + ((i & 1) ? Cfg::P_OFF1 : Cfg::P_OFF0) + 16 * part, pk);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p + (i & 1));
+    }
+
+    // ---- epilogue: O / l -> fp16 head slice; the two threads of a row take alternate 16-byte chunks
+    mbar_wait(bar_o + ((n_tiles - 1) & 1), ((n_tiles - 1) >> 1) & 1, 4);
+    tc_fence_after();
+    if (Cfg::MMA_ROWSUM) {
+      uint32_t lcol[8];
+      tmem_ld8_sync(t_lane + Cfg::O_OFF + Cfg::L_COL, lcol);
+      l_run = __uint_as_float(lcol[0]);
+    } else {
+      s_x[part * 128 + row] = l_run;
+      bar_sync_named(pair_bar);
+      l_run += s_x[(part ^ 1) * 128 + row];
+    }
+    const float inv = 1.f / l_run;
+    __half* dst = p.out + (static_cast<size_t>(b) * p.q_len + q_row) * (static_cast<size_t>(p.heads) * D) +
+                  static_cast<size_t>(head) * D;
+#pragma unroll
+    for (int c = 0; c < D / 8; ++c) {
+      if ((c & 1) != part) continue;
+      uint32_t o[8];
+      tmem_ld8_sync(t_lane + Cfg::O_OFF + c * 8, o);
+      if (q_row < p.q_len) {
+        uint4 pkt;
+        pkt.x = pack_half2(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
+        pkt.y = pack_half2(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
+        pkt.z = pack_half2(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
+        pkt.w = pack_half2(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
+        reinterpret_cast<uint4*>(dst)[c] = pkt;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == Cfg::QK_WARP) tmem_dealloc<Cfg::TMEM_COLS>(tmem);
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 
@@ -1017,9 +1364,25 @@ static int launch_wide(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
   return check_launch("fresco_attn_wide_kernel");
 }
 
+template <int D, int POLY>
+static int launch_duo(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, dim3 grid,
+                      cudaStream_t stream) {
+  using Cfg = DuoCfg<D>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(fresco_attn_duo_kernel<D, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(attn duo)");
+    attr_set = true;
+  }
+  fresco_attn_duo_kernel<D, POLY><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tq, tk, tv, p);
+  return check_launch("fresco_attn_duo_kernel");
+}
+
 static int wide_split(int head_dim) {       // threads per query row under the current options; 0 = pipelined kernel
   int wide = option(OPT_ATTN_WIDE, -1);
   if (wide < 0) wide = default_split(head_dim);
+  if (wide == 3) return head_dim <= 64 ? 3 : (head_dim <= 80 ? 4 : 0);   // 3 = duo kernel (head_dim <= 64)
   if (wide >= 4) return head_dim <= 80 ? 4 : 2;       // four accumulators of head_dim 128 do not fit TMEM
   return wide >= 1 ? 2 : 0;
 }
@@ -1046,6 +1409,13 @@ static int launch_attn(const void* q, const void* k, const void* v, void* out, i
   dim3 grid((q_len + kTileM - 1) / kTileM, heads, batch_q);
   const int poly = option(OPT_ATTN_POLY, kPolyDefault);
   const int split = wide_split(D);
+  if constexpr (D <= 64) {
+    if (split == 3) {
+      if (poly == 4) return launch_duo<D, 4>(tq, tk, tv, p, grid, stream);
+      if (poly == 8) return launch_duo<D, 8>(tq, tk, tv, p, grid, stream);
+      return launch_duo<D, 0>(tq, tk, tv, p, grid, stream);
+    }
+  }
   if constexpr (D <= 80) {
     if (split == 4) return launch_wide<D, 4>(tq, tk, tv, p, grid, stream);
   }
@@ -1076,7 +1446,8 @@ extern "C" int fresco_debug_attn_trace(long long* host_out) {
 extern "C" const char* fresco_attn_variant(int head_dim) {
   static thread_local char buf[96];
   const int split = wide_split(head_dim);
-  if (split > 0) snprintf(buf, sizeof(buf), "fresco_attn_wide_kernel<%d,%d>", head_dim, split);
+  if (split == 3) snprintf(buf, sizeof(buf), "fresco_attn_duo_kernel<%d,poly%d>", head_dim, option(OPT_ATTN_POLY, kPolyDefault));
+  else if (split > 0) snprintf(buf, sizeof(buf), "fresco_attn_wide_kernel<%d,%d>", head_dim, split);
   else snprintf(buf, sizeof(buf), "fresco_attn_kernel<%d,poly%d> (pipelined)", head_dim, option(OPT_ATTN_POLY, kPolyDefault));
   return buf;
 }

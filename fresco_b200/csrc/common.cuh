@@ -25,6 +25,17 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// The single thread of a warp that issues TMA / tcgen05.mma / tcgen05.commit.  Selecting it with elect.sync (and not
+// with `lane == 0`) matters: the compiler then knows that exactly one thread runs the branch and keeps descriptors and
+// TMEM addresses in uniform registers; behind `lane == 0` every UTCHMMA / UTMALDG is wrapped in a
+// vote-and-broadcast loop (ELECT / R2UR.BROADCAST / BRA.U.ANY), which cost the issuing thread 60-70 clocks per
+// instruction in round 1's traces.  -DFRESCO_ISSUER_LANE0 restores the old form for A/B measurements.
+#ifdef FRESCO_ISSUER_LANE0
+#define FRESCO_ISSUER_THREAD(lane) ((lane) == 0)
+#else
+#define FRESCO_ISSUER_THREAD(lane) (::fresco::elect_one())
+#endif
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

@@ -87,7 +87,7 @@ tile_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 
   if (warp == 4) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (FRESCO_ISSUER_THREAD(lane)) {
       int it = 0;
       for (int t = 0; t < p.n_iter; ++t) {
         const int n0 = (n_tile0 + t) * 128;
@@ -110,7 +110,7 @@ tile_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     }
   } else if (warp == 5) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (FRESCO_ISSUER_THREAD(lane)) {
       constexpr uint32_t idesc_k = make_idesc_f16(128, 128, 0);
       constexpr uint32_t idesc_mn = make_idesc_f16(128, 64, 1);
       int it = 0;

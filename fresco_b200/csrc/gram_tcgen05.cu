@@ -109,7 +109,7 @@ gram2_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ 
 
   if (warp == 4) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (FRESCO_ISSUER_THREAD(lane)) {
       int it = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         int b, I, Jp;
@@ -136,7 +136,7 @@ gram2_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ 
     }
   } else if (warp == 5) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (FRESCO_ISSUER_THREAD(lane)) {
       constexpr uint32_t idesc = make_idesc_f16(128, 256, MODE == G2_GRAD ? 1 : 0);
       constexpr uint32_t idesc_negb = idesc | (1u << 14);                                      // B operand negated
       int it = 0, t = 0;

@@ -75,6 +75,8 @@ VARIANTS = [
     dict(),                                                              # the defaults (per head_dim)
     dict(FRESCO_ATTN_WIDE=2),                                            # two threads per query row
     dict(FRESCO_ATTN_WIDE=4),                                            # four: head_dim <= 80
+    dict(FRESCO_ATTN_WIDE=3),                                            # duo kernel (shared running max): head_dim <= 64
+    dict(FRESCO_ATTN_WIDE=3, FRESCO_ATTN_POLY=4),
     dict(FRESCO_ATTN_WIDE=0, FRESCO_ATTN_POLY=0, FRESCO_ATTN_ROWSUM=0),
     dict(FRESCO_ATTN_WIDE=0, FRESCO_ATTN_POLY=0, FRESCO_ATTN_ROWSUM=1),
     dict(FRESCO_ATTN_WIDE=0, FRESCO_ATTN_POLY=4, FRESCO_ATTN_ROWSUM=1),
