@@ -36,6 +36,8 @@ _SIGNATURES = {
     "fresco_warp_fuse_chain": (c_int, [_P, _P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "fresco_warp_taps": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P]),
     "fresco_warp_loss_fwd_bwd": (c_int, [_P] * 8 + [c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "fresco_warp_loss_fwd_bwd_halo": (c_int, [_P] * 8 + [c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P,
+                                              c_int, _P]),
     "fresco_gram_normalize": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P]),
     "fresco_gram_sign": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_float, _P]),
     "fresco_gram_grad": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_float, _P, c_size_t, _P]),

@@ -681,7 +681,10 @@ __global__ void warp_loss_kernel(const float* __restrict__ cs, const float* __re
                                  const float* __restrict__ bwd_keep, const uint4* __restrict__ bwd_ell,
                                  const uint4* __restrict__ fwd_ell, const int32_t* __restrict__ ovf /*[2][frames][n_ovf][3]*/,
                                  int n_ovf, float* __restrict__ grad, float* __restrict__ loss_acc, int accumulate,
-                                 int frames, int channels, int h, int w, float k /* 2 / numel */) {
+                                 int frames, int channels, int h, int w, float k /* 2 / numel */,
+                                 const float* __restrict__ halo_cs, float* __restrict__ halo_grad) {
+  // halo_cs != null: OPEN chain (frame-sharded batch) -- the "next" frame of the last pair is the halo plane
+  // [chunks, channels, h, w] (the following rank's first frame) and what it receives goes to halo_grad, overwritten
   extern __shared__ float sm[];
   const int hw = h * w;
   float* c1 = sm;
@@ -696,11 +699,16 @@ __global__ void warp_loss_kernel(const float* __restrict__ cs, const float* __re
   for (int i = threadIdx.x; i < hw; i += blockDim.x) c2[i] = cs[plane_of(0) + i];
   for (int f = 0; f < frames; ++f) {
     const int fn = (f + 1) % frames;
+    const bool to_halo = halo_cs != nullptr && f + 1 == frames;
+    const long long halo_off = ((long long)b * channels + c) * hw;
     float* t = c1;
     c1 = c2;                                                    // previous "next" plane becomes c1
     c2 = t;
     __syncthreads();
-    for (int i = threadIdx.x; i < hw; i += blockDim.x) c2[i] = cs[plane_of(fn) + i];
+    {
+      const float* nsrc = to_halo ? halo_cs + halo_off : cs + plane_of(fn);
+      for (int i = threadIdx.x; i < hw; i += blockDim.x) c2[i] = nsrc[i];
+    }
     __syncthreads();
     const float* bf = bwd_flow + (long long)f * 2 * hw;
     const float* ff = fwd_flow + (long long)f * 2 * hw;
@@ -732,12 +740,12 @@ __global__ void warp_loss_kernel(const float* __restrict__ cs, const float* __re
     }
     __syncthreads();
     const bool a_add = accumulate || f > 0;                     // frame f   : first touched at f == 0
-    const bool b_add = accumulate || f == frames - 1;           // frame f+1 : first touched here, except the wrap to 0
+    const bool b_add = !to_halo && (accumulate || f == frames - 1);   // frame f+1 : first touched here, except the wrap to 0
     // adjoint as a gather: 8 packed (source, weight) slots per destination pixel (ELL), two 16-byte loads per row
     const uint4* eb = bwd_ell + (long long)f * hw * 2;
     const uint4* ef = fwd_ell + (long long)f * hw * 2;
     float* ga = grad + plane_of(f);
-    float* gb = grad + plane_of(fn);
+    float* gb = to_halo ? halo_grad + halo_off : grad + plane_of(fn);
     auto gather8 = [&](const uint4* ell, int q, const float* sv) {
       const uint4 e0 = __ldg(ell + 2 * q), e1 = __ldg(ell + 2 * q + 1);
       const uint32_t e[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
@@ -752,7 +760,7 @@ __global__ void warp_loss_kernel(const float* __restrict__ cs, const float* __re
       const float acc = s2[q] - gather8(eb, q, s1);
       ga[q] = a_add ? ga[q] + acc : acc;
     }
-    if (frames == 2) __syncthreads();                           // ga / gb alias the same two planes
+    if (frames <= 2) __syncthreads();                           // ga / gb alias the same two planes
     // d/dc2 = s1 - W_ff^T s2      (frame f+1)
 #pragma unroll 4
     for (int q = threadIdx.x; q < hw; q += blockDim.x) {
@@ -803,7 +811,8 @@ warp_loss_group_kernel(const float* __restrict__ cs, const float* __restrict__ f
                        const float* __restrict__ bwd_keep, const uint4* __restrict__ bwd_ell,
                        const uint4* __restrict__ fwd_ell, const int32_t* __restrict__ ovf /*[2][frames][n_ovf][3]*/,
                        int n_ovf, float* __restrict__ grad, float* __restrict__ loss_acc, int accumulate, int frames,
-                       int channels, int planes_total, int h, int w, int G, float k /* 2 / numel */) {
+                       int channels, int planes_total, int h, int w, int G, float k /* 2 / numel */,
+                       const float* __restrict__ halo_cs, float* __restrict__ halo_grad /* open chain, see warp_loss_kernel */) {
   extern __shared__ float sm[];
   const int hw = h * w;
   const int K = KT * G;
@@ -829,13 +838,14 @@ warp_loss_group_kernel(const float* __restrict__ cs, const float* __restrict__ f
     own_base[kk] = ((long long)b * frames * channels + c) * hw;
   }
   auto load_plane = [&](float* dst, int f) {                  // frame f of all K planes -> dst (coalesced along pixels)
-    for (int idx = t; idx < K * hw; idx += T) {
+    for (int idx = t; idx < K * hw; idx += T) {                 // f == frames: the halo plane (open chain)
       const int slot = idx / hw, i = idx - slot * hw;
       const int pl = blockIdx.x * K + slot;
       float v = 0.f;
       if (pl < planes_total) {
         const int b = pl / channels, c = pl % channels;
-        v = cs[((long long)(b * frames + f) * channels + c) * hw + i];
+        v = (f == frames) ? halo_cs[((long long)b * channels + c) * hw + i]
+                          : cs[((long long)(b * frames + f) * channels + c) * hw + i];
       }
       dst[idx] = v;
     }
@@ -847,7 +857,7 @@ warp_loss_group_kernel(const float* __restrict__ cs, const float* __restrict__ f
 
   load_plane(cur, 0);
   for (int f = 0; f < frames; ++f) {
-    const int fn = (f + 1 == frames) ? 0 : f + 1;
+    const int fn = (f + 1 == frames) ? (halo_cs != nullptr ? frames : 0) : f + 1;
     load_plane(nxt, fn);
     __syncthreads();
     // ---- residuals of pair (f, fn): taps once per pixel, applied to the KT planes of this thread
@@ -938,7 +948,10 @@ warp_loss_group_kernel(const float* __restrict__ cs, const float* __restrict__ f
       for (int kk = 0; kk < KT; ++kk) {
         if (own_live[kk]) {
           float* dst = grad + own_base[kk] + goff_a + q;
-          const float val = (carry[pp * KT + kk] + ga[kk]) * k;   // frame f: its term as "next" of pair f-1 + this pair
+          // frame f: this pair's term + its term as "next" of pair f-1.  Two rounded products and one add, never
+          // (carry + ga) * k: a frame-sharded batch adds the carry of a shard's first frame on the host (halo exchange)
+          // and must reproduce these bits
+          const float val = __fadd_rn(__fmul_rn(ga[kk], k), __fmul_rn(carry[pp * KT + kk], k));
           *dst = accumulate ? *dst + val : val;
         }
         carry[pp * KT + kk] = gb[kk];
@@ -973,7 +986,14 @@ warp_loss_group_kernel(const float* __restrict__ cs, const float* __restrict__ f
     if (!active || q >= hw) continue;
 #pragma unroll
     for (int kk = 0; kk < KT; ++kk)
-      if (own_live[kk]) grad[own_base[kk] + q] += carry[pp * KT + kk] * k;
+      if (own_live[kk]) {
+        if (halo_grad != nullptr) {                            // open chain: the following rank's first frame receives it
+          const int pl = blockIdx.x * K + kk * G + g;
+          halo_grad[((long long)(pl / channels) * channels + pl % channels) * hw + q] = __fmul_rn(carry[pp * KT + kk], k);
+        } else {
+          grad[own_base[kk] + q] = __fadd_rn(grad[own_base[kk] + q], __fmul_rn(carry[pp * KT + kk], k));
+        }
+      }
   }
   if (loss_acc != nullptr) {
     __shared__ float red[32];
@@ -1007,7 +1027,8 @@ warp_loss_quad_kernel(const float* __restrict__ cs, const float* __restrict__ fw
                       const float* __restrict__ bwd_keep, const uint4* __restrict__ bwd_ell,
                       const uint4* __restrict__ fwd_ell, const int32_t* __restrict__ ovf /*[2][frames][n_ovf][3]*/,
                       int n_ovf, float* __restrict__ grad, float* __restrict__ loss_acc, int accumulate, int frames,
-                      int channels, int h, int w, float k) {
+                      int channels, int h, int w, float k, const float* __restrict__ halo_cs,
+                      float* __restrict__ halo_grad /* open chain, see warp_loss_kernel */) {
   extern __shared__ float4 smq[];
   const int hw = h * w;
   float4* cur = smq;                                          // [NQ][hw] frame f,     4 channels per pixel
@@ -1019,8 +1040,9 @@ warp_loss_quad_kernel(const float* __restrict__ cs, const float* __restrict__ fw
   const int b = pl0 / channels, c0 = pl0 % channels;
   const long long fstride = (long long)channels * hw;
   const long long base = ((long long)b * frames * channels + c0) * hw;      // frame 0, channel c0
-  auto load_frame = [&](float4* dst, int f) {
-    const float* src = cs + base + (long long)f * fstride;
+  const long long halo_base = ((long long)b * channels + c0) * hw;            // halo planes: [chunks, channels, h, w]
+  auto load_frame = [&](float4* dst, int f) {                                 // f == frames: the halo plane (open chain)
+    const float* src = (f == frames) ? halo_cs + halo_base : cs + base + (long long)f * fstride;
 #pragma unroll
     for (int pp = 0; pp < P; ++pp) {
       const int q = t + pp * T;
@@ -1042,7 +1064,7 @@ warp_loss_quad_kernel(const float* __restrict__ cs, const float* __restrict__ fw
 
   load_frame(cur, 0);
   for (int f = 0; f < frames; ++f) {
-    const int fn = (f + 1 == frames) ? 0 : f + 1;
+    const int fn = (f + 1 == frames) ? (halo_cs != nullptr ? frames : 0) : f + 1;
     load_frame(nxt, fn);
     __syncthreads();
     // ---- residuals of pair (f, fn): taps and keep masks once per pixel, applied to the 4 NQ channels
@@ -1158,8 +1180,11 @@ warp_loss_quad_kernel(const float* __restrict__ cs, const float* __restrict__ fw
           if (live) {
             const float4 cr = carry[pp][nq];
             float* g4 = gdst + (long long)nq * 4 * hw;
-            const float v0 = (cr.x + ga[nq].x) * k, v1 = (cr.y + ga[nq].y) * k, v2 = (cr.z + ga[nq].z) * k,
-                        v3 = (cr.w + ga[nq].w) * k;
+            // two rounded products and one add, never (carry + ga) * k (see warp_loss_group_kernel)
+            const float v0 = __fadd_rn(__fmul_rn(ga[nq].x, k), __fmul_rn(cr.x, k));
+            const float v1 = __fadd_rn(__fmul_rn(ga[nq].y, k), __fmul_rn(cr.y, k));
+            const float v2 = __fadd_rn(__fmul_rn(ga[nq].z, k), __fmul_rn(cr.z, k));
+            const float v3 = __fadd_rn(__fmul_rn(ga[nq].w, k), __fmul_rn(cr.w, k));
             if (accumulate) {
               g4[q] += v0, g4[hw + q] += v1, g4[2 * hw + q] += v2, g4[3 * hw + q] += v3;
             } else {
@@ -1201,9 +1226,17 @@ warp_loss_quad_kernel(const float* __restrict__ cs, const float* __restrict__ fw
     if (q < hw) {
 #pragma unroll
       for (int nq = 0; nq < NQ; ++nq) {
-        float* g0 = grad + base + (long long)nq * 4 * hw;
         const float4 cr = carry[pp][nq];
-        g0[q] += cr.x * k, g0[hw + q] += cr.y * k, g0[2 * hw + q] += cr.z * k, g0[3 * hw + q] += cr.w * k;
+        if (halo_grad != nullptr) {                              // open chain: the following rank's first frame receives it
+          float* g0 = halo_grad + halo_base + (long long)nq * 4 * hw;
+          g0[q] = __fmul_rn(cr.x, k), g0[hw + q] = __fmul_rn(cr.y, k);
+          g0[2 * hw + q] = __fmul_rn(cr.z, k), g0[3 * hw + q] = __fmul_rn(cr.w, k);
+        } else {
+          float* g0 = grad + base + (long long)nq * 4 * hw;
+          g0[q] = __fadd_rn(g0[q], __fmul_rn(cr.x, k)), g0[hw + q] = __fadd_rn(g0[hw + q], __fmul_rn(cr.y, k));
+          g0[2 * hw + q] = __fadd_rn(g0[2 * hw + q], __fmul_rn(cr.z, k));
+          g0[3 * hw + q] = __fadd_rn(g0[3 * hw + q], __fmul_rn(cr.w, k));
+        }
       }
     }
   }
@@ -1653,12 +1686,26 @@ extern "C" int fresco_warp_loss_fwd_bwd(const float* cs, const float* fwd_flow, 
                                         const void* fwd_ell, const int32_t* overflow, int n_overflow, float* grad,
                                         float* loss_acc, int accumulate, int chunks, int frames, int channels, int h,
                                         int w, void* stream) {
+  return fresco_warp_loss_fwd_bwd_halo(cs, fwd_flow, bwd_flow, fwd_keep, bwd_keep, bwd_ell, fwd_ell, overflow, n_overflow,
+                                       grad, loss_acc, accumulate, chunks, frames, channels, h, w, nullptr, nullptr,
+                                       frames, stream);
+}
+
+extern "C" int fresco_warp_loss_fwd_bwd_halo(const float* cs, const float* fwd_flow, const float* bwd_flow,
+                                             const float* fwd_keep, const float* bwd_keep, const void* bwd_ell,
+                                             const void* fwd_ell, const int32_t* overflow, int n_overflow, float* grad,
+                                             float* loss_acc, int accumulate, int chunks, int frames, int channels,
+                                             int h, int w, const float* halo_cs, float* halo_grad, int total_frames,
+                                             void* stream) {
   if (!cs || !fwd_flow || !bwd_flow || !fwd_keep || !bwd_keep || !grad || !bwd_ell || !fwd_ell)
     return set_error(FRESCO_ERR_ARG, "fresco_warp_loss_fwd_bwd: null pointer");
   if (n_overflow > 0 && !overflow) return set_error(FRESCO_ERR_ARG, "fresco_warp_loss_fwd_bwd: overflow list missing");
-  if (chunks <= 0 || frames < 2 || channels <= 0 || h <= 0 || w <= 0 || h * w > 65535)
+  if ((halo_cs == nullptr) != (halo_grad == nullptr))
+    return set_error(FRESCO_ERR_ARG, "fresco_warp_loss_fwd_bwd_halo: halo_cs and halo_grad go together");
+  const int min_frames = halo_cs != nullptr ? 1 : 2;
+  if (chunks <= 0 || frames < min_frames || total_frames < frames || channels <= 0 || h <= 0 || w <= 0 || h * w > 65535)
     return set_error(FRESCO_ERR_ARG, "fresco_warp_loss_fwd_bwd: bad shape (frames >= 2, h*w <= 65535)");
-  const double numel = (double)chunks * frames * channels * h * w;
+  const double numel = (double)chunks * total_frames * channels * h * w;      // the mean runs over the WHOLE batch
   const float kk = (float)(2.0 / numel);
   cudaStream_t s = (cudaStream_t)stream;
   // ---- channel-quad kernel: 4 NQ planes per CTA interleaved in shared memory (48 bytes per pixel and quad)
@@ -1678,7 +1725,7 @@ extern "C" int fresco_warp_loss_fwd_bwd(const float* cs, const float* fwd_flow, 
     }                                                                                                                   \
     warp_loss_quad_kernel<PP, QQ><<<grid_q, threads, smem_q, s>>>(                                                      \
         cs, fwd_flow, bwd_flow, fwd_keep, bwd_keep, (const uint4*)bwd_ell, (const uint4*)fwd_ell, overflow, n_overflow, \
-        grad, loss_acc, accumulate, frames, channels, h, w, kk);                                                        \
+        grad, loss_acc, accumulate, frames, channels, h, w, kk, halo_cs, halo_grad);                                    \
     return check_launch("warp_loss_quad_kernel");                                                                       \
   }
       LQ(1, 4) LQ(2, 2) LQ(4, 1) LQ(1, 2) LQ(2, 1) LQ(1, 1)
@@ -1716,7 +1763,7 @@ extern "C" int fresco_warp_loss_fwd_bwd(const float* cs, const float* fwd_flow, 
     warp_loss_group_kernel<PP, KK><<<grid, T, smem, s>>>(cs, fwd_flow, bwd_flow, fwd_keep, bwd_keep,                    \
                                                          (const uint4*)bwd_ell, (const uint4*)fwd_ell, overflow,        \
                                                          n_overflow, grad, loss_acc, accumulate, frames, channels,      \
-                                                         planes, h, w, G, kk);                                          \
+                                                         planes, h, w, G, kk, halo_cs, halo_grad);                      \
     rc = check_launch("warp_loss_group_kernel");                                                                        \
   }
       LOSS_CASE(1, 1) LOSS_CASE(1, 2) LOSS_CASE(1, 4)
@@ -1741,7 +1788,7 @@ extern "C" int fresco_warp_loss_fwd_bwd(const float* cs, const float* fwd_flow, 
   }
   warp_loss_kernel<<<chunks * channels, 256, smem, s>>>(
       cs, fwd_flow, bwd_flow, fwd_keep, bwd_keep, (const uint4*)bwd_ell, (const uint4*)fwd_ell, overflow, n_overflow,
-      grad, loss_acc, accumulate, frames, channels, h, w, kk);
+      grad, loss_acc, accumulate, frames, channels, h, w, kk, halo_cs, halo_grad);
   return check_launch("warp_loss_kernel");
 }
 

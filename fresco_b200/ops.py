@@ -241,19 +241,39 @@ def warp_adjoint_pair(bwd_flow, fwd_flow) -> WarpAdjoint:
     return WarpAdjoint(warp_adjoint_ell(bwd_flow), warp_adjoint_ell(fwd_flow))
 
 
+class WarpAdjointSlice:
+    """Frames [lo, hi) of a :class:`WarpAdjoint` (a frame-sharded batch keeps only its own pairs)."""
+
+    def __init__(self, full: WarpAdjoint, lo: int, hi: int):
+        self.bwd = {"ell_packed": full.bwd["ell_packed"][lo:hi].contiguous()}
+        self.fwd = {"ell_packed": full.fwd["ell_packed"][lo:hi].contiguous()}
+        self.n_ovf = full.n_ovf
+        self.ovf = full.ovf[:, lo:hi].contiguous()
+
+
 def warp_loss_fwd_bwd(cs, fwd_flow, bwd_flow, fwd_keep, bwd_keep, grad, loss_acc=None, accumulate=False,
-                      adjoint=None):
-    """``adjoint`` = :class:`WarpAdjoint` from :func:`warp_adjoint_pair` (cached per batch by the caller)."""
+                      adjoint=None, halo_cs=None, halo_grad=None, total_frames=None):
+    """``adjoint`` = :class:`WarpAdjoint` from :func:`warp_adjoint_pair` (cached per batch by the caller).
+    ``halo_cs`` / ``halo_grad`` [chunks, C, h, w] fp32 + ``total_frames``: the open-chain form of a frame-sharded batch
+    (fresco_warp_loss_fwd_bwd_halo): ``cs`` holds this rank's frames, the per-pair operands its slice."""
     chunks, frames, C, h, w = cs.shape
     if adjoint is None:
         adjoint = warp_adjoint_pair(bwd_flow, fwd_flow)
     a = adjoint
+    if (halo_cs is None) != (halo_grad is None):
+        raise L.FrescoError("warp_loss_fwd_bwd: halo_cs and halo_grad go together")
+    if halo_cs is not None and (tuple(halo_cs.shape) != (chunks, C, h, w) or tuple(halo_grad.shape) != (chunks, C, h, w)
+                                or not halo_cs.is_contiguous() or not halo_grad.is_contiguous()):
+        raise L.FrescoError("warp_loss_fwd_bwd: halo planes must be contiguous [chunks, C, h, w]")
+    if fwd_flow.shape[0] != frames or a.bwd["ell_packed"].shape[0] != frames:
+        raise L.FrescoError("warp_loss_fwd_bwd: per-pair operands must have one entry per local frame")
     lp = L.ptr(loss_acc) if loss_acc is not None else None
     ev = _prof_begin()
-    L.check(L.lib().fresco_warp_loss_fwd_bwd(L.ptr(cs), L.ptr(fwd_flow), L.ptr(bwd_flow), L.ptr(fwd_keep),
-                                             L.ptr(bwd_keep), L.ptr(a.bwd["ell_packed"]), L.ptr(a.fwd["ell_packed"]),
-                                             L.ptr(a.ovf), int(a.n_ovf), L.ptr(grad), lp, 1 if accumulate else 0,
-                                             chunks, frames, C, h, w, L.stream()), "fresco_warp_loss_fwd_bwd")
+    L.check(L.lib().fresco_warp_loss_fwd_bwd_halo(
+        L.ptr(cs), L.ptr(fwd_flow), L.ptr(bwd_flow), L.ptr(fwd_keep), L.ptr(bwd_keep), L.ptr(a.bwd["ell_packed"]),
+        L.ptr(a.fwd["ell_packed"]), L.ptr(a.ovf), int(a.n_ovf), L.ptr(grad), lp, 1 if accumulate else 0, chunks, frames, C, h,
+        w, L.ptr(halo_cs) if halo_cs is not None else None, L.ptr(halo_grad) if halo_grad is not None else None,
+        int(total_frames) if total_frames is not None else frames, L.stream()), "fresco_warp_loss_fwd_bwd_halo")
     # SURVEY 8d, O2: read c1, c2 + write g1, g2 = 4 fp32 passes (the fused kernels move 2 + 1/N of them)
     _prof_end(ev, "warp_loss_C%d_%dx%d" % (C, h, w), 16.0 * cs.numel(), "hbm")
     return grad

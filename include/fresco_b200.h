@@ -124,6 +124,19 @@ int fresco_warp_loss_fwd_bwd(const float* cs, const float* fwd_flow, const float
                              const float* bwd_keep, const void* bwd_ell, const void* fwd_ell, const int32_t* overflow,
                              int n_overflow, float* grad, float* loss_acc, int accumulate, int chunks, int frames,
                              int channels, int h, int w, void* stream);
+/* Open-chain form for a frame-sharded batch (exchange 3; the reference's ring is
+ * src/diffusion_hacked.py:444,461-466): this rank holds `frames` consecutive frames of a ring of `total_frames`; pair
+ * f = (frame f, frame f+1) uses flow / keep / ELL entry f of the arrays passed (the caller passes its slice); the "next"
+ * frame of the last pair is halo_cs float [chunks, channels, h, w] (the following rank's first frame) and what that
+ * frame receives from the pair is written to halo_grad (same shape, overwritten), to be added to the following rank's
+ * grad of its first frame.  The loss mean runs over total_frames.  halo_cs = halo_grad = NULL and total_frames = frames
+ * is fresco_warp_loss_fwd_bwd.  frames >= 1.  Results are bit-identical to the closed ring (every gradient element is
+ * the same sum of the same two rounded products).                                                              */
+int fresco_warp_loss_fwd_bwd_halo(const float* cs, const float* fwd_flow, const float* bwd_flow, const float* fwd_keep,
+                                  const float* bwd_keep, const void* bwd_ell, const void* fwd_ell,
+                                  const int32_t* overflow, int n_overflow, float* grad, float* loss_acc, int accumulate,
+                                  int chunks, int frames, int channels, int h, int w, const float* halo_cs,
+                                  float* halo_grad, int total_frames, void* stream);
 
 /* ---- O3: spatial-consistency (normalised Gram, L1) loss, forward + backward -----------------
  * replaces src/diffusion_hacked.py:469-476 and its backward.

@@ -84,7 +84,7 @@ VARIANTS = [
 ]
 
 
-@pytest.mark.parametrize("variant", VARIANTS, ids=lambda v: ",".join(f"{k[12:]}={x}" for k, x in v.items()))
+@pytest.mark.parametrize("variant", VARIANTS, ids=lambda v: "-".join(f"{k[12:]}{x}" for k, x in v.items()) or "default")
 @pytest.mark.parametrize("d", [40, 64, 80, 128])
 def test_attention_variants_all_head_dims(fb, attn_opts, variant, d):
     """ragged q / kv tails, shared K/V, a peaky softmax (gain 4: lazy rescale path), kv lengths that leave one key
@@ -326,6 +326,41 @@ def test_temporal_loss_adjoint_overflow_path(fb):
                              keep_b.reshape(N, h, h).cuda().contiguous(), grad3, loss3, accumulate=False, adjoint=adj)
     assert abs(loss3.item() - float(loss_ref3)) < 1e-5 * abs(float(loss_ref3))
     assert (grad3.cpu() - grad_ref3).abs().max().item() < 1e-6 + 2e-4 * grad_ref3.abs().max().item()
+
+
+@pytest.mark.parametrize("N,C,h,world", [(8, 640, 64, 2), (8, 1280, 16, 4), (8, 1280, 8, 8), (6, 6, 24, 3), (8, 24, 40, 2)])
+def test_temporal_loss_open_chain_equals_ring(fb, N, C, h, world):
+    """Exchange 3 of the frame partition: every "rank" evaluates its own pairs with the following rank's first
+    frame as halo (fresco_warp_loss_fwd_bwd_halo) and hands the halo gradient on; the assembled gradient must be
+    BIT-identical to the closed ring over all N frames -- quad kernel, channel-grouped kernel (C % 4 != 0 is not
+    needed: 40x40 planes of 24 channels) and the generic one (C = 6)."""
+    flows, occs, cs = _layer_case(N, C, h, seed=7 * h + world)
+    ff, bf, fo, bo = O._resize_flow_occ(flows, occs, h / flows[0].shape[2])
+    dev = "cuda"
+    cs = cs.to(dev)
+    ff, bf = ff.to(dev).contiguous(), bf.to(dev).contiguous()
+    kf, kb = (1 - fo).reshape(N, h, h).to(dev).contiguous(), (1 - bo).reshape(N, h, h).to(dev).contiguous()
+    adj = fb.ops.warp_adjoint_pair(bf, ff)
+    ring = torch.empty_like(cs)
+    loss_ring = torch.zeros(1, device=dev)
+    fb.ops.warp_loss_fwd_bwd(cs, ff, bf, kf, kb, ring, loss_ring, adjoint=adj)
+    grads, halos = [], []
+    loss = torch.zeros(1, device=dev)
+    n = N // world
+    for r in range(world):
+        lo, hi = r * n, (r + 1) * n
+        mine = cs[:, lo:hi].contiguous()
+        halo_cs = cs[:, hi % N].contiguous()
+        g = torch.full_like(mine, 7.0)
+        hg = torch.full_like(halo_cs, 9.0)
+        fb.ops.warp_loss_fwd_bwd(mine, ff[lo:hi], bf[lo:hi], kf[lo:hi], kb[lo:hi], g, loss,
+                                 adjoint=fb.ops.WarpAdjointSlice(adj, lo, hi), halo_cs=halo_cs, halo_grad=hg, total_frames=N)
+        grads.append(g)
+        halos.append(hg)
+    for r in range(world):                                   # rank r's halo gradient belongs to rank r+1's first frame
+        grads[(r + 1) % world][:, 0] += halos[r]
+    assert torch.equal(torch.cat(grads, 1), ring)
+    assert abs(loss.item() - loss_ring.item()) < 1e-5 * abs(loss_ring.item())
 
 
 @pytest.mark.parametrize("N,C,h", [(8, 1280, 32), (8, 640, 64)])
