@@ -368,27 +368,79 @@ def spatial_loss_grad(cs_bcl, target, intra_weight, grad_bcl, loss_acc=None):
     ops.gram_grad(tsign, xhat, norms, grad_bcl, intra_weight)
 
 
+class _OptKernels:
+    """Compute steps of optimize_feature on the product path: the hand-written kernels behind ``ops``.  (The gloo tests
+    inject torch stand-ins with the same methods to exercise the exchange logic on CPU.)"""
+
+    def temporal_prepare(self, flows, occs, h: int, lo: int, hi: int, total: int):
+        _, fwd_flow, bwd_flow, fwd_occ, bwd_occ = resize_flows_occs(flows, occs, h)
+        w = fwd_flow.shape[-1]
+        adjoint = adjoint_csr(flows, occs, h)                   # per-batch: cached on the flow tensors
+        fwd_keep = (1 - fwd_occ).reshape(total, h, w)
+        bwd_keep = (1 - bwd_occ).reshape(total, h, w)
+        if (lo, hi) != (0, total):
+            adjoint = ops.WarpAdjointSlice(adjoint, lo, hi)
+        return {"fwd_flow": fwd_flow[lo:hi].contiguous(), "bwd_flow": bwd_flow[lo:hi].contiguous(),
+                "fwd_keep": fwd_keep[lo:hi].contiguous(), "bwd_keep": bwd_keep[lo:hi].contiguous(), "adjoint": adjoint}
+
+    def temporal(self, cs, prep, grad, loss_acc, halo_cs=None, halo_grad=None, total_frames=None):
+        ops.warp_loss_fwd_bwd(cs, prep["fwd_flow"], prep["bwd_flow"], prep["fwd_keep"], prep["bwd_keep"], grad, loss_acc,
+                              accumulate=False, adjoint=prep["adjoint"], halo_cs=halo_cs, halo_grad=halo_grad,
+                              total_frames=total_frames)
+
+    def spatial(self, cs_bcl, target, weight, grad_bcl, loss_acc):
+        spatial_loss_grad(cs_bcl, target, weight, grad_bcl, loss_acc)
+
+    def adam(self, cs, grad, exp_avg, exp_avg_sq, it):
+        ops.adam_step(cs, grad, exp_avg, exp_avg_sq, it, lr=0.2)
+
+    def adain(self, cs_bchw, sample):
+        return ops.adain(cs_bchw, sample.contiguous())
+
+
 @torch.no_grad()
 def optimize_feature(sample, flows, occs, correlation_matrix=[], intra_weight=1e2, iters=20, unet_chunk_size=2,
-                     optimize_temporal=True, trace: Optional[OptimizeTrace] = None):
+                     optimize_temporal=True, trace: Optional[OptimizeTrace] = None, shard=None, backend=None):
     """FRESCO-guided optimisation of decoder features (src/diffusion_hacked.py:416-488):
     ``iters`` Adam steps (lr 0.2) on the temporal-consistency L1 loss and the
     normalised-Gram L1 loss, then AdaIN back to the statistics of ``sample``.
-    Loss gradients are closed-form CUDA kernels (no autograd graph)."""
+    Loss gradients are closed-form CUDA kernels (no autograd graph).
+
+    ``shard=(world, rank, group | comm)`` (not in the reference): ``sample`` and the entries of ``correlation_matrix``
+    hold this rank's frames of ONE frame-sharded batch; ``flows`` / ``occs`` are the whole batch's (every rank builds the
+    same per-batch parameters).  The spatial term, Adam and AdaIN are per frame.  The temporal term couples frame f with
+    frame f+1 of the ring (:444): per Adam iteration every rank receives the following rank's first frame as a halo,
+    evaluates its own pairs in the open-chain form and sends the halo's gradient on (two neighbour exchanges of
+    [chunks, C, h, w] fp32 per iteration).  The result is bit-identical to the unsharded call when the ranks hold a
+    power-of-two share of the frames (the loss weights stay exact)."""
     have_temporal = flows is not None and occs is not None and optimize_temporal
     if (not have_temporal) and (intra_weight == 0 or len(correlation_matrix) == 0):
         return sample
+    be = backend if backend is not None else _OptKernels()
     n = sample.shape[0] // unet_chunk_size
     _, C, h, w = sample.shape
+    world = 1 if shard is None else int(shard[0])
+    comm = None
+    lo, total = 0, n
+    if world > 1:
+        from .dist import RingComm, frame_range
+        rank = int(shard[1])
+        third = shard[2] if len(shard) > 2 else None
+        comm = third if hasattr(third, "shift") else RingComm(world, rank, third)
+        total = n * world
+        if have_temporal and flows[0].shape[0] != total:
+            raise FrescoError("optimize_feature: flows must cover the whole batch (%d frames), got %d"
+                              % (total, flows[0].shape[0]))
+        lo = frame_range(total, world, rank)[0]
     cs = sample.to(torch.float32).reshape(unet_chunk_size, n, C, h, w).contiguous().clone()
     grad = torch.empty_like(cs)
     exp_avg = torch.zeros_like(cs)
     exp_avg_sq = torch.zeros_like(cs)
     if have_temporal:
-        _, fwd_flow, bwd_flow, fwd_occ, bwd_occ = resize_flows_occs(flows, occs, h)
-        fwd_keep = (1 - fwd_occ).reshape(n, h, w).contiguous()
-        bwd_keep = (1 - bwd_occ).reshape(n, h, w).contiguous()
-        adjoint = adjoint_csr(flows, occs, h)                   # per-batch: cached on the flow tensors
+        prep = be.temporal_prepare(flows, occs, h, lo, lo + n, total)
+        if comm is not None:
+            first, halo_cs, halo_grad, from_prev = (torch.empty(unet_chunk_size, C, h, w, dtype=torch.float32,
+                                                                device=sample.device) for _ in range(4))
     target = None
     for tmp in correlation_matrix:
         if h * w == tmp.shape[1]:
@@ -397,22 +449,31 @@ def optimize_feature(sample, flows, occs, correlation_matrix=[], intra_weight=1e
     spatial = target is not None and intra_weight > 0
     if spatial and not isinstance(target, GramTarget):
         target = target.to(torch.float32).contiguous()
+    # F.l1_loss averages over the frames of the WHOLE batch: a rank's share of the weight (exact for power-of-two shares)
+    weight = intra_weight * (float(n) / float(total))
     loss_acc = torch.zeros(1, dtype=torch.float32, device=sample.device) if trace is not None else None
     for it in range(1, iters + 1):
         if loss_acc is not None:
             loss_acc.zero_()
-        if have_temporal:
-            ops.warp_loss_fwd_bwd(cs, fwd_flow, bwd_flow, fwd_keep, bwd_keep, grad, loss_acc, accumulate=False,
-                                  adjoint=adjoint)
+        if have_temporal and comm is not None:
+            first.copy_(cs[:, 0])
+            comm.shift(first, halo_cs, -1)                      # my first frame is the previous rank's halo
+            be.temporal(cs, prep, grad, loss_acc, halo_cs, halo_grad, total)
+            comm.shift(halo_grad, from_prev, +1)                # what my first frame receives from the previous rank's last pair
+            grad[:, 0] += from_prev
+        elif have_temporal:
+            be.temporal(cs, prep, grad, loss_acc)
         else:
             grad.zero_()
         if spatial:
-            spatial_loss_grad(cs.view(unet_chunk_size * n, C, h * w), target, intra_weight,
-                              grad.view(unet_chunk_size * n, C, h * w), loss_acc)
-        ops.adam_step(cs, grad, exp_avg, exp_avg_sq, it, lr=0.2)
+            be.spatial(cs.view(unet_chunk_size * n, C, h * w), target, weight, grad.view(unet_chunk_size * n, C, h * w),
+                       loss_acc)
+        be.adam(cs, grad, exp_avg, exp_avg_sq, it)
         if trace is not None:
+            if comm is not None:
+                comm.all_reduce_sum(loss_acc)
             trace.losses.append(float(loss_acc.item()))
-    return ops.adain(cs.view(unet_chunk_size * n, C, h, w), sample.contiguous())
+    return be.adain(cs.view(unet_chunk_size * n, C, h, w), sample)
 
 
 def my_forward(self, steps=[], layers=[0, 1, 2, 3], flows=None, occs=None, correlation_matrix=[],
@@ -450,16 +511,11 @@ def my_forward(self, steps=[], layers=[0, 1, 2, 3], flows=None, occs=None, corre
                 up_samples.append(feat)
                 if not optimise:
                     return None
-                if shard is not None and shard[0] > 1:
-                    # frame-sharded batch: the warp chain re-shards by channel (flow_utils.warp_tensor); the feature
-                    # optimisation is not sharded (its temporal term couples neighbouring frames every Adam iteration)
-                    if (flows is not None and occs is not None and optimize_temporal) or \
-                            (intra_weight != 0 and len(correlation_matrix) > 0):
-                        raise FrescoError("optimize_feature on a frame-sharded batch is not supported")
-                    new = feat
-                else:
-                    new = optimize_feature(feat, flows, occs, correlation_matrix, intra_weight, iters,
-                                           optimize_temporal=optimize_temporal)
+                # frame-sharded batch (shard != None): optimize_feature exchanges one boundary frame per Adam iteration
+                # with its ring neighbours, warp_tensor re-shards the chain by channel
+                new = optimize_feature(feat, flows, occs, correlation_matrix, intra_weight, iters,
+                                       optimize_temporal=optimize_temporal,
+                                       shard=shard if (shard is not None and shard[0] > 1) else None)
                 if saliency is not None:
                     new = warp_tensor(new, flows, occs, saliency, 2, shard=shard)
                 if "hidden_states" in h_kwargs:

@@ -37,6 +37,29 @@ def frame_range(n_frames: int, world: int, rank: int) -> Tuple[int, int]:
     return rank * per, (rank + 1) * per
 
 
+class RingComm:
+    """Neighbour exchange of the frame ring (exchange 3): ``shift(send, recv, +1)`` sends ``send`` to rank+1
+    and fills ``recv`` from rank-1 (``-1``: the other way round).  One batched NCCL send/recv pair on the current
+    stream: no host synchronisation, capturable in a CUDA graph.  Tests inject an object with the same method."""
+
+    def __init__(self, world: int, rank: int, group=None):
+        self.world, self.rank, self.group = world, rank, group
+
+    def _peer(self, r: int) -> int:
+        r %= self.world
+        return dist.get_global_rank(self.group, r) if self.group is not None else r
+
+    def shift(self, send: torch.Tensor, recv: torch.Tensor, direction: int) -> None:
+        dst, src = self._peer(self.rank + direction), self._peer(self.rank - direction)
+        reqs = dist.batch_isend_irecv([dist.P2POp(dist.isend, send, dst, self.group),
+                                       dist.P2POp(dist.irecv, recv, src, self.group)])
+        for r in reqs:
+            r.wait()
+
+    def all_reduce_sum(self, t: torch.Tensor) -> None:
+        dist.all_reduce(t, group=self.group)
+
+
 class _OpsBackend:
     """the product path: hand-written sm_100a kernels"""
 

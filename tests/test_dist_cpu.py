@@ -293,3 +293,111 @@ def test_sharded_warp_tensor_world2_gloo():
         p.join(120)
         assert p.exitcode == 0
     assert ret.get(timeout=5) == 1
+
+
+# ------------------------------------------------------------------------------------------------ ring-halo feature optimisation
+class TorchOptBackend:
+    """torch stand-ins for the compute steps of optimize_feature (fresco_warp_loss_fwd_bwd[_halo], the Gram-L1 kernels,
+    fresco_adam_step, fresco_adain), written from the oracle's formulas"""
+
+    def __init__(self, O):
+        self.O = O
+
+    def temporal_prepare(self, flows, occs, h, lo, hi, total):
+        ff, bf, fo, bo = self.O._resize_flow_occ(flows, occs, h / flows[0].shape[2])
+        return {"ff": ff[lo:hi], "bf": bf[lo:hi], "mf": (1 - fo)[lo:hi], "mb": (1 - bo)[lo:hi]}
+
+    def temporal(self, cs, prep, grad, loss_acc, halo_cs=None, halo_grad=None, total_frames=None):
+        O = self.O
+        b, n, c, h, w = cs.shape
+        rep = lambda t: t.repeat(b, 1, 1, 1)
+        ff, bf, mf, mb = rep(prep["ff"]), rep(prep["bf"]), rep(prep["mf"]), rep(prep["mb"])
+        if halo_cs is None:
+            loss, g = O.temporal_loss_and_grad(cs, ff, bf, mf, mb)
+        else:
+            ext = torch.cat([cs, halo_cs[:, None]], 1)
+            c1 = ext[:, :n].reshape(b * n, c, h, w)
+            c2 = ext[:, 1:].reshape(b * n, c, h, w)
+            r1 = c2 - O.flow_warp(c1, bf)
+            r2 = c1 - O.flow_warp(c2, ff)
+            k = 2.0 / (b * total_frames * c * h * w)
+            loss = ((r1 * mb).abs() + (r2 * mf).abs()).sum() * k
+            s1, s2 = torch.sign(r1) * mb * k, torch.sign(r2) * mf * k
+            g = (s2 - O.flow_warp_adjoint(s1, bf)).view(b, n, c, h, w).clone()
+            g2 = (s1 - O.flow_warp_adjoint(s2, ff)).view(b, n, c, h, w)
+            g[:, 1:] += g2[:, :-1]
+            halo_grad.copy_(g2[:, -1])
+        grad.copy_(g)
+        if loss_acc is not None:
+            loss_acc += loss
+
+    def spatial(self, cs_bcl, target, weight, grad_bcl, loss_acc):
+        B, C, L = cs_bcl.shape
+        loss, g = self.O.spatial_loss_and_grad(cs_bcl.reshape(1, B, C, L, 1), target, weight)
+        grad_bcl += g.reshape(B, C, L)
+        if loss_acc is not None:
+            loss_acc += loss
+
+    def adam(self, cs, grad, m, v, it):
+        m.mul_(0.9).add_(grad, alpha=0.1)
+        v.mul_(0.999).addcmul_(grad, grad, value=0.001)
+        cs.sub_((0.2 / (1 - 0.9 ** it)) * m / (v.sqrt() / math.sqrt(1 - 0.999 ** it) + 1e-8))
+
+    def adain(self, cs_bchw, sample):
+        return self.O.adain(cs_bchw.to(sample.dtype), sample)
+
+
+def _optimize_worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from fresco_b200 import diffusion_hacked as dh
+    from oracle import fresco_oracle as O
+    N, chunks, C, h = 4, 2, 6, 8
+    flows, occs = O.synth_flows(N, 64, 64, seed=11, mag=5.0)
+    g = torch.Generator().manual_seed(4)
+    base = torch.randn(chunks, 1, C, h, h, generator=g)
+    feat = (base + 0.5 * torch.randn(chunks, N, C, h, h, generator=g)).reshape(chunks * N, C, h, h)
+    ref = feat + 0.3 * torch.randn(feat.shape, generator=g)
+    X = ref.reshape(chunks * N, C, h * h).transpose(1, 2)
+    Xh = X / (X ** 2).sum(2, keepdim=True) ** 0.5
+    target = torch.bmm(Xh, Xh.transpose(1, 2))
+    lo, hi = rank * N // world, (rank + 1) * N // world
+    sel = torch.cat([torch.arange(c * N + lo, c * N + hi) for c in range(chunks)])
+    ok = True
+    be = TorchOptBackend(O)
+    for temporal, spatial in ((True, True), (True, False), (False, True)):
+        corr = [target] if spatial else []
+        corr_l = [target[sel]] if spatial else []
+        tr_full, tr_mine = dh.OptimizeTrace(), dh.OptimizeTrace()
+        full = dh.optimize_feature(feat, flows, occs, corr, iters=6, optimize_temporal=temporal, trace=tr_full, backend=be)
+        want = O.optimize_feature(feat, flows, occs, corr, iters=6, optimize_temporal=temporal)
+        mine = dh.optimize_feature(feat[sel].contiguous(), flows, occs, corr_l, iters=6, optimize_temporal=temporal,
+                                   trace=tr_mine, shard=(world, rank, None), backend=be)
+        ok = ok and (full - want).abs().max().item() < 1e-4                    # the host loop itself against the oracle
+        ok = ok and (mine - full[sel]).abs().max().item() < 1e-4               # sharded == unsharded
+        ok = ok and all(abs(a - b) < 1e-4 * abs(a) for a, b in zip(tr_full.losses, tr_mine.losses))
+    t = torch.tensor([1 if ok else 0])
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        ret.put(int(t.item()))
+    dist.destroy_process_group()
+
+
+def test_sharded_optimize_feature_world2_gloo():
+    """optimize_feature on a frame-sharded batch (ring halo of one boundary frame per Adam iteration, SURVEY 8e exchange
+    3): both ranks together == the unsharded call == the oracle, loss curves included."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    procs = [ctx.Process(target=_optimize_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert ret.get(timeout=5) == 1

@@ -363,6 +363,89 @@ def test_temporal_loss_open_chain_equals_ring(fb, N, C, h, world):
     assert abs(loss.item() - loss_ring.item()) < 1e-5 * abs(loss_ring.item())
 
 
+class _LockstepRing:
+    """Ring communicator for `world` ranks emulated by threads of ONE process on one GPU: a rank holds the lock while it
+    issues work and gives it up only inside an exchange, so the ranks' kernel sequences interleave exactly at the halo
+    exchanges (all on the same stream: program order is execution order)."""
+
+    def __init__(self, world):
+        import threading
+        self.world = world
+        self.lock = threading.Lock()
+        self.barrier = threading.Barrier(world)
+        self.slots = [None] * world
+
+    class _Comm:
+        def __init__(self, ring, rank):
+            self.ring, self.rank = ring, rank
+
+        def _publish(self, t):
+            r = self.ring
+            r.slots[self.rank] = t
+            r.lock.release()
+            r.barrier.wait()
+            r.lock.acquire()
+
+        def _done(self):
+            r = self.ring
+            r.lock.release()
+            r.barrier.wait()
+            r.lock.acquire()
+
+        def shift(self, send, recv, direction):
+            self._publish(send)
+            recv.copy_(self.ring.slots[(self.rank - direction) % self.ring.world])
+            self._done()
+
+        def all_reduce_sum(self, t):
+            self._publish(t.clone())
+            total = sum(self.ring.slots[1:], self.ring.slots[0].clone())
+            self._done()
+            t.copy_(total)
+
+    def comm(self, rank):
+        return self._Comm(self, rank)
+
+
+@pytest.mark.parametrize("N,C,h,world", [(8, 640, 64, 2), (8, 1280, 16, 4)])
+def test_optimize_feature_ring_halo_bit_identical(fb, N, C, h, world):
+    """optimize_feature on a frame-sharded batch (the ranks emulated by threads in lock step, real kernels): temporal +
+    Gram-L1 terms, Adam, AdaIN -- the ranks' outputs together are BIT-identical to the unsharded call."""
+    import threading
+    flows, occs, cs = _layer_case(N, C, h, seed=31 + h)
+    flows = [f.cuda() for f in flows]
+    occs = [o.cuda() for o in occs]
+    sample = cs.reshape(2 * N, C, h, h).half().cuda()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    ref = (sample.float() + 0.5 * torch.randn(sample.shape, device="cuda", generator=g)).half()
+    target = fb.dh.gram_targets([ref])[0]
+    full = fb.dh.optimize_feature(sample, flows, occs, correlation_matrix=[target], iters=6)
+    ring = _LockstepRing(world)
+    n = N // world
+    outs, errs = [None] * world, []
+
+    def run(rank):
+        ring.lock.acquire()
+        try:
+            sel = torch.cat([torch.arange(c * N + rank * n, c * N + (rank + 1) * n) for c in range(2)]).cuda()
+            tgt = fb.dh.GramTarget(target.yhat[sel].contiguous())
+            outs[rank] = (sel, fb.dh.optimize_feature(sample[sel].contiguous(), flows, occs, correlation_matrix=[tgt], iters=6,
+                                                      shard=(world, rank, ring.comm(rank))))
+        except Exception as e:                                  # noqa: BLE001 (reported below; a dead rank must not hang the others)
+            errs.append(e)
+            ring.barrier.abort()
+        finally:
+            ring.lock.release()
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(300)
+    assert not errs, errs
+    for sel, out in outs:
+        assert torch.equal(out, full[sel])
+
+
 @pytest.mark.parametrize("N,C,h", [(8, 1280, 32), (8, 640, 64)])
 def test_spatial_loss_teacher_forced_layer_shapes(fb, N, C, h):
     """O3 at layers 2 and 3 of config 3 ([16,1280,32,32], [16,640,64,64]): loss, sign matrix exact outside the fp16
