@@ -211,8 +211,17 @@ class Workload:
         if shard is not None:
             # frame-sharded batch: FRESCO attention (K/V all-gather, trajectory all-to-alls) + the warp_tensor fusion of
             # config 2 with the chain re-sharded by channel (two all-to-alls per decoder feature)
-            dh.apply_FRESCO_opt(self.pipe, steps=OPT_STEPS, flows=self.flows, occs=self.occs, correlation_matrix=[],
-                                optimize_temporal=False, saliency=self.saliency, shard=(shard[0], shard[1], None))
+            gram = []
+            if optimise:
+                # + config 3's work on the sharded batch: Gram targets of this rank's frames, temporal term through the
+                # ring-halo exchange (one boundary frame per Adam iteration to each neighbour)
+                with torch.no_grad():
+                    feats = self.pipe.unet(torch.cat([self.latents] * 2), TIMESTEPS[-1], encoder_hidden_states=self.prompt,
+                                           return_dict=False)[1:]
+                gram = dh.gram_targets(feats)
+            dh.apply_FRESCO_opt(self.pipe, steps=OPT_STEPS, flows=self.flows, occs=self.occs, correlation_matrix=gram,
+                                intra_weight=1e2, iters=20, optimize_temporal=optimise, saliency=self.saliency,
+                                shard=(shard[0], shard[1], None))
             return
         if optimise:
             # BASELINE configs[2]: FRESCO feature optimisation (20 Adam iterations, temporal + Gram-L1 loss) on the 4
@@ -524,7 +533,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the kernels side pass and the GPU eager baseline")
     ap.add_argument("--cpu-sample-frames", type=int, default=2)
     ap.add_argument("--cpu-budget-s", type=float, default=150.0)
-    ap.add_argument("--workload", default="auto", choices=["auto", "config2", "config3", "config4", "config5", "replicas"],
+    ap.add_argument("--workload", default="auto", choices=["auto", "config2", "config3", "config4", "config4opt", "config5", "replicas"],
                     help="auto: config2 on one GPU, config4 (ONE N=16 batch frame-sharded) on several; config3: + feature "
                          "optimisation and GMFlow's correlation kernel; replicas: one independent N=8 batch per GPU")
     ap.add_argument("--graphs", default="auto", choices=["auto", "on", "off"],
@@ -545,7 +554,7 @@ def main():
         workload = "config2"
         replicas = True
     else:
-        replicas = world > 1 and workload not in ("config4", "config5")
+        replicas = world > 1 and workload not in ("config4", "config4opt", "config5")
     config = {"workload": "N=8 keyframes 512x512 (CFG batch 16), SD1.5-shaped random-init fp16 UNet, FRESCO "
                           "attention (cross-frame + spatial step 0 + temporal t>=350) on 6 decoder layers + "
                           "warp_tensor fusion on 4 decoder features; 15-step DDPM schedule t=700..0 walked cyclically",
@@ -584,25 +593,28 @@ def main():
                        " + warp_tensor fusion on 4 decoder features" + (", frame-sharded over the ranks" if world > 1 else ""),
                        "resolution": res,
                        "parallelism": "one GPU" if world == 1 else "frame-sharded x%d (strong scaling of one batch)" % world})
-    elif workload == "config4":
+    elif workload in ("config4", "config4opt"):
         # every rank must build the same per-batch parameters (same seed); only the frame slice differs
         n_frames = N_FRAMES_SHARDED
-        wl = Workload(device, seed=0, n_frames=n_frames, shard=(world, rank))
+        wl = Workload(device, seed=0, n_frames=n_frames, shard=(world, rank), optimise=workload == "config4opt")
         config.update({"workload": "ONE batch of N=16 keyframes 512x512 (CFG batch 32) frame-sharded over the ranks, SD1.5-"
                        "shaped random-init fp16 UNet, FRESCO attention on 6 decoder layers: one NCCL all-gather of the "
                        "compacted K/V per layer + trajectory-sharded temporal attention (two all-to-alls per layer while "
                        "it is on) + warp_tensor fusion on 4 decoder features re-sharded by channel (two all-to-alls each); "
                        "value counts 8-keyframe batch-steps (one step of this batch = 2)",
                        "frames": n_frames, "parallelism": "frame-sharded x%d (strong scaling of one batch)" % world})
+        if workload == "config4opt":
+            config["workload"] += ("; + optimize_feature (20 Adam iterations, temporal + Gram-L1) on the 4 decoder features "
+                                   "on 10 of 15 steps, sharded by frames: ring halo of one boundary frame per iteration")
     else:
         wl = Workload(device, seed=rank, optimise=workload == "config3", with_gmflow=workload == "config3")
     if workload == "config3":
         config["workload"] += ("; + optimize_feature (20 Adam iters, temporal + Gram-L1) on 4 decoder features, 10 of 15 "
                                "steps; + GMFlow global correlation (8 pairs, 128 x 64 x 64, bidirectional) once per cycle")
-    shard_check = sharded_selfcheck(wl, world, rank) if (world > 1 and workload in ("config4", "config5")) else None
+    shard_check = sharded_selfcheck(wl, world, rank) if (world > 1 and workload in ("config4", "config4opt", "config5")) else None
     if shard_check is not None and not shard_check["bit_identical_to_unsharded"]:
         raise SystemExit("config 4: the frame-sharded layer is not bit-identical to the unsharded one")
-    sharded = world > 1 and workload in ("config4", "config5")
+    sharded = world > 1 and workload in ("config4", "config4opt", "config5")
     use_graphs = args.graphs == "on" or (args.graphs == "auto" and sharded)
     graph_note = None
     if use_graphs:
@@ -651,7 +663,7 @@ def main():
     # ---- e2e: pinned-host inputs / outputs copied inside the timed region
     ms_e2e = timed_region(wl, args.steps, 1, True, world)
 
-    units = (n_frames / float(N_FRAMES)) if workload in ("config4", "config5") else (world if replicas else 1)
+    units = (n_frames / float(N_FRAMES)) if workload in ("config4", "config4opt", "config5") else (world if replicas else 1)
     value = units * args.steps / (ms / 1000.0)
     e2e_value = units * args.steps / (ms_e2e / 1000.0)
     h2d = wl.latents_host.numel() * 2 + wl.prompt_host.numel() * 2

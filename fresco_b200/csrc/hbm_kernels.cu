@@ -676,6 +676,11 @@ __global__ void warp_taps_kernel(const float* __restrict__ flow, int32_t* __rest
   }
 }
 
+// overflow lists (destinations with more than 8 taps) are sorted by destination; -1 pads the tail
+__device__ __forceinline__ bool ovf_run_head(const int32_t* __restrict__ o, int e) {
+  return o[3 * e] >= 0 && (e == 0 || o[3 * (e - 1)] != o[3 * e]);
+}
+
 __global__ void warp_loss_kernel(const float* __restrict__ cs, const float* __restrict__ fwd_flow,
                                  const float* __restrict__ bwd_flow, const float* __restrict__ fwd_keep,
                                  const float* __restrict__ bwd_keep, const uint4* __restrict__ bwd_ell,
@@ -771,9 +776,24 @@ __global__ void warp_loss_kernel(const float* __restrict__ cs, const float* __re
       __syncthreads();
       const int32_t* ob = ovf + ((long long)0 * frames + f) * n_ovf * 3;
       const int32_t* of = ovf + ((long long)1 * frames + f) * n_ovf * 3;
+      // entries are sorted by destination: the thread that holds the head of a run sums the run in list order (no
+      // atomics: the result does not depend on scheduling, which the frame-sharded bit-identity tests rely on)
       for (int e = threadIdx.x; e < n_ovf; e += blockDim.x) {
-        if (ob[3 * e] >= 0) atomicAdd(ga + ob[3 * e], -__int_as_float(ob[3 * e + 2]) * s1[ob[3 * e + 1]]);
-        if (of[3 * e] >= 0) atomicAdd(gb + of[3 * e], -__int_as_float(of[3 * e + 2]) * s2[of[3 * e + 1]]);
+        if (ovf_run_head(ob, e)) {
+          float acc = 0.f;
+          for (int e2 = e; e2 < n_ovf && ob[3 * e2] == ob[3 * e]; ++e2)
+            acc = fmaf(-__int_as_float(ob[3 * e2 + 2]), s1[ob[3 * e2 + 1]], acc);
+          ga[ob[3 * e]] += acc;
+        }
+      }
+      __syncthreads();                                          // (frames <= 2: ga and gb may be the same plane)
+      for (int e = threadIdx.x; e < n_ovf; e += blockDim.x) {
+        if (ovf_run_head(of, e)) {
+          float acc = 0.f;
+          for (int e2 = e; e2 < n_ovf && of[3 * e2] == of[3 * e]; ++e2)
+            acc = fmaf(-__int_as_float(of[3 * e2 + 2]), s2[of[3 * e2 + 1]], acc);
+          gb[of[3 * e]] += acc;
+        }
       }
     }
   }
@@ -888,17 +908,22 @@ warp_loss_group_kernel(const float* __restrict__ cs, const float* __restrict__ f
       }
     }
     __syncthreads();
-    // ---- destinations hit by more than 8 taps of the forward-flow warp (rare): their extra terms of d/dc2 go
-    //      through the dead frame-f planes, which the gather below adds in
+    // ---- destinations hit by more than 8 taps of the backward-flow warp: their extra terms of d/dc1 (frame f) go
+    //      through the dead frame-f planes and join ga BEFORE it meets the carry -- a frame-sharded batch adds the carry
+    //      of a shard's first frame on the host and must see the same association.  Entries are sorted by destination:
+    //      the thread that holds the head of a run sums the run in list order (no atomics, deterministic).
     if (n_ovf > 0) {
       for (int idx = t; idx < K * hw; idx += T) cur[idx] = 0.f;
       __syncthreads();
-      const int32_t* of = ovf + ((long long)1 * frames + f) * n_ovf * 3;
+      const int32_t* ob = ovf + ((long long)0 * frames + f) * n_ovf * 3;
       for (int e = t; e < n_ovf; e += T) {
-        if (of[3 * e] < 0) continue;
-        const float wgt = __int_as_float(of[3 * e + 2]);
-        for (int slot = 0; slot < K; ++slot)
-          atomicAdd(cur + slot * hw + of[3 * e], -wgt * __half2float(s2[slot * hw + of[3 * e + 1]]));
+        if (!ovf_run_head(ob, e)) continue;
+        for (int slot = 0; slot < K; ++slot) {
+          float acc = 0.f;
+          for (int e2 = e; e2 < n_ovf && ob[3 * e2] == ob[3 * e]; ++e2)
+            acc = fmaf(-__int_as_float(ob[3 * e2 + 2]), __half2float(s1[slot * hw + ob[3 * e2 + 1]]), acc);
+          cur[slot * hw + ob[3 * e]] = acc;
+        }
       }
       __syncthreads();
     }
@@ -916,7 +941,7 @@ warp_loss_group_kernel(const float* __restrict__ cs, const float* __restrict__ f
         const int slot = kk * G + g;
         ga[kk] = __half2float(s2[slot * hw + q]);             // d/dc1 = s2 - W_bf^T s1   (frame f)
         gb[kk] = __half2float(s1[slot * hw + q]);             // d/dc2 = s1 - W_ff^T s2   (frame fn)
-        if (n_ovf > 0) gb[kk] += cur[slot * hw + q];
+        if (n_ovf > 0) ga[kk] += cur[slot * hw + q];
       }
       {
         const uint4 e0 = __ldg(ebp + 2 * q), e1 = __ldg(ebp + 2 * q + 1);
@@ -957,24 +982,31 @@ warp_loss_group_kernel(const float* __restrict__ cs, const float* __restrict__ f
         carry[pp * KT + kk] = gb[kk];
       }
     }
-    __syncthreads();                                           // s1 / s2 / cur are rewritten by the next pair
-    // ---- destinations with more than 8 taps of the backward-flow warp: extra terms of d/dc1, frame f is final in
-    //      global memory now
+    // ---- destinations with more than 8 taps of the forward-flow warp: extra terms of d/dc2, added to the carry
     if (n_ovf > 0) {
-      const int32_t* ob = ovf + ((long long)0 * frames + f) * n_ovf * 3;
+      __syncthreads();
+      for (int idx = t; idx < K * hw; idx += T) cur[idx] = 0.f;
+      __syncthreads();
+      const int32_t* of = ovf + ((long long)1 * frames + f) * n_ovf * 3;
       for (int e = t; e < n_ovf; e += T) {
-        if (ob[3 * e] < 0) continue;
-        const float wgt = __int_as_float(ob[3 * e + 2]);
+        if (!ovf_run_head(of, e)) continue;
         for (int slot = 0; slot < K; ++slot) {
-          const int pl = blockIdx.x * K + slot;
-          if (pl >= planes_total) break;
-          const int b = pl / channels, c = pl % channels;
-          atomicAdd(grad + ((long long)(b * frames + f) * channels + c) * hw + ob[3 * e],
-                    -wgt * __half2float(s1[slot * hw + ob[3 * e + 1]]) * k);
+          float acc = 0.f;
+          for (int e2 = e; e2 < n_ovf && of[3 * e2] == of[3 * e]; ++e2)
+            acc = fmaf(-__int_as_float(of[3 * e2 + 2]), __half2float(s2[slot * hw + of[3 * e2 + 1]]), acc);
+          cur[slot * hw + of[3 * e]] = acc;
         }
       }
       __syncthreads();
+#pragma unroll
+      for (int pp = 0; pp < P; ++pp) {
+        const int q = q0 + pp * T;
+        if (!active || q >= hw) continue;
+#pragma unroll
+        for (int kk = 0; kk < KT; ++kk) carry[pp * KT + kk] += cur[(kk * G + g) * hw + q];
+      }
     }
+    __syncthreads();                                           // s1 / s2 / cur are rewritten by the next pair
     float* tmp = cur;                                          // frame fn becomes frame f of the next pair
     cur = nxt;
     nxt = tmp;
@@ -1102,22 +1134,24 @@ warp_loss_quad_kernel(const float* __restrict__ cs, const float* __restrict__ fw
       }
     }
     __syncthreads();
-    // ---- destinations hit by more than 8 taps of the forward-flow warp (rare): extra terms of d/dc2 through the dead
-    //      frame-f planes, which the gather below adds in
+    // ---- destinations hit by more than 8 taps of the backward-flow warp: extra terms of d/dc1 (frame f) through the
+    //      dead frame-f planes; they join ga BEFORE it meets the carry (see warp_loss_group_kernel); run heads only, runs
+    //      summed in list order: no atomics, deterministic
     if (n_ovf > 0) {
       for (int q = t; q < NQ * hw; q += T) cur[q] = make_float4(0.f, 0.f, 0.f, 0.f);
       __syncthreads();
-      const int32_t* of = ovf + ((long long)1 * frames + f) * n_ovf * 3;
+      const int32_t* ob = ovf + ((long long)0 * frames + f) * n_ovf * 3;
       for (int e = t; e < n_ovf; e += T) {
-        if (of[3 * e] < 0) continue;
-        const float wgt = -__int_as_float(of[3 * e + 2]);
+        if (!ovf_run_head(ob, e)) continue;
         for (int nq = 0; nq < NQ; ++nq) {
-          const float4 v = h4_to_f4(s2[nq * hw + of[3 * e + 1]]);
-          float* dst = reinterpret_cast<float*>(cur + nq * hw + of[3 * e]);
-          atomicAdd(dst + 0, wgt * v.x);
-          atomicAdd(dst + 1, wgt * v.y);
-          atomicAdd(dst + 2, wgt * v.z);
-          atomicAdd(dst + 3, wgt * v.w);
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int e2 = e; e2 < n_ovf && ob[3 * e2] == ob[3 * e]; ++e2) {
+            const float wgt = -__int_as_float(ob[3 * e2 + 2]);
+            const float4 v = h4_to_f4(s1[nq * hw + ob[3 * e2 + 1]]);
+            acc.x = fmaf(wgt, v.x, acc.x), acc.y = fmaf(wgt, v.y, acc.y);
+            acc.z = fmaf(wgt, v.z, acc.z), acc.w = fmaf(wgt, v.w, acc.w);
+          }
+          cur[nq * hw + ob[3 * e]] = acc;
         }
       }
       __syncthreads();
@@ -1140,7 +1174,7 @@ warp_loss_quad_kernel(const float* __restrict__ cs, const float* __restrict__ fw
           gb[nq] = h4_to_f4(s1[nq * hw + qq]);                  // d/dc2 = s1 - W_ff^T s2   (frame fn)
           if (n_ovf > 0) {
             const float4 o = cur[nq * hw + qq];
-            gb[nq].x += o.x, gb[nq].y += o.y, gb[nq].z += o.z, gb[nq].w += o.w;
+            ga[nq].x += o.x, ga[nq].y += o.y, ga[nq].z += o.z, ga[nq].w += o.w;
           }
         }
         {
@@ -1195,26 +1229,39 @@ warp_loss_quad_kernel(const float* __restrict__ cs, const float* __restrict__ fw
         }
       }
     }
-    __syncthreads();                                           // s1 / s2 / cur are rewritten by the next pair
-    // ---- destinations with more than 8 taps of the backward-flow warp: extra terms of d/dc1 (frame f is final in
-    //      global memory now)
+    // ---- destinations with more than 8 taps of the forward-flow warp: extra terms of d/dc2, added to the carry
     if (n_ovf > 0) {
-      const int32_t* ob = ovf + ((long long)0 * frames + f) * n_ovf * 3;
-      float* gdst = grad + base + (long long)f * fstride;
+      __syncthreads();
+      for (int q = t; q < NQ * hw; q += T) cur[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      __syncthreads();
+      const int32_t* of = ovf + ((long long)1 * frames + f) * n_ovf * 3;
       for (int e = t; e < n_ovf; e += T) {
-        if (ob[3 * e] < 0) continue;
-        const float wgt = -__int_as_float(ob[3 * e + 2]) * k;
+        if (!ovf_run_head(of, e)) continue;
         for (int nq = 0; nq < NQ; ++nq) {
-          const float4 v = h4_to_f4(s1[nq * hw + ob[3 * e + 1]]);
-          float* g4 = gdst + (long long)nq * 4 * hw + ob[3 * e];
-          atomicAdd(g4, wgt * v.x);
-          atomicAdd(g4 + hw, wgt * v.y);
-          atomicAdd(g4 + 2 * hw, wgt * v.z);
-          atomicAdd(g4 + 3 * hw, wgt * v.w);
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int e2 = e; e2 < n_ovf && of[3 * e2] == of[3 * e]; ++e2) {
+            const float wgt = -__int_as_float(of[3 * e2 + 2]);
+            const float4 v = h4_to_f4(s2[nq * hw + of[3 * e2 + 1]]);
+            acc.x = fmaf(wgt, v.x, acc.x), acc.y = fmaf(wgt, v.y, acc.y);
+            acc.z = fmaf(wgt, v.z, acc.z), acc.w = fmaf(wgt, v.w, acc.w);
+          }
+          cur[nq * hw + of[3 * e]] = acc;
         }
       }
       __syncthreads();
+#pragma unroll
+      for (int pp = 0; pp < P; ++pp) {
+        const int q = t + pp * T;
+        if (q < hw) {
+#pragma unroll
+          for (int nq = 0; nq < NQ; ++nq) {
+            const float4 o = cur[nq * hw + q];
+            carry[pp][nq].x += o.x, carry[pp][nq].y += o.y, carry[pp][nq].z += o.z, carry[pp][nq].w += o.w;
+          }
+        }
+      }
     }
+    __syncthreads();                                           // s1 / s2 / cur are rewritten by the next pair
     float4* tmp = cur;                                          // frame fn becomes frame f of the next pair
     cur = nxt;
     nxt = tmp;

@@ -328,12 +328,14 @@ def test_temporal_loss_adjoint_overflow_path(fb):
     assert (grad3.cpu() - grad_ref3).abs().max().item() < 1e-6 + 2e-4 * grad_ref3.abs().max().item()
 
 
-@pytest.mark.parametrize("N,C,h,world", [(8, 640, 64, 2), (8, 1280, 16, 4), (8, 1280, 8, 8), (6, 6, 24, 3), (8, 24, 40, 2)])
+@pytest.mark.parametrize("N,C,h,world", [(8, 640, 64, 2), (8, 1280, 16, 4), (8, 1280, 8, 8), (6, 6, 24, 3), (8, 24, 40, 2),
+                                         (4, 4, 100, 2)])
 def test_temporal_loss_open_chain_equals_ring(fb, N, C, h, world):
     """Exchange 3 of the frame partition: every "rank" evaluates its own pairs with the following rank's first
     frame as halo (fresco_warp_loss_fwd_bwd_halo) and hands the halo gradient on; the assembled gradient must be
-    BIT-identical to the closed ring over all N frames -- quad kernel, channel-grouped kernel (C % 4 != 0 is not
-    needed: 40x40 planes of 24 channels) and the generic one (C = 6)."""
+    BIT-identical to the closed ring over all N frames, ELL overflow lists included (they are summed in list order, no
+    atomics) -- quad kernel, channel-grouped kernel (C = 6 / 24) and the one-plane-per-CTA kernel (100 x 100 planes;
+    that one associates the overflow terms differently, so it is bit-identical only when no ELL row overflows)."""
     flows, occs, cs = _layer_case(N, C, h, seed=7 * h + world)
     ff, bf, fo, bo = O._resize_flow_occ(flows, occs, h / flows[0].shape[2])
     dev = "cuda"
@@ -359,7 +361,11 @@ def test_temporal_loss_open_chain_equals_ring(fb, N, C, h, world):
         halos.append(hg)
     for r in range(world):                                   # rank r's halo gradient belongs to rank r+1's first frame
         grads[(r + 1) % world][:, 0] += halos[r]
-    assert torch.equal(torch.cat(grads, 1), ring)
+    got = torch.cat(grads, 1)
+    if h * h > 9216 and adj.n_ovf > 0:
+        assert (got - ring).abs().max().item() < 1e-6 * ring.abs().max().item()
+    else:
+        assert torch.equal(got, ring), (adj.n_ovf, (got - ring).abs().max().item())
     assert abs(loss.item() - loss_ring.item()) < 1e-5 * abs(loss_ring.item())
 
 
