@@ -1147,11 +1147,17 @@ fresco_attn_duo_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
     const unsigned long long scale2 = pack_f2(scale_log2, scale_log2);
     const int pair_bar = 1 + quarter;          // named barrier of the two warps that share these 32 rows
     float m_run = -INFINITY, l_run = 0.f;
+    // warp-uniform "this tile needs the mask / bias path", reduced to two compares per tile: the ragged tail starts at
+    // tile i_tail (first tile whose 32 keys of this part reach past kv_len), and this warp's 32 rows [r0, r0 + 32) meet
+    // the diagonal in exactly one 32-key part (both are 32-aligned): tile i_diag of the part with 64 i + 32 part == r0
+    const int tail_num = kv_len - 32 * part - 32;
+    const int i_tail = tail_num >= 0 ? tail_num / kTileN + 1 : 0;
+    const int r0 = q0 + quarter * 32;
+    const int i_diag = (use_bias && r0 >= 32 * part && ((r0 - 32 * part) % kTileN) == 0) ? (r0 - 32 * part) / kTileN : -1;
 
     for (int i = 0; i < n_tiles; ++i) {
       const int col0 = i * kTileN + 32 * part;
-      const bool special = (col0 + 32 > kv_len) ||
-                           (use_bias && (q0 + quarter * 32) < col0 + 32 && (q0 + quarter * 32 + 32) > col0);
+      const bool special = (i >= i_tail) || (i == i_diag);
       mbar_wait(bar_s + (i & 1), (i >> 1) & 1, 2);
       tc_fence_after();
       uint32_t r[32];
@@ -1280,6 +1286,331 @@ fresco_attn_duo_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
 }
 
 // ---------------------------------------------------------------------------------------------
+// the "twin" kernel: TWO 128-row query tiles per CTA, 128-key tiles, one thread per query row (1 CTA per SM)
+// ---------------------------------------------------------------------------------------------
+// Written from the round-2 profiles (profiles/r02_attn_*_hot_*.txt): the 64-key kernels above execute 368 (pipelined)
+// to 572 (duo) warp-instructions per 128 x 64 tile of which 161 are the softmax arithmetic itself -- waits, arrivals,
+// buffer indexing, the lazy-max test and the polling loops are paid per (warp, tile) whatever the tile holds -- and the
+// issue slots (56-68 % busy), not the MUFU pipe (65 %), are what every structure runs into at ~840 clocks per tile.
+// Here a softmax thread owns a whole row of a 128-key tile (128 scores in registers: one CTA per SM leaves 200 registers
+// per thread), so the per-tile overhead is paid once per 128 keys, and there are only two barrier operations per
+// tile: P overwrites the first half of the S columns it was computed from (the thread has them in registers), the score
+// MMA of the next tile is issued behind the P V MMA by the same thread, so "S_j is ready" implies "P V_{j-1} has
+// retired" -- no P-buffer or O-stability waits at all.  The two query tiles (A, B) take turns: while the warps of A
+// are in their exponentials the tensor core runs P V / Q K^T for B.
+//
+//   TMEM  S_A [0,128)  S_B [128,256)  (fp32 scores; P = fp16 in columns [0,64) of the same region)
+//         O_A [256,256+DPAD)  O_B [384,384+DPAD)   row sums (ones-MMA) in the 16 columns behind each O
+template <int D>
+struct TwinCfg {
+  static constexpr int KV = 128;                          // keys per tile
+  static constexpr int NATOM = (D + 63) / 64;
+  static constexpr int KSTEPS = (D + 15) / 16;
+  static constexpr int DPAD = KSTEPS * 16;
+  static constexpr int N0 = DPAD < 64 ? DPAD : 64;
+  static constexpr int N1 = DPAD - N0;
+  static constexpr int S_OFF_A = 0, S_OFF_B = 128, O_OFF_A = 256, O_OFF_B = 384;
+  static constexpr int L_COL = DPAD;                      // row-sum columns sit right behind O (DPAD + 16 <= 128)
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int TILE_BYTES = NATOM * kQAtomBytes;  // a [128 rows x D] tile: Q tile, K tile or V tile
+  static constexpr int STAGES = NATOM == 1 ? 4 : 2;
+  static constexpr int STAGE_BYTES = 2 * TILE_BYTES;      // K | V
+  static constexpr int SMEM_BYTES = 1024 + 2 * TILE_BYTES + STAGES * STAGE_BYTES + 2048 + 256;
+  // 8 softmax warps + MMA issuer + TMA producer + 2 idle warps: three whole warpgroups, so that setmaxnreg can move
+  // registers from the issuer warpgroup (40 each) to the softmax warpgroups (232 each: a 128-score row plus its packed
+  // half live in registers); 384 threads x 168 = the whole register file
+  static constexpr int THREADS = 384;
+  static constexpr int MMA_WARP = 8, TMA_WARP = 9;
+};
+
+__device__ __forceinline__ void tmem_ld_wait_dep128(uint32_t (&r)[128]) {
+#define FR8(b) "+r"(r[b]), "+r"(r[b + 1]), "+r"(r[b + 2]), "+r"(r[b + 3]), "+r"(r[b + 4]), "+r"(r[b + 5]), "+r"(r[b + 6]), "+r"(r[b + 7])
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : FR8(0), FR8(8), FR8(16), FR8(24) : : "memory");
+  asm volatile("" : FR8(32), FR8(40), FR8(48), FR8(56) : : "memory");
+  asm volatile("" : FR8(64), FR8(72), FR8(80), FR8(88) : : "memory");
+  asm volatile("" : FR8(96), FR8(104), FR8(112), FR8(120) : : "memory");
+#undef FR8
+}
+// Waits of the twin kernel: no out-of-line call on the time-out path.  ptxas caps a whole kernel at its smallest
+// setmaxnreg value as soon as the kernel contains a real function call (mbar_timeout's printf), which would leave the
+// softmax warps 40 registers instead of 232; the watchdog therefore just traps.
+__device__ __forceinline__ void mbar_wait_trap(uint64_t* bar, uint32_t parity) {
+  uint32_t polls = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++polls > FRESCO_WATCHDOG_POLLS) __trap();
+  }
+}
+// one elected lane of a converged warp arrives (no branch, no divergence)
+__device__ __forceinline__ void mbar_arrive_elected(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "@P mbarrier.arrive.shared::cta.b64 _, [%0];\n\t}\n" ::"r"(smem_u32(bar))
+      : "memory");
+}
+
+template <int D, int POLY>
+__global__ void __launch_bounds__(TwinCfg<D>::THREADS, 1)
+fresco_attn_twin_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                        const __grid_constant__ CUtensorMap tm_v, const AttnParams p) {
+  using Cfg = TwinCfg<D>;
+  constexpr int ST = Cfg::STAGES;
+  constexpr int KV = Cfg::KV;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_q = smem;                                         // [2][TILE_BYTES]  query tiles A, B
+  uint8_t* s_kv = smem + 2 * Cfg::TILE_BYTES;                  // [ST][K tile | V tile]
+  uint8_t* s_ones = s_kv + ST * Cfg::STAGE_BYTES;              // [16 keys x 128 B] of fp16 1.0
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ones + 2048);
+  uint64_t* bar_q = bars + 0;
+  uint64_t* bar_kv_full = bars + 1;            // [ST]
+  uint64_t* bar_kv_empty = bars + 1 + ST;      // [ST]
+  uint64_t* bar_s = bars + 1 + 2 * ST;         // [2]  S_X(j) ready (and P V_X(j-1) retired); phase j & 1
+  uint64_t* bar_p = bar_s + 2;                 // [2]  P_X(j) written by the four warps of X; phase j & 1
+  uint64_t* bar_o = bar_s + 4;                 // [2]  last P V_X retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s + 6);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * (2 * kTileM);
+  const int head = blockIdx.y;
+  const int b = blockIdx.z;
+  const int b_kv = b / p.q_per_kv;
+  const int n_tiles = (p.kv_len + KV - 1) / KV;
+
+  if (warp == Cfg::TMA_WARP && lane == 0) {
+    mbar_init(bar_q, 1);
+    for (int s = 0; s < ST; ++s) {
+      mbar_init(bar_kv_full + s, 1);
+      mbar_init(bar_kv_empty + s, 1);
+    }
+    for (int x = 0; x < 2; ++x) {
+      mbar_init(bar_s + x, 1);
+      mbar_init(bar_p + x, 4);
+      mbar_init(bar_o + x, 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == Cfg::MMA_WARP) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tm_q);
+      tma_prefetch_desc(&tm_k);
+      tma_prefetch_desc(&tm_v);
+    }
+    __syncwarp();
+    tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  }
+  for (int i = threadIdx.x; i < 2048 / 4; i += Cfg::THREADS) reinterpret_cast<uint32_t*>(s_ones)[i] = 0x3C003C00u;
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp >= 8) {
+    // ------------------------------------------------------------ issuer warpgroup (warps 10, 11 idle)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+  if (warp == Cfg::TMA_WARP) {
+    // ------------------------------------------------------------ TMA producer
+    if (FRESCO_ISSUER_THREAD(lane)) {
+      mbar_expect_tx(bar_q, 2 * Cfg::TILE_BYTES);
+#pragma unroll
+      for (int x = 0; x < 2; ++x)
+#pragma unroll
+        for (int a = 0; a < Cfg::NATOM; ++a)
+          tma_load_4d(s_q + x * Cfg::TILE_BYTES + a * kQAtomBytes, &tm_q, bar_q, a * 64, head, q0 + x * kTileM, b);
+      for (int t = 0; t < n_tiles; ++t) {
+        const int st = t % ST;
+        if (t >= ST) mbar_wait_trap(bar_kv_empty + st, ((t / ST) - 1) & 1);
+        uint8_t* sk = s_kv + st * Cfg::STAGE_BYTES;
+        mbar_expect_tx(bar_kv_full + st, Cfg::STAGE_BYTES);
+#pragma unroll
+        for (int a = 0; a < Cfg::NATOM; ++a) {
+          tma_load_4d(sk + a * kQAtomBytes, &tm_k, bar_kv_full + st, a * 64, head, t * KV, b_kv);
+          tma_load_4d(sk + Cfg::TILE_BYTES + a * kQAtomBytes, &tm_v, bar_kv_full + st, a * 64, head, t * KV, b_kv);
+        }
+      }
+    }
+  } else if (warp == Cfg::MMA_WARP) {
+    // ------------------------------------------------------------ the one MMA issuer: per key tile j and query tile X
+    //      P_X(j-1) V(j-1) -> O_X, then Q_X K(j)^T -> S_X (in that order: the score MMA overwrites the columns P sits in)
+    if (FRESCO_ISSUER_THREAD(lane)) {
+      constexpr uint32_t idesc_qk = make_idesc_f16(kTileM, KV, 0);
+      constexpr uint32_t idesc_pv0 = make_idesc_f16(kTileM, Cfg::N0, 1);
+      constexpr uint32_t idesc_pv1 = make_idesc_f16(kTileM, Cfg::N1 > 0 ? Cfg::N1 : 16, 1);
+      constexpr uint32_t idesc_ones = make_idesc_f16(kTileM, 16, 1);
+      const uint32_t ones_desc_addr = smem_u32(s_ones);
+      auto issue_pv = [&](int x, int t) {                  // O_X (+)= P_X(t) V(t), l_X (+)= P_X(t) 1
+        const uint32_t v_addr = smem_u32(s_kv + (t % ST) * Cfg::STAGE_BYTES + Cfg::TILE_BYTES);
+        const uint32_t s_tmem = tmem + (x ? Cfg::S_OFF_B : Cfg::S_OFF_A);
+        const uint32_t o_tmem = tmem + (x ? Cfg::O_OFF_B : Cfg::O_OFF_A);
+#pragma unroll 1                                     // (rolled: the unrolled descriptor set does not fit the issuer's registers)
+        for (int k2 = 0; k2 < KV / 16; ++k2) {
+          const uint32_t acc = (k2 > 0 || t > 0) ? 1u : 0u;
+          const uint32_t p_tmem = s_tmem + k2 * 8;
+          umma_ts(o_tmem, p_tmem, make_smem_desc_sw128(v_addr + k2 * 2048, kQAtomBytes, 1024), idesc_pv0, acc);
+          if (Cfg::N1 > 0)
+            umma_ts(o_tmem + 64, p_tmem, make_smem_desc_sw128(v_addr + kQAtomBytes + k2 * 2048, kQAtomBytes, 1024),
+                    idesc_pv1, acc);
+          umma_ts(o_tmem + Cfg::L_COL, p_tmem, make_smem_desc_sw128(ones_desc_addr, 2048, 1024), idesc_ones, acc);
+        }
+      };
+      auto issue_qk = [&](int x, int t) {                  // S_X = Q_X K(t)^T
+        const uint32_t q_addr = smem_u32(s_q + x * Cfg::TILE_BYTES);
+        const uint32_t k_addr = smem_u32(s_kv + (t % ST) * Cfg::STAGE_BYTES);
+        const uint32_t d_tmem = tmem + (x ? Cfg::S_OFF_B : Cfg::S_OFF_A);
+#pragma unroll
+        for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
+          const uint32_t off = (ks >> 2) * kQAtomBytes + (ks & 3) * 32;
+          umma_ss(d_tmem, make_smem_desc_sw128(q_addr + off, 16, 1024), make_smem_desc_sw128(k_addr + off, 16, 1024),
+                  idesc_qk, ks > 0);
+        }
+      };
+      mbar_wait_trap(bar_q, 0);
+      for (int t = 0; t < n_tiles; ++t) {
+        mbar_wait_trap(bar_kv_full + t % ST, (t / ST) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int x = 0; x < 2; ++x) {
+          if (t > 0) {
+            mbar_wait_trap(bar_p + x, (t - 1) & 1);          // P_X(t-1) is in TMEM
+            tc_fence_after();
+            issue_pv(x, t - 1);
+          }
+          issue_qk(x, t);
+          umma_commit(bar_s + x);                            // S_X(t) ready  (=> P V_X(t-1) retired: same issuer, in order)
+        }
+        if (t > 0) umma_commit(bar_kv_empty + (t - 1) % ST);  // K(t-1), V(t-1) consumed by both query tiles
+      }
+#pragma unroll
+      for (int x = 0; x < 2; ++x) {
+        mbar_wait_trap(bar_p + x, (n_tiles - 1) & 1);
+        tc_fence_after();
+        issue_pv(x, n_tiles - 1);
+        umma_commit(bar_o + x);
+      }
+    }
+  }
+  } else {
+    // ------------------------------------------------------------ softmax warps: query tile X = warp / 4, one row per thread
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    const int x = warp >> 2, quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t t_lane = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
+    const uint32_t s_lane = t_lane + (x ? Cfg::S_OFF_B : Cfg::S_OFF_A);
+    const uint32_t o_lane = t_lane + (x ? Cfg::O_OFF_B : Cfg::O_OFF_A);
+    const int q_row = q0 + x * kTileM + row;
+    const int kv_len = p.kv_len;
+    const float scale_log2 = p.scale_log2, bias_log2 = p.diag_bias_log2;
+    const bool use_bias = bias_log2 != 0.f;
+    const unsigned long long scale2 = pack_f2(scale_log2, scale_log2);
+    // warp-uniform special tiles: the ragged tail (last tile) and the tile that holds this warp's diagonal
+    const int j_tail = (kv_len % KV) ? n_tiles - 1 : n_tiles;
+    const int j_diag = use_bias ? (q0 + x * kTileM) / KV : -1;
+    float m_run = -INFINITY;
+
+    for (int j = 0; j < n_tiles; ++j) {
+      mbar_wait_trap(bar_s + x, j & 1);
+      tc_fence_after();
+      uint32_t r[128];
+      tmem_ld32(s_lane + 0, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+      tmem_ld32(s_lane + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+      tmem_ld32(s_lane + 64, *reinterpret_cast<uint32_t(*)[32]>(&r[64]));
+      tmem_ld32(s_lane + 96, *reinterpret_cast<uint32_t(*)[32]>(&r[96]));
+      tmem_ld_wait_dep128(r);
+      if (j >= j_tail || j == j_diag) {                    // rare path: fold mask / bias into the raw scores
+        const int col0 = j * KV;
+#pragma unroll
+        for (int c = 0; c < 128; ++c) {
+          float v = __uint_as_float(r[c]);
+          if (use_bias && col0 + c == q_row) v += bias_log2 / scale_log2;
+          if (col0 + c >= kv_len) v = -INFINITY;
+          r[c] = __float_as_uint(v);
+        }
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 128; c += 8) {
+        mx0 = max3(mx0, __uint_as_float(r[c]), __uint_as_float(r[c + 1]));
+        mx1 = max3(mx1, __uint_as_float(r[c + 2]), __uint_as_float(r[c + 3]));
+        mx2 = max3(mx2, __uint_as_float(r[c + 4]), __uint_as_float(r[c + 5]));
+        mx3 = max3(mx3, __uint_as_float(r[c + 6]), __uint_as_float(r[c + 7]));
+      }
+      const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
+      // ---- lazy running max: raise it (and rescale this row of O and l in TMEM) only when it grows by more than 2^8.
+      //      O is stable here: S_X(j) ready implies P V_X(j-1) retired.
+      if (j == 0) {
+        m_run = m_tile;
+      } else {
+        const bool need = m_tile > m_run + 8.0f;
+        if (__any_sync(0xffffffffu, need)) {
+          const float alpha = need ? fast_exp2(m_run - m_tile) : 1.0f;
+          if (need) m_run = m_tile;
+#pragma unroll
+          for (int c = 0; c < (Cfg::DPAD + 16) / 8; ++c) {
+            uint32_t o[8];
+            tmem_ld8_sync(o_lane + c * 8, o);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+            tmem_st8(o_lane + c * 8, o);
+          }
+        }
+      }
+      // ---- p = exp2(s * scale - m) -> fp16, 32 keys at a time into columns [0, 64) of the S region
+      const unsigned long long negm2 = pack_f2(-m_run, -m_run);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int cc = 0; cc < 32; cc += 2) {
+          const int c = g * 32 + cc;
+          float t0, t1, e0, e1;
+          unpack_f2(fma2(pack_f2(__uint_as_float(r[c]), __uint_as_float(r[c + 1])), scale2, negm2), t0, t1);
+          if (POLY > 0 && ((c >> 1) % (POLY > 0 ? POLY : 1)) == (POLY - 1)) {
+            exp2_poly_x2(t0, t1, e0, e1);
+          } else {
+            e0 = fast_exp2(t0);
+            e1 = fast_exp2(t1);
+          }
+          pk[cc >> 1] = pack_half2(e0, e1);
+        }
+        tmem_st16(s_lane + g * 16, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      mbar_arrive_elected(bar_p + x);
+    }
+
+    // ---- epilogue: O / l -> fp16 head slice of this row
+    mbar_wait_trap(bar_o + x, 0);
+    tc_fence_after();
+    uint32_t lcol[8];
+    tmem_ld8_sync(o_lane + Cfg::L_COL, lcol);
+    const float inv = 1.f / __uint_as_float(lcol[0]);
+    __half* dst = p.out + (static_cast<size_t>(b) * p.q_len + q_row) * (static_cast<size_t>(p.heads) * D) +
+                  static_cast<size_t>(head) * D;
+#pragma unroll
+    for (int c = 0; c < D / 8; ++c) {
+      uint32_t o[8];
+      tmem_ld8_sync(o_lane + c * 8, o);
+      if (q_row < p.q_len) {
+        uint4 pkt;
+        pkt.x = pack_half2(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
+        pkt.y = pack_half2(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
+        pkt.z = pack_half2(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
+        pkt.w = pack_half2(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
+        reinterpret_cast<uint4*>(dst)[c] = pkt;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == Cfg::MMA_WARP) tmem_dealloc<Cfg::TMEM_COLS>(tmem);
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 
@@ -1379,9 +1710,25 @@ static int launch_duo(const CUtensorMap& tq, const CUtensorMap& tk, const CUtens
   return check_launch("fresco_attn_duo_kernel");
 }
 
+template <int D, int POLY>
+static int launch_twin(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, dim3 grid,
+                       cudaStream_t stream) {
+  using Cfg = TwinCfg<D>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(fresco_attn_twin_kernel<D, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(attn twin)");
+    attr_set = true;
+  }
+  fresco_attn_twin_kernel<D, POLY><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tq, tk, tv, p);
+  return check_launch("fresco_attn_twin_kernel");
+}
+
 static int wide_split(int head_dim) {       // threads per query row under the current options; 0 = pipelined kernel
   int wide = option(OPT_ATTN_WIDE, -1);
   if (wide < 0) wide = default_split(head_dim);
+  if (wide == 5) return head_dim <= 80 ? 5 : 0;                          // 5 = twin kernel (128-key tiles)
   if (wide == 3) return head_dim <= 64 ? 3 : (head_dim <= 80 ? 4 : 0);   // 3 = duo kernel (head_dim <= 64)
   if (wide >= 4) return head_dim <= 80 ? 4 : 2;       // four accumulators of head_dim 128 do not fit TMEM
   return wide >= 1 ? 2 : 0;
@@ -1394,9 +1741,11 @@ static int launch_attn(const void* q, const void* k, const void* v, void* out, i
   CUtensorMap tq, tk, tv;
   const int batch_kv = batch_q / q_per_kv;
   const long long C = (long long)heads * D;
+  const int split = wide_split(D);
+  const int kv_box = split == 5 ? 128 : kTileN;                      // key rows per TMA box
   if (make_head_tile_map(&tq, q, D, heads, q_len, batch_q, kTileM, C, C * q_len)) return FRESCO_ERR_TENSORMAP;
-  if (make_head_tile_map(&tk, k, D, heads, kv_len, batch_kv, kTileN, kv_row_stride, kv_batch_stride)) return FRESCO_ERR_TENSORMAP;
-  if (make_head_tile_map(&tv, v, D, heads, kv_len, batch_kv, kTileN, kv_row_stride, kv_batch_stride)) return FRESCO_ERR_TENSORMAP;
+  if (make_head_tile_map(&tk, k, D, heads, kv_len, batch_kv, kv_box, kv_row_stride, kv_batch_stride)) return FRESCO_ERR_TENSORMAP;
+  if (make_head_tile_map(&tv, v, D, heads, kv_len, batch_kv, kv_box, kv_row_stride, kv_batch_stride)) return FRESCO_ERR_TENSORMAP;
   AttnParams p;
   p.out = static_cast<__half*>(out);
   p.q_len = q_len;
@@ -1408,7 +1757,14 @@ static int launch_attn(const void* q, const void* k, const void* v, void* out, i
   p.ablate = option(OPT_ATTN_ABLATE, 0);
   dim3 grid((q_len + kTileM - 1) / kTileM, heads, batch_q);
   const int poly = option(OPT_ATTN_POLY, kPolyDefault);
-  const int split = wide_split(D);
+  if constexpr (D <= 80) {
+    if (split == 5) {
+      dim3 grid2((q_len + 2 * kTileM - 1) / (2 * kTileM), heads, batch_q);
+      if (poly == 4) return launch_twin<D, 4>(tq, tk, tv, p, grid2, stream);
+      if (poly == 8) return launch_twin<D, 8>(tq, tk, tv, p, grid2, stream);
+      return launch_twin<D, 0>(tq, tk, tv, p, grid2, stream);
+    }
+  }
   if constexpr (D <= 64) {
     if (split == 3) {
       if (poly == 4) return launch_duo<D, 4>(tq, tk, tv, p, grid, stream);
@@ -1446,7 +1802,8 @@ extern "C" int fresco_debug_attn_trace(long long* host_out) {
 extern "C" const char* fresco_attn_variant(int head_dim) {
   static thread_local char buf[96];
   const int split = wide_split(head_dim);
-  if (split == 3) snprintf(buf, sizeof(buf), "fresco_attn_duo_kernel<%d,poly%d>", head_dim, option(OPT_ATTN_POLY, kPolyDefault));
+  if (split == 5) snprintf(buf, sizeof(buf), "fresco_attn_twin_kernel<%d,poly%d>", head_dim, option(OPT_ATTN_POLY, kPolyDefault));
+  else if (split == 3) snprintf(buf, sizeof(buf), "fresco_attn_duo_kernel<%d,poly%d>", head_dim, option(OPT_ATTN_POLY, kPolyDefault));
   else if (split > 0) snprintf(buf, sizeof(buf), "fresco_attn_wide_kernel<%d,%d>", head_dim, split);
   else snprintf(buf, sizeof(buf), "fresco_attn_kernel<%d,poly%d> (pipelined)", head_dim, option(OPT_ATTN_POLY, kPolyDefault));
   return buf;

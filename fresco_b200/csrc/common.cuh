@@ -53,14 +53,21 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// try_wait suspends the thread until the phase completes or a time limit passes.  The default limit is short: round-2
+// profiles show softmax warps going round the poll loop 2-5 times per tile (9 instructions each, in competition with
+// the warps that do have work for the same issue slots).  The hint asks for up to FRESCO_TRYWAIT_NS before giving up;
+// completion still wakes the thread at once.
+#ifndef FRESCO_TRYWAIT_NS
+#define FRESCO_TRYWAIT_NS 2000
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred P;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
       "selp.b32 %0, 1, 0, P;\n\t}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "n"(FRESCO_TRYWAIT_NS)
       : "memory");
   return ok != 0;
 }
@@ -76,10 +83,10 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Watchdog: a lost arrival would otherwise hang the GPU until the driver's own limit.  After ~2^26 failed
+// Watchdog: a lost arrival would otherwise hang the GPU until the driver's own limit.  After ~2^22 failed
 // polls (seconds) the waiter reports which barrier it was stuck on and traps, turning a hang into an error.
 #ifndef FRESCO_WATCHDOG_POLLS
-#define FRESCO_WATCHDOG_POLLS (1u << 26)
+#define FRESCO_WATCHDOG_POLLS (1u << 22)          /* each failed try_wait may block up to FRESCO_TRYWAIT_NS */
 #endif
 static __device__ __noinline__ void mbar_timeout(const uint64_t* bar, uint32_t parity, int tag) {
   printf("fresco_b200 watchdog: block (%d,%d,%d) thread %d stuck on mbarrier smem+0x%x parity %u tag %d\n",
