@@ -1299,8 +1299,13 @@ fresco_attn_duo_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
 // retired" -- no P-buffer or O-stability waits at all.  The two query tiles (A, B) take turns: while the warps of A
 // are in their exponentials the tensor core runs P V / Q K^T for B.
 //
-//   TMEM  S_A [0,128)  S_B [128,256)  (fp32 scores; P = fp16 in columns [0,64) of the same region)
-//         O_A [256,256+DPAD)  O_B [384,384+DPAD)   row sums (ones-MMA) in the 16 columns behind each O
+// When the O accumulators leave room (head_dim <= 48) the scores rotate through THREE 128-column regions shared by the
+// two query tiles (sequence A0 B0 A1 B1 ...: score tile n lives in region n % 3), so Q K^T of a query tile's NEXT key
+// tile runs while its warps are still in the exponentials of the current one; with two regions (head_dim 64 / 80) a
+// query tile's next scores can only be computed after its P V has read P.
+//
+//   TMEM  S regions [0,128) [128,256) ([256,384))  (fp32 scores; P = fp16 in columns [0,64) of the same region)
+//         O_A, O_B behind them, DPAD columns each + 16 columns of row sums (ones-MMA)
 template <int D>
 struct TwinCfg {
   static constexpr int KV = 128;                          // keys per tile
@@ -1309,8 +1314,10 @@ struct TwinCfg {
   static constexpr int DPAD = KSTEPS * 16;
   static constexpr int N0 = DPAD < 64 ? DPAD : 64;
   static constexpr int N1 = DPAD - N0;
-  static constexpr int S_OFF_A = 0, S_OFF_B = 128, O_OFF_A = 256, O_OFF_B = 384;
-  static constexpr int L_COL = DPAD;                      // row-sum columns sit right behind O (DPAD + 16 <= 128)
+  static constexpr int NBUF = (DPAD + 16 <= 64) ? 3 : 2;  // score regions
+  static constexpr int O_STRIDE = NBUF == 3 ? 64 : 128;
+  static constexpr int O_OFF_A = NBUF * 128, O_OFF_B = O_OFF_A + O_STRIDE;
+  static constexpr int L_COL = DPAD;                      // row-sum columns sit right behind O
   static constexpr int TMEM_COLS = 512;
   static constexpr int TILE_BYTES = NATOM * kQAtomBytes;  // a [128 rows x D] tile: Q tile, K tile or V tile
   static constexpr int STAGES = NATOM == 1 ? 4 : 2;
@@ -1365,10 +1372,11 @@ fresco_attn_twin_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   uint64_t* bar_q = bars + 0;
   uint64_t* bar_kv_full = bars + 1;            // [ST]
   uint64_t* bar_kv_empty = bars + 1 + ST;      // [ST]
-  uint64_t* bar_s = bars + 1 + 2 * ST;         // [2]  S_X(j) ready (and P V_X(j-1) retired); phase j & 1
-  uint64_t* bar_p = bar_s + 2;                 // [2]  P_X(j) written by the four warps of X; phase j & 1
-  uint64_t* bar_o = bar_s + 4;                 // [2]  last P V_X retired
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s + 6);
+  constexpr int NB = Cfg::NBUF;
+  uint64_t* bar_s = bars + 1 + 2 * ST;         // [NB] score tile n ready in region n % NB; phase (n / NB) & 1
+  uint64_t* bar_p = bar_s + 3;                 // [NB] P of score tile n written by the four warps of its query tile
+  uint64_t* bar_pv = bar_s + 6;                // [2]  P V_X(j) retired (O_X stable); phase j & 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s + 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -1384,11 +1392,12 @@ fresco_attn_twin_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       mbar_init(bar_kv_full + s, 1);
       mbar_init(bar_kv_empty + s, 1);
     }
-    for (int x = 0; x < 2; ++x) {
-      mbar_init(bar_s + x, 1);
-      mbar_init(bar_p + x, 4);
-      mbar_init(bar_o + x, 1);
+    for (int k = 0; k < NB; ++k) {
+      mbar_init(bar_s + k, 1);
+      mbar_init(bar_p + k, 4);
     }
+    mbar_init(bar_pv + 0, 1);
+    mbar_init(bar_pv + 1, 1);
     fence_barrier_init();
   }
   if (warp == Cfg::MMA_WARP) {
@@ -1432,17 +1441,20 @@ fresco_attn_twin_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       }
     }
   } else if (warp == Cfg::MMA_WARP) {
-    // ------------------------------------------------------------ the one MMA issuer: per key tile j and query tile X
-    //      P_X(j-1) V(j-1) -> O_X, then Q_X K(j)^T -> S_X (in that order: the score MMA overwrites the columns P sits in)
+    // ------------------------------------------------------------ the one MMA issuer.  Score tiles in sequence n = 0, 1, ...
+    //      (n = 2 t + x): NB score MMAs up front, then per n: wait for P(n), P(n) V(t) -> O_X, and behind it Q K^T of
+    //      score tile n + NB into the region P(n) was read from (same thread: the tensor core keeps the order)
     if (FRESCO_ISSUER_THREAD(lane)) {
       constexpr uint32_t idesc_qk = make_idesc_f16(kTileM, KV, 0);
       constexpr uint32_t idesc_pv0 = make_idesc_f16(kTileM, Cfg::N0, 1);
       constexpr uint32_t idesc_pv1 = make_idesc_f16(kTileM, Cfg::N1 > 0 ? Cfg::N1 : 16, 1);
       constexpr uint32_t idesc_ones = make_idesc_f16(kTileM, 16, 1);
       const uint32_t ones_desc_addr = smem_u32(s_ones);
-      auto issue_pv = [&](int x, int t) {                  // O_X (+)= P_X(t) V(t), l_X (+)= P_X(t) 1
+      // score tile n = 2 * t + x (query tile x, key tile t) lives in region n % NB
+      auto issue_pv = [&](int n) {                         // O_X (+)= P(n) V(t), l_X (+)= P(n) 1
+        const int x = n & 1, t = n >> 1;
         const uint32_t v_addr = smem_u32(s_kv + (t % ST) * Cfg::STAGE_BYTES + Cfg::TILE_BYTES);
-        const uint32_t s_tmem = tmem + (x ? Cfg::S_OFF_B : Cfg::S_OFF_A);
+        const uint32_t s_tmem = tmem + (n % NB) * 128;
         const uint32_t o_tmem = tmem + (x ? Cfg::O_OFF_B : Cfg::O_OFF_A);
 #pragma unroll 1                                     // (rolled: the unrolled descriptor set does not fit the issuer's registers)
         for (int k2 = 0; k2 < KV / 16; ++k2) {
@@ -1455,39 +1467,34 @@ fresco_attn_twin_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
           umma_ts(o_tmem + Cfg::L_COL, p_tmem, make_smem_desc_sw128(ones_desc_addr, 2048, 1024), idesc_ones, acc);
         }
       };
-      auto issue_qk = [&](int x, int t) {                  // S_X = Q_X K(t)^T
+      auto issue_qk = [&](int n) {                         // S(n) = Q_X K(t)^T
+        const int x = n & 1, t = n >> 1;
+        if (x == 0) {                                      // first use of key tile t
+          mbar_wait_trap(bar_kv_full + t % ST, (t / ST) & 1);
+          tc_fence_after();
+        }
         const uint32_t q_addr = smem_u32(s_q + x * Cfg::TILE_BYTES);
         const uint32_t k_addr = smem_u32(s_kv + (t % ST) * Cfg::STAGE_BYTES);
-        const uint32_t d_tmem = tmem + (x ? Cfg::S_OFF_B : Cfg::S_OFF_A);
+        const uint32_t d_tmem = tmem + (n % NB) * 128;
 #pragma unroll
         for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
           const uint32_t off = (ks >> 2) * kQAtomBytes + (ks & 3) * 32;
           umma_ss(d_tmem, make_smem_desc_sw128(q_addr + off, 16, 1024), make_smem_desc_sw128(k_addr + off, 16, 1024),
                   idesc_qk, ks > 0);
         }
+        umma_commit(bar_s + n % NB);
       };
+      const int n_total = 2 * n_tiles;
       mbar_wait_trap(bar_q, 0);
-      for (int t = 0; t < n_tiles; ++t) {
-        mbar_wait_trap(bar_kv_full + t % ST, (t / ST) & 1);
+      for (int n = 0; n < NB && n < n_total; ++n) issue_qk(n);
+      for (int n = 0; n < n_total; ++n) {
+        mbar_wait_trap(bar_p + n % NB, (n / NB) & 1);        // P(n) is in TMEM
         tc_fence_after();
-#pragma unroll
-        for (int x = 0; x < 2; ++x) {
-          if (t > 0) {
-            mbar_wait_trap(bar_p + x, (t - 1) & 1);          // P_X(t-1) is in TMEM
-            tc_fence_after();
-            issue_pv(x, t - 1);
-          }
-          issue_qk(x, t);
-          umma_commit(bar_s + x);                            // S_X(t) ready  (=> P V_X(t-1) retired: same issuer, in order)
-        }
-        if (t > 0) umma_commit(bar_kv_empty + (t - 1) % ST);  // K(t-1), V(t-1) consumed by both query tiles
-      }
-#pragma unroll
-      for (int x = 0; x < 2; ++x) {
-        mbar_wait_trap(bar_p + x, (n_tiles - 1) & 1);
-        tc_fence_after();
-        issue_pv(x, n_tiles - 1);
-        umma_commit(bar_o + x);
+        issue_pv(n);
+        umma_commit(bar_pv + (n & 1));
+        if (n & 1) umma_commit(bar_kv_empty + (n >> 1) % ST);   // K(t), V(t) consumed by both query tiles
+        // region n % NB is free once P V(n) has read P: the score MMA issued behind it (same thread, in order) may reuse it
+        if (n + NB < n_total) issue_qk(n + NB);
       }
     }
   }
@@ -1497,7 +1504,6 @@ fresco_attn_twin_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     const int x = warp >> 2, quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const uint32_t t_lane = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
-    const uint32_t s_lane = t_lane + (x ? Cfg::S_OFF_B : Cfg::S_OFF_A);
     const uint32_t o_lane = t_lane + (x ? Cfg::O_OFF_B : Cfg::O_OFF_A);
     const int q_row = q0 + x * kTileM + row;
     const int kv_len = p.kv_len;
@@ -1508,9 +1514,11 @@ fresco_attn_twin_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     const int j_tail = (kv_len % KV) ? n_tiles - 1 : n_tiles;
     const int j_diag = use_bias ? (q0 + x * kTileM) / KV : -1;
     float m_run = -INFINITY;
+    int buf = x % NB, ph = 0;                              // region and phase of score tile n = 2 j + x
 
     for (int j = 0; j < n_tiles; ++j) {
-      mbar_wait_trap(bar_s + x, j & 1);
+      const uint32_t s_lane = t_lane + buf * 128;
+      mbar_wait_trap(bar_s + buf, ph);
       tc_fence_after();
       uint32_t r[128];
       tmem_ld32(s_lane + 0, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
@@ -1537,13 +1545,14 @@ fresco_attn_twin_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         mx3 = max3(mx3, __uint_as_float(r[c + 6]), __uint_as_float(r[c + 7]));
       }
       const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
-      // ---- lazy running max: raise it (and rescale this row of O and l in TMEM) only when it grows by more than 2^8.
-      //      O is stable here: S_X(j) ready implies P V_X(j-1) retired.
+      // ---- lazy running max: raise it (and rescale this row of O and l in TMEM) only when it grows by more than 2^8
       if (j == 0) {
         m_run = m_tile;
       } else {
         const bool need = m_tile > m_run + 8.0f;
         if (__any_sync(0xffffffffu, need)) {
+          mbar_wait_trap(bar_pv + x, (j - 1) & 1);           // O_X may only be touched once P V_X(j-1) has retired
+          tc_fence_after();
           const float alpha = need ? fast_exp2(m_run - m_tile) : 1.0f;
           if (need) m_run = m_tile;
 #pragma unroll
@@ -1579,11 +1588,18 @@ fresco_attn_twin_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      mbar_arrive_elected(bar_p + x);
+      mbar_arrive_elected(bar_p + buf);
+      // n += 2
+      if (NB == 3) {
+        if (buf == 0) buf = 2;
+        else { buf -= 1; ph ^= 1; }
+      } else {
+        ph ^= 1;
+      }
     }
 
     // ---- epilogue: O / l -> fp16 head slice of this row
-    mbar_wait_trap(bar_o + x, 0);
+    mbar_wait_trap(bar_pv + x, (n_tiles - 1) & 1);
     tc_fence_after();
     uint32_t lcol[8];
     tmem_ld8_sync(o_lane + Cfg::L_COL, lcol);
@@ -1656,14 +1672,18 @@ static int make_head_tile_map(CUtensorMap* map, const void* base, int head_dim, 
 
 // Tuning knobs (fresco_internal.h: option(); environment variable of the same name read once, fresco_set_option()
 // overrides).  The defaults are the measured best on B200 per head_dim (profiles/README.md, attention sweep):
-//   FRESCO_ATTN_WIDE    -1 = per head_dim (below), 0 = pipelined kernel, 2 | 4 = wide kernel, that many threads per row
-//   FRESCO_ATTN_POLY    pipelined kernel: 0 | 4 | 8, every n-th pair of exponentials on the FMA pipe
+//   FRESCO_ATTN_WIDE    -1 = per head_dim (below), 0 = pipelined kernel, 2 | 4 = wide kernel (that many threads per
+//                       row), 3 = duo kernel (head_dim <= 64), 5 = twin kernel (head_dim <= 80)
+//   FRESCO_ATTN_POLY    every n-th pair of exponentials on the FMA pipe: 0 | 4 | 8 (twin kernel at head_dim 40: 2..6, 8);
+//                       -1 / unset = 4 for the twin kernel, 0 elsewhere
 //   FRESCO_ATTN_ROWSUM  pipelined kernel, head_dim 40: row sums from the tensor core
-constexpr int kPolyDefault = 0;
 constexpr int kRowsumDefault = 1;
-// threads per query row of the default kernel (0 = pipelined kernel): TF/s measured at L = 4096, 8 frames:
-//   d = 40: pipelined 446, wide2 436, wide4 353;  d = 80: pipelined 510, wide2 529, wide4 585;  d = 128: 510 / 508 / -
-constexpr int default_split(int head_dim) { return (head_dim == 64 || head_dim == 80) ? 4 : 0; }
+// The default kernel per head_dim.  TF/s measured in isolation at the config-2 shapes (profiles/r02_attn_microbench_*):
+//   d = 40 (L 4096, Lk 15587): pipelined 451, duo 449, wide2 426, wide4 343, twin 529, twin + poly4 562   [torch SDPA 620]
+//   d = 80 (L 1024, Lk 3897):  pipelined 520, wide2 540, wide4 587, twin 605, twin + poly4 644            [torch SDPA 858]
+//   d = 128: pipelined 510, wide2 508, pipelined + poly4 543                                              [torch SDPA 849]
+constexpr int default_split(int head_dim) { return (head_dim == 40 || head_dim == 80) ? 5 : (head_dim == 64 ? 4 : 0); }
+static int poly_option(int split) { return option(OPT_ATTN_POLY, split == 5 ? 4 : 0); }
 
 template <int D, int POLY, bool ROWSUM>
 static int launch_pipelined(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
@@ -1756,10 +1776,16 @@ static int launch_attn(const void* q, const void* k, const void* v, void* out, i
   p.diag_bias_log2 = diag_bias * 1.4426950408889634f;
   p.ablate = option(OPT_ATTN_ABLATE, 0);
   dim3 grid((q_len + kTileM - 1) / kTileM, heads, batch_q);
-  const int poly = option(OPT_ATTN_POLY, kPolyDefault);
+  const int poly = poly_option(split);
   if constexpr (D <= 80) {
     if (split == 5) {
       dim3 grid2((q_len + 2 * kTileM - 1) / (2 * kTileM), heads, batch_q);
+      if constexpr (D == 40) {                                    // (the measured sweep of the FMA-pipe share)
+        if (poly == 2) return launch_twin<D, 2>(tq, tk, tv, p, grid2, stream);
+        if (poly == 3) return launch_twin<D, 3>(tq, tk, tv, p, grid2, stream);
+        if (poly == 5) return launch_twin<D, 5>(tq, tk, tv, p, grid2, stream);
+        if (poly == 6) return launch_twin<D, 6>(tq, tk, tv, p, grid2, stream);
+      }
       if (poly == 4) return launch_twin<D, 4>(tq, tk, tv, p, grid2, stream);
       if (poly == 8) return launch_twin<D, 8>(tq, tk, tv, p, grid2, stream);
       return launch_twin<D, 0>(tq, tk, tv, p, grid2, stream);
@@ -1802,10 +1828,10 @@ extern "C" int fresco_debug_attn_trace(long long* host_out) {
 extern "C" const char* fresco_attn_variant(int head_dim) {
   static thread_local char buf[96];
   const int split = wide_split(head_dim);
-  if (split == 5) snprintf(buf, sizeof(buf), "fresco_attn_twin_kernel<%d,poly%d>", head_dim, option(OPT_ATTN_POLY, kPolyDefault));
-  else if (split == 3) snprintf(buf, sizeof(buf), "fresco_attn_duo_kernel<%d,poly%d>", head_dim, option(OPT_ATTN_POLY, kPolyDefault));
+  if (split == 5) snprintf(buf, sizeof(buf), "fresco_attn_twin_kernel<%d,poly%d>", head_dim, poly_option(split));
+  else if (split == 3) snprintf(buf, sizeof(buf), "fresco_attn_duo_kernel<%d,poly%d>", head_dim, poly_option(split));
   else if (split > 0) snprintf(buf, sizeof(buf), "fresco_attn_wide_kernel<%d,%d>", head_dim, split);
-  else snprintf(buf, sizeof(buf), "fresco_attn_kernel<%d,poly%d> (pipelined)", head_dim, option(OPT_ATTN_POLY, kPolyDefault));
+  else snprintf(buf, sizeof(buf), "fresco_attn_kernel<%d,poly%d> (pipelined)", head_dim, poly_option(split));
   return buf;
 }
 
