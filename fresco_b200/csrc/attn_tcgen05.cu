@@ -1312,22 +1312,33 @@ struct TwinCfg {
   static constexpr int NATOM = (D + 63) / 64;
   static constexpr int KSTEPS = (D + 15) / 16;
   static constexpr int DPAD = KSTEPS * 16;
-  static constexpr int N0 = DPAD < 64 ? DPAD : 64;
-  static constexpr int N1 = DPAD - N0;
-  static constexpr int NBUF = (DPAD + 16 <= 64) ? 3 : 2;  // score regions
+  // Row sums l = sum_j p_j come out of the tensor core.  FOLD: V column D (zero-filled by TMA: the tensor map ends at
+  // head_dim) is overwritten with 1.0 in shared memory by the two spare warps of the issuer warpgroup before the P V
+  // MMAs of a key tile are issued, so O column D IS the row sum and a tile costs no extra MMA.  Needs a spare column
+  // inside the atoms that are loaded (head_dim 40, 80); head_dim 64 multiplies P by a constant tile of ones instead.
+  static constexpr int PVN = ((D + 1 + 15) / 16) * 16;    // O columns with the folded row sum
+#ifdef FRESCO_TWIN_NOFOLD                                   /* A/B measurements only */
+  static constexpr bool FOLD = false;
+#else
+  static constexpr bool FOLD = PVN <= NATOM * 64;
+#endif
+  static constexpr int OCOLS = FOLD ? PVN : DPAD + 16;
+  static constexpr int N0 = (FOLD ? PVN : DPAD) < 64 ? (FOLD ? PVN : DPAD) : 64;
+  static constexpr int N1 = (FOLD ? PVN : DPAD) - N0;
+  static constexpr int NBUF = (OCOLS <= 64) ? 3 : 2;      // score regions
   static constexpr int O_STRIDE = NBUF == 3 ? 64 : 128;
   static constexpr int O_OFF_A = NBUF * 128, O_OFF_B = O_OFF_A + O_STRIDE;
-  static constexpr int L_COL = DPAD;                      // row-sum columns sit right behind O
+  static constexpr int L_COL = FOLD ? D : DPAD;           // O column that holds the row sum
   static constexpr int TMEM_COLS = 512;
   static constexpr int TILE_BYTES = NATOM * kQAtomBytes;  // a [128 rows x D] tile: Q tile, K tile or V tile
   static constexpr int STAGES = NATOM == 1 ? 4 : 2;
   static constexpr int STAGE_BYTES = 2 * TILE_BYTES;      // K | V
-  static constexpr int SMEM_BYTES = 1024 + 2 * TILE_BYTES + STAGES * STAGE_BYTES + 2048 + 256;
+  static constexpr int SMEM_BYTES = 1024 + 2 * TILE_BYTES + STAGES * STAGE_BYTES + 2048 + 512;
   // 8 softmax warps + MMA issuer + TMA producer + 2 idle warps: three whole warpgroups, so that setmaxnreg can move
-  // registers from the issuer warpgroup (40 each) to the softmax warpgroups (232 each: a 128-score row plus its packed
+  // registers from the issuer warpgroup (64 each) to the softmax warpgroups (224 each: a 128-score row plus its packed
   // half live in registers); 384 threads x 168 = the whole register file
   static constexpr int THREADS = 384;
-  static constexpr int MMA_WARP = 8, TMA_WARP = 9;
+  static constexpr int MMA_WARP = 8, TMA_WARP = 9, PATCH_WARP0 = 10;
 };
 
 __device__ __forceinline__ void tmem_ld_wait_dep128(uint32_t (&r)[128]) {
@@ -1376,7 +1387,8 @@ fresco_attn_twin_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   uint64_t* bar_s = bars + 1 + 2 * ST;         // [NB] score tile n ready in region n % NB; phase (n / NB) & 1
   uint64_t* bar_p = bar_s + 3;                 // [NB] P of score tile n written by the four warps of its query tile
   uint64_t* bar_pv = bar_s + 6;                // [2]  P V_X(j) retired (O_X stable); phase j & 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s + 8);
+  uint64_t* bar_vp = bar_s + 8;                // [ST] ones column written into V tile t (FOLD)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s + 8 + ST);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -1398,6 +1410,7 @@ fresco_attn_twin_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     }
     mbar_init(bar_pv + 0, 1);
     mbar_init(bar_pv + 1, 1);
+    for (int s = 0; s < ST; ++s) mbar_init(bar_vp + s, 2);
     fence_barrier_init();
   }
   if (warp == Cfg::MMA_WARP) {
@@ -1418,7 +1431,7 @@ fresco_attn_twin_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
 
   if (warp >= 8) {
     // ------------------------------------------------------------ issuer warpgroup (warps 10, 11 idle)
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
   if (warp == Cfg::TMA_WARP) {
     // ------------------------------------------------------------ TMA producer
     if (FRESCO_ISSUER_THREAD(lane)) {
@@ -1456,7 +1469,7 @@ fresco_attn_twin_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         const uint32_t v_addr = smem_u32(s_kv + (t % ST) * Cfg::STAGE_BYTES + Cfg::TILE_BYTES);
         const uint32_t s_tmem = tmem + (n % NB) * 128;
         const uint32_t o_tmem = tmem + (x ? Cfg::O_OFF_B : Cfg::O_OFF_A);
-#pragma unroll 1                                     // (rolled: the unrolled descriptor set does not fit the issuer's registers)
+#pragma unroll
         for (int k2 = 0; k2 < KV / 16; ++k2) {
           const uint32_t acc = (k2 > 0 || t > 0) ? 1u : 0u;
           const uint32_t p_tmem = s_tmem + k2 * 8;
@@ -1464,7 +1477,8 @@ fresco_attn_twin_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
           if (Cfg::N1 > 0)
             umma_ts(o_tmem + 64, p_tmem, make_smem_desc_sw128(v_addr + kQAtomBytes + k2 * 2048, kQAtomBytes, 1024),
                     idesc_pv1, acc);
-          umma_ts(o_tmem + Cfg::L_COL, p_tmem, make_smem_desc_sw128(ones_desc_addr, 2048, 1024), idesc_ones, acc);
+          if (!Cfg::FOLD)
+            umma_ts(o_tmem + Cfg::L_COL, p_tmem, make_smem_desc_sw128(ones_desc_addr, 2048, 1024), idesc_ones, acc);
         }
       };
       auto issue_qk = [&](int n) {                         // S(n) = Q_X K(t)^T
@@ -1489,6 +1503,7 @@ fresco_attn_twin_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       for (int n = 0; n < NB && n < n_total; ++n) issue_qk(n);
       for (int n = 0; n < n_total; ++n) {
         mbar_wait_trap(bar_p + n % NB, (n / NB) & 1);        // P(n) is in TMEM
+        if (Cfg::FOLD && !(n & 1)) mbar_wait_trap(bar_vp + (n >> 1) % ST, ((n >> 1) / ST) & 1);   // V(t) has its ones column
         tc_fence_after();
         issue_pv(n);
         umma_commit(bar_pv + (n & 1));
@@ -1497,10 +1512,28 @@ fresco_attn_twin_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         if (n + NB < n_total) issue_qk(n + NB);
       }
     }
+  } else if (Cfg::FOLD) {
+    // ------------------------------------------------------------ warps 10, 11: the ones column of every V tile
+    constexpr int a_ones = D / 64, c_ones = D % 64;              // atom and column inside the atom
+    constexpr int chunk = (c_ones * 2) / 16, byte = (c_ones * 2) % 16;
+    const int tid = (warp - Cfg::PATCH_WARP0) * 32 + lane;       // 0..63: rows tid and tid + 64
+    for (int t = 0; t < n_tiles; ++t) {
+      const int st = t % ST;
+      mbar_wait_trap(bar_kv_full + st, (t / ST) & 1);            // the TMA writes of V(t) have landed
+      uint8_t* v_tile = s_kv + st * Cfg::STAGE_BYTES + Cfg::TILE_BYTES + a_ones * kQAtomBytes;
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int r = tid + rr * 64;                             // 128-byte swizzle: 16-byte chunk index ^= row % 8
+        *reinterpret_cast<uint16_t*>(v_tile + r * 128 + ((chunk ^ (r & 7)) << 4) + byte) = 0x3C00u;
+      }
+      fence_proxy_async_smem();                                  // generic-proxy writes -> visible to the MMA's reads
+      __syncwarp();
+      mbar_arrive_elected(bar_vp + st);
+    }
   }
   } else {
     // ------------------------------------------------------------ softmax warps: query tile X = warp / 4, one row per thread
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     const int x = warp >> 2, quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const uint32_t t_lane = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
@@ -1556,7 +1589,7 @@ fresco_attn_twin_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
           const float alpha = need ? fast_exp2(m_run - m_tile) : 1.0f;
           if (need) m_run = m_tile;
 #pragma unroll
-          for (int c = 0; c < (Cfg::DPAD + 16) / 8; ++c) {
+          for (int c = 0; c < Cfg::OCOLS / 8; ++c) {
             uint32_t o[8];
             tmem_ld8_sync(o_lane + c * 8, o);
 #pragma unroll
@@ -1602,8 +1635,8 @@ fresco_attn_twin_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     mbar_wait_trap(bar_pv + x, (n_tiles - 1) & 1);
     tc_fence_after();
     uint32_t lcol[8];
-    tmem_ld8_sync(o_lane + Cfg::L_COL, lcol);
-    const float inv = 1.f / __uint_as_float(lcol[0]);
+    tmem_ld8_sync(o_lane + (Cfg::L_COL / 8) * 8, lcol);
+    const float inv = 1.f / __uint_as_float(lcol[Cfg::L_COL % 8]);
     __half* dst = p.out + (static_cast<size_t>(b) * p.q_len + q_row) * (static_cast<size_t>(p.heads) * D) +
                   static_cast<size_t>(head) * D;
 #pragma unroll
