@@ -1315,12 +1315,12 @@ struct TwinCfg {
   // Row sums l = sum_j p_j come out of the tensor core.  FOLD: V column D (zero-filled by TMA: the tensor map ends at
   // head_dim) is overwritten with 1.0 in shared memory by the two spare warps of the issuer warpgroup before the P V
   // MMAs of a key tile are issued, so O column D IS the row sum and a tile costs no extra MMA.  Needs a spare column
-  // inside the atoms that are loaded (head_dim 40, 80); head_dim 64 multiplies P by a constant tile of ones instead.
+  // inside the one atom that is loaded (head_dim 40); head_dim 64 / 80 multiply P by a constant tile of ones instead.
   static constexpr int PVN = ((D + 1 + 15) / 16) * 16;    // O columns with the folded row sum
 #ifdef FRESCO_TWIN_NOFOLD                                   /* A/B measurements only */
   static constexpr bool FOLD = false;
 #else
-  static constexpr bool FOLD = PVN <= NATOM * 64;
+  static constexpr bool FOLD = NATOM == 1 && PVN <= 64;   // (head_dim 80 measured 2.5 % faster with the ones-MMA)
 #endif
   static constexpr int OCOLS = FOLD ? PVN : DPAD + 16;
   static constexpr int N0 = (FOLD ? PVN : DPAD) < 64 ? (FOLD ? PVN : DPAD) : 64;
@@ -1335,7 +1335,7 @@ struct TwinCfg {
   static constexpr int STAGE_BYTES = 2 * TILE_BYTES;      // K | V
   static constexpr int SMEM_BYTES = 1024 + 2 * TILE_BYTES + STAGES * STAGE_BYTES + 2048 + 512;
   // 8 softmax warps + MMA issuer + TMA producer + 2 idle warps: three whole warpgroups, so that setmaxnreg can move
-  // registers from the issuer warpgroup (64 each) to the softmax warpgroups (224 each: a 128-score row plus its packed
+  // registers from the issuer warpgroup (56 each) to the softmax warpgroups (224 each: 2 x 224 + 56 = 3 x 168, the pool the CTA is launched with: a 128-score row plus its packed
   // half live in registers); 384 threads x 168 = the whole register file
   static constexpr int THREADS = 384;
   static constexpr int MMA_WARP = 8, TMA_WARP = 9, PATCH_WARP0 = 10;
@@ -1431,7 +1431,7 @@ fresco_attn_twin_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
 
   if (warp >= 8) {
     // ------------------------------------------------------------ issuer warpgroup (warps 10, 11 idle)
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == Cfg::TMA_WARP) {
     // ------------------------------------------------------------ TMA producer
     if (FRESCO_ISSUER_THREAD(lane)) {

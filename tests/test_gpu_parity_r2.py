@@ -703,6 +703,18 @@ def _nccl_worker(rank, world, port, ret):
     sel = torch.cat([torch.arange(c * N + lo, c * N + hi) for c in range(chunks)]).to(dev)
     mine = fu.warp_tensor(feat[sel].contiguous(), flows, occs, sal, chunks, shard=(world, rank, None))
     ok = ok and bool(torch.equal(mine, full[sel]))
+    # optimize_feature on the frame shard (ring halo of one boundary frame per Adam iteration over NCCL send/recv)
+    feat32 = torch.randn(chunks * N, 64, 32, 32, generator=torch.Generator().manual_seed(4)).half().to(dev)
+    ref32 = (feat32.float() + 0.5 * torch.randn(feat32.shape, generator=torch.Generator().manual_seed(5)).to(dev)).half()
+    target = dh.gram_targets([ref32])[0]
+    full = dh.optimize_feature(feat32, flows, occs, correlation_matrix=[target], iters=5)
+    mine = dh.optimize_feature(feat32[sel].contiguous(), flows, occs, correlation_matrix=[dh.GramTarget(target.yhat[sel].contiguous())],
+                               iters=5, shard=(world, rank, None))
+    ok_opt = bool(torch.equal(mine, full[sel]))
+    if not ok_opt:
+        print("rank %d: sharded optimize_feature differs: max |d| = %g" % (rank, (mine.float() - full[sel].float()).abs().max().item()),
+              flush=True)
+    ok = ok and ok_opt
     t = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
@@ -711,8 +723,9 @@ def _nccl_worker(rank, world, port, ret):
 
 
 def test_sharded_attention_nccl_world2_bit_identical(fb):
-    """frame-sharded FRESCO attention over NCCL on two GPUs (K/V all-gather, trajectory all-to-alls) == unsharded,
-    bit for bit, all 8 mode combinations.  Needs two devices (gpurun --gpus 2); skipped on a one-GPU box."""
+    """frame-sharded FRESCO attention over NCCL on two GPUs (K/V all-gather, trajectory all-to-alls), the channel-resharded
+    warp chain and the ring-halo optimize_feature == unsharded, bit for bit.  Needs two devices (gpurun --gpus 2);
+    skipped on a one-GPU box."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import socket
