@@ -3,38 +3,36 @@
 // Replaces the two dense F.scaled_dot_product_attention calls of the reference processor
 // (src/diffusion_hacked.py:281-285 and :303-305).
 //
-// Pipelined kernel (all head dims): one CTA owns a 128-row query tile of one (batch, head) and streams K/V in 64-row
-// tiles.
+// Common to both kernels in this file: tcgen05 / TMEM / TMA flash attention.  Token-major [batch, tokens, heads*head_dim]
+// fp16 tensors are consumed in place -- the TMA tensor map views them as {head_dim, heads, tokens, batch}; a
+// {64,1,rows,1} box lands one head's tile in the canonical 128B-swizzled K-major layout; columns >= head_dim and rows
+// >= tokens are hardware zero-filled (no padding passes for head_dim 40 / 80 or ragged lengths).  S = Q K^T by
+// tcgen05.mma kind::f16 SS into TMEM (fp32); softmax threads own TMEM lanes (= query rows): tcgen05.ld, row max
+// (FMNMX3), p = exp2(s*scale*log2e - m) with packed fma.rn.f32x2 and, for every n-th pair, a polynomial on the FMA
+// pipe; P goes back to TMEM as fp16 (tcgen05.st) and O += P V runs as a TS MMA (A = P from TMEM, B = V read MN-major
+// from the same swizzled tile), accumulated in TMEM over all key tiles; the running max is lazy (O is rescaled only
+// when a tile exceeds it by more than 2^8); row sums come out of the tensor core.
 //
-//   warps 0-3   softmax       one query row per thread (= one TMEM lane).  The 64 scores of a tile are read from
-//                             TMEM once into registers; row max; p = exp2(s*scale*log2e - m) with packed fp32x2
-//                             math; P is written to its own TMEM region as fp16.
+//   fresco_attn_twin_kernel   (head_dim <= 80: the FRESCO shapes) two 128-row query tiles per CTA, 128-key tiles, one CTA
+//                             per SM; see the comment above the kernel.
+//   fresco_attn_kernel        ("pipelined", every head_dim; the default above 80: GMFlow's d = 128) one 128-row query
+//                             tile per CTA, 64-key tiles, S and P double-buffered, two CTAs per SM at head_dim <= 64:
+//
+//   warps 0-3   softmax       one query row per thread.  The 64 scores of a tile are read from TMEM once into registers.
 //   producer    TMA           Q once, K/V tiles through a 4/5-stage mbarrier ring
-//   QK issuer   tcgen05.mma   S_i = Q K_i^T (SS, M128 N64, fp32) into one of TWO S buffers, issued as soon as the
-//                             softmax threads hold S_{i-2} in registers, so scores are always ready ahead of time
-//   PV issuer   tcgen05.mma   O += P_i V_i (TS, P from TMEM, V MN-major), accumulated in TMEM across all tiles; for
-//                             head_dim 40 one more N=16 MMA per K-step against a tile of ones yields the row sums
+//   QK issuer   tcgen05.mma   S_i = Q K_i^T (M128 N64) into one of TWO S buffers, issued as soon as the softmax threads
+//                             hold S_{i-2} in registers, so scores are always ready ahead of time
+//   PV issuer   tcgen05.mma   O += P_i V_i; for head_dim 40 one more N=16 MMA per K-step against a tile of ones yields
+//                             the row sums
+//   With one CTA per SM (head_dim 80/128) each of the three roles has its own warp (224 threads).  With two CTAs per
+//   SM (head_dim 40/64) the producer shares a thread with the QK issuer and refills the ring without ever blocking.
+//   TMEM: S0 64 + S1 64 + P0 32 + P1 32 + O <= 64 columns = 256 -> two CTAs per SM for d <= 64.
 //
-// With one CTA per SM (head_dim 80/128) each of the three roles has its own warp (224 threads).  With two CTAs per
-// SM (head_dim 40/64) a seventh warp would cost the softmax threads the 168 registers they need, so the producer
-// shares a thread with the QK issuer and refills the ring without ever blocking (192 threads).
-//
-// The running row max is lazy: it is raised (and O rescaled in TMEM by the owning thread) only when a tile
-// exceeds it by more than 2^8, so the common tile costs no O traffic at all and the softmax warps never wait
-// for an MMA round trip (S and P are both double-buffered).  TMEM: S0 64 + S1 64 + P0 32 + P1 32 + O <= 64
-// columns = 256 -> two CTAs per SM for d <= 64.
-//
-// Token-major [batch, tokens, heads*head_dim] fp16 tensors are consumed in place: the TMA tensor map views
-// them as {head_dim, heads, tokens, batch}; a {64,1,rows,1} box lands one head's tile in the canonical
-// 128B-swizzled K-major layout; columns >= head_dim and rows >= tokens are hardware zero-filled.
-//
-// What bounds it (measured, tools/pipe_probe.cu, tools/softmax_mix_probe.cu, tools/trace_attn.py): at head_dim 40 a
-// tile is 192 tensor-core clocks but 512 MUFU clocks, and a warp cannot overlap its own MUFU.EX2 (8 clk) with its
-// half-rate max / fma2 / add2 / pack instructions (2 clk each): the bare arithmetic of a tile costs 854 clk with one
-// softmax warp per sub-partition, 671 with two (this kernel; 820 measured with TMEM traffic and barriers) and 562
-// with four.  Variants that were built, measured slower and removed again (numbers in DESIGN.md section 3.1): four
-// CTAs per SM without pipelining, prefetching the next tile's scores, and two query tiles per CTA taking turns on the
-// MUFU pipe.  The "wide" kernel further down (several threads per query row) wins at head_dim 64 / 80.
+// What bounds them (measured: tools/pipe_probe.cu, tools/softmax_mix_probe.cu, profiles/r02_attn_*_hot*.txt): at
+// head_dim 40 a 128 x 64 tile is 192 tensor-core clocks but 512 MUFU clocks, and every 64-key structure that was tried
+// ended at ~840 clocks per tile with the issue slots 56-68 % busy: 368 (pipelined) to 572 warp-instructions per tile, of
+// which 161 are the softmax arithmetic.  The twin kernel pays the per-tile overhead once per 128 keys and has no
+// P-buffer / O-stability waits by construction; its exponentials are split between the MUFU and the FMA pipe.
 #include "common.cuh"
 #include "fresco_internal.h"
 
@@ -549,743 +547,6 @@ fresco_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 }
 
 // ---------------------------------------------------------------------------------------------
-// the "wide" kernel: SPLIT threads per query row (split-KV inside the CTA), every head_dim
-// ---------------------------------------------------------------------------------------------
-// Written from two measurements (attention).  (1) A softmax warp runs a serial chain per tile (wait S, TMEM
-// load, row max, ex2, pack, TMEM store, arrive) of about 1600 SM clocks for 64 scores per thread, of which the ex2 pipe
-// is busy 512: the kernel's speed is set by how many softmax warps share an SM sub-partition (854 clocks of bare
-// arithmetic per tile with one, 671 with two, 562 with four), and the pipelined kernel above cannot have more than two
-// (one at head_dim 80/128) because a thread that holds a whole 64-score row needs 168 registers.  (2) Issuing a
-// tcgen05.mma costs the issuing thread 60-70 clocks whatever its shape, so a single issuer thread caps a CTA at about
-// one tile per 65 * (MMAs per tile) clocks: the first version of this kernel (one thread issuing everything) was
-// slower than the pipelined kernel for that reason alone.
-//
-// Here every query row is shared by SPLIT threads (warps w, w + 4, ...; the same TMEM lane quarter), each owning
-// 64 / SPLIT of a tile's keys -- and nothing else is shared: each part keeps its own running max, its own row sum
-// and its own O accumulator, exactly as if the keys had been split over SPLIT kernels (split-KV), and the partial
-// results are merged once, in the epilogue:   O = sum_p 2^(m_p - m) O_p / sum_p 2^(m_p - m) l_p,   m = max_p m_p.
-// head_dim <= 48 runs two CTAs of eight softmax warps per SM (four per sub-partition), larger head dims one CTA of
-// eight (SPLIT 2) or sixteen (SPLIT 4) softmax warps.  The TMA producer, the score-MMA issuer and one or two P V issuers
-// are single threads in warps of their own.
-//
-//   TMEM  S0 [0,64), S1 [64,128) fp32 (double-buffered scores); P (fp16, 32 columns per buffer; two buffers when the
-//         CTA has TMEM to itself) at 128; O_0 .. O_{SPLIT-1}, DPAD columns each, behind it.  Row sums are accumulated by
-//         the softmax threads (fp32), so a tile costs ceil(d/16) + 4 * ceil(d/64) MMA instructions and nothing else.
-template <int D, int SPLIT_>
-struct WideCfg {
-  static constexpr int SPLIT = SPLIT_;
-  static constexpr int KEYS = kTileN / SPLIT;         // keys per softmax thread and tile
-  static constexpr int NATOM = (D + 63) / 64;
-  static constexpr int KSTEPS = (D + 15) / 16;
-  static constexpr int DPAD = KSTEPS * 16;
-  static constexpr int N0 = DPAD < 64 ? DPAD : 64;    // P V columns from V atom 0
-  static constexpr int N1 = DPAD - N0;                // ... from V atom 1
-  static constexpr int S_OFF0 = 0, S_OFF1 = 64, P_OFF = 128;
-  static constexpr bool SMALL = 128 + 32 + SPLIT * DPAD <= 256;      // fits half of TMEM: two CTAs per SM
-  static constexpr int PBUF = SMALL ? 1 : 2;          // P buffers
-  static constexpr int O_OFF = P_OFF + 32 * PBUF;
-  static constexpr int TMEM_COLS = SMALL ? 256 : 512;
-  static_assert(O_OFF + SPLIT * DPAD <= TMEM_COLS, "TMEM budget");
-  static constexpr int CTAS = SMALL ? 2 : 1;
-  static constexpr int NPV = (NATOM > 1) ? 2 : 1;     // P V issuer threads (each owns SPLIT / NPV accumulators)
-  static constexpr int STAGES = NATOM == 1 ? 5 : 4;
-  static constexpr int Q_BYTES = NATOM * kQAtomBytes;
-  static constexpr int STAGE_BYTES = 2 * NATOM * kKVAtomBytes;
-  static constexpr int SMEM_BYTES = 1024 + Q_BYTES + STAGES * STAGE_BYTES + SPLIT * 128 * 8 + 512;
-  static constexpr int SOFTMAX_WARPS = 4 * SPLIT;
-  // (the TMA producer has a warp of its own: sharing a thread with the score-MMA issuer was measured 9 % slower)
-  static constexpr int QK_WARP = SOFTMAX_WARPS, PV_WARP0 = SOFTMAX_WARPS + 1, TMA_WARP = SOFTMAX_WARPS + 1 + NPV;
-  static constexpr int THREADS = (SOFTMAX_WARPS + 2 + NPV) * 32;
-};
-
-// tcgen05.wait::ld that names the loaded registers as in/outputs, so the compiler cannot move their uses above it
-__device__ __forceinline__ void tmem_ld_wait_dep32(uint32_t (&r)[32]) {
-#define FR8(b) "+r"(r[b]), "+r"(r[b + 1]), "+r"(r[b + 2]), "+r"(r[b + 3]), "+r"(r[b + 4]), "+r"(r[b + 5]), "+r"(r[b + 6]), "+r"(r[b + 7])
-  asm volatile("tcgen05.wait::ld.sync.aligned;" : FR8(0), FR8(8), FR8(16), FR8(24) : : "memory");
-#undef FR8
-}
-__device__ __forceinline__ void tmem_ld_wait_dep16(uint32_t (&r)[16]) {
-#define FR8(b) "+r"(r[b]), "+r"(r[b + 1]), "+r"(r[b + 2]), "+r"(r[b + 3]), "+r"(r[b + 4]), "+r"(r[b + 5]), "+r"(r[b + 6]), "+r"(r[b + 7])
-  asm volatile("tcgen05.wait::ld.sync.aligned;" : FR8(0), FR8(8) : : "memory");
-#undef FR8
-}
-
-template <int D, int SPLIT>
-__global__ void __launch_bounds__(WideCfg<D, SPLIT>::THREADS, WideCfg<D, SPLIT>::CTAS)
-fresco_attn_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
-                        const __grid_constant__ CUtensorMap tm_v, const AttnParams p) {
-  using Cfg = WideCfg<D, SPLIT>;
-  constexpr int ST = Cfg::STAGES;
-  constexpr int KEYS = Cfg::KEYS;
-  constexpr int PB = Cfg::PBUF;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* s_q = smem;
-  uint8_t* s_kv = smem + Cfg::Q_BYTES;
-  float2* s_ml = reinterpret_cast<float2*>(s_kv + ST * Cfg::STAGE_BYTES);   // [SPLIT][128] {running max, row sum}
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ml + SPLIT * 128);
-  uint64_t* bar_q = bars + 0;
-  uint64_t* bar_kv_full = bars + 1;            // [ST]
-  uint64_t* bar_kv_empty = bars + 1 + ST;      // [ST]  1 (score issuer) + NPV arrivals
-  uint64_t* bar_s = bars + 1 + 2 * ST;         // [2]   S_t ready in buffer t & 1; phase (t >> 1) & 1
-  uint64_t* bar_c = bar_s + 2;                 // [2]   S_t copied to registers by every softmax warp (buffer free)
-  uint64_t* bar_p = bar_s + 4;                 // [PB][NPV] the P columns of issuer j's parts written for tile t
-  uint64_t* bar_o = bar_s + 8;                 // [PB][NPV] P V of those parts retired (P buffer free, O stable)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s + 12);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * kTileM;
-  const int head = blockIdx.y;
-  const int b = blockIdx.z;
-  const int b_kv = b / p.q_per_kv;
-  const int n_tiles = (p.kv_len + kTileN - 1) / kTileN;
-  constexpr int PARTS_PER_PV = SPLIT / Cfg::NPV;       // accumulators (= key parts) per P V issuer
-
-  if (warp == Cfg::QK_WARP && lane == 0) {
-    mbar_init(bar_q, 1);
-    for (int s = 0; s < ST; ++s) {
-      mbar_init(bar_kv_full + s, 1);
-      mbar_init(bar_kv_empty + s, 1 + Cfg::NPV);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(bar_s + i, 1);
-      mbar_init(bar_c + i, Cfg::SOFTMAX_WARPS);
-    }
-    for (int i = 0; i < PB * Cfg::NPV; ++i) {
-      mbar_init(bar_p + i, 4 * PARTS_PER_PV);            // one elected arrival per softmax warp of those parts
-      mbar_init(bar_o + i, 1);
-    }
-    fence_barrier_init();
-  }
-  if (warp == Cfg::PV_WARP0) {
-    if (lane == 0) {
-      tma_prefetch_desc(&tm_q);
-      tma_prefetch_desc(&tm_k);
-      tma_prefetch_desc(&tm_v);
-    }
-    __syncwarp();
-    tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-
-  auto load_kv_tile = [&](int t) {                     // K/V tile t -> ring stage t % ST (the stage is free)
-    const int st = t % ST;
-    uint8_t* sk = s_kv + st * Cfg::STAGE_BYTES;
-    uint8_t* sv = sk + Cfg::NATOM * kKVAtomBytes;
-    mbar_expect_tx(bar_kv_full + st, Cfg::STAGE_BYTES);
-#pragma unroll
-    for (int a = 0; a < Cfg::NATOM; ++a) {
-      tma_load_4d(sk + a * kKVAtomBytes, &tm_k, bar_kv_full + st, a * 64, head, t * kTileN, b_kv);
-      tma_load_4d(sv + a * kKVAtomBytes, &tm_v, bar_kv_full + st, a * 64, head, t * kTileN, b_kv);
-    }
-  };
-  auto load_q = [&]() {
-    mbar_expect_tx(bar_q, Cfg::Q_BYTES);
-#pragma unroll
-    for (int a = 0; a < Cfg::NATOM; ++a) tma_load_4d(s_q + a * kQAtomBytes, &tm_q, bar_q, a * 64, head, q0, b);
-  };
-
-  if (warp == Cfg::TMA_WARP) {
-    // ------------------------------------------------------------ TMA producer
-    if (FRESCO_ISSUER_THREAD(lane)) {
-      load_q();
-      for (int t = 0; t < n_tiles; ++t) {
-        if (t >= ST) mbar_wait_backoff(bar_kv_empty + t % ST, ((t / ST) - 1) & 1, 32, 40);
-        load_kv_tile(t);
-      }
-    }
-  } else if (warp == Cfg::QK_WARP) {
-    // ------------------------------------------------------------ score-MMA issuer
-    if (FRESCO_ISSUER_THREAD(lane)) {
-      constexpr uint32_t idesc_qk = make_idesc_f16(kTileM, kTileN, 0);
-      const uint32_t q_addr = smem_u32(s_q);
-      mbar_wait(bar_q, 0, 41);
-      for (int t = 0; t < n_tiles; ++t) {
-        const int st = t % ST;
-        if (t >= 2) mbar_wait(bar_c + (t & 1), ((t - 2) >> 1) & 1, 42);       // S buffer t & 1 is in registers
-        mbar_wait(bar_kv_full + st, (t / ST) & 1, 43);
-        tc_fence_after();
-        const uint32_t k_addr = smem_u32(s_kv + st * Cfg::STAGE_BYTES);
-        const uint32_t d_tmem = tmem + ((t & 1) ? Cfg::S_OFF1 : Cfg::S_OFF0);
-#pragma unroll
-        for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
-          const uint32_t qoff = (ks >> 2) * kQAtomBytes + (ks & 3) * 32;
-          const uint32_t koff = (ks >> 2) * kKVAtomBytes + (ks & 3) * 32;
-          umma_ss(d_tmem, make_smem_desc_sw128(q_addr + qoff, 16, 1024), make_smem_desc_sw128(k_addr + koff, 16, 1024),
-                  idesc_qk, ks > 0);
-        }
-        umma_commit(bar_s + (t & 1));
-        umma_commit(bar_kv_empty + st);                                    // K_t consumed
-      }
-    }
-  } else if (warp >= Cfg::PV_WARP0 && warp < Cfg::PV_WARP0 + Cfg::NPV) {
-    // ------------------------------------------------------------ P V issuer j: accumulators [j*PPV, (j+1)*PPV)
-    if (FRESCO_ISSUER_THREAD(lane)) {
-      const int j = warp - Cfg::PV_WARP0;
-      constexpr uint32_t idesc_pv0 = make_idesc_f16(kTileM, Cfg::N0, 1);
-      constexpr uint32_t idesc_pv1 = make_idesc_f16(kTileM, Cfg::N1 > 0 ? Cfg::N1 : 16, 1);
-      constexpr int KS_PER_PART = (kTileN / 16) / SPLIT;                   // 16-key MMA steps per key part
-      for (int t = 0; t < n_tiles; ++t) {
-        const int st = t % ST;
-        const int pb = t % PB;
-        mbar_wait_backoff(bar_p + pb * Cfg::NPV + j, (t / PB) & 1, 20, 44);   // P_t of my parts in TMEM
-        mbar_wait(bar_kv_full + st, (t / ST) & 1, 45);                     // V_t landed long ago; observe it
-        tc_fence_after();
-        const uint32_t v_addr = smem_u32(s_kv + st * Cfg::STAGE_BYTES + Cfg::NATOM * kKVAtomBytes);
-#pragma unroll
-        for (int pp = 0; pp < PARTS_PER_PV; ++pp) {
-          const int part = j * PARTS_PER_PV + pp;
-          const uint32_t o_tmem = tmem + Cfg::O_OFF + part * Cfg::DPAD;
-#pragma unroll
-          for (int kk = 0; kk < KS_PER_PART; ++kk) {
-            const int k2 = part * KS_PER_PART + kk;                        // 16-key step inside the tile
-            const uint32_t p_tmem = tmem + Cfg::P_OFF + pb * 32 + k2 * 8;
-            const uint32_t acc = (t > 0 || kk > 0) ? 1u : 0u;
-            umma_ts(o_tmem, p_tmem, make_smem_desc_sw128(v_addr + k2 * 2048, kKVAtomBytes, 1024), idesc_pv0, acc);
-            if (Cfg::N1 > 0)
-              umma_ts(o_tmem + 64, p_tmem, make_smem_desc_sw128(v_addr + kKVAtomBytes + k2 * 2048, kKVAtomBytes, 1024),
-                      idesc_pv1, acc);
-          }
-        }
-        umma_commit(bar_kv_empty + st);                                    // V_t consumed (my share)
-        umma_commit(bar_o + pb * Cfg::NPV + j);
-      }
-    }
-  } else {
-    // ------------------------------------------------------------ softmax warps: (row, key part)
-    const int quarter = warp & 3, part = warp >> 2;
-    const int jpv = part / PARTS_PER_PV;                   // the P V issuer that owns this part's accumulator
-    const int row = quarter * 32 + lane;                   // query row inside the tile == TMEM lane
-    const uint32_t t_lane = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
-    const uint32_t o_mine = t_lane + Cfg::O_OFF + part * Cfg::DPAD;
-    const int q_row = q0 + row;
-    const int kv_len = p.kv_len;
-    const float scale_log2 = p.scale_log2, bias_log2 = p.diag_bias_log2;
-    const bool use_bias = bias_log2 != 0.f;
-    const unsigned long long scale2 = pack_f2(scale_log2, scale_log2);
-    float m_run = -INFINITY, l_run = 0.f;
-
-    auto load_scores = [&](uint32_t (&r)[KEYS], int i) {   // this part's scores of tile i: TMEM -> registers
-      mbar_wait(bar_s + (i & 1), (i >> 1) & 1, 2);
-      tc_fence_after();
-      const uint32_t addr = t_lane + ((i & 1) ? Cfg::S_OFF1 : Cfg::S_OFF0) + KEYS * part;
-      if constexpr (KEYS == 32) {
-        tmem_ld32(addr, r);
-        tmem_ld_wait_dep32(r);
-      } else {
-        tmem_ld16(addr, r);
-        tmem_ld_wait_dep16(r);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_c + (i & 1));         // S buffer i & 1 may be overwritten by Q K_{i+2}^T
-    };
-    auto tile_max = [&](uint32_t (&r)[KEYS], int i) -> float {     // (mask / bias folded in) row max * scale
-      const int col0 = i * kTileN + KEYS * part;           // first key of this thread's part of the tile
-      // warp-uniform: does this part of the tile need masking (ragged tail) or the diagonal bias?
-      const bool special = (col0 + KEYS > kv_len) ||
-                           (use_bias && (q0 + quarter * 32) < col0 + KEYS && (q0 + quarter * 32 + 32) > col0);
-      if (special) {                                        // rare path: fold mask / bias into the raw scores
-#pragma unroll
-        for (int j = 0; j < KEYS; ++j) {
-          const int col = col0 + j;
-          float v = __uint_as_float(r[j]);
-          if (use_bias && col == q_row) v += bias_log2 / scale_log2;
-          if (col >= kv_len) v = -INFINITY;
-          r[j] = __float_as_uint(v);
-        }
-      }
-      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-      for (int j = 0; j < KEYS; j += 8) {
-        mx0 = max3(mx0, __uint_as_float(r[j]), __uint_as_float(r[j + 1]));
-        mx1 = max3(mx1, __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-        mx2 = max3(mx2, __uint_as_float(r[j + 4]), __uint_as_float(r[j + 5]));
-        mx3 = max3(mx3, __uint_as_float(r[j + 6]), __uint_as_float(r[j + 7]));
-      }
-      return fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
-    };
-    auto tile_exp = [&](uint32_t (&r)[KEYS], int i, float m_tile) {   // lazy max, exponentials, P stores (not waited for)
-      const int pb = i % PB;
-      // ---- lazy running max of THIS part: raise it (and rescale O_part in TMEM) only when it grows by more than 2^8.
-      //      (m_run stays -inf while every key of this part has been masked; exp2(-inf) = 0 keeps P, l and O at zero.)
-      if (i == 0) {
-        m_run = m_tile;
-      } else {
-        const bool need = m_tile > m_run + 8.0f;           // also true for the first unmasked tile after m_run = -inf
-        if (__any_sync(0xffffffffu, need)) {
-          // O_part may only be touched once P_{i-1} V_{i-1} has retired (rare path, so the wait is affordable)
-          mbar_wait(bar_o + ((i - 1) % PB) * Cfg::NPV + jpv, ((i - 1) / PB) & 1, 5);
-          tc_fence_after();
-          const float alpha = need ? fast_exp2(m_run - m_tile) : 1.0f;   // 0 when m_run was -inf (O, l are 0 then)
-          if (need) {
-            l_run *= alpha;
-            m_run = m_tile;
-          }
-#pragma unroll
-          for (int c = 0; c < Cfg::DPAD / 8; ++c) {
-            uint32_t o[8];
-            tmem_ld8_sync(o_mine + c * 8, o);               // (its wait also covers the prefetched scores: harmless)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
-            tmem_st8(o_mine + c * 8, o);
-          }
-        }
-      }
-      // ---- p = exp2(s*scale - m) -> fp16 into this part's columns of the P buffer; row sum in fp32
-      const float neg_m = (m_run == -INFINITY) ? 0.f : -m_run;           // all-masked so far: s = -inf -> p = 0, not NaN
-      const unsigned long long negm2 = pack_f2(neg_m, neg_m);
-      unsigned long long sum2[2] = {pack_f2(0.f, 0.f), pack_f2(0.f, 0.f)};
-      // the P buffer was last read by P V of tile i - PB: its retirement is almost always long past
-      if (i >= PB) {
-        mbar_wait(bar_o + pb * Cfg::NPV + jpv, ((i - PB) / PB) & 1, 3);
-        tc_fence_after();
-      }
-      // 16 keys at a time: exponentials, pack, store (the packed registers are recycled by the next 16)
-#pragma unroll
-      for (int g = 0; g < KEYS / 16; ++g) {
-        uint32_t pk[8];
-#pragma unroll
-        for (int jj = 0; jj < 16; jj += 2) {
-          const int j = g * 16 + jj;
-          float t0, t1, e0, e1;
-          unpack_f2(fma2(pack_f2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), scale2, negm2), t0, t1);
-          e0 = fast_exp2(t0);
-          e1 = fast_exp2(t1);
-          sum2[(j >> 1) & 1] = add2(sum2[(j >> 1) & 1], pack_f2(e0, e1));
-          pk[jj >> 1] = pack_half2(e0, e1);
-        }
-        tmem_st8(t_lane + Cfg::P_OFF + pb * 32 + (KEYS / 2) * part + g * 8, pk);
-      }
-      float sa, sb;
-      unpack_f2(add2(sum2[0], sum2[1]), sa, sb);
-      l_run += sa + sb;
-    };
-    auto publish = [&](int i) {                                       // P_i is in TMEM: tell its P V issuer
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_p + (i % PB) * Cfg::NPV + jpv);
-    };
-
-    // (prefetching tile i+1's scores into a second register set before working on tile i was measured 5-20 % slower:
-    //  the extra registers cost more than the hidden TMEM latency buys)
-    uint32_t r[KEYS];
-    for (int i = 0; i < n_tiles; ++i) {
-      load_scores(r, i);
-      tile_exp(r, i, tile_max(r, i));
-      publish(i);
-    }
-
-    // ---- epilogue: merge the SPLIT parts of every row, O / l -> fp16 head slice
-    mbar_wait(bar_o + ((n_tiles - 1) % PB) * Cfg::NPV + jpv, ((n_tiles - 1) / PB) & 1, 4);
-    tc_fence_after();
-    s_ml[part * 128 + row] = make_float2(m_run, l_run);
-    // every accumulator of the row is read below: wait for the other issuers' last P V as well
-#pragma unroll
-    for (int j = 0; j < Cfg::NPV; ++j)
-      if (j != jpv) mbar_wait(bar_o + ((n_tiles - 1) % PB) * Cfg::NPV + j, ((n_tiles - 1) / PB) & 1, 6);
-    tc_fence_after();
-    asm volatile("bar.sync 1, %0;" ::"n"(Cfg::SOFTMAX_WARPS * 32) : "memory");          // the softmax warps only
-    float m_all = -INFINITY;
-#pragma unroll
-    for (int q = 0; q < SPLIT; ++q) m_all = fmaxf(m_all, s_ml[q * 128 + row].x);   // finite: some key of the row is unmasked
-    float wgt[SPLIT], denom = 0.f;
-#pragma unroll
-    for (int q = 0; q < SPLIT; ++q) {
-      const float2 ml = s_ml[q * 128 + row];
-      wgt[q] = fast_exp2(ml.x - m_all);
-      denom += wgt[q] * ml.y;
-    }
-    const float inv = 1.f / denom;
-    __half* dst = p.out + (static_cast<size_t>(b) * p.q_len + q_row) * (static_cast<size_t>(p.heads) * D) +
-                  static_cast<size_t>(head) * D;
-#pragma unroll
-    for (int c = 0; c < D / 8; ++c) {
-      if ((c % SPLIT) != part) continue;                    // the SPLIT threads of a row share its 16-byte chunks
-      float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int q = 0; q < SPLIT; ++q) {
-        uint32_t o[8];
-        tmem_ld8_sync(t_lane + Cfg::O_OFF + q * Cfg::DPAD + c * 8, o);
-        const float wq = wgt[q] * inv;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = fmaf(__uint_as_float(o[j]), wq, f[j]);
-      }
-      if (q_row < p.q_len) {
-        uint4 pkt;
-        pkt.x = pack_half2(f[0], f[1]);
-        pkt.y = pack_half2(f[2], f[3]);
-        pkt.z = pack_half2(f[4], f[5]);
-        pkt.w = pack_half2(f[6], f[7]);
-        reinterpret_cast<uint4*>(dst)[c] = pkt;
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == Cfg::PV_WARP0) tmem_dealloc<Cfg::TMEM_COLS>(tmem);
-}
-
-// ---------------------------------------------------------------------------------------------
-// the "duo" kernel: TWO threads per query row that share ONE running max and ONE accumulator (head_dim <= 64)
-// ---------------------------------------------------------------------------------------------
-// Why: the pipelined kernel's softmax warp runs a serial chain per tile (wait S, TMEM load, row max, 64 exponentials,
-// pack, TMEM store, arrive) with ~350 clocks of pure latency in it, and two such warps per sub-partition (two CTAs
-// per SM, 168 registers per thread) cannot cover each other's bubbles: 800 clocks per 128 x 64 tile against a MUFU
-// floor of 512.  The wide kernel has four warps per sub-partition but splits the KEYS with private running max / O per
-// part, which at head_dim 40 leaves TMEM for a single P buffer -- and every tile then waits for the previous tile's P V
-// to retire (820 clocks per tile).  Here the row is split between two threads (32 keys each, < 100 registers) but
-// nothing else is: one running max, agreed through a named-barrier OR-reduction that costs one instruction on the
-// common tile, one O accumulator, row sums from the tensor core -- so S and P stay double-buffered in 256 TMEM columns,
-// two CTAs of eight softmax warps per SM = four softmax warps per sub-partition.
-template <int D>
-struct DuoCfg {
-  static_assert(D <= 64, "one K/V atom");
-  static constexpr int KSTEPS = (D + 15) / 16;
-  static constexpr int DPAD = KSTEPS * 16;
-  static constexpr int S_OFF0 = 0, S_OFF1 = 64, P_OFF0 = 128, P_OFF1 = 160, O_OFF = 192;
-  static constexpr int TMEM_COLS = 256;
-  static constexpr int STAGES = 5;
-  static constexpr bool MMA_ROWSUM = DPAD + 16 <= 64;      // row sums from the tensor core (16 spare O columns)
-  static constexpr int L_COL = 48;
-  static constexpr int ONES_BYTES = MMA_ROWSUM ? 2048 : 0;
-  static constexpr int Q_BYTES = kQAtomBytes;
-  static constexpr int STAGE_BYTES = 2 * kKVAtomBytes;
-  static constexpr int SMEM_BYTES = 1024 + Q_BYTES + STAGES * STAGE_BYTES + ONES_BYTES + 2 * 128 * 4 + 256;
-  static constexpr int SOFTMAX_WARPS = 8;
-  static constexpr int QK_WARP = 8, PV_WARP = 9;           // the score issuer also feeds the K/V ring (never blocking)
-  static constexpr int THREADS = 320;
-};
-
-// OR of `pred` over the `threads` threads that use named barrier `id` (also a barrier for them)
-template <int ID>
-__device__ __forceinline__ bool bar_red_or_id(bool pred) {          // 64 threads: the two warps of a row quarter
-  uint32_t out;
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\t"
-      "setp.ne.b32 q, %2, 0;\n\t"
-      "barrier.cta.red.or.pred p, %1, 64, q;\n\t"
-      "selp.b32 %0, 1, 0, p;\n\t}\n"
-      : "=r"(out)
-      : "n"(ID), "r"((uint32_t)pred)
-      : "memory");
-  return out != 0;
-}
-__device__ __forceinline__ bool bar_red_or(int id, bool pred) {     // id in [1, 4]: immediates keep "used barriers" at 5
-  switch (id) {
-    case 1: return bar_red_or_id<1>(pred);
-    case 2: return bar_red_or_id<2>(pred);
-    case 3: return bar_red_or_id<3>(pred);
-    default: return bar_red_or_id<4>(pred);
-  }
-}
-__device__ __forceinline__ void bar_sync_named(int id) {
-  switch (id) {
-    case 1: asm volatile("barrier.cta.sync 1, 64;" ::: "memory"); break;
-    case 2: asm volatile("barrier.cta.sync 2, 64;" ::: "memory"); break;
-    case 3: asm volatile("barrier.cta.sync 3, 64;" ::: "memory"); break;
-    default: asm volatile("barrier.cta.sync 4, 64;" ::: "memory"); break;
-  }
-}
-
-template <int D, int POLY>
-__global__ void __launch_bounds__(DuoCfg<D>::THREADS, 2)
-fresco_attn_duo_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
-                       const __grid_constant__ CUtensorMap tm_v, const AttnParams p) {
-  using Cfg = DuoCfg<D>;
-  constexpr int ST = Cfg::STAGES;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* s_q = smem;
-  uint8_t* s_kv = smem + Cfg::Q_BYTES;
-  uint8_t* s_ones = s_kv + ST * Cfg::STAGE_BYTES;
-  float* s_x = reinterpret_cast<float*>(s_ones + Cfg::ONES_BYTES);   // [2][128] tile max (slow path) / row sum (epilogue)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_x + 2 * 128);
-  uint64_t* bar_q = bars + 0;
-  uint64_t* bar_kv_full = bars + 1;            // [ST]
-  uint64_t* bar_kv_empty = bars + 1 + ST;      // [ST]
-  uint64_t* bar_s = bars + 1 + 2 * ST;         // [2]  S buffer b holds tile i (i & 1 == b)
-  uint64_t* bar_p = bar_s + 2;                 // [2]  P_i written (one arrival per softmax warp)
-  uint64_t* bar_o = bar_s + 4;                 // [2]  P_i V_i retired (P buffer free, O stable)
-  uint64_t* bar_c = bar_s + 6;                 // [2]  S_i is in registers everywhere (S buffer free)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s + 8);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * kTileM;
-  const int head = blockIdx.y;
-  const int b = blockIdx.z;
-  const int b_kv = b / p.q_per_kv;
-  const int n_tiles = (p.kv_len + kTileN - 1) / kTileN;
-
-  if (warp == Cfg::PV_WARP && lane == 0) {
-    mbar_init(bar_q, 1);
-    for (int s = 0; s < ST; ++s) {
-      mbar_init(bar_kv_full + s, 1);
-      mbar_init(bar_kv_empty + s, 2);          // released by the score issuer (K read) and by the P V issuer (V read)
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(bar_s + i, 1);
-      mbar_init(bar_p + i, Cfg::SOFTMAX_WARPS);
-      mbar_init(bar_o + i, 1);
-      mbar_init(bar_c + i, Cfg::SOFTMAX_WARPS);
-    }
-    fence_barrier_init();
-  }
-  if (warp == Cfg::QK_WARP) {
-    if (lane == 0) {
-      tma_prefetch_desc(&tm_q);
-      tma_prefetch_desc(&tm_k);
-      tma_prefetch_desc(&tm_v);
-    }
-    __syncwarp();
-    tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
-  }
-  if (Cfg::MMA_ROWSUM) {
-    for (int i = threadIdx.x; i < Cfg::ONES_BYTES / 4; i += Cfg::THREADS) reinterpret_cast<uint32_t*>(s_ones)[i] = 0x3C003C00u;
-    fence_proxy_async_smem();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-
-  auto load_kv_tile = [&](int t) {
-    const int st = t % ST;
-    uint8_t* sk = s_kv + st * Cfg::STAGE_BYTES;
-    mbar_expect_tx(bar_kv_full + st, Cfg::STAGE_BYTES);
-    tma_load_4d(sk, &tm_k, bar_kv_full + st, 0, head, t * kTileN, b_kv);
-    tma_load_4d(sk + kKVAtomBytes, &tm_v, bar_kv_full + st, 0, head, t * kTileN, b_kv);
-  };
-
-  if (warp == Cfg::QK_WARP) {
-    // ------------------------------------------------------------ score-MMA issuer + TMA producer
-    if (FRESCO_ISSUER_THREAD(lane)) {
-      constexpr uint32_t idesc_qk = make_idesc_f16(kTileM, kTileN, 0);
-      const uint32_t q_addr = smem_u32(s_q);
-      int next_load = 0;
-      auto refill = [&]() {                     // issue every K/V tile load whose ring stage is free; never blocks
-        while (next_load < n_tiles) {
-          if (next_load >= ST && !mbar_test_wait(bar_kv_empty + next_load % ST, ((next_load / ST) - 1) & 1)) break;
-          load_kv_tile(next_load);
-          ++next_load;
-        }
-      };
-      auto issue_qk = [&](int t) {
-        const int st = t % ST;
-        uint32_t polls = 0;
-        while (!mbar_try_wait(bar_kv_full + st, (t / ST) & 1)) {
-          refill();
-          if (++polls > FRESCO_WATCHDOG_POLLS) mbar_timeout(bar_kv_full + st, (t / ST) & 1, 60);
-        }
-        tc_fence_after();
-        const uint32_t k_addr = smem_u32(s_kv + st * Cfg::STAGE_BYTES);
-        const uint32_t d_tmem = tmem + ((t & 1) ? Cfg::S_OFF1 : Cfg::S_OFF0);
-#pragma unroll
-        for (int ks = 0; ks < Cfg::KSTEPS; ++ks)
-          umma_ss(d_tmem, make_smem_desc_sw128(q_addr + ks * 32, 16, 1024), make_smem_desc_sw128(k_addr + ks * 32, 16, 1024),
-                  idesc_qk, ks > 0);
-        umma_commit(bar_s + (t & 1));
-        umma_commit(bar_kv_empty + st);
-      };
-      mbar_expect_tx(bar_q, Cfg::Q_BYTES);
-      tma_load_4d(s_q, &tm_q, bar_q, 0, head, q0, b);
-      refill();
-      mbar_wait(bar_q, 0, 61);
-      issue_qk(0);
-      if (n_tiles > 1) issue_qk(1);
-      for (int t = 0; t + 2 < n_tiles; ++t) {
-        refill();
-        uint32_t polls = 0;
-        while (!mbar_try_wait(bar_c + (t & 1), (t >> 1) & 1)) {      // S buffer t & 1 is in registers
-          refill();
-          if (++polls > FRESCO_WATCHDOG_POLLS) mbar_timeout(bar_c + (t & 1), (t >> 1) & 1, 62);
-        }
-        issue_qk(t + 2);
-      }
-      while (next_load < n_tiles) refill();
-    }
-  } else if (warp == Cfg::PV_WARP) {
-    // ------------------------------------------------------------ P V MMA issuer
-    if (FRESCO_ISSUER_THREAD(lane)) {
-      constexpr uint32_t idesc_pv = make_idesc_f16(kTileM, Cfg::DPAD, 1);
-      constexpr uint32_t idesc_ones = make_idesc_f16(kTileM, 16, 1);
-      for (int t = 0; t < n_tiles; ++t) {
-        const int st = t % ST;
-        mbar_wait_backoff(bar_p + (t & 1), (t >> 1) & 1, 20, 63);
-        mbar_wait(bar_kv_full + st, (t / ST) & 1, 64);
-        tc_fence_after();
-        const uint32_t v_addr = smem_u32(s_kv + st * Cfg::STAGE_BYTES + kKVAtomBytes);
-#pragma unroll
-        for (int k2 = 0; k2 < kTileN / 16; ++k2) {
-          const uint32_t acc = (k2 > 0 || t > 0) ? 1u : 0u;
-          const uint32_t p_tmem = tmem + ((t & 1) ? Cfg::P_OFF1 : Cfg::P_OFF0) + k2 * 8;
-          umma_ts(tmem + Cfg::O_OFF, p_tmem, make_smem_desc_sw128(v_addr + k2 * 2048, kKVAtomBytes, 1024), idesc_pv, acc);
-          if (Cfg::MMA_ROWSUM)
-            umma_ts(tmem + Cfg::O_OFF + Cfg::L_COL, p_tmem, make_smem_desc_sw128(smem_u32(s_ones), 2048, 1024),
-                    idesc_ones, acc);
-        }
-        umma_commit(bar_kv_empty + st);
-        umma_commit(bar_o + (t & 1));
-      }
-    }
-  } else {
-    // ------------------------------------------------------------ softmax warps: (row quarter, key half)
-    const int quarter = warp & 3, part = warp >> 2;
-    const int row = quarter * 32 + lane;
-    const uint32_t t_lane = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
-    const int q_row = q0 + row;
-    const int kv_len = p.kv_len;
-    const float scale_log2 = p.scale_log2, bias_log2 = p.diag_bias_log2;
-    const bool use_bias = bias_log2 != 0.f;
-    const unsigned long long scale2 = pack_f2(scale_log2, scale_log2);
-    const int pair_bar = 1 + quarter;          // named barrier of the two warps that share these 32 rows
-    float m_run = -INFINITY, l_run = 0.f;
-    // warp-uniform "this tile needs the mask / bias path", reduced to two compares per tile: the ragged tail starts at
-    // tile i_tail (first tile whose 32 keys of this part reach past kv_len), and this warp's 32 rows [r0, r0 + 32) meet
-    // the diagonal in exactly one 32-key part (both are 32-aligned): tile i_diag of the part with 64 i + 32 part == r0
-    const int tail_num = kv_len - 32 * part - 32;
-    const int i_tail = tail_num >= 0 ? tail_num / kTileN + 1 : 0;
-    const int r0 = q0 + quarter * 32;
-    const int i_diag = (use_bias && r0 >= 32 * part && ((r0 - 32 * part) % kTileN) == 0) ? (r0 - 32 * part) / kTileN : -1;
-
-    for (int i = 0; i < n_tiles; ++i) {
-      const int col0 = i * kTileN + 32 * part;
-      const bool special = (i >= i_tail) || (i == i_diag);
-      mbar_wait(bar_s + (i & 1), (i >> 1) & 1, 2);
-      tc_fence_after();
-      uint32_t r[32];
-      tmem_ld32(t_lane + ((i & 1) ? Cfg::S_OFF1 : Cfg::S_OFF0) + 32 * part, r);
-      tmem_ld_wait_dep32(r);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_c + (i & 1));
-      if (special) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int col = col0 + j;
-          float v = __uint_as_float(r[j]);
-          if (use_bias && col == q_row) v += bias_log2 / scale_log2;
-          if (col >= kv_len) v = -INFINITY;
-          r[j] = __float_as_uint(v);
-        }
-      }
-      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        mx0 = max3(mx0, __uint_as_float(r[j]), __uint_as_float(r[j + 1]));
-        mx1 = max3(mx1, __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-        mx2 = max3(mx2, __uint_as_float(r[j + 4]), __uint_as_float(r[j + 5]));
-        mx3 = max3(mx3, __uint_as_float(r[j + 6]), __uint_as_float(r[j + 7]));
-      }
-      const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
-      // ---- lazy running max shared by the two threads of a row: one OR-reducing barrier on the common tile
-      if (bar_red_or(pair_bar, i == 0 || m_tile > m_run + 8.0f)) {
-        s_x[part * 128 + row] = m_tile;
-        bar_sync_named(pair_bar);
-        const float m_new = fmaxf(m_tile, s_x[(part ^ 1) * 128 + row]);
-        const bool need = (i == 0) || (m_new > m_run + 8.0f);
-        if (i > 0) {
-          // O may only be touched once P_{i-1} V_{i-1} has retired
-          mbar_wait(bar_o + ((i - 1) & 1), ((i - 1) >> 1) & 1, 5);
-          tc_fence_after();
-          const float alpha = need ? fast_exp2(m_run - m_new) : 1.0f;     // m_run = -inf cannot happen for i > 0 unless
-          l_run *= alpha;                                                 // every key so far was masked (O = l = 0 then)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {                                   // this thread's half of the 64 O columns
-            uint32_t o[8];
-            const uint32_t addr = t_lane + Cfg::O_OFF + part * 32 + c * 8;
-            tmem_ld8_sync(addr, o);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
-            tmem_st8(addr, o);
-          }
-        }
-        if (need) m_run = m_new;
-      }
-      // ---- P buffer (i & 1) was last read by P_{i-2} V_{i-2}: retired long ago in the common case
-      if (i >= 2) {
-        mbar_wait(bar_o + (i & 1), ((i - 2) >> 1) & 1, 3);
-        tc_fence_after();
-      }
-      const float neg_m = (m_run == -INFINITY) ? 0.f : -m_run;
-      const unsigned long long negm2 = pack_f2(neg_m, neg_m);
-#pragma unroll
-      for (int j = 0; j < 32; j += 2) {
-        float t0, t1;
-        unpack_f2(fma2(pack_f2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), scale2, negm2), t0, t1);
-        if (POLY > 0 && ((j >> 1) % (POLY > 0 ? POLY : 1)) == (POLY - 1)) {
-          float p0, p1;
-          exp2_poly_x2(t0, t1, p0, p1);
-          r[j] = __float_as_uint(p0);
-          r[j + 1] = __float_as_uint(p1);
-        } else {
-          r[j] = __float_as_uint(fast_exp2(t0));
-          r[j + 1] = __float_as_uint(fast_exp2(t1));
-        }
-      }
-      if (!Cfg::MMA_ROWSUM) {
-        unsigned long long sum2[2] = {pack_f2(0.f, 0.f), pack_f2(0.f, 0.f)};
-#pragma unroll
-        for (int j = 0; j < 32; j += 2)
-          sum2[(j >> 1) & 1] = add2(sum2[(j >> 1) & 1], pack_f2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])));
-        float sa, sb;
-        unpack_f2(add2(sum2[0], sum2[1]), sa, sb);
-        l_run += sa + sb;
-      }
-      uint32_t pk[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) pk[j] = pack_half2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
-      tmem_st16(t_lane + ((i & 1) ? Cfg::P_OFF1 : Cfg::P_OFF0) + 16 * part, pk);
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_p + (i & 1));
-    }
-
-    // ---- epilogue: O / l -> fp16 head slice; the two threads of a row take alternate 16-byte chunks
-    mbar_wait(bar_o + ((n_tiles - 1) & 1), ((n_tiles - 1) >> 1) & 1, 4);
-    tc_fence_after();
-    if (Cfg::MMA_ROWSUM) {
-      uint32_t lcol[8];
-      tmem_ld8_sync(t_lane + Cfg::O_OFF + Cfg::L_COL, lcol);
-      l_run = __uint_as_float(lcol[0]);
-    } else {
-      s_x[part * 128 + row] = l_run;
-      bar_sync_named(pair_bar);
-      l_run += s_x[(part ^ 1) * 128 + row];
-    }
-    const float inv = 1.f / l_run;
-    __half* dst = p.out + (static_cast<size_t>(b) * p.q_len + q_row) * (static_cast<size_t>(p.heads) * D) +
-                  static_cast<size_t>(head) * D;
-#pragma unroll
-    for (int c = 0; c < D / 8; ++c) {
-      if ((c & 1) != part) continue;
-      uint32_t o[8];
-      tmem_ld8_sync(t_lane + Cfg::O_OFF + c * 8, o);
-      if (q_row < p.q_len) {
-        uint4 pkt;
-        pkt.x = pack_half2(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
-        pkt.y = pack_half2(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
-        pkt.z = pack_half2(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
-        pkt.w = pack_half2(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
-        reinterpret_cast<uint4*>(dst)[c] = pkt;
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == Cfg::QK_WARP) tmem_dealloc<Cfg::TMEM_COLS>(tmem);
-}
-
-// ---------------------------------------------------------------------------------------------
 // the "twin" kernel: TWO 128-row query tiles per CTA, 128-key tiles, one thread per query row (1 CTA per SM)
 // ---------------------------------------------------------------------------------------------
 // Written from the round-2 profiles (profiles/r02_attn_*_hot_*.txt): the 64-key kernels above execute 368 (pipelined)
@@ -1306,8 +567,9 @@ fresco_attn_duo_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
 //
 //   TMEM  S regions [0,128) [128,256) ([256,384))  (fp32 scores; P = fp16 in columns [0,64) of the same region)
 //         O_A, O_B behind them, DPAD columns each + 16 columns of row sums (ones-MMA)
-template <int D>
+template <int D, int SPLIT_>
 struct TwinCfg {
+  static constexpr int SPLIT = SPLIT_;                    // threads per query row: 1, or 2 (64 keys of a tile each)
   static constexpr int KV = 128;                          // keys per tile
   static constexpr int NATOM = (D + 63) / 64;
   static constexpr int KSTEPS = (D + 15) / 16;
@@ -1333,12 +595,18 @@ struct TwinCfg {
   static constexpr int TILE_BYTES = NATOM * kQAtomBytes;  // a [128 rows x D] tile: Q tile, K tile or V tile
   static constexpr int STAGES = NATOM == 1 ? 4 : 2;
   static constexpr int STAGE_BYTES = 2 * TILE_BYTES;      // K | V
-  static constexpr int SMEM_BYTES = 1024 + 2 * TILE_BYTES + STAGES * STAGE_BYTES + 2048 + 512;
-  // 8 softmax warps + MMA issuer + TMA producer + 2 idle warps: three whole warpgroups, so that setmaxnreg can move
-  // registers from the issuer warpgroup (56 each) to the softmax warpgroups (224 each: 2 x 224 + 56 = 3 x 168, the pool the CTA is launched with: a 128-score row plus its packed
-  // half live in registers); 384 threads x 168 = the whole register file
-  static constexpr int THREADS = 384;
-  static constexpr int MMA_WARP = 8, TMA_WARP = 9, PATCH_WARP0 = 10;
+  static constexpr int SMEM_BYTES = 1024 + 2 * TILE_BYTES + STAGES * STAGE_BYTES + 2048 + 512 + 2048;
+  // SPLIT 1: 8 softmax warps + MMA issuer + TMA producer + the two V-patch warps: three whole warpgroups, so that
+  // setmaxnreg can move registers from the issuer warpgroup (56 each) to the softmax warpgroups (224 each: a 128-score
+  // row plus its packed half live in registers; 2 x 224 + 56 = 3 x 168, the pool the CTA is launched with).
+  // SPLIT 2: 16 softmax warps (four per sub-partition, 64 scores each) + the same four: 640 threads x 96 registers.
+  static constexpr int SOFTMAX_WARPS = 8 * SPLIT;
+  static constexpr int MMA_WARP = SOFTMAX_WARPS, TMA_WARP = SOFTMAX_WARPS + 1, PATCH_WARP0 = SOFTMAX_WARPS + 2;
+  static constexpr int THREADS = (SOFTMAX_WARPS + 4) * 32;
+  static constexpr int XCH_BYTES = SPLIT == 2 ? 2 * 2 * 128 * 4 : 0;    // tile maxima of the two threads of a row
+  // TMEM columns (inside a score region) of the P operand of 16-key step k2: SPLIT 1 packs the 128 keys into columns
+  // [0, 64); with SPLIT 2 every thread overwrites the start of its OWN 64 score columns: [0, 32) and [64, 96)
+  __host__ __device__ static constexpr int p_col(int k2) { return SPLIT == 1 ? k2 * 8 : (k2 >> 2) * 64 + (k2 & 3) * 8; }
 };
 
 __device__ __forceinline__ void tmem_ld_wait_dep128(uint32_t (&r)[128]) {
@@ -1367,11 +635,26 @@ __device__ __forceinline__ void mbar_arrive_elected(uint64_t* bar) {
       : "memory");
 }
 
-template <int D, int POLY>
-__global__ void __launch_bounds__(TwinCfg<D>::THREADS, 1)
+// OR of `pred` over the 64 threads (two warps) that use named barrier `id`; also a barrier for them
+__device__ __forceinline__ bool bar_red_or64(int id, bool pred) {
+  uint32_t out;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 q, %2, 0;\n\t"
+      "barrier.cta.red.or.pred p, %1, 64, q;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(out)
+      : "r"(id), "r"((uint32_t)pred)
+      : "memory");
+  return out != 0;
+}
+__device__ __forceinline__ void bar_sync64(int id) { asm volatile("barrier.cta.sync %0, 64;" ::"r"(id) : "memory"); }
+
+template <int D, int POLY, int SPLIT>
+__global__ void __launch_bounds__(TwinCfg<D, SPLIT>::THREADS, 1)
 fresco_attn_twin_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                         const __grid_constant__ CUtensorMap tm_v, const AttnParams p) {
-  using Cfg = TwinCfg<D>;
+  using Cfg = TwinCfg<D, SPLIT>;
   constexpr int ST = Cfg::STAGES;
   constexpr int KV = Cfg::KV;
   extern __shared__ uint8_t smem_raw[];
@@ -1389,6 +672,7 @@ fresco_attn_twin_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   uint64_t* bar_pv = bar_s + 6;                // [2]  P V_X(j) retired (O_X stable); phase j & 1
   uint64_t* bar_vp = bar_s + 8;                // [ST] ones column written into V tile t (FOLD)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s + 8 + ST);
+  float* s_xch = reinterpret_cast<float*>(bar_s + 8 + ST + 2);      // [2 query tiles][2 halves][128 rows] (SPLIT 2)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -1406,7 +690,7 @@ fresco_attn_twin_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     }
     for (int k = 0; k < NB; ++k) {
       mbar_init(bar_s + k, 1);
-      mbar_init(bar_p + k, 4);
+      mbar_init(bar_p + k, 4 * SPLIT);
     }
     mbar_init(bar_pv + 0, 1);
     mbar_init(bar_pv + 1, 1);
@@ -1429,9 +713,9 @@ fresco_attn_twin_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp >= 8) {
-    // ------------------------------------------------------------ issuer warpgroup (warps 10, 11 idle)
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  if (warp >= Cfg::SOFTMAX_WARPS) {
+    // ------------------------------------------------------------ issuer warpgroup
+    if (SPLIT == 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == Cfg::TMA_WARP) {
     // ------------------------------------------------------------ TMA producer
     if (FRESCO_ISSUER_THREAD(lane)) {
@@ -1472,7 +756,7 @@ fresco_attn_twin_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
 #pragma unroll
         for (int k2 = 0; k2 < KV / 16; ++k2) {
           const uint32_t acc = (k2 > 0 || t > 0) ? 1u : 0u;
-          const uint32_t p_tmem = s_tmem + k2 * 8;
+          const uint32_t p_tmem = s_tmem + Cfg::p_col(k2);
           umma_ts(o_tmem, p_tmem, make_smem_desc_sw128(v_addr + k2 * 2048, kQAtomBytes, 1024), idesc_pv0, acc);
           if (Cfg::N1 > 0)
             umma_ts(o_tmem + 64, p_tmem, make_smem_desc_sw128(v_addr + kQAtomBytes + k2 * 2048, kQAtomBytes, 1024),
@@ -1513,7 +797,7 @@ fresco_attn_twin_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       }
     }
   } else if (Cfg::FOLD) {
-    // ------------------------------------------------------------ warps 10, 11: the ones column of every V tile
+    // ------------------------------------------------------------ the two spare warps: the ones column of every V tile
     constexpr int a_ones = D / 64, c_ones = D % 64;              // atom and column inside the atom
     constexpr int chunk = (c_ones * 2) / 16, byte = (c_ones * 2) % 16;
     const int tid = (warp - Cfg::PATCH_WARP0) * 32 + lane;       // 0..63: rows tid and tid + 64
@@ -1532,6 +816,7 @@ fresco_attn_twin_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     }
   }
   } else {
+    if constexpr (SPLIT == 1) {
     // ------------------------------------------------------------ softmax warps: query tile X = warp / 4, one row per thread
     asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     const int x = warp >> 2, quarter = warp & 3;
@@ -1652,6 +937,136 @@ fresco_attn_twin_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         reinterpret_cast<uint4*>(dst)[c] = pkt;
       }
     }
+    } else {
+    // ------------------------------------------------------------ softmax warps, two threads per row: query tile X = warp / 8,
+    //      key half = (warp / 4) % 2 (keys [64 half, 64 half + 64) of every tile), rows by warp % 4 (the TMEM lane quarter).
+    //      The two threads of a row agree on ONE running max through a named-barrier OR-reduction (one instruction on
+    //      the common tile) and share one accumulator; each overwrites the start of its own score columns with its P.
+    const int x = warp >> 3, half = (warp >> 2) & 1, quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t t_lane = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
+    const uint32_t o_lane = t_lane + (x ? Cfg::O_OFF_B : Cfg::O_OFF_A);
+    const int q_row = q0 + x * kTileM + row;
+    const int kv_len = p.kv_len;
+    const float scale_log2 = p.scale_log2, bias_log2 = p.diag_bias_log2;
+    const bool use_bias = bias_log2 != 0.f;
+    const unsigned long long scale2 = pack_f2(scale_log2, scale_log2);
+    const int pair_bar = 1 + x * 4 + quarter;              // named barrier of the two warps that share these 32 rows
+    float* xch_mine = s_xch + (x * 2 + half) * 128 + row;
+    float* xch_other = s_xch + (x * 2 + (half ^ 1)) * 128 + row;
+    // warp-uniform special tiles of this key half: the ragged tail and the tile that holds this warp's diagonal
+    const int tail_num = kv_len - 64 * half - 64;
+    const int j_tail = tail_num >= 0 ? tail_num / KV + 1 : 0;
+    const int d0 = q0 + x * kTileM + quarter * 32 - 64 * half;
+    const int j_diag = (use_bias && d0 >= 0 && (d0 % KV) < 64) ? d0 / KV : -1;
+    float m_run = -INFINITY;
+    int buf = x % NB, ph = 0;
+
+    for (int j = 0; j < n_tiles; ++j) {
+      const uint32_t s_lane = t_lane + buf * 128 + 64 * half;
+      mbar_wait_trap(bar_s + buf, ph);
+      tc_fence_after();
+      uint32_t r[64];
+      tmem_ld32(s_lane + 0, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+      tmem_ld32(s_lane + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+      tmem_ld_wait_dep64(r);
+      if (j >= j_tail || j == j_diag) {
+        const int col0 = j * KV + 64 * half;
+#pragma unroll
+        for (int c = 0; c < 64; ++c) {
+          float v = __uint_as_float(r[c]);
+          if (use_bias && col0 + c == q_row) v += bias_log2 / scale_log2;
+          if (col0 + c >= kv_len) v = -INFINITY;
+          r[c] = __float_as_uint(v);
+        }
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 64; c += 8) {
+        mx0 = max3(mx0, __uint_as_float(r[c]), __uint_as_float(r[c + 1]));
+        mx1 = max3(mx1, __uint_as_float(r[c + 2]), __uint_as_float(r[c + 3]));
+        mx2 = max3(mx2, __uint_as_float(r[c + 4]), __uint_as_float(r[c + 5]));
+        mx3 = max3(mx3, __uint_as_float(r[c + 6]), __uint_as_float(r[c + 7]));
+      }
+      const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
+      // ---- lazy running max shared by the two threads of a row
+      if (bar_red_or64(pair_bar, j == 0 || m_tile > m_run + 8.0f)) {
+        *xch_mine = m_tile;
+        bar_sync64(pair_bar);
+        const float m_new = fmaxf(m_tile, *xch_other);
+        const bool need = (j == 0) || (m_new > m_run + 8.0f);
+        if (j > 0) {
+          mbar_wait_trap(bar_pv + x, (j - 1) & 1);           // O_X may only be touched once P V_X(j-1) has retired
+          tc_fence_after();
+          const float alpha = need ? fast_exp2(m_run - m_new) : 1.0f;
+#pragma unroll
+          for (int c = 0; c < Cfg::OCOLS / 8; ++c) {           // the two threads take alternate 8-column chunks of the row
+            if ((c & 1) != half) continue;
+            uint32_t o[8];
+            tmem_ld8_sync(o_lane + c * 8, o);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+            tmem_st8(o_lane + c * 8, o);
+          }
+        }
+        if (need) m_run = m_new;
+      }
+      // ---- p = exp2(s * scale - m) -> fp16, 32 keys at a time over the start of this thread's own score columns
+      const float neg_m = (m_run == -INFINITY) ? 0.f : -m_run;
+      const unsigned long long negm2 = pack_f2(neg_m, neg_m);
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int cc = 0; cc < 32; cc += 2) {
+          const int c = g * 32 + cc;
+          float t0, t1, e0, e1;
+          unpack_f2(fma2(pack_f2(__uint_as_float(r[c]), __uint_as_float(r[c + 1])), scale2, negm2), t0, t1);
+          if (POLY > 0 && ((c >> 1) % (POLY > 0 ? POLY : 1)) == (POLY - 1)) {
+            exp2_poly_x2(t0, t1, e0, e1);
+          } else {
+            e0 = fast_exp2(t0);
+            e1 = fast_exp2(t1);
+          }
+          pk[cc >> 1] = pack_half2(e0, e1);
+        }
+        tmem_st16(s_lane + g * 16, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      mbar_arrive_elected(bar_p + buf);
+      if (NB == 3) {
+        if (buf == 0) buf = 2;
+        else { buf -= 1; ph ^= 1; }
+      } else {
+        ph ^= 1;
+      }
+    }
+
+    // ---- epilogue: O / l -> fp16 head slice; the two threads of a row take alternate 16-byte chunks
+    mbar_wait_trap(bar_pv + x, (n_tiles - 1) & 1);
+    tc_fence_after();
+    uint32_t lcol[8];
+    tmem_ld8_sync(o_lane + (Cfg::L_COL / 8) * 8, lcol);
+    const float inv = 1.f / __uint_as_float(lcol[Cfg::L_COL % 8]);
+    __half* dst = p.out + (static_cast<size_t>(b) * p.q_len + q_row) * (static_cast<size_t>(p.heads) * D) +
+                  static_cast<size_t>(head) * D;
+#pragma unroll
+    for (int c = 0; c < D / 8; ++c) {
+      if ((c & 1) != half) continue;
+      uint32_t o[8];
+      tmem_ld8_sync(o_lane + c * 8, o);
+      if (q_row < p.q_len) {
+        uint4 pkt;
+        pkt.x = pack_half2(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
+        pkt.y = pack_half2(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
+        pkt.z = pack_half2(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
+        pkt.w = pack_half2(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
+        reinterpret_cast<uint4*>(dst)[c] = pkt;
+      }
+    }
+    }
   }
 
   tc_fence_before();
@@ -1704,19 +1119,30 @@ static int make_head_tile_map(CUtensorMap* map, const void* base, int head_dim, 
 }
 
 // Tuning knobs (fresco_internal.h: option(); environment variable of the same name read once, fresco_set_option()
-// overrides).  The defaults are the measured best on B200 per head_dim (profiles/README.md, attention sweep):
-//   FRESCO_ATTN_WIDE    -1 = per head_dim (below), 0 = pipelined kernel, 2 | 4 = wide kernel (that many threads per
-//                       row), 3 = duo kernel (head_dim <= 64), 5 = twin kernel (head_dim <= 80)
-//   FRESCO_ATTN_POLY    every n-th pair of exponentials on the FMA pipe: 0 | 4 | 8 (twin kernel at head_dim 40: 2..6, 8);
-//                       -1 / unset = 4 for the twin kernel, 0 elsewhere
+// overrides).  The defaults are the measured best on B200 per head_dim:
+//   FRESCO_ATTN_WIDE    -1 / unset = per head_dim (below); 0 = pipelined kernel (64-key tiles, any head_dim);
+//                       1 | 2 = twin kernel with that many threads per query row (head_dim <= 80)
+//   FRESCO_ATTN_POLY    every n-th pair of exponentials on the FMA pipe: 0 | 4 | 8; -1 / unset = per kernel (below)
 //   FRESCO_ATTN_ROWSUM  pipelined kernel, head_dim 40: row sums from the tensor core
 constexpr int kRowsumDefault = 1;
-// The default kernel per head_dim.  TF/s measured in isolation at the config-2 shapes (profiles/r02_attn_microbench_*):
-//   d = 40 (L 4096, Lk 15587): pipelined 451, duo 449, wide2 426, wide4 343, twin 529, twin + poly4 562   [torch SDPA 620]
-//   d = 80 (L 1024, Lk 3897):  pipelined 520, wide2 540, wide4 587, twin 605, twin + poly4 644            [torch SDPA 858]
-//   d = 128: pipelined 510, wide2 508, pipelined + poly4 543                                              [torch SDPA 849]
-constexpr int default_split(int head_dim) { return (head_dim == 40 || head_dim == 80) ? 5 : (head_dim == 64 ? 4 : 0); }
-static int poly_option(int split) { return option(OPT_ATTN_POLY, split == 5 ? 4 : 0); }
+// TFLOP/s measured in isolation at the config-2 shapes (profiles/r02_attn_microbench_*.jsonl; +-2 % run to run):
+//   d = 40 (L 4096, Lk 15587): pipelined 451 | twin/1 531, poly8 563, poly4 594 | twin/2 543, poly4 584, poly8 617  [torch SDPA 622]
+//   d = 80 (L 1024, Lk 3897):  pipelined 520 | twin/1 628, poly4 680 | twin/2 624, poly4 635, poly8 659              [torch SDPA 868]
+//   d = 64 (L 2048, Lk 2048):  twin/1 poly4 540 | twin/2 534;   d = 128: pipelined 510, poly4 543                       [SDPA 849]
+// Built, measured slower and removed again (numbers in DESIGN.md 3.1): a "wide" kernel (2 / 4 threads per row with
+// private running max and accumulator per key part: 426 / 343 at d = 40, 587 at d = 80), a "duo" kernel (two threads per
+// row sharing one running max, 64-key tiles: 449), a 4-CTA-per-SM kernel without pipelining, prefetched scores, and two
+// query tiles taking strict turns on the MUFU pipe.
+constexpr int default_rows_split(int head_dim) { return head_dim == 40 ? 2 : (head_dim <= 80 ? 1 : 0); }
+static int twin_split(int head_dim) {       // 0 = pipelined kernel, 1 | 2 = twin kernel, threads per query row
+  int w = option(OPT_ATTN_WIDE, -1);
+  if (w < 0) w = default_rows_split(head_dim);
+  if (head_dim > 80) return 0;
+  return w <= 0 ? 0 : (w >= 2 ? 2 : 1);
+}
+static int poly_option(int head_dim, int split) {
+  return option(OPT_ATTN_POLY, split == 0 ? 0 : ((head_dim == 40 && split == 2) ? 8 : 4));
+}
 
 template <int D, int POLY, bool ROWSUM>
 static int launch_pipelined(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
@@ -1733,58 +1159,19 @@ static int launch_pipelined(const CUtensorMap& tq, const CUtensorMap& tk, const 
   return check_launch("fresco_attn_kernel");
 }
 
-template <int D, int SPLIT>
-static int launch_wide(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, dim3 grid,
-                       cudaStream_t stream) {
-  using Cfg = WideCfg<D, SPLIT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(fresco_attn_wide_kernel<D, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(attn wide)");
-    attr_set = true;
-  }
-  fresco_attn_wide_kernel<D, SPLIT><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tq, tk, tv, p);
-  return check_launch("fresco_attn_wide_kernel");
-}
-
-template <int D, int POLY>
-static int launch_duo(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, dim3 grid,
-                      cudaStream_t stream) {
-  using Cfg = DuoCfg<D>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(fresco_attn_duo_kernel<D, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(attn duo)");
-    attr_set = true;
-  }
-  fresco_attn_duo_kernel<D, POLY><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tq, tk, tv, p);
-  return check_launch("fresco_attn_duo_kernel");
-}
-
-template <int D, int POLY>
+template <int D, int POLY, int SPLIT>
 static int launch_twin(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, dim3 grid,
                        cudaStream_t stream) {
-  using Cfg = TwinCfg<D>;
+  using Cfg = TwinCfg<D, SPLIT>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(fresco_attn_twin_kernel<D, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(fresco_attn_twin_kernel<D, POLY, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(attn twin)");
     attr_set = true;
   }
-  fresco_attn_twin_kernel<D, POLY><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tq, tk, tv, p);
+  fresco_attn_twin_kernel<D, POLY, SPLIT><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tq, tk, tv, p);
   return check_launch("fresco_attn_twin_kernel");
-}
-
-static int wide_split(int head_dim) {       // threads per query row under the current options; 0 = pipelined kernel
-  int wide = option(OPT_ATTN_WIDE, -1);
-  if (wide < 0) wide = default_split(head_dim);
-  if (wide == 5) return head_dim <= 80 ? 5 : 0;                          // 5 = twin kernel (128-key tiles)
-  if (wide == 3) return head_dim <= 64 ? 3 : (head_dim <= 80 ? 4 : 0);   // 3 = duo kernel (head_dim <= 64)
-  if (wide >= 4) return head_dim <= 80 ? 4 : 2;       // four accumulators of head_dim 128 do not fit TMEM
-  return wide >= 1 ? 2 : 0;
 }
 
 template <int D>
@@ -1794,8 +1181,8 @@ static int launch_attn(const void* q, const void* k, const void* v, void* out, i
   CUtensorMap tq, tk, tv;
   const int batch_kv = batch_q / q_per_kv;
   const long long C = (long long)heads * D;
-  const int split = wide_split(D);
-  const int kv_box = split == 5 ? 128 : kTileN;                      // key rows per TMA box
+  const int split = twin_split(D);
+  const int kv_box = split > 0 ? 128 : kTileN;                       // key rows per TMA box
   if (make_head_tile_map(&tq, q, D, heads, q_len, batch_q, kTileM, C, C * q_len)) return FRESCO_ERR_TENSORMAP;
   if (make_head_tile_map(&tk, k, D, heads, kv_len, batch_kv, kv_box, kv_row_stride, kv_batch_stride)) return FRESCO_ERR_TENSORMAP;
   if (make_head_tile_map(&tv, v, D, heads, kv_len, batch_kv, kv_box, kv_row_stride, kv_batch_stride)) return FRESCO_ERR_TENSORMAP;
@@ -1809,32 +1196,20 @@ static int launch_attn(const void* q, const void* k, const void* v, void* out, i
   p.diag_bias_log2 = diag_bias * 1.4426950408889634f;
   p.ablate = option(OPT_ATTN_ABLATE, 0);
   dim3 grid((q_len + kTileM - 1) / kTileM, heads, batch_q);
-  const int poly = poly_option(split);
+  const int poly = poly_option(D, split);
   if constexpr (D <= 80) {
-    if (split == 5) {
+    if (split > 0) {
       dim3 grid2((q_len + 2 * kTileM - 1) / (2 * kTileM), heads, batch_q);
-      if constexpr (D == 40) {                                    // (the measured sweep of the FMA-pipe share)
-        if (poly == 2) return launch_twin<D, 2>(tq, tk, tv, p, grid2, stream);
-        if (poly == 3) return launch_twin<D, 3>(tq, tk, tv, p, grid2, stream);
-        if (poly == 5) return launch_twin<D, 5>(tq, tk, tv, p, grid2, stream);
-        if (poly == 6) return launch_twin<D, 6>(tq, tk, tv, p, grid2, stream);
+      if (split == 2) {
+        if (poly == 4) return launch_twin<D, 4, 2>(tq, tk, tv, p, grid2, stream);
+        if (poly == 8) return launch_twin<D, 8, 2>(tq, tk, tv, p, grid2, stream);
+        return launch_twin<D, 0, 2>(tq, tk, tv, p, grid2, stream);
       }
-      if (poly == 4) return launch_twin<D, 4>(tq, tk, tv, p, grid2, stream);
-      if (poly == 8) return launch_twin<D, 8>(tq, tk, tv, p, grid2, stream);
-      return launch_twin<D, 0>(tq, tk, tv, p, grid2, stream);
+      if (poly == 4) return launch_twin<D, 4, 1>(tq, tk, tv, p, grid2, stream);
+      if (poly == 8) return launch_twin<D, 8, 1>(tq, tk, tv, p, grid2, stream);
+      return launch_twin<D, 0, 1>(tq, tk, tv, p, grid2, stream);
     }
   }
-  if constexpr (D <= 64) {
-    if (split == 3) {
-      if (poly == 4) return launch_duo<D, 4>(tq, tk, tv, p, grid, stream);
-      if (poly == 8) return launch_duo<D, 8>(tq, tk, tv, p, grid, stream);
-      return launch_duo<D, 0>(tq, tk, tv, p, grid, stream);
-    }
-  }
-  if constexpr (D <= 80) {
-    if (split == 4) return launch_wide<D, 4>(tq, tk, tv, p, grid, stream);
-  }
-  if (split >= 2) return launch_wide<D, 2>(tq, tk, tv, p, grid, stream);
   if constexpr (AttnCfg<D, true>::MMA_ROWSUM) {
     if (option(OPT_ATTN_ROWSUM, kRowsumDefault)) {
       if (poly == 4) return launch_pipelined<D, 4, true>(tq, tk, tv, p, grid, stream);
@@ -1860,11 +1235,9 @@ extern "C" int fresco_debug_attn_trace(long long* host_out) {
 // which kernel fresco_attn_fwd launches for a head dim under the current options (bench.py names it in its JSON line)
 extern "C" const char* fresco_attn_variant(int head_dim) {
   static thread_local char buf[96];
-  const int split = wide_split(head_dim);
-  if (split == 5) snprintf(buf, sizeof(buf), "fresco_attn_twin_kernel<%d,poly%d>", head_dim, poly_option(split));
-  else if (split == 3) snprintf(buf, sizeof(buf), "fresco_attn_duo_kernel<%d,poly%d>", head_dim, poly_option(split));
-  else if (split > 0) snprintf(buf, sizeof(buf), "fresco_attn_wide_kernel<%d,%d>", head_dim, split);
-  else snprintf(buf, sizeof(buf), "fresco_attn_kernel<%d,poly%d> (pipelined)", head_dim, poly_option(split));
+  const int split = twin_split(head_dim);
+  if (split > 0) snprintf(buf, sizeof(buf), "fresco_attn_twin_kernel<%d,poly%d,%d>", head_dim, poly_option(head_dim, split), split);
+  else snprintf(buf, sizeof(buf), "fresco_attn_kernel<%d,poly%d> (pipelined)", head_dim, poly_option(head_dim, split));
   return buf;
 }
 

@@ -73,13 +73,13 @@ def attn_opts(fb):
 
 VARIANTS = [
     dict(),                                                              # the defaults (per head_dim)
-    dict(FRESCO_ATTN_WIDE=2),                                            # two threads per query row
-    dict(FRESCO_ATTN_WIDE=4),                                            # four: head_dim <= 80
-    dict(FRESCO_ATTN_WIDE=3),                                            # duo kernel (shared running max): head_dim <= 64
-    dict(FRESCO_ATTN_WIDE=3, FRESCO_ATTN_POLY=4),
-    dict(FRESCO_ATTN_WIDE=5),                                            # twin kernel (128-key tiles): head_dim <= 80
-    dict(FRESCO_ATTN_WIDE=5, FRESCO_ATTN_POLY=4),
-    dict(FRESCO_ATTN_WIDE=0, FRESCO_ATTN_POLY=0, FRESCO_ATTN_ROWSUM=0),
+    dict(FRESCO_ATTN_WIDE=1, FRESCO_ATTN_POLY=0),                        # twin kernel, one thread per query row
+    dict(FRESCO_ATTN_WIDE=1, FRESCO_ATTN_POLY=4),
+    dict(FRESCO_ATTN_WIDE=1, FRESCO_ATTN_POLY=8),
+    dict(FRESCO_ATTN_WIDE=2, FRESCO_ATTN_POLY=0),                        # twin kernel, two threads per query row
+    dict(FRESCO_ATTN_WIDE=2, FRESCO_ATTN_POLY=4),
+    dict(FRESCO_ATTN_WIDE=2, FRESCO_ATTN_POLY=8),
+    dict(FRESCO_ATTN_WIDE=0, FRESCO_ATTN_POLY=0, FRESCO_ATTN_ROWSUM=0),  # pipelined kernel
     dict(FRESCO_ATTN_WIDE=0, FRESCO_ATTN_POLY=0, FRESCO_ATTN_ROWSUM=1),
     dict(FRESCO_ATTN_WIDE=0, FRESCO_ATTN_POLY=4, FRESCO_ATTN_ROWSUM=1),
     dict(FRESCO_ATTN_WIDE=0, FRESCO_ATTN_POLY=8, FRESCO_ATTN_ROWSUM=0),
@@ -89,10 +89,9 @@ VARIANTS = [
 @pytest.mark.parametrize("variant", VARIANTS, ids=lambda v: "-".join(f"{k[12:]}{x}" for k, x in v.items()) or "default")
 @pytest.mark.parametrize("d", [40, 64, 80, 128])
 def test_attention_variants_all_head_dims(fb, attn_opts, variant, d):
-    """ragged q / kv tails, shared K/V, a peaky softmax (gain 4: lazy rescale path), kv lengths that leave one key
-    half of the wide kernel fully masked (20, 33, 77), the diagonal bias + k-scale of spatial-guided attention."""
-    if variant.get("FRESCO_ATTN_WIDE") == 4 and d > 80:
-        pytest.skip("four threads per row: head_dim <= 80 only")
+    """ragged q / kv tails, shared K/V, a peaky softmax (gain 4 / 8: lazy rescale path), kv lengths that leave one key
+    half of a two-threads-per-row tile fully masked (20, 33, 77), the diagonal bias + k-scale of spatial-guided attention.
+    (head_dim 128 always runs the pipelined kernel: the twin variants are the same launch there.)"""
     attn_opts(**variant)
     heads = 2
     g = torch.Generator(device="cuda").manual_seed(17 + d)

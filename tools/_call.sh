@@ -1,8 +1,5 @@
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=index,name --format=csv > gpurun_out/r02_2gpu.txt 2>&1
-timeout 600 python -m pytest tests/test_gpu_parity_r2.py -m gpu -q -x -k "nccl" 2>&1 | tail -12 > gpurun_out/r02_2gpu_nccl_test.txt
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 15 --warmup 3 > gpurun_out/r02_bench_config4_2gpu.json 2> gpurun_out/r02_bench_config4_2gpu.err
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 15 --warmup 3 --workload config4opt > gpurun_out/r02_bench_config4opt_2gpu.json 2> gpurun_out/r02_bench_config4opt_2gpu.err
-timeout 400 python bench.py --workload config4 --steps 15 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/r02_bench_config4_1gpu.json 2> gpurun_out/r02_bench_config4_1gpu.err
-timeout 500 python bench.py --workload config4opt --steps 15 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/r02_bench_config4opt_1gpu.json 2> gpurun_out/r02_bench_config4opt_1gpu.err
-tail -5 gpurun_out/r02_2gpu_nccl_test.txt | cut -c1-300; for f in config4_2gpu config4opt_2gpu config4_1gpu config4opt_1gpu; do echo == $f; cut -c1-330 gpurun_out/r02_bench_$f.json; tail -3 gpurun_out/r02_bench_$f.err | cut -c1-300; done
+timeout 300 python -m pytest tests/test_gpu_parity_r2.py -m gpu -q -x -k "WIDE6" 2>&1 | tail -8 > gpurun_out/r02_twin16_parity.txt
+timeout 400 python tools/bench_attn.py default FRESCO_ATTN_WIDE=6 FRESCO_ATTN_WIDE=6,FRESCO_ATTN_POLY=0 FRESCO_ATTN_WIDE=6,FRESCO_ATTN_POLY=8 FRESCO_ATTN_WIDE=5 FRESCO_ATTN_WIDE=4 > gpurun_out/r02_attn_microbench_twin16.jsonl 2>&1
+FRESCO_ATTN_WIDE=6 PROF_ITERS=1 timeout 300 ncu --set full --clock-control none --import-source on -k "regex:fresco_attn" -c 1 -f -o gpurun_out/r02_attn_twin16 python tools/prof_kernels.py > gpurun_out/r02_ncu_twin16.log 2>&1
+tail -4 gpurun_out/r02_twin16_parity.txt | cut -c1-300; cat gpurun_out/r02_attn_microbench_twin16.jsonl | cut -c1-400

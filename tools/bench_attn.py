@@ -19,6 +19,7 @@ SHAPES = [  # B, L, Lk, heads, d, q_per_kv
     (16, 1024, 3897, 8, 80, 8),       # level A, cross-frame
     (16, 1024, 1024, 8, 80, 1),       # level A, spatial-guided
     (32, 1024, 1024, 1, 128, 1),      # GMFlow-like single head, d = 128
+    (16, 2048, 2048, 5, 64, 1),       # head_dim 64 (not a FRESCO shape: picks the default kernel for it)
 ]
 OPTS = ("FRESCO_ATTN_WIDE", "FRESCO_ATTN_POLY", "FRESCO_ATTN_ROWSUM")
 
