@@ -1126,14 +1126,15 @@ static int make_head_tile_map(CUtensorMap* map, const void* base, int head_dim, 
 //   FRESCO_ATTN_ROWSUM  pipelined kernel, head_dim 40: row sums from the tensor core
 constexpr int kRowsumDefault = 1;
 // TFLOP/s measured in isolation at the config-2 shapes (profiles/r02_attn_microbench_*.jsonl; +-2 % run to run):
-//   d = 40 (L 4096, Lk 15587): pipelined 451 | twin/1 531, poly8 563, poly4 594 | twin/2 543, poly4 584, poly8 617  [torch SDPA 622]
-//   d = 80 (L 1024, Lk 3897):  pipelined 520 | twin/1 628, poly4 680 | twin/2 624, poly4 635, poly8 659              [torch SDPA 868]
-//   d = 64 (L 2048, Lk 2048):  twin/1 poly4 540 | twin/2 534;   d = 128: pipelined 510, poly4 543                       [SDPA 849]
+//   d = 40 (L 4096, Lk 15587): pipelined 445 | twin/1 531, poly8 563, poly4 594 | twin/2 543, poly4 584, poly8 621  [torch SDPA 620]
+//   d = 80 (L 1024, Lk 3897):  pipelined 516 | twin/1 628, poly4 679 | twin/2 624, poly4 636, poly8 659              [torch SDPA 854]
+//   d = 64 (L 2048, Lk 2048):  pipelined 597 | twin/1 poly4 561 | twin/2 poly4 525                                    [torch SDPA 750]
+//   d = 128 (L 1024, Lk 1024): pipelined 510, poly4 543                                                               [torch SDPA 846]
 // Built, measured slower and removed again (numbers in DESIGN.md 3.1): a "wide" kernel (2 / 4 threads per row with
 // private running max and accumulator per key part: 426 / 343 at d = 40, 587 at d = 80), a "duo" kernel (two threads per
 // row sharing one running max, 64-key tiles: 449), a 4-CTA-per-SM kernel without pipelining, prefetched scores, and two
 // query tiles taking strict turns on the MUFU pipe.
-constexpr int default_rows_split(int head_dim) { return head_dim == 40 ? 2 : (head_dim <= 80 ? 1 : 0); }
+constexpr int default_rows_split(int head_dim) { return head_dim == 40 ? 2 : (head_dim == 80 ? 1 : 0); }
 static int twin_split(int head_dim) {       // 0 = pipelined kernel, 1 | 2 = twin kernel, threads per query row
   int w = option(OPT_ATTN_WIDE, -1);
   if (w < 0) w = default_rows_split(head_dim);

@@ -1,5 +1,6 @@
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_parity_r2.py -m gpu -q -x -k "WIDE6" 2>&1 | tail -8 > gpurun_out/r02_twin16_parity.txt
-timeout 400 python tools/bench_attn.py default FRESCO_ATTN_WIDE=6 FRESCO_ATTN_WIDE=6,FRESCO_ATTN_POLY=0 FRESCO_ATTN_WIDE=6,FRESCO_ATTN_POLY=8 FRESCO_ATTN_WIDE=5 FRESCO_ATTN_WIDE=4 > gpurun_out/r02_attn_microbench_twin16.jsonl 2>&1
-FRESCO_ATTN_WIDE=6 PROF_ITERS=1 timeout 300 ncu --set full --clock-control none --import-source on -k "regex:fresco_attn" -c 1 -f -o gpurun_out/r02_attn_twin16 python tools/prof_kernels.py > gpurun_out/r02_ncu_twin16.log 2>&1
-tail -4 gpurun_out/r02_twin16_parity.txt | cut -c1-300; cat gpurun_out/r02_attn_microbench_twin16.jsonl | cut -c1-400
+nvidia-smi --query-gpu=index,name --format=csv > gpurun_out/r02_8gpu.txt 2>&1
+timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus 8 --steps 15 --warmup 3 > gpurun_out/r02_bench_config4_8gpu.json 2> gpurun_out/r02_bench_config4_8gpu.err
+timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29522 bench.py --gpus 4 --steps 15 --warmup 3 > gpurun_out/r02_bench_config4_4gpu.json 2> gpurun_out/r02_bench_config4_4gpu.err
+timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29523 bench.py --gpus 8 --steps 15 --warmup 3 --workload config4opt > gpurun_out/r02_bench_config4opt_8gpu.json 2> gpurun_out/r02_bench_config4opt_8gpu.err
+for f in config4_8gpu config4_4gpu config4opt_8gpu; do echo == $f; grep '^{' gpurun_out/r02_bench_$f.json | cut -c1-260; tail -2 gpurun_out/r02_bench_$f.err | cut -c1-300; done
