@@ -1,6 +1,6 @@
 """GPU parity tests added in round 2: the shapes the bench actually executes ("parity gaps").
 
-* every compiled attention variant (pipelined / wide / narrow, FMA-pipe exponentials) at every head_dim,
+* every compiled attention variant (twin kernel with one / two threads per row, pipelined kernel, FMA-pipe exponentials) at every head_dim,
 * golden set B (N = 3, 64 x 96 plane, head_dim 80 -- odd frame count, non-square) through the kernels,
 * temporal-guided attention at the bench shapes (N = 8, 8 heads, d = 40, L = 4096 and d = 80, L = 1024),
 * teacher-forced single-iteration optimize_feature pieces at [16,1280,32,32] and [16,640,64,64], and the
