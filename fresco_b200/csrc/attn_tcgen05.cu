@@ -669,10 +669,15 @@ fresco_attn_twin_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   constexpr int NB = Cfg::NBUF;
   uint64_t* bar_s = bars + 1 + 2 * ST;         // [NB] score tile n ready in region n % NB; phase (n / NB) & 1
   uint64_t* bar_p = bar_s + 3;                 // [NB] P of score tile n written by the four warps of its query tile
-  uint64_t* bar_pv = bar_s + 6;                // [2]  P V_X(j) retired (O_X stable); phase j & 1
+  uint64_t* bar_pv = bar_s + 6;                // [2]  P V_X(j) retired (O_X stable); phase j & 1 (lazy-max rescale only)
   uint64_t* bar_vp = bar_s + 8;                // [ST] ones column written into V tile t (FOLD)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s + 8 + ST);
-  float* s_xch = reinterpret_cast<float*>(bar_s + 8 + ST + 2);      // [2 query tiles][2 halves][128 rows] (SPLIT 2)
+  // [2] the LAST P V_X retired, completed exactly once.  The epilogue must not use bar_pv for this: with three score
+  // regions "S_X(T-1) is ready" only implies that P V_X(T-3) has retired, so bar_pv[X] may be two completions behind
+  // when a warp reaches the epilogue, and a parity wait cannot tell "T - 2 completions" from "T" (found with
+  // tools/twin_protocol_model.py; on the GPU the margin -- a whole softmax tile -- always hid it)
+  uint64_t* bar_fin = bar_s + 8 + ST;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s + 10 + ST);
+  float* s_xch = reinterpret_cast<float*>(bar_s + 12 + ST);         // [2 query tiles][2 halves][128 rows] (SPLIT 2)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -694,6 +699,8 @@ fresco_attn_twin_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     }
     mbar_init(bar_pv + 0, 1);
     mbar_init(bar_pv + 1, 1);
+    mbar_init(bar_fin + 0, 1);
+    mbar_init(bar_fin + 1, 1);
     for (int s = 0; s < ST; ++s) mbar_init(bar_vp + s, 2);
     fence_barrier_init();
   }
@@ -791,6 +798,7 @@ fresco_attn_twin_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         tc_fence_after();
         issue_pv(n);
         umma_commit(bar_pv + (n & 1));
+        if (n + 2 >= n_total) umma_commit(bar_fin + (n & 1));   // the last P V of this query tile
         if (n & 1) umma_commit(bar_kv_empty + (n >> 1) % ST);   // K(t), V(t) consumed by both query tiles
         // region n % NB is free once P V(n) has read P: the score MMA issued behind it (same thread, in order) may reuse it
         if (n + NB < n_total) issue_qk(n + NB);
@@ -917,7 +925,7 @@ fresco_attn_twin_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     }
 
     // ---- epilogue: O / l -> fp16 head slice of this row
-    mbar_wait_trap(bar_pv + x, (n_tiles - 1) & 1);
+    mbar_wait_trap(bar_fin + x, 0);
     tc_fence_after();
     uint32_t lcol[8];
     tmem_ld8_sync(o_lane + (Cfg::L_COL / 8) * 8, lcol);
@@ -1045,7 +1053,7 @@ fresco_attn_twin_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     }
 
     // ---- epilogue: O / l -> fp16 head slice; the two threads of a row take alternate 16-byte chunks
-    mbar_wait_trap(bar_pv + x, (n_tiles - 1) & 1);
+    mbar_wait_trap(bar_fin + x, 0);
     tc_fence_after();
     uint32_t lcol[8];
     tmem_ld8_sync(o_lane + (Cfg::L_COL / 8) * 8, lcol);

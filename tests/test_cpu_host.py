@@ -43,6 +43,30 @@ def test_argument_errors_do_not_touch_the_gpu(built_lib):
     assert rc == -1
 
 
+def test_default_attention_kernel_per_head_dim(built_lib):
+    """Host-side kernel selection through the C ABI (no launch): the measured-best kernel per head_dim is the default,
+    the options select the other parity-tested variants, negative values restore the defaults, unknown names fail."""
+    l = built_lib.lib()
+    names = ("FRESCO_ATTN_WIDE", "FRESCO_ATTN_POLY")
+    for n in names:
+        assert l.fresco_set_option(n.encode(), -1) == 0
+    v = lambda d: l.fresco_attn_variant(d).decode()
+    assert v(40) == "fresco_attn_twin_kernel<40,poly8,2>"          # two threads per row at the dominant FRESCO shape
+    assert v(80) == "fresco_attn_twin_kernel<80,poly4,1>"
+    assert v(64).startswith("fresco_attn_kernel<64,poly0>") and v(128).startswith("fresco_attn_kernel<128,poly0>")
+    try:
+        assert l.fresco_set_option(b"FRESCO_ATTN_WIDE", 1) == 0 and l.fresco_set_option(b"FRESCO_ATTN_POLY", 0) == 0
+        assert v(40) == "fresco_attn_twin_kernel<40,poly0,1>" and v(64) == "fresco_attn_twin_kernel<64,poly0,1>"
+        assert v(128).startswith("fresco_attn_kernel<128")          # the twin kernel stops at head_dim 80
+        assert l.fresco_set_option(b"FRESCO_ATTN_WIDE", 0) == 0
+        assert v(40).startswith("fresco_attn_kernel<40,poly0>")
+        assert l.fresco_set_option(b"FRESCO_NO_SUCH_OPTION", 1) == -1
+    finally:
+        for n in names:
+            l.fresco_set_option(n.encode(), -1)
+    assert v(40) == "fresco_attn_twin_kernel<40,poly8,2>"
+
+
 def test_no_cpu_fallback(built_lib):
     from fresco_b200 import ops
     from fresco_b200._lib import FrescoError
