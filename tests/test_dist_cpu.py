@@ -6,6 +6,7 @@ import os
 import socket
 import sys
 
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -385,19 +386,21 @@ def _optimize_worker(rank, world, port, ret):
     dist.destroy_process_group()
 
 
-def test_sharded_optimize_feature_world2_gloo():
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_optimize_feature_gloo(world):
     """optimize_feature on a frame-sharded batch (ring halo of one boundary frame per Adam iteration, SURVEY 8e exchange
-    3): both ranks together == the unsharded call == the oracle, loss curves included."""
+    3): all ranks together == the unsharded call == the oracle, loss curves included.  World 4 leaves ONE frame per rank
+    (every pair crosses a rank boundary; previous and next neighbour differ)."""
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
     ctx = mp.get_context("spawn")
     ret = ctx.Queue()
-    procs = [ctx.Process(target=_optimize_worker, args=(r, 2, port, ret)) for r in range(2)]
+    procs = [ctx.Process(target=_optimize_worker, args=(r, world, port, ret)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
-        p.join(180)
+        p.join(240)
         assert p.exitcode == 0
     assert ret.get(timeout=5) == 1
