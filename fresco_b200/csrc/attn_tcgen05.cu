@@ -547,26 +547,32 @@ fresco_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 }
 
 // ---------------------------------------------------------------------------------------------
-// the "twin" kernel: TWO 128-row query tiles per CTA, 128-key tiles, one thread per query row (1 CTA per SM)
+// the "twin" kernel: TWO 128-row query tiles per CTA, 128-key tiles, one CTA per SM, one or two threads per query row
 // ---------------------------------------------------------------------------------------------
-// Written from the round-2 profiles (profiles/r02_attn_*_hot_*.txt): the 64-key kernels above execute 368 (pipelined)
-// to 572 (duo) warp-instructions per 128 x 64 tile of which 161 are the softmax arithmetic itself -- waits, arrivals,
-// buffer indexing, the lazy-max test and the polling loops are paid per (warp, tile) whatever the tile holds -- and the
-// issue slots (56-68 % busy), not the MUFU pipe (65 %), are what every structure runs into at ~840 clocks per tile.
-// Here a softmax thread owns a whole row of a 128-key tile (128 scores in registers: one CTA per SM leaves 200 registers
-// per thread), so the per-tile overhead is paid once per 128 keys, and there are only two barrier operations per
-// tile: P overwrites the first half of the S columns it was computed from (the thread has them in registers), the score
-// MMA of the next tile is issued behind the P V MMA by the same thread, so "S_j is ready" implies "P V_{j-1} has
-// retired" -- no P-buffer or O-stability waits at all.  The two query tiles (A, B) take turns: while the warps of A
-// are in their exponentials the tensor core runs P V / Q K^T for B.
+// Written from the round-2 profiles (profiles/r02_attn_*_hot*.txt): the 64-key kernels execute 368 (pipelined) to 572
+// (two threads per row) warp-instructions per 128 x 64 tile of which 161 are the softmax arithmetic itself -- waits,
+// arrivals, buffer indexing, the lazy-max test and the polling loops are paid per (warp, tile) whatever the tile holds --
+// and the issue slots (56-68 % busy), not the MUFU pipe (65 %), are what every such structure runs into at ~840 clocks
+// per tile.  Here the per-tile overhead is paid once per 128 keys, and a softmax warp has only two barrier operations per
+// tile (wait for S, announce P): P overwrites the start of the score columns it was computed from (the thread has them
+// in registers), and the score MMA that reuses a region is issued behind the P V MMA that reads it by the SAME thread
+// (the tensor core keeps the order) -- no P-buffer wait exists, and O is only waited for on the rare lazy-max rescale.
+// The two query tiles (A, B) interleave: while the warps of A are in their exponentials the tensor core works for B.
 //
 // When the O accumulators leave room (head_dim <= 48) the scores rotate through THREE 128-column regions shared by the
 // two query tiles (sequence A0 B0 A1 B1 ...: score tile n lives in region n % 3), so Q K^T of a query tile's NEXT key
 // tile runs while its warps are still in the exponentials of the current one; with two regions (head_dim 64 / 80) a
 // query tile's next scores can only be computed after its P V has read P.
 //
-//   TMEM  S regions [0,128) [128,256) ([256,384))  (fp32 scores; P = fp16 in columns [0,64) of the same region)
-//         O_A, O_B behind them, DPAD columns each + 16 columns of row sums (ones-MMA)
+// SPLIT = 1: one thread per query row holds the whole 128-score row (setmaxnreg: 224 registers for the softmax
+// warpgroups).  SPLIT = 2: two threads per row, 64 keys each -- four softmax warps per sub-partition to cover each
+// other's fixed-latency stalls; they agree on ONE running max through a named-barrier OR-reduction and share one
+// accumulator, so nothing is merged at the end.
+//
+//   TMEM  S regions [0,128) [128,256) ([256,384))   fp32 scores; P = fp16 over the start of the same columns
+//         O_A, O_B behind them (64 columns each with three regions, 128 with two); row sums: O column head_dim (FOLD)
+//         or 16 columns behind O (ones-MMA)
+//   The synchronisation protocol is restated and model-checked in tools/twin_protocol_model.py.
 template <int D, int SPLIT_>
 struct TwinCfg {
   static constexpr int SPLIT = SPLIT_;                    // threads per query row: 1, or 2 (64 keys of a tile each)
