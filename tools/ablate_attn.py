@@ -1,4 +1,5 @@
-"""Ablation of the attention kernel (results are wrong on purpose; timing only): which stage sets the pace?"""
+"""Ablation of the pipelined attention kernel (FRESCO_ATTN_WIDE=0, built with FRESCO_NVCC_EXTRA=-DFRESCO_ATTN_ABLATE_BUILD;
+results are wrong on purpose; timing only): which stage sets the pace?"""
 import json, os, subprocess, sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 code = r'''
@@ -18,6 +19,6 @@ names = {0: "baseline", 1: "no exp2 (MUFU)", 2: "no S load (TMEM->RF)", 4: "no P
          32: "no QK MMA", 64: "no K/V TMA after the first ring fill", 40: "no MMAs at all", 104: "no MMAs, no TMA",
          23: "no softmax work (exp, S load, P store, max)", 127: "barrier skeleton only"}
 for a, n in names.items():
-    env = dict(os.environ, FRESCO_ATTN_ABLATE=str(a))
+    env = dict(os.environ, FRESCO_ATTN_ABLATE=str(a), FRESCO_ATTN_WIDE="0")      # the pipelined kernel carries the ablation switches
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
     print(json.dumps({"ablate": a, "what": n, "ms": r.stdout.strip() or r.stderr[-300:]}))

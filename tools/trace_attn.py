@@ -1,8 +1,11 @@
-"""Per-stage SM-clock stamps of one attention CTA (needs a -DFRESCO_ATTN_TRACE build: FRESCO_NVCC_EXTRA=-DFRESCO_ATTN_TRACE)."""
+"""Per-stage SM-clock stamps of one CTA of the PIPELINED attention kernel (needs a -DFRESCO_ATTN_TRACE build:
+FRESCO_NVCC_EXTRA=-DFRESCO_ATTN_TRACE; the stamps are compiled into fresco_attn_kernel only)."""
 import ctypes, os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from fresco_b200 import ops, _lib
+
+_lib.set_option("FRESCO_ATTN_WIDE", 0)
 
 d = int(sys.argv[1]) if len(sys.argv) > 1 else 40
 B, L, Lk, H, qpk = (16, 4096, 11874, 8, 8) if d == 40 else (16, 1024, 11874, 8, 8)
