@@ -473,3 +473,63 @@ def test_pipe_step_host_logic_against_reference(golden, monkeypatch):
         assert (prev - T(g[f"{tag}_prev"])).abs().max() < 1e-5 and (x0 - T(g[f"{tag}_x0"])).abs().max() < 1e-5
         prev, x0 = pf.step(Pipe, raw, ts, sample, torch.Generator().manual_seed(5), repeat_noise=rep, guidance_scale=7.5)
         assert (prev - T(g[f"{tag}_prev"])).abs().max() < 1e-5 and (x0 - T(g[f"{tag}_x0"])).abs().max() < 1e-5
+
+
+def test_get_intraframe_paras_host_logic_on_harness_unet(monkeypatch):
+    """P2 (src/diffusion_hacked.py:843-901) end to end on CPU: stub scheduler / VAE, the harness UNet with the hook surface
+    installed, torch stand-ins for the kernels.  The store pass must leave the six decoder self-attention inputs in the
+    controller (in call order, store switched off again, guidance flags off), and the returned targets must be the
+    reference's formula -- bmm of the row-normalised decoder features, fp32 [2N, hw, hw] -- on the four decoder features
+    of that same pass."""
+    from fresco_b200 import diffusion_hacked as dh
+    from fresco_b200.harness.sd15_unet import FakePipe, SD15UNet
+    monkeypatch.setattr(dh, "ops", _TorchOps)
+    torch.manual_seed(1)
+    unet = SD15UNet(block_out=(32, 64, 128, 128), heads=8, cross_dim=24)
+    pipe = FakePipe(unet)
+    ac = torch.linspace(0.999, 0.01, 1000)
+
+    class Sched(_Sched):
+        timesteps = torch.arange(950, -1, -50)
+
+    class VAE:
+        class config:
+            scaling_factor = 0.5
+
+        @staticmethod
+        def encode(x):
+            class D:
+                latent_dist = None
+
+            d = D()
+            d.latent_dist = d
+            d.sample = lambda: torch.nn.functional.avg_pool2d(x, 8)[:, :1].repeat(1, 4, 1, 1)
+            return d
+
+    pipe.scheduler, pipe.vae, pipe._execution_device = Sched(ac), VAE(), torch.device("cpu")
+    pipe.prepare_latents = lambda B, C, H, W, dtype, device, generator, latents=None: torch.randn(
+        B, C, H // 8, W // 8, generator=generator, dtype=dtype)
+    proc = dh.apply_FRESCO_attn(pipe)
+    N = 2
+    imgs = torch.rand(N, 3, 128, 128) * 2 - 1
+    pe = torch.randn(2 * N, 7, 24)
+    corr = dh.get_intraframe_paras(pipe, imgs, proc, pe, seed=3)
+    ctrl = proc.controller
+    assert not ctrl.store and not ctrl.use_cfattn and not ctrl.use_intraattn and not ctrl.use_interattn
+    stored = ctrl.stored_attn["decoder_attn"]
+    assert [tuple(t.shape) for t in stored] == [(2 * N, 64, 64)] * 3 + [(2 * N, 256, 32)] * 3   # up_blocks.2 then .3
+    # the same pass again, by hand: identical noise (same seed), hooks recording the decoder features
+    g = torch.Generator().manual_seed(3)
+    lat = pipe.prepare_latents(N, 4, 128, 128, pe.dtype, torch.device("cpu"), g)
+    x0 = 0.5 * VAE.encode(imgs).latent_dist.sample()
+    lat = pipe.scheduler.add_noise(x0, lat, Sched.timesteps[-1])
+    with torch.no_grad():
+        out = pipe.unet(torch.cat([lat] * 2), Sched.timesteps[-1], encoder_hidden_states=pe, return_dict=False)
+    assert len(out) == 5 and len(corr) == 4
+    for tgt, feat in zip(corr, out[1:]):
+        v = feat.reshape(feat.shape[0], feat.shape[1], -1).transpose(1, 2)
+        v = v / ((v ** 2).sum(dim=2, keepdim=True) ** 0.5)
+        want = torch.bmm(v, v.transpose(-1, -2)).to(torch.float32)
+        assert tgt.dtype == torch.float32 and tuple(tgt.shape) == tuple(want.shape)
+        assert torch.allclose(tgt, want, atol=1e-6)
+        assert torch.allclose(torch.diagonal(tgt, dim1=1, dim2=2), torch.ones(tgt.shape[0], tgt.shape[1]), atol=1e-5)
